@@ -1,0 +1,281 @@
+// rb_build.h — host-side scene preparation shared by the CUDA library and the host emulation used
+// for debugging: validates the flat description, derives per-shape constants, flattens placed nodes
+// into physical paths (DFS pre-order, id 0 = top) and builds one threaded BVH per mother node.
+#ifndef RB_BUILD_H
+#define RB_BUILD_H
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rb_scene.h"
+
+struct NotSupported : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct Invalid : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+struct Box {
+  double lo[3], hi[3];
+};
+static Box box_empty() { return Box{{1e300, 1e300, 1e300}, {-1e300, -1e300, -1e300}}; }
+static void box_add(Box& b, const double* p) {
+  for (int i = 0; i < 3; i++) {
+    b.lo[i] = std::min(b.lo[i], p[i]);
+    b.hi[i] = std::max(b.hi[i], p[i]);
+  }
+}
+static Box box_transform(const Box& b, const DMat& m) {  // local -> master
+  Box o = box_empty();
+  for (int c = 0; c < 8; c++) {
+    double l[3] = {c & 1 ? b.hi[0] : b.lo[0], c & 2 ? b.hi[1] : b.lo[1], c & 4 ? b.hi[2] : b.lo[2]}, q[3];
+    for (int i = 0; i < 3; i++) q[i] = m.t[i] + m.r[3 * i] * l[0] + m.r[3 * i + 1] * l[1] + m.r[3 * i + 2] * l[2];
+    box_add(o, q);
+  }
+  return o;
+}
+static DMat mat_identity() {
+  DMat m;
+  memset(&m, 0, sizeof(m));
+  m.r[0] = m.r[4] = m.r[8] = 1;
+  return m;
+}
+static DMat mat_mul(const DMat& a, const DMat& b) {
+  DMat o;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) o.r[3 * i + j] = a.r[3 * i] * b.r[j] + a.r[3 * i + 1] * b.r[3 + j] + a.r[3 * i + 2] * b.r[6 + j];
+    o.t[i] = a.t[i] + a.r[3 * i] * b.t[0] + a.r[3 * i + 1] * b.t[1] + a.r[3 * i + 2] * b.t[2];
+  }
+  return o;
+}
+
+struct SceneBuilder {
+  const rbg_scene_desc* D;
+  std::vector<DShape> shapes;
+  std::vector<double> dpar;
+  std::vector<DMat> mats;
+  std::vector<Box> shape_box;
+  std::vector<int> shape_depth;
+  std::vector<DNode> nodes;
+  std::vector<DBvh> bvh;
+  std::vector<std::string> names;
+
+  DMat mat(int id) const {
+    if (id < 0) return mat_identity();
+    DMat m;
+    memcpy(m.r, D->matrices[id].rot, sizeof(m.r));
+    memcpy(m.t, D->matrices[id].tr, sizeof(m.t));
+    return m;
+  }
+  void build_shapes() {
+    const double deg = M_PI / 180.;
+    shapes.resize(D->nshapes);
+    shape_box.resize(D->nshapes);
+    shape_depth.assign(D->nshapes, 0);
+    for (int i = 0; i < D->nmatrices; i++) mats.push_back(mat(i));
+    for (int i = 0; i < D->nshapes; i++) {  // operands always precede their composite (export order)
+      const rbg_shape& s = D->shapes[i];
+      const double* P = D->dpar + s.ipar;
+      DShape& o = shapes[i];
+      o.type = s.type; o.left = s.left; o.right = s.right; o.lmat = s.lmat; o.rmat = s.rmat;
+      o.ipar = (int)dpar.size();
+      Box b = box_empty();
+      auto setbox = [&](double x, double y, double zlo, double zhi) { b = Box{{-x, -y, zlo}, {x, y, zhi}}; };
+      switch (s.type) {
+        case RBG_SHAPE_BBOX:
+          dpar.insert(dpar.end(), P, P + 6);
+          b = Box{{P[3] - P[0], P[4] - P[1], P[5] - P[2]}, {P[3] + P[0], P[4] + P[1], P[5] + P[2]}};
+          break;
+        case RBG_SHAPE_TUBE:
+          dpar.insert(dpar.end(), P, P + 3);
+          setbox(P[1], P[1], -P[2], P[2]);
+          break;
+        case RBG_SHAPE_SPHERE: {
+          dpar.insert(dpar.end(), P, P + 6);
+          int flags = (P[2] > 0 ? 1 : 0) | (P[3] < 180 ? 2 : 0) | (fabs(P[5] - P[4] - 360.) > 1e-9 ? 4 : 0);
+          double v[9] = {cos(P[2] * deg), sin(P[2] * deg), cos(P[3] * deg), sin(P[3] * deg), cos(P[4] * deg), sin(P[4] * deg), cos(P[5] * deg),
+                         sin(P[5] * deg), (double)flags};
+          dpar.insert(dpar.end(), v, v + 9);
+          dpar.push_back(0);
+          double zc[4] = {P[0] * v[0], P[0] * v[2], P[1] * v[0], P[1] * v[2]};
+          double zlo = *std::min_element(zc, zc + 4), zhi = *std::max_element(zc, zc + 4);
+          double rho = (P[2] <= 90 && 90 <= P[3]) ? P[1] : P[1] * std::max(v[1], v[3]);
+          setbox(rho, rho, zlo, zhi);
+          break;
+        }
+        case RBG_SHAPE_PARABOLOID: {
+          dpar.insert(dpar.end(), P, P + 3);
+          double dd = 1. / (P[1] * P[1] - P[0] * P[0]);
+          dpar.push_back(2. * P[2] * dd);
+          dpar.push_back(-P[2] * (P[0] * P[0] + P[1] * P[1]) * dd);
+          double rm = std::max(P[0], P[1]);
+          setbox(rm, rm, -P[2], P[2]);
+          break;
+        }
+        case RBG_SHAPE_PGON: {
+          int ne = (int)P[2], nz = (int)P[3];
+          if (fabs(P[1] - 360.) > 1e-9) throw NotSupported("TGeoPgon with dphi != 360 is not supported on the device path");
+          if (ne < 3 || nz < 2) throw Invalid("TGeoPgon needs nedges >= 3 and nz >= 2");
+          double rmx = 0;
+          for (int k = 0; k < nz; k++) {
+            if (P[4 + 3 * k + 1] > 0) throw NotSupported("TGeoPgon with rmin > 0 is not supported on the device path");
+            rmx = std::max(rmx, P[4 + 3 * k + 2]);
+          }
+          dpar.insert(dpar.end(), P, P + 4 + 3 * nz);
+          for (int e = 0; e < ne; e++) {
+            double ph = (P[0] + (e + 0.5) * P[1] / ne) * deg;
+            dpar.push_back(cos(ph));
+            dpar.push_back(sin(ph));
+          }
+          double R = rmx / cos(M_PI / ne);
+          setbox(R, R, P[4], P[4 + 3 * (nz - 1)]);
+          break;
+        }
+        case RBG_SHAPE_PCON: throw NotSupported("TGeoPcon is not supported on the device path yet");
+        case RBG_SHAPE_ASPHERE: {
+          int n1 = (int)P[8], n2 = (int)P[9];
+          dpar.insert(dpar.end(), P, P + 12 + n1 + n2);
+          setbox(P[7], P[7], P[10] - P[11], P[10] + P[11]);
+          break;
+        }
+        case RBG_SHAPE_WINSTON2D:
+        case RBG_SHAPE_WINSTONPOLY: {
+          double r1 = P[0], r2 = P[1], theta = asin(r2 / r1), dz = (r1 + r2) / tan(theta) / 2., f = r2 * (1 + sin(theta));
+          double v[8] = {r1, r2, P[2], theta, dz, f, cos(theta), sin(theta)};
+          dpar.insert(dpar.end(), v, v + 8);
+          if (s.type == RBG_SHAPE_WINSTON2D) setbox(r1, P[2], -dz, dz);
+          else {
+            double R = r1 / cos(M_PI / std::max(3, (int)P[2]));
+            setbox(R, R, -dz, dz);
+          }
+          break;
+        }
+        case RBG_SHAPE_UNION:
+        case RBG_SHAPE_INTERSECTION:
+        case RBG_SHAPE_SUBTRACTION: {
+          if (s.left < 0 || s.left >= i || s.right < 0 || s.right >= i) throw Invalid("composite operand out of order");
+          Box bl = box_transform(shape_box[s.left], mat(s.lmat)), br = box_transform(shape_box[s.right], mat(s.rmat));
+          if (s.type == RBG_SHAPE_UNION)
+            for (int k = 0; k < 3; k++) { b.lo[k] = std::min(bl.lo[k], br.lo[k]); b.hi[k] = std::max(bl.hi[k], br.hi[k]); }
+          else if (s.type == RBG_SHAPE_INTERSECTION)
+            for (int k = 0; k < 3; k++) { b.lo[k] = std::max(bl.lo[k], br.lo[k]); b.hi[k] = std::min(bl.hi[k], br.hi[k]); }
+          else b = bl;
+          shape_depth[i] = 1 + std::max(shape_depth[s.left], shape_depth[s.right]);
+          break;
+        }
+        default: throw Invalid("unknown shape type");
+      }
+      shape_box[i] = b;
+    }
+  }
+  // DFS pre-order flattening of placed nodes into physical paths
+  int flatten(int vol, const DMat& g, int mother, int overlap, const std::string& name) {
+    if (vol < 0 || vol >= D->nvolumes) throw Invalid("bad volume id");
+    int id = (int)nodes.size();
+    if (id > 2000000) throw Invalid("too many physical nodes");
+    DNode n;
+    memset(&n, 0, sizeof(n));
+    n.g = g;
+    n.volume = vol;
+    n.shape = D->volumes[vol].shape;
+    n.type = D->volumes[vol].type;
+    n.mother = mother;
+    n.overlap = overlap;
+    nodes.push_back(n);
+    names.push_back(name);
+    const rbg_volume& v = D->volumes[vol];
+    std::vector<int> kids;
+    for (int k = 0; k < v.nnodes; k++) {
+      const rbg_node& nd = D->nodes[v.first_node + k];
+      std::string nm = std::string(D->names + D->volumes[nd.volume].name) + "_" + std::to_string(nd.copy_no);
+      kids.push_back(flatten(nd.volume, mat_mul(g, mat(nd.matrix)), id, nd.overlap, nm));
+    }
+    build_bvh(id, kids);
+    return id;
+  }
+  Box world_box(int node) const {
+    Box b = box_transform(shape_box[nodes[node].shape], nodes[node].g);
+    for (int k = 0; k < 3; k++) {
+      double m = 1e-6 + 1e-9 * std::max(fabs(b.lo[k]), fabs(b.hi[k]));
+      b.lo[k] -= m;
+      b.hi[k] += m;
+    }
+    return b;
+  }
+  int bvh_rec(std::vector<std::pair<int, Box>>& items, int lo, int hi) {
+    int me = (int)bvh.size();
+    bvh.push_back(DBvh());
+    Box b = box_empty();
+    for (int i = lo; i < hi; i++) { box_add(b, items[i].second.lo); box_add(b, items[i].second.hi); }
+    memcpy(bvh[me].lo, b.lo, sizeof(b.lo));
+    memcpy(bvh[me].hi, b.hi, sizeof(b.hi));
+    if (hi - lo == 1) {
+      bvh[me].child = items[lo].first;
+    } else {
+      bvh[me].child = -1;
+      int axis = 0;
+      double ext = -1;
+      for (int k = 0; k < 3; k++) {
+        double clo = 1e300, chi = -1e300;
+        for (int i = lo; i < hi; i++) {
+          double c = 0.5 * (items[i].second.lo[k] + items[i].second.hi[k]);
+          clo = std::min(clo, c);
+          chi = std::max(chi, c);
+        }
+        if (chi - clo > ext) { ext = chi - clo; axis = k; }
+      }
+      int mid = (lo + hi) / 2;
+      std::nth_element(items.begin() + lo, items.begin() + mid, items.begin() + hi, [axis](const std::pair<int, Box>& a, const std::pair<int, Box>& c) {
+        return a.second.lo[axis] + a.second.hi[axis] < c.second.lo[axis] + c.second.hi[axis];
+      });
+      bvh_rec(items, lo, mid);
+      bvh_rec(items, mid, hi);
+    }
+    bvh[me].skip = (int)bvh.size();  // fixed up to -1 at the end of this tree by the caller
+    return me;
+  }
+  void build_bvh(int node, const std::vector<int>& kids) {
+    nodes[node].bvh_first = (int)bvh.size();
+    nodes[node].bvh_count = 0;
+    if (kids.empty()) return;
+    std::vector<std::pair<int, Box>> items;
+    for (int k : kids) items.emplace_back(k, world_box(k));
+    int first = (int)bvh.size();
+    bvh_rec(items, 0, (int)items.size());
+    int end = (int)bvh.size();
+    for (int i = first; i < end; i++)
+      if (bvh[i].skip >= end) bvh[i].skip = -1;
+    nodes[node].bvh_count = end - first;
+  }
+};
+
+static int scene_depth_needed(const SceneBuilder& B) {
+  int d = 0;
+  for (int v : B.shape_depth) d = std::max(d, v);
+  return d;
+}
+
+static void validate_desc(const rbg_scene_desc* D) {
+  if (!D) throw Invalid("null scene description");
+  if (D->abi_version != RBG_ABI_VERSION) throw Invalid("scene description ABI version mismatch");
+  if (D->top_volume >= D->nvolumes) throw Invalid("top volume out of range");
+  for (int i = 0; i < D->nvolumes; i++) {
+    const rbg_volume& v = D->volumes[i];
+    if (v.shape < 0 || v.shape >= D->nshapes) throw Invalid("volume with bad shape id");
+    if (v.first_node < 0 || v.first_node + v.nnodes > D->nnodes) throw Invalid("volume with bad node slice");
+    if (v.first_border < 0 || v.first_border + v.nborders > D->nborders) throw Invalid("volume with bad border slice");
+    if (v.index >= D->nindices || v.mirror >= D->nmirrors || v.focal >= D->nfocals) throw Invalid("volume with bad table id");
+  }
+  for (int i = 0; i < D->nmultilayers; i++) {
+    const rbg_multilayer& m = D->multilayers[i];
+    if (m.n < 2 || m.n > RB_MAX_TMM_LAYERS * 64 || m.first < 0 || m.first + m.n > D->nlayers) throw Invalid("bad multilayer");
+  }
+  for (int i = 0; i < D->nmirrors; i++)
+    if (D->mirrors[i].graph2d >= 0) throw NotSupported("TGraph2D mirror reflectance is not supported on the device path");
+}
+
+#endif

@@ -1,0 +1,1644 @@
+// rb_device.cuh — per-ray fp64 math of the B200 tracer: analytic shapes (ROOT TGeo primitives +
+// ROBAST AGeo* shapes + boolean composites), flattened navigation with a threaded BVH, surface
+// physics (Snell/Fresnel, mirrors, Lambertian, Gaussian roughness, multilayer TMM, absorption, QE)
+// and the Philox counter RNG.  One thread owns one ray; everything lives in registers.
+//
+// Reference behaviour being reproduced (file:line under /root/reference):
+//   state machine            src/AOpticsManager.cxx:335-520   
+//   DoFresnel / DoReflection src/AOpticsManager.cxx:52-247, GetFacetNormal :250-301
+//   AGeoAsphericDisk         src/AGeoAsphericDisk.cxx:96-153,246-347,363-684
+//   AGeoWinstonCone2D/Poly   src/AGeoWinstonCone2D.cxx:59-98,120-428 ; src/AGeoWinstonConePoly.cxx:67-226,293-309
+//   AMultilayer              src/AMultilayer.cxx:26-56,120-209,240-481 ; include/AMultilayer.h:114-132
+//   indices / mirrors / QE   src/A*Formula.cxx, include/ARefractiveIndex.h:36-65, src/AMirror.cxx:39-60,
+//                            src/AFocalSurface.cxx:35-52, src/AOpticalComponent.cxx:51-65
+//   ROOT TGeoNavigator / TGeo shapes / TGraph / TH2: external dependency, SURVEY.md Appendix B.
+// All functions are RB_HD so that the same source also builds for the host in tests/emul (a
+// debugging aid on the GPU-less build box; never part of the product library).
+#ifndef RB_DEVICE_CUH
+#define RB_DEVICE_CUH
+
+#include <math.h>
+
+#include "rb_scene.h"
+
+#define RB_BIG 1e30
+#define RB_TOL 1e-10
+#define RB_PI 3.14159265358979323846
+#define RB_C_CM 2.99792458e10 /* TMath::C()*m() in cm/s */
+
+// ------------------------------------------------------------------ small vector helpers
+struct V3 {
+  double x, y, z;
+};
+RB_HD inline V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+RB_HD inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RB_HD inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RB_HD inline V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+RB_HD inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RB_HD inline V3 along(V3 p, V3 d, double t) { return v3(p.x + t * d.x, p.y + t * d.y, p.z + t * d.z); }
+RB_HD inline double sqr(double v) { return v * v; }
+RB_HD inline double rb_min(double a, double b) { return a < b ? a : b; }
+RB_HD inline double rb_max(double a, double b) { return a > b ? a : b; }
+RB_HD inline double rb_atan2(double y, double x) {  // TMath::ATan2
+  if (x != 0) return atan2(y, x);
+  if (y == 0) return 0;
+  return y > 0 ? RB_PI / 2 : -RB_PI / 2;
+}
+RB_HD inline double rb_acos(double x) { return x < -1. ? RB_PI : (x > 1. ? 0 : acos(x)); }
+RB_HD inline double rb_asin(double x) { return x < -1. ? -RB_PI / 2 : (x > 1. ? RB_PI / 2 : asin(x)); }
+
+RB_HD inline V3 to_local(const DMat& m, V3 p) {
+  double a = p.x - m.t[0], b = p.y - m.t[1], c = p.z - m.t[2];
+  return v3(a * m.r[0] + b * m.r[3] + c * m.r[6], a * m.r[1] + b * m.r[4] + c * m.r[7], a * m.r[2] + b * m.r[5] + c * m.r[8]);
+}
+RB_HD inline V3 to_local_vec(const DMat& m, V3 d) {
+  return v3(d.x * m.r[0] + d.y * m.r[3] + d.z * m.r[6], d.x * m.r[1] + d.y * m.r[4] + d.z * m.r[7], d.x * m.r[2] + d.y * m.r[5] + d.z * m.r[8]);
+}
+RB_HD inline V3 to_master_vec(const DMat& m, V3 l) {
+  return v3(l.x * m.r[0] + l.y * m.r[1] + l.z * m.r[2], l.x * m.r[3] + l.y * m.r[4] + l.z * m.r[5], l.x * m.r[6] + l.y * m.r[7] + l.z * m.r[8]);
+}
+
+// ------------------------------------------------------------------ Philox4x32-10, key=(seed), ctr=(ray id, draw#)
+struct Philox {
+  uint32_t k0, k1, id0, id1, ndraw;
+};
+RB_HD inline uint32_t rb_mulhi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+RB_HD inline void philox_block(Philox& g, uint32_t o[4]) {
+  uint32_t c0 = g.id0, c1 = g.id1, c2 = g.ndraw++, c3 = 0u, k0 = g.k0, k1 = g.k1;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = rb_mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = rb_mulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+RB_HD inline double philox_u53(uint32_t a, uint32_t b) { return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) / 9007199254740992.0; }
+RB_HD inline double rng_uniform(Philox& g) {
+  uint32_t o[4];
+  philox_block(g, o);
+  return philox_u53(o[0], o[1]);
+}
+RB_HD inline double rng_gaus(Philox& g, double mean, double sigma) {
+  uint32_t o[4];
+  philox_block(g, o);
+  double u1 = philox_u53(o[0], o[1]), u2 = philox_u53(o[2], o[3]);
+  return mean + sigma * sqrt(-2. * log(u1)) * cos(2 * RB_PI * u2);
+}
+
+// ================================================================== tables: TGraph::Eval, TH2::Interpolate
+RB_HD inline double graph_eval(const DScene& sc, int g, double x) {
+  const rbg_graph gr = sc.graphs[g];
+  const double *X = sc.gx + gr.first, *Y = sc.gy + gr.first;
+  int n = gr.n;
+  if (n == 0) return 0;
+  if (n == 1) return Y[0];
+  // points are sorted by x at scene build: bracket by binary search, extrapolate from the end pairs
+  int lo = 0, hi = n - 1;
+  if (x <= X[0]) { if (x == X[0]) return Y[0]; lo = 0; hi = 1; }
+  else if (x >= X[n - 1]) { if (x == X[n - 1]) return Y[n - 1]; lo = n - 2; hi = n - 1; }
+  else {
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (X[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (X[lo] == x) return Y[lo];
+  }
+  if (X[lo] == X[hi]) return Y[lo];
+  return Y[hi] + (x - X[hi]) * (Y[lo] - Y[hi]) / (X[lo] - X[hi]);
+}
+
+RB_HD inline int th2_findbin(double x, double lo, double hi, int n) { return x < lo ? 0 : (!(x < hi) ? n + 1 : 1 + int(n * (x - lo) / (hi - lo))); }
+RB_HD inline double th2_interp(const DScene& sc, int h, double x, double y) {
+  const rbg_th2 H = sc.th2[h];
+  const double* v = sc.th2v + H.first;
+  double wx = (H.xmax - H.xmin) / H.nx, wy = (H.ymax - H.ymin) / H.ny;
+  int bx = th2_findbin(x, H.xmin, H.xmax, H.nx), by = th2_findbin(y, H.ymin, H.ymax, H.ny);
+  if (bx < 1 || bx > H.nx || by < 1 || by > H.ny) return 0;
+  double ddx = (H.xmin + bx * wx) - x, ddy = (H.ymin + by * wy) - y;
+  int ix1 = ddx <= wx / 2 ? bx : bx - 1, iy1 = ddy <= wy / 2 ? by : by - 1;
+  double x1 = H.xmin + (ix1 - 0.5) * wx, x2 = H.xmin + (ix1 + 0.5) * wx, y1 = H.ymin + (iy1 - 0.5) * wy, y2 = H.ymin + (iy1 + 0.5) * wy;
+  int bx1 = ix1 < 1 ? 1 : ix1, bx2 = ix1 + 1 > H.nx ? H.nx : ix1 + 1, by1 = iy1 < 1 ? 1 : iy1, by2 = iy1 + 1 > H.ny ? H.ny : iy1 + 1;
+  double q11 = v[(bx1 - 1) + H.nx * (by1 - 1)], q12 = v[(bx1 - 1) + H.nx * (by2 - 1)], q21 = v[(bx2 - 1) + H.nx * (by1 - 1)],
+         q22 = v[(bx2 - 1) + H.nx * (by2 - 1)];
+  double dd = 1.0 * (x2 - x1) * (y2 - y1);
+  return 1.0 * q11 / dd * (x2 - x) * (y2 - y) + 1.0 * q21 / dd * (x - x1) * (y2 - y) + 1.0 * q12 / dd * (x2 - x) * (y - y1) +
+         1.0 * q22 / dd * (x - x1) * (y - y1);
+}
+
+// ================================================================== refractive index n(λ), k(λ)
+RB_HD inline double index_k1(const DScene& sc, int id, double lambda) {
+  if (id < 0) return 0.;
+  int kg = sc.indices[id].kgraph;
+  return kg >= 0 ? graph_eval(sc, kg, lambda) : 0.;
+}
+RB_HD inline double index_n1(const DScene& sc, int id, double lambda) {
+  if (id < 0) return 1.;
+  const rbg_index& x = sc.indices[id];
+  const double* p = x.par;
+  double l = lambda / 1e-4;  // cm -> µm
+  if (x.kind == RBG_INDEX_SELLMEIER) {
+    double l2 = l * l;
+    return sqrt(1 + p[0] * l2 / (l2 - p[3]) + p[1] * l2 / (l2 - p[4]) + p[2] * l2 / (l2 - p[5]));
+  }
+  if (x.kind == RBG_INDEX_SCHOTT) {
+    double l2 = l * l, i2 = 1. / l2, i4 = i2 * i2;
+    return sqrt(p[0] + p[1] * l2 + p[2] * i2 + p[3] * i4 + p[4] * i4 * i2 + p[5] * i4 * i4);
+  }
+  if (x.kind == RBG_INDEX_CAUCHY) {
+    double i2 = 1. / (l * l);
+    return p[0] + p[1] * i2 + p[2] * i2 * i2;
+  }
+  return x.ngraph >= 0 ? graph_eval(sc, x.ngraph, lambda) : 1.;
+}
+RB_HD inline double index_n(const DScene& sc, int id, double lambda) {
+  if (id >= 0 && sc.indices[id].kind == RBG_INDEX_MIXED) {
+    const rbg_index& x = sc.indices[id];
+    return index_n1(sc, x.mix_a, lambda) * x.frac_a + index_n1(sc, x.mix_b, lambda) * x.frac_b;  // one mixing level
+  }
+  return index_n1(sc, id, lambda);
+}
+RB_HD inline double index_k(const DScene& sc, int id, double lambda) {
+  if (id >= 0 && sc.indices[id].kind == RBG_INDEX_MIXED) {
+    const rbg_index& x = sc.indices[id];
+    return index_k1(sc, x.mix_a, lambda) * x.frac_a + index_k1(sc, x.mix_b, lambda) * x.frac_b;
+  }
+  return index_k1(sc, id, lambda);
+}
+
+// ================================================================== complex helpers + coherent TMM
+struct Cx {
+  double re, im;
+};
+RB_HD inline Cx cx(double r, double i) { Cx c; c.re = r; c.im = i; return c; }
+RB_HD inline Cx operator+(Cx a, Cx b) { return cx(a.re + b.re, a.im + b.im); }
+RB_HD inline Cx operator-(Cx a, Cx b) { return cx(a.re - b.re, a.im - b.im); }
+RB_HD inline Cx operator*(Cx a, Cx b) { return cx(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+RB_HD inline Cx operator*(double s, Cx a) { return cx(s * a.re, s * a.im); }
+RB_HD inline Cx operator/(Cx a, Cx b) {  // Smith's algorithm
+  if (fabs(b.re) >= fabs(b.im)) {
+    double r = b.im / b.re, den = b.re + b.im * r;
+    return cx((a.re + a.im * r) / den, (a.im - a.re * r) / den);
+  }
+  double r = b.re / b.im, den = b.re * r + b.im;
+  return cx((a.re * r + a.im) / den, (a.im * r - a.re) / den);
+}
+RB_HD inline double cabs2(Cx a) { return a.re * a.re + a.im * a.im; }
+RB_HD inline Cx cconj(Cx a) { return cx(a.re, -a.im); }
+RB_HD inline Cx csqrt_(Cx z) {  // principal branch
+  double m = hypot(z.re, z.im);
+  if (m == 0) return cx(0, 0);
+  double s = sqrt(0.5 * (m + fabs(z.re)));
+  double o = z.im / (2 * s);
+  if (z.re >= 0) return cx(s, o);
+  return cx(fabs(o), z.im >= 0 ? s : -s);
+}
+RB_HD inline Cx cexp_(Cx z) {
+  double e = exp(z.re);
+  return cx(e * cos(z.im), e * sin(z.im));
+}
+RB_HD inline Cx clog_(Cx z) { return cx(log(hypot(z.re, z.im)), atan2(z.im, z.re)); }
+RB_HD inline Cx ccos_(Cx z) { return cx(cos(z.re) * cosh(z.im), -sin(z.re) * sinh(z.im)); }
+RB_HD inline Cx csin_(Cx z) { return cx(sin(z.re) * cosh(z.im), cos(z.re) * sinh(z.im)); }
+RB_HD inline Cx casin_(Cx z) {  // asin z = -i log(i z + sqrt(1 - z^2))
+  Cx w = csqrt_(cx(1, 0) - z * z);
+  Cx l = clog_(cx(-z.im + w.re, z.re + w.im));
+  return cx(l.im, -l.re);
+}
+RB_HD inline bool tmm_is_forward(Cx n, Cx theta) {
+  Cx nc = n * ccos_(theta);
+  if (fabs(nc.im) > 100 * 2.220446049250313e-16) return nc.im > 0;
+  return nc.re > 0;
+}
+// one polarisation (pol 0 = s, 1 = p)
+RB_HD inline void tmm_coherent(const DScene& sc, int ml, int pol, double th0, double lam, double& R, double& T) {
+  const rbg_multilayer M = sc.multilayers[ml];
+  int N = M.n;
+  Cx n0 = cx(1, 0), nprev = cx(1, 0), thprev = cx(0, 0), n_last = cx(1, 0), th_last = cx(0, 0);
+  Cx n0s = cx(0, 0);
+  Cx m00 = cx(1, 0), m01 = cx(0, 0), m10 = cx(0, 0), m11 = cx(1, 0);
+  Cx r0 = cx(0, 0), t0 = cx(1, 0);
+  for (int i = 0; i < N; i++) {
+    const rbg_layer L = sc.layers[M.first + i];
+    Cx ni = cx(index_n(sc, L.index, lam), index_k(sc, L.index, lam));
+    Cx thi;
+    if (i == 0) {
+      n0 = ni;
+      n0s = ni * csin_(cx(th0, 0));
+      thi = casin_(n0s / ni);
+      if (!tmm_is_forward(ni, thi)) thi = cx(RB_PI - thi.re, -thi.im);
+    } else {
+      thi = casin_(n0s / ni);
+      if (i == N - 1 && !tmm_is_forward(ni, thi)) thi = cx(RB_PI - thi.re, -thi.im);
+      // interface (i-1) -> i
+      Cx ci = ccos_(thprev), cf = ccos_(thi), r, t;
+      Cx ii = nprev * ci;
+      if (pol == 0) {
+        Cx ff = ni * cf;
+        r = (ii - ff) / (ii + ff);
+        t = (2. * ii) / (ii + ff);
+      } else {
+        Cx fi = ni * ci, i_f = nprev * cf;
+        r = (fi - i_f) / (fi + i_f);
+        t = (2. * ii) / (fi + i_f);
+      }
+      if (i == 1) { r0 = r; t0 = t; }
+      else {
+        // layer i-1 is an inner layer: M_{i-1} = (1/t) diag(e^{-iδ}, e^{iδ}) [[1,r],[r,1]]
+        Cx kz = ((2 * RB_PI) * (nprev * ci));
+        kz = cx(kz.re / lam, kz.im / lam);
+        double d = sc.layers[M.first + i - 1].thickness;
+        Cx delta = cx(kz.re * d, kz.im * d);
+        if (delta.im > 35) delta.im = 35;
+        Cx em = cexp_(cx(delta.im, -delta.re)), ep = cexp_(cx(-delta.im, delta.re));  // exp(-iδ), exp(iδ)
+        Cx s = cx(1, 0) / t;
+        Cx d00 = s * em, d11 = s * ep;
+        Cx a00 = d00, a01 = d00 * r, a10 = d11 * r, a11 = d11;
+        Cx q00 = m00 * a00 + m01 * a10, q01 = m00 * a01 + m01 * a11, q10 = m10 * a00 + m11 * a10, q11 = m10 * a01 + m11 * a11;
+        m00 = q00; m01 = q01; m10 = q10; m11 = q11;
+      }
+    }
+    nprev = ni;
+    thprev = thi;
+    n_last = ni;
+    th_last = thi;
+  }
+  Cx b00 = cx(1, 0) / t0, b01 = r0 / t0;
+  Cx q00 = b00 * m00 + b01 * m10, q10 = b01 * m00 + b00 * m10;
+  Cx r = q10 / q00, t = cx(1, 0) / q00;
+  R = cabs2(r);
+  Cx cf = ccos_(th_last), ci = ccos_(cx(th0, 0));
+  double tt = cabs2(t);  // |t*t| = |t|^2
+  if (pol == 0) T = tt * ((n_last * cf).re / (n0 * ci).re);
+  else T = tt * ((n_last * cconj(cf)).re / (n0 * cconj(ci)).re);
+}
+RB_HD inline void tmm_mixed(const DScene& sc, int ml, double th, double lam, double& R, double& T) {
+  const rbg_multilayer M = sc.multilayers[ml];
+  if (M.table_r >= 0 && M.table_t >= 0) {
+    R = th2_interp(sc, M.table_r, lam, th);
+    T = th2_interp(sc, M.table_t, lam, th);
+    return;
+  }
+  double rp, tp, rs, ts;
+  tmm_coherent(sc, ml, 1, th, lam, rp, tp);
+  tmm_coherent(sc, ml, 0, th, lam, rs, ts);
+  R = (rp + rs) / 2.;
+  T = (tp + ts) / 2.;
+}
+
+// ================================================================== primitive shapes
+// Small fixed-capacity candidate list: crossing parameters of all bounding surfaces of a
+// non-convex primitive; intervals between sorted candidates are classified by Contains().
+#define RB_MAXC 12
+struct Cands {
+  double t[RB_MAXC];
+  int n;
+};
+RB_HD inline void cand_add(Cands& c, double t) {
+  if (!(t > 1e-11) || t > 1e29 || c.n >= RB_MAXC) return;
+  int i = c.n++;
+  while (i > 0 && c.t[i - 1] > t) { c.t[i] = c.t[i - 1]; i--; }
+  c.t[i] = t;
+}
+RB_HD inline void cand_quadratic(Cands& c, double A, double B, double C) {
+  if (fabs(A) < 1e-300 || fabs(A) < 1e-14 * fabs(B)) {
+    if (B != 0) cand_add(c, -C / B);
+    return;
+  }
+  double disc = B * B - 4 * A * C;
+  if (disc < 0) return;
+  double s = sqrt(disc), q = -0.5 * (B + (B >= 0 ? s : -s));
+  cand_add(c, q / A);
+  if (q != 0) cand_add(c, C / q);
+}
+
+// ---- TGeoBBox  P: dx,dy,dz,ox,oy,oz
+RB_HD inline bool bbox_contains(const double* P, V3 p) { return !(fabs(p.x - P[3]) > P[0] || fabs(p.y - P[4]) > P[1] || fabs(p.z - P[5]) > P[2]); }
+RB_HD inline double bbox_dist_in(const double* P, V3 p, V3 d) {
+  double np[3] = {p.x - P[3], p.y - P[4], p.z - P[5]}, dd[3] = {d.x, d.y, d.z}, smin = RB_BIG;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (dd[i] != 0) {
+      double s = dd[i] > 0 ? (P[i] - np[i]) / dd[i] : -(P[i] + np[i]) / dd[i];
+      if (s < 0) return 0.0;
+      if (s < smin) smin = s;
+    }
+  return smin;
+}
+RB_HD inline double bbox_dist_out(const double* P, V3 p, V3 d, double step) {
+  double np[3] = {p.x - P[3], p.y - P[4], p.z - P[5]}, dd[3] = {d.x, d.y, d.z}, saf[3];
+  bool in = true;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    saf[i] = fabs(np[i]) - P[i];
+    if (saf[i] >= step) return RB_BIG;
+    if (in && saf[i] > 0) in = false;
+  }
+  if (in) {
+    int j = 0;
+    double ss = saf[0];
+    if (saf[1] > ss) { ss = saf[1]; j = 1; }
+    if (saf[2] > ss) j = 2;
+    if (np[j] * dd[j] > 0) return RB_BIG;
+    return 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (saf[i] < 0) continue;
+    if (np[i] * dd[i] >= 0) continue;
+    double snxt = saf[i] / fabs(dd[i]);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      if (j != i && fabs(np[j] + snxt * dd[j]) > P[j]) ok = false;
+    if (ok) return snxt;
+  }
+  return RB_BIG;
+}
+RB_HD inline V3 bbox_normal(const double* P, V3 p, V3 d) {
+  double s0 = fabs(P[0] - fabs(p.x - P[3])), s1 = fabs(P[1] - fabs(p.y - P[4])), s2 = fabs(P[2] - fabs(p.z - P[5]));
+  int i = s1 < s0 ? 1 : 0;
+  if (s2 < (i ? s1 : s0)) i = 2;
+  if (i == 0) return v3(d.x > 0 ? 1 : -1, 0, 0);
+  if (i == 1) return v3(0, d.y > 0 ? 1 : -1, 0);
+  return v3(0, 0, d.z > 0 ? 1 : -1);
+}
+
+// ---- TGeoTube  P: rmin,rmax,dz
+RB_HD inline void tube_roots(double rsq, double nsq, double rdotn, double radius, double& b, double& delta) {
+  double inv = 1. / nsq;
+  b = inv * rdotn;
+  double c = inv * (rsq - radius * radius);
+  delta = b * b - c;
+  delta = delta > 0 ? sqrt(delta) : -1;
+}
+RB_HD inline bool tube_contains(const double* P, V3 p) {
+  if (fabs(p.z) > P[2]) return false;
+  double r2 = p.x * p.x + p.y * p.y;
+  return !(r2 < P[0] * P[0] || r2 > P[1] * P[1]);
+}
+RB_HD inline double tube_dist_in(double rmin, double rmax, double dz, V3 p, V3 d) {
+  double sz = RB_BIG;
+  if (d.z != 0) {
+    sz = ((d.z >= 0 ? dz : -dz) - p.z) / d.z;
+    if (sz <= 0) return 0.0;
+  }
+  double nsq = d.x * d.x + d.y * d.y;
+  if (fabs(nsq) < RB_TOL) return sz;
+  double rsq = p.x * p.x + p.y * p.y, rdotn = p.x * d.x + p.y * d.y, b, dl;
+  if (rmin > 0) {
+    if (rsq <= rmin * rmin + RB_TOL) {
+      if (rdotn < 0) return 0.0;
+    } else if (rdotn < 0) {
+      tube_roots(rsq, nsq, rdotn, rmin, b, dl);
+      if (dl > 0) {
+        double sr = -b - dl;
+        if (sr > 0) return rb_min(sz, sr);
+      }
+    }
+  }
+  if (rsq >= rmax * rmax - RB_TOL && rdotn >= 0) return 0.0;
+  tube_roots(rsq, nsq, rdotn, rmax, b, dl);
+  if (dl > 0) {
+    double sr = -b + dl;
+    if (sr > 0) return rb_min(sz, sr);
+  }
+  return 0.;
+}
+RB_HD inline double tube_dist_out(double rmin, double rmax, double dz, V3 p, V3 d) {
+  double rmaxsq = rmax * rmax, rminsq = rmin * rmin, zi = dz - fabs(p.z);
+  bool inz = !(zi < 0);
+  if (!inz) {
+    if (p.z * d.z >= 0) return RB_BIG;
+    double s = -zi / fabs(d.z), xi = p.x + s * d.x, yi = p.y + s * d.y, r2 = xi * xi + yi * yi;
+    if (rminsq <= r2 && r2 <= rmaxsq) return s;
+  }
+  double rsq = p.x * p.x + p.y * p.y, nsq = d.x * d.x + d.y * d.y, rdotn = p.x * d.x + p.y * d.y, b, dl;
+  bool inrmax = rsq <= rmaxsq + RB_TOL, inrmin = rsq >= rminsq - RB_TOL;
+  if (inz && inrmin && inrmax) {  // on a boundary within machine precision
+    double r = sqrt(rsq);
+    if (zi < rmax - r && (fabs(rmin) < RB_TOL || zi < r - rmin)) return p.z * d.z < 0 ? 0.0 : RB_BIG;
+    if ((rmaxsq - rsq) < (rsq - rminsq)) return rdotn >= 0 ? RB_BIG : 0.0;
+    if (fabs(rmin) < RB_TOL) return 0.0;
+    if (rdotn >= 0) return 0.0;
+    if (fabs(nsq) < RB_TOL) return RB_BIG;
+    tube_roots(rsq, nsq, rdotn, rmin, b, dl);
+    if (dl > 0) {
+      double s = -b + dl;
+      if (s > 0 && fabs(p.z + s * d.z) <= dz) return s;
+    }
+    return RB_BIG;
+  }
+  if (fabs(nsq) < RB_TOL) return RB_BIG;
+  if (!inrmax) {
+    tube_roots(rsq, nsq, rdotn, rmax, b, dl);
+    if (dl > 0) {
+      double s = -b - dl;
+      if (s > 0 && fabs(p.z + s * d.z) <= dz) return s;
+    }
+  }
+  if (rmin > 0) {
+    tube_roots(rsq, nsq, rdotn, rmin, b, dl);
+    if (dl > 0) {
+      double s = -b + dl;
+      if (s > 0 && fabs(p.z + s * d.z) <= dz) return s;
+    }
+  }
+  return RB_BIG;
+}
+RB_HD inline V3 tube_normal(const double* P, V3 p, V3 d) {
+  double r = sqrt(p.x * p.x + p.y * p.y);
+  double s0 = fabs(P[2] - fabs(p.z)), s1 = P[0] > 1e-10 ? fabs(r - P[0]) : RB_BIG, s2 = fabs(P[1] - r);
+  if (s0 <= s1 && s0 <= s2) return v3(0, 0, d.z >= 0 ? 1 : -1);
+  double phi = rb_atan2(p.y, p.x), nx = cos(phi), ny = sin(phi);
+  if (nx * d.x + ny * d.y < 0) { nx = -nx; ny = -ny; }
+  return v3(nx, ny, 0);
+}
+
+// ---- TGeoParaboloid  P: rlo,rhi,dz,a,b   (z = a r^2 + b)
+RB_HD inline bool para_contains(const double* P, V3 p) {
+  if (fabs(p.z) > P[2]) return false;
+  double aa = P[3] * (p.z - P[4]);
+  if (aa < 0) return false;
+  return !(aa < P[3] * P[3] * (p.x * p.x + p.y * p.y));
+}
+RB_HD inline double para_surface(const double* P, V3 p, V3 d, bool in) {
+  double rsq = p.x * p.x + p.y * p.y, fa = P[3];
+  double a = fa * (d.x * d.x + d.y * d.y), b = 2. * fa * (p.x * d.x + p.y * d.y) - d.z, c = fa * rsq + P[4] - p.z;
+  if (fabs(a) < RB_TOL) {
+    if (fabs(b) < RB_TOL) return RB_BIG;
+    double dist = -c / b;
+    return dist < 0 ? RB_BIG : dist;
+  }
+  double ainv = 1. / a, sum = -b * ainv, prod = c * ainv, delta = sum * sum - 4. * prod;
+  if (delta < 0) return RB_BIG;
+  delta = sqrt(delta);
+  double sone = ainv >= 0 ? 1. : -1.;
+  for (int i = -1; i < 2; i += 2) {
+    double dist = 0.5 * (sum + i * sone * delta);
+    if (dist < 0) continue;
+    if (dist < 1.E-8) {
+      double talf = -2. * fa * sqrt(rsq), phi = rb_atan2(p.y, p.x);
+      double ndotd = talf * (cos(phi) * d.x + sin(phi) * d.y) + d.z;
+      if (!in) ndotd = -ndotd;
+      if (ndotd < 0) return dist;
+    } else return dist;
+  }
+  return RB_BIG;
+}
+RB_HD inline double para_dist_in(const double* P, V3 p, V3 d) {
+  double dz = RB_BIG;
+  if (d.z < 0) dz = -(p.z + P[2]) / d.z;
+  else if (d.z > 0) dz = (P[2] - p.z) / d.z;
+  return rb_min(dz, para_surface(P, p, d, true));
+}
+RB_HD inline double para_dist_out(const double* P, V3 p, V3 d) {
+  if (p.z <= -P[2]) {
+    if (d.z <= 0) return RB_BIG;
+    double s = -(P[2] + p.z) / d.z, xn = p.x + s * d.x, yn = p.y + s * d.y;
+    if (xn * xn + yn * yn <= P[0] * P[0]) return s;
+  } else if (p.z >= P[2]) {
+    if (d.z >= 0) return RB_BIG;
+    double s = (P[2] - p.z) / d.z, xn = p.x + s * d.x, yn = p.y + s * d.y;
+    if (xn * xn + yn * yn <= P[1] * P[1]) return s;
+  }
+  double s = para_surface(P, p, d, false);
+  if (s > 1E20) return s;
+  return fabs(p.z + s * d.z) <= P[2] ? s : RB_BIG;
+}
+RB_HD inline V3 para_normal(const double* P, V3 p, V3 d) {
+  if ((fabs(p.z) - P[2]) > -1E-5) return v3(0, 0, d.z >= 0 ? 1. : -1.);
+  double safz = P[2] - fabs(p.z), r = sqrt(p.x * p.x + p.y * p.y), safr = fabs(r - sqrt((p.z - P[4]) / P[3]));
+  if (safz < safr) return v3(0, 0, d.z >= 0 ? 1. : -1.);
+  double talf = -2. * P[3] * r, calf = 1. / sqrt(1. + talf * talf), salf = talf * calf, phi = rb_atan2(p.y, p.x);
+  V3 n = v3(salf * cos(phi), salf * sin(phi), calf);
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
+// ---- TGeoSphere  P: rmin,rmax,th1,th2,ph1,ph2(deg), c1,s1,c2,s2, cp1,sp1,cp2,sp2, flags
+RB_HD inline bool sphere_contains(const double* P, V3 p) {
+  double r2 = dot(p, p);
+  if (P[0] > 0 && r2 < P[0] * P[0]) return false;
+  if (r2 > P[1] * P[1]) return false;
+  if (r2 < 1E-20) return true;
+  int flags = (int)P[14];
+  if (flags & 4) {
+    double phi = rb_atan2(p.y, p.x) * 180. / RB_PI;
+    while (phi < P[4]) phi += 360.;
+    if (phi - P[4] > P[5] - P[4]) return false;
+  }
+  if (flags & 3) {
+    double ct = p.z / sqrt(r2);  // theta >= th1 <=> cos(theta) <= cos(th1)
+    if ((flags & 1) && ct > P[6]) return false;
+    if ((flags & 2) && ct < P[8]) return false;
+  }
+  return true;
+}
+RB_HD inline double sphere_dist(const double* P, V3 p, V3 d, bool from_inside) {
+  Cands c;
+  c.n = 0;
+  double a = dot(d, d), b = 2 * dot(p, d), pp = dot(p, p);
+  if (P[0] > 0) cand_quadratic(c, a, b, pp - P[0] * P[0]);
+  cand_quadratic(c, a, b, pp - P[1] * P[1]);
+  int flags = (int)P[14];
+  double dxy = d.x * d.x + d.y * d.y, pdxy = p.x * d.x + p.y * d.y, pxy = p.x * p.x + p.y * p.y;
+  if (flags & 1) {
+    double c2 = P[6] * P[6], s2 = P[7] * P[7];
+    cand_quadratic(c, dxy * c2 - d.z * d.z * s2, 2 * (pdxy * c2 - p.z * d.z * s2), pxy * c2 - p.z * p.z * s2);
+  }
+  if (flags & 2) {
+    double c2 = P[8] * P[8], s2 = P[9] * P[9];
+    cand_quadratic(c, dxy * c2 - d.z * d.z * s2, 2 * (pdxy * c2 - p.z * d.z * s2), pxy * c2 - p.z * p.z * s2);
+  }
+  if (flags & 4) {
+    double den = d.y * P[10] - d.x * P[11];
+    if (den != 0) cand_add(c, -(p.y * P[10] - p.x * P[11]) / den);
+    den = d.y * P[12] - d.x * P[13];
+    if (den != 0) cand_add(c, -(p.y * P[12] - p.x * P[13]) / den);
+  }
+  double prev = 0;
+  for (int i = 0; i < c.n; i++) {
+    double t = c.t[i];
+    if (t - prev < 1e-12) { prev = t; continue; }
+    bool in = sphere_contains(P, along(p, d, 0.5 * (prev + t)));
+    if (from_inside ? !in : in) return prev;
+    prev = t;
+  }
+  return from_inside ? prev : RB_BIG;
+}
+RB_HD inline V3 sphere_normal(const double* P, V3 p, V3 d) {
+  double r = sqrt(dot(p, p)), rxy = sqrt(p.x * p.x + p.y * p.y);
+  int flags = (int)P[14];
+  double best = P[0] > 0 ? fabs(r - P[0]) : RB_BIG;
+  int which = 0;
+  double s = fabs(P[1] - r);
+  if (s < best) { best = s; which = 1; }
+  // distance to a theta cone: r * |sin(theta - th)|, with sin(theta - th) = (rxy*cos(th) - z*sin(th))/r
+  if (flags & 1) { s = fabs(rxy * P[6] - p.z * P[7]); if (s < best) { best = s; which = 2; } }
+  if (flags & 2) { s = fabs(rxy * P[8] - p.z * P[9]); if (s < best) { best = s; which = 3; } }
+  if (flags & 4) {
+    s = fabs(p.y * P[10] - p.x * P[11]); if (s < best) { best = s; which = 4; }
+    s = fabs(p.y * P[12] - p.x * P[13]); if (s < best) { best = s; which = 5; }
+  }
+  V3 n;
+  if (which < 2) n = r > 0 ? v3(p.x / r, p.y / r, p.z / r) : v3(0, 0, 1);
+  else if (which < 4) {
+    double cth = which == 2 ? P[6] : P[8], sth = which == 2 ? P[7] : P[9];
+    double cph = rxy > 0 ? p.x / rxy : 1, sph = rxy > 0 ? p.y / rxy : 0;
+    n = v3(cth * cph, cth * sph, -sth);
+  } else n = which == 4 ? v3(-P[11], P[10], 0) : v3(-P[13], P[12], 0);
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
+// ---- TGeoPgon (rmin == 0, full 360 deg; enforced at scene build)
+// P: phi1,dphi,nedges,nz, nz x (z,rmin,rmax), nedges x (cos,sin) of the edge-centre azimuths.
+// The solid is a stack of convex slabs: each slab is clipped analytically (2 z planes + nedges side
+// planes); no trigonometry per ray.
+RB_HD inline double pgon_proj_max(const double* P, V3 p) {
+  int ne = (int)P[2], nz = (int)P[3];
+  const double* cs = P + 4 + 3 * nz;
+  double m = -RB_BIG;
+  for (int e = 0; e < ne; e++) m = rb_max(m, p.x * cs[2 * e] + p.y * cs[2 * e + 1]);
+  return m;
+}
+RB_HD inline bool pgon_contains(const double* P, V3 p) {
+  int nz = (int)P[3];
+  const double* sec = P + 4;
+  if (p.z < sec[0] || p.z > sec[3 * (nz - 1)]) return false;
+  double r = pgon_proj_max(P, p);
+  int iz = 0;
+  for (int i = 1; i < nz; i++)
+    if (sec[3 * i] <= p.z) iz = i;
+  if (iz == nz - 1) return !(r > sec[3 * iz + 2]);
+  double dz = sec[3 * (iz + 1)] - sec[3 * iz];
+  if (dz < 1E-8) return !(r > rb_max(sec[3 * iz + 2], sec[3 * (iz + 1) + 2]));
+  double rmax = sec[3 * iz + 2] + (p.z - sec[3 * iz]) / dz * (sec[3 * (iz + 1) + 2] - sec[3 * iz + 2]);
+  return !(r > rmax);
+}
+// ray interval inside slab k; returns false if empty
+RB_HD inline bool pgon_slab(const double* P, int k, V3 p, V3 d, double& tin, double& tout) {
+  int ne = (int)P[2], nz = (int)P[3];
+  const double* sec = P + 4;
+  const double* cs = P + 4 + 3 * nz;
+  double z0 = sec[3 * k], z1 = sec[3 * (k + 1)], r0 = sec[3 * k + 2], r1 = sec[3 * (k + 1) + 2], dz = z1 - z0;
+  if (dz < 1E-8) return false;
+  tin = -RB_BIG;
+  tout = RB_BIG;
+  if (d.z != 0) {
+    double ta = (z0 - p.z) / d.z, tb = (z1 - p.z) / d.z;
+    tin = rb_min(ta, tb);
+    tout = rb_max(ta, tb);
+  } else if (p.z < z0 || p.z > z1) return false;
+  double s = (r1 - r0) / dz, base = r0 + (p.z - z0) * s;
+  for (int e = 0; e < ne; e++) {
+    // half-space: x c + y s - (r0 + (z - z0) s) <= 0
+    double f0 = p.x * cs[2 * e] + p.y * cs[2 * e + 1] - base, fd = d.x * cs[2 * e] + d.y * cs[2 * e + 1] - s * d.z;
+    if (fd > 0) tout = rb_min(tout, -f0 / fd);
+    else if (fd < 0) tin = rb_max(tin, -f0 / fd);
+    else if (f0 > 0) return false;
+  }
+  return tin < tout;
+}
+RB_HD inline double pgon_dist_out(const double* P, V3 p, V3 d) {
+  int nz = (int)P[3];
+  double best = RB_BIG;
+  for (int k = 0; k + 1 < nz; k++) {
+    double tin, tout;
+    if (!pgon_slab(P, k, p, d, tin, tout)) continue;
+    if (tout <= 1e-11) continue;
+    double t = tin > 0 ? tin : 0.0;
+    if (tout - t < 1e-12) continue;
+    if (t < best) best = t;
+  }
+  return best;
+}
+RB_HD inline double pgon_dist_in(const double* P, V3 p, V3 d) {
+  int nz = (int)P[3];
+  double cur = 0;
+  for (int iter = 0; iter < nz; iter++) {
+    bool advanced = false;
+    for (int k = 0; k + 1 < nz; k++) {
+      double tin, tout;
+      if (!pgon_slab(P, k, p, d, tin, tout)) continue;
+      if (tin <= cur + 1e-9 && tout > cur + 1e-9) { cur = tout; advanced = true; }
+    }
+    if (!advanced) break;
+  }
+  return cur;
+}
+RB_HD inline V3 pgon_normal(const double* P, V3 p, V3 d) {
+  int ne = (int)P[2], nz = (int)P[3];
+  const double* sec = P + 4;
+  const double* cs = P + 4 + 3 * nz;
+  int eb = 0;
+  double r = -RB_BIG;
+  for (int e = 0; e < ne; e++) {
+    double pr = p.x * cs[2 * e] + p.y * cs[2 * e + 1];
+    if (pr > r) { r = pr; eb = e; }
+  }
+  double best = RB_BIG;
+  V3 n = v3(0, 0, 1);
+  for (int i = 0; i < nz; i++) {
+    bool cap = i == 0 || i == nz - 1;
+    bool step = (i + 1 < nz && sec[3 * (i + 1)] - sec[3 * i] < 1e-8) || (i > 0 && sec[3 * i] - sec[3 * (i - 1)] < 1e-8);
+    if (!cap && !step) continue;
+    double s = fabs(p.z - sec[3 * i]);
+    if (s < best) { best = s; n = v3(0, 0, 1); }
+  }
+  for (int k = 0; k + 1 < nz; k++) {
+    double z0 = sec[3 * k], z1 = sec[3 * (k + 1)], dz = z1 - z0;
+    if (dz < 1e-8 || p.z < z0 - 1e-6 || p.z > z1 + 1e-6) continue;
+    double s = (sec[3 * (k + 1) + 2] - sec[3 * k + 2]) / dz, rr = sec[3 * k + 2] + (p.z - z0) * s, nn = sqrt(1 + s * s);
+    double dist = fabs(r - rr) / nn;
+    if (dist < best) { best = dist; n = v3(cs[2 * eb] / nn, cs[2 * eb + 1] / nn, -s / nn); }
+  }
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
+// ---- AGeoAsphericDisk  P: z1,z2,c1,c2,k1,k2,rmin,rmax,n1,n2,oz,dz,K1[],K2[]
+RB_HD inline bool asph_F(const double* P, int s, double r, double& out) {
+  double c = P[1 + s], kap = P[3 + s], z0 = P[s - 1];
+  int n = (int)P[7 + s];
+  const double* K = s == 1 ? P + 12 : P + 12 + (int)P[8];
+  double r2 = r * r, pp = r2 * c * c * kap;
+  if (1 - pp < 0) return false;
+  double poly = 0;
+  for (int i = n - 1; i >= 0; i--) poly = (poly + K[i]) * r2;  // sum K_i r^(2(i+1)), Horner in r^2
+  out = z0 + r2 * c / (1 + sqrt(1 - pp)) + poly;
+  return true;
+}
+RB_HD inline bool asph_dF(const double* P, int s, double r, double& out) {
+  double c = P[1 + s], kap = P[3 + s];
+  int n = (int)P[7 + s];
+  const double* K = s == 1 ? P + 12 : P + 12 + (int)P[8];
+  double r2 = r * r, pp = r2 * c * c * kap;
+  if (1 - pp <= 0) return false;
+  double poly = 0;
+  for (int i = n - 1; i >= 0; i--) poly = poly * r2 + 2 * (i + 1) * K[i];  // sum 2(i+1) K_i r^(2i), then * r
+  out = r * c / sqrt(1 - pp) + poly * r;
+  return true;
+}
+RB_HD inline bool asph_contains(const double* P, V3 p) {
+  double r = sqrt(p.x * p.x + p.y * p.y);
+  if (r > P[7] || r < P[6]) return false;
+  double f1, f2;
+  if (!asph_F(P, 1, r, f1) || !asph_F(P, 2, r, f2)) return false;
+  return !(p.z < f1 || f2 < p.z);
+}
+// ray / even-asphere intersection: conic closed-form start, then Newton on the sag (cap 100, |e|<1e-10)
+RB_HD inline double asph_surface(const double* P, int s, V3 pt, V3 dir) {
+  double d = P[s - 1], curve = P[1 + s], kappa = P[3 + s];
+  int npol = (int)P[7 + s];
+  const double* K = s == 1 ? P + 12 : P + 12 + (int)P[8];
+  double H2 = pt.x * pt.x + pt.y * pt.y, zr = pt.z - d;
+  double p = -(zr * dir.z + pt.x * dir.x + pt.y * dir.y);
+  double M = p * dir.z + zr, M2 = zr * zr + H2 - p * p;
+  double w = (M2 * curve - 2 * M);
+  double check = 1 - w * curve / dir.z / dir.z;
+  if (check < 0) return RB_BIG;
+  double q = p + w / (dir.z * (1 + sqrt(check)));
+  double nx = pt.x + q * dir.x, ny = pt.y + q * dir.y, nz = pt.z + q * dir.z - d;
+  double ck = curve * kappa, cc = kappa * curve * curve;
+  for (int i = 0;; i++) {
+    if (i > 100) return RB_BIG;
+    H2 = nx * nx + ny * ny;
+    check = 1 - cc * H2;
+    if (check < 0) return RB_BIG;
+    double l = sqrt(check), x = 0, v = 0;
+    for (int j = npol - 1; j >= 0; j--) {
+      x = (x + K[j]) * H2;
+      v = v * H2 + 2 * (j + 1) * K[j];
+    }
+    if (curve != 0) x += (1 - l) / curve / kappa;
+    v = ck + l * v;
+    double m = -nx * v, n = -ny * v, inv = 1. / sqrt(l * l + m * m + n * n);
+    l *= inv; m *= inv; n *= inv;
+    check = dir.z * l + dir.x * m + dir.y * n;
+    if (check == 0) return RB_BIG;
+    double e = l * (x - nz) / check;
+    nx += e * dir.x; ny += e * dir.y; nz += e * dir.z;
+    if (fabs(e) < 1e-10) break;
+  }
+  nz += d;
+  double ex = nx - pt.x, ey = ny - pt.y, ez = nz - pt.z;
+  if (dir.x * ex + dir.y * ey + dir.z * ez < 0) return RB_BIG;
+  double rho = sqrt(nx * nx + ny * ny);
+  if (rho < P[6] || rho > P[7]) return RB_BIG;
+  return sqrt(ex * ex + ey * ey + ez * ez);
+}
+RB_HD inline double asph_cylinder(const double* P, double R, V3 pt, V3 dir) {
+  double rsq = pt.x * pt.x + pt.y * pt.y, nsq = dir.x * dir.x + dir.y * dir.y;
+  if (sqrt(nsq) < RB_TOL) return RB_BIG;
+  double rdotn = pt.x * dir.x + pt.y * dir.y, b, delta;
+  tube_roots(rsq, nsq, rdotn, R, b, delta);
+  if (delta < 0) return RB_BIG;
+  double t1 = -b + delta, t2 = -b - delta;
+  if (t1 < 0 && t2 < 0) return RB_BIG;
+  double zmin, zmax;
+  if (!asph_F(P, 1, R, zmin) || !asph_F(P, 2, R, zmax)) return RB_BIG;
+  if (t2 > 0) {
+    double z1 = t1 * dir.z + pt.z, z2 = t2 * dir.z + pt.z;
+    if (z1 < zmin || zmax < z1) t1 = RB_BIG;
+    if (z2 < zmin || zmax < z2) t2 = RB_BIG;
+    return t1 < t2 ? t1 : t2;
+  }
+  bool zin = zmin <= pt.z && pt.z <= zmax;
+  if (t2 == 0) {
+    if (t1 > 0) {
+      if (zin) return 0;
+      double z1 = t1 * dir.z + pt.z;
+      if (zmin <= z1 && z1 <= zmax) return t1;
+    } else if (t1 == 0 && zin) return 0;
+    return RB_BIG;
+  }
+  if (t1 > 0) {
+    double z1 = t1 * dir.z + pt.z;
+    if (zmin <= z1 && z1 <= zmax) return t1;
+  } else if (t1 == 0 && zin) return 0;
+  return RB_BIG;
+}
+RB_HD inline double asph_dist4(const double* P, V3 p, V3 d) {
+  double m = asph_surface(P, 1, p, d);
+  m = rb_min(m, asph_surface(P, 2, p, d));
+  if (P[6] > 0) m = rb_min(m, asph_cylinder(P, P[6], p, d));
+  return rb_min(m, asph_cylinder(P, P[7], p, d));
+}
+RB_HD inline double asph_dist_out(const double* P, V3 p, V3 d, double step) {
+  if (tube_dist_out(P[6], P[7], P[11], v3(p.x, p.y, p.z - P[10]), d) >= step) return RB_BIG;
+  return asph_dist4(P, p, d);
+}
+RB_HD inline V3 asph_normal(const double* P, V3 p, V3 d) {
+  double r = sqrt(p.x * p.x + p.y * p.y), phi = atan2(p.y, p.x);
+  double best = P[6] > 0 ? fabs(r - P[6]) : RB_BIG, f, df = 0;
+  int which = 0;
+  double s = fabs(r - P[7]);
+  if (s < best) { best = s; which = 1; }
+  double dfs = 0;
+  for (int k = 1; k <= 2; k++) {
+    double saf = RB_BIG;
+    if (asph_F(P, k, r, f) && asph_dF(P, k, r, df)) saf = fabs(f - p.z) / sqrt(1 + df * df);
+    if (saf < best) { best = saf; which = 1 + k; dfs = df; }
+  }
+  double nx = 0, nz = 0;
+  if (which < 2) nx = 1;
+  else if (dfs == 0) nz = 1;
+  else { double inv = 1. / sqrt(1 + dfs * dfs); nx = dfs * inv; nz = -inv; }
+  V3 n = v3(nx * cos(phi), nx * sin(phi), nz);
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
+// ---- AGeoWinstonCone2D / Poly  P: r1,r2,(dy|npoly),theta,dz,f,cos(theta),sin(theta)
+RB_HD inline bool win_R(const double* P, double z, double& out) {
+  if (fabs(z) > P[4] + 1e-10) return false;
+  double sint = P[7], cost = P[6], f = P[5], t = z + P[4];
+  double a0 = t * t * sint * sint - 4. * f * (t * cost + f), a1 = 2. * t * sint * cost + 4. * f * sint, a2 = cost * cost;
+  out = (-a1 + sqrt(a1 * a1 - 4. * a0 * a2)) / (2 * a2) - P[1];
+  return true;
+}
+RB_HD inline bool win_dRdZ(const double* P, double z, double& out) {
+  if (fabs(z) > P[4] + 1e-10) return false;
+  double sint = P[7], cost = P[6], f = P[5], t = z + P[4];
+  double a0 = t * t * sint * sint - 4. * f * (t * cost + f), a1 = 2. * t * sint * cost + 4. * f * sint, a2 = cost * cost;
+  double da0 = 2 * t * sint * sint - 4 * f * cost, da1 = 2 * sint * cost;
+  out = (-da1 + (a1 * da1 - 2 * da0 * a2) / sqrt(a1 * a1 - 4 * a0 * a2)) / (2 * a2);
+  return true;
+}
+// intersection with the tilted parabola of the face at azimuth phi (cphi,sphi), accepted within |azimuth| <= open/2
+RB_HD inline double win_parabola(const double* P, V3 pt, V3 dir, double cphi, double sphi, double open) {
+  double x = cphi * pt.x + sphi * pt.y, y = -sphi * pt.x + cphi * pt.y, z = pt.z;
+  double px = cphi * dir.x + sphi * dir.y, py = -sphi * dir.x + cphi * dir.y, pz = dir.z;
+  if (px == 0 && pz == 0) return RB_BIG;
+  double r1 = P[0], r2 = P[1], theta = P[3], DZ = P[4], f = P[5], cost = P[6], sint = P[7];
+  double X = cost * (x + r2) + (z + DZ) * sint, Z = -sint * (x + r2) + (z + DZ) * cost + f;
+  double tanA = tan(rb_atan2(pz, px) - theta);
+  double tmp = tanA * tanA - (X * tanA - Z) / f;
+  if (tmp < 0) return RB_BIG;
+  double Xc[2];
+  if (DZ * 2 / fabs(tanA) < RB_TOL) { Xc[0] = X; Xc[1] = X; }
+  else { double sq = sqrt(tmp); Xc[0] = 2 * f * (tanA + sq); Xc[1] = 2 * f * (tanA - sq); }
+  double best = RB_BIG;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    double Zc = Xc[k] * Xc[k] / 4. / f;
+    double xc = cost * Xc[k] - sint * (Zc - f) - r2, zc = sint * Xc[k] + cost * (Zc - f) - DZ, yc;
+    if (fabs(px) <= fabs(pz) && fabs(py) <= fabs(pz)) yc = y + (zc - z) * py / pz;
+    else if (fabs(py) <= fabs(px) && fabs(pz) <= fabs(px)) yc = y + (xc - x) * py / px;
+    else yc = y + (fabs(px) < 1e-5 ? (zc - z) * py / pz : (xc - x) * py / px);
+    double ddx = xc - x, ddy = yc - y, ddz = zc - z;
+    if (xc < r2 || r1 < xc || zc < -DZ || DZ < zc || ddx * px + ddz * pz < 0) continue;
+    if (fabs(rb_atan2(yc, xc)) <= open / 2.) best = rb_min(best, sqrt(ddx * ddx + ddy * ddy + ddz * ddz));
+  }
+  return best;
+}
+RB_HD inline bool win_inside_polygon(int n, double x, double y, double r) {
+  double th = rb_atan2(y, x), w = RB_PI / n;
+  while (th > w) th -= 2 * w;
+  while (th < -w) th += 2 * w;
+  return !(sqrt(x * x + y * y) * cos(th) > r);
+}
+RB_HD inline bool win_contains(const double* P, bool poly, V3 p) {
+  double r;
+  if (poly) {
+    if (fabs(p.z) > P[4]) return false;
+    if (!win_R(P, p.z, r)) return false;
+    return win_inside_polygon((int)P[2], p.x, p.y, r);
+  }
+  if (fabs(p.y) > P[2] || fabs(p.z) > P[4]) return false;
+  if (!win_R(P, p.z, r)) return false;
+  return !(fabs(p.x) > r);
+}
+RB_HD inline double win_dist_in(const double* P, bool poly, V3 p, V3 d) {
+  double best = RB_BIG;
+  if (d.z < 0) best = -(p.z + P[4]) / d.z;
+  else if (d.z > 0) best = (P[4] - p.z) / d.z;
+  if (poly) {
+    int n = (int)P[2];
+    for (int i = 0; i < n; i++) {
+      double ph = i * 2 * RB_PI / n;
+      best = rb_min(best, win_parabola(P, p, d, cos(ph), sin(ph), RB_PI));
+    }
+    return best;
+  }
+  if (d.y < 0) best = rb_min(best, -(p.y + P[2]) / d.y);
+  else if (d.y > 0) best = rb_min(best, (P[2] - p.y) / d.y);
+  best = rb_min(best, win_parabola(P, p, d, 1., 0., RB_PI));
+  return rb_min(best, win_parabola(P, p, d, cos(RB_PI), sin(RB_PI), RB_PI));
+}
+RB_HD inline double win_dist_out(const double* P, bool poly, V3 p, V3 d) {
+  double DZ = P[4];
+  if (poly) {
+    int n = (int)P[2];
+    if (p.z <= -DZ) {
+      if (d.z <= 0) return RB_BIG;
+      double s = -(DZ + p.z) / d.z;
+      if (win_inside_polygon(n, p.x + s * d.x, p.y + s * d.y, P[1])) return s;
+    } else if (p.z >= DZ) {
+      if (d.z >= 0) return RB_BIG;
+      double s = (DZ - p.z) / d.z;
+      if (win_inside_polygon(n, p.x + s * d.x, p.y + s * d.y, P[0])) return s;
+    }
+    double best = RB_BIG;
+    for (int i = 0; i < n; i++) {
+      double ph = i * 2 * RB_PI / n;
+      best = rb_min(best, win_parabola(P, p, d, cos(ph), sin(ph), 2 * RB_PI / n));
+    }
+    return best;
+  }
+  double DY = P[2], r;
+  if (p.z <= -DZ) {
+    if (d.z <= 0) return RB_BIG;
+    double s = -(DZ + p.z) / d.z;
+    if (fabs(p.x + s * d.x) <= P[1] && fabs(p.y + s * d.y) <= DY) return s;
+  } else if (p.z >= DZ) {
+    if (d.z >= 0) return RB_BIG;
+    double s = (DZ - p.z) / d.z;
+    if (fabs(p.x + s * d.x) <= P[0] && fabs(p.y + s * d.y) <= DY) return s;
+  }
+  if (p.y <= -DY) {
+    if (d.y <= 0) return RB_BIG;
+    double s = -(DY + p.y) / d.y, xn = p.x + s * d.x, zn = p.z + s * d.z;
+    if (fabs(zn) <= DZ && win_R(P, zn, r) && fabs(xn) <= r) return s;
+  } else if (p.y >= DY) {
+    if (d.y >= 0) return RB_BIG;
+    double s = (DY - p.y) / d.y, xn = p.x + s * d.x, zn = p.z + s * d.z;
+    if (fabs(zn) <= DZ && win_R(P, zn, r) && fabs(xn) <= r) return s;
+  }
+  double s0 = win_parabola(P, p, d, 1., 0., RB_PI);
+  if (!(fabs(p.y + s0 * d.y) <= DY)) s0 = RB_BIG;
+  double s1 = win_parabola(P, p, d, cos(RB_PI), sin(RB_PI), RB_PI);
+  if (!(fabs(p.y + s1 * d.y) <= DY)) s1 = RB_BIG;
+  return rb_min(s0, s1);
+}
+RB_HD inline V3 win_normal(const double* P, bool poly, V3 p, V3 d) {
+  double r, dr = 0;
+  V3 n;
+  if (poly) {
+    int np = (int)P[2];
+    double w = RB_PI / np, s0 = fabs(fabs(P[4]) - fabs(p.z));
+    double phi = rb_atan2(p.y, p.x);
+    while (phi > w) phi -= 2 * w;
+    while (phi < -w) phi += 2 * w;
+    double s1 = win_R(P, p.z, r) ? fabs(r - sqrt(p.x * p.x + p.y * p.y) * cos(phi)) : RB_BIG;
+    if (!(s1 < s0)) n = v3(0, 0, 1);
+    else {
+      phi = rb_atan2(p.y, p.x);
+      if (phi < -w) phi += 2 * RB_PI;
+      int k = (int)floor((phi + w) / (2 * w));
+      win_dRdZ(P, p.z, dr);
+      n = v3(cos(k * 2 * w), sin(k * 2 * w), -dr);
+    }
+  } else {
+    double s0 = fabs(fabs(P[2]) - fabs(p.y)), s1 = fabs(fabs(P[4]) - fabs(p.z)), s2 = win_R(P, p.z, r) ? fabs(r - fabs(p.x)) : RB_BIG;
+    if (s0 <= s1 && s0 <= s2) n = v3(0, 1, 0);
+    else if (s1 <= s2) n = v3(0, 0, 1);
+    else {
+      win_dRdZ(P, p.z, dr);
+      n = v3(1, 0, p.x > 0 ? -dr : dr);
+    }
+  }
+  double inv = 1. / sqrt(dot(n, n));
+  n = inv * n;
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
+// ================================================================== shape dispatch, boolean composites
+// DEPTH = remaining boolean nesting levels compiled in (scene build picks the instantiation).
+template <int DEPTH> struct Csg {
+  static RB_HD RB_NOINLINE bool contains(const DScene& sc, int sh, V3 p);
+  static RB_HD RB_NOINLINE double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel);
+  static RB_HD RB_NOINLINE double dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel);
+  static RB_HD RB_NOINLINE V3 normal(const DScene& sc, int sh, V3 p, V3 d, int sel);
+};
+
+RB_HD inline bool prim_contains(const DScene& sc, const DShape& s, V3 p) {
+  const double* P = sc.dpar + s.ipar;
+  switch (s.type) {
+    case RBG_SHAPE_BBOX: return bbox_contains(P, p);
+    case RBG_SHAPE_TUBE: return tube_contains(P, p);
+    case RBG_SHAPE_SPHERE: return sphere_contains(P, p);
+    case RBG_SHAPE_PARABOLOID: return para_contains(P, p);
+    case RBG_SHAPE_PGON: return pgon_contains(P, p);
+    case RBG_SHAPE_ASPHERE: return asph_contains(P, p);
+    case RBG_SHAPE_WINSTON2D: return win_contains(P, false, p);
+    case RBG_SHAPE_WINSTONPOLY: return win_contains(P, true, p);
+  }
+  return false;
+}
+RB_HD inline double prim_dist_in(const DScene& sc, const DShape& s, V3 p, V3 d) {
+  const double* P = sc.dpar + s.ipar;
+  switch (s.type) {
+    case RBG_SHAPE_BBOX: return bbox_dist_in(P, p, d);
+    case RBG_SHAPE_TUBE: return tube_dist_in(P[0], P[1], P[2], p, d);
+    case RBG_SHAPE_SPHERE: return sphere_dist(P, p, d, true);
+    case RBG_SHAPE_PARABOLOID: return para_dist_in(P, p, d);
+    case RBG_SHAPE_PGON: return pgon_dist_in(P, p, d);
+    case RBG_SHAPE_ASPHERE: return asph_dist4(P, p, d);
+    case RBG_SHAPE_WINSTON2D: return win_dist_in(P, false, p, d);
+    case RBG_SHAPE_WINSTONPOLY: return win_dist_in(P, true, p, d);
+  }
+  return RB_BIG;
+}
+RB_HD inline double prim_dist_out(const DScene& sc, const DShape& s, V3 p, V3 d, double step) {
+  const double* P = sc.dpar + s.ipar;
+  switch (s.type) {
+    case RBG_SHAPE_BBOX: return bbox_dist_out(P, p, d, step);
+    case RBG_SHAPE_TUBE: return tube_dist_out(P[0], P[1], P[2], p, d);
+    case RBG_SHAPE_SPHERE: return sphere_dist(P, p, d, false);
+    case RBG_SHAPE_PARABOLOID: return para_dist_out(P, p, d);
+    case RBG_SHAPE_PGON: return pgon_dist_out(P, p, d);
+    case RBG_SHAPE_ASPHERE: return asph_dist_out(P, p, d, step);
+    case RBG_SHAPE_WINSTON2D: return win_dist_out(P, false, p, d);
+    case RBG_SHAPE_WINSTONPOLY: return win_dist_out(P, true, p, d);
+  }
+  return RB_BIG;
+}
+RB_HD inline V3 prim_normal(const DScene& sc, const DShape& s, V3 p, V3 d) {
+  const double* P = sc.dpar + s.ipar;
+  switch (s.type) {
+    case RBG_SHAPE_BBOX: return bbox_normal(P, p, d);
+    case RBG_SHAPE_TUBE: return tube_normal(P, p, d);
+    case RBG_SHAPE_SPHERE: return sphere_normal(P, p, d);
+    case RBG_SHAPE_PARABOLOID: return para_normal(P, p, d);
+    case RBG_SHAPE_PGON: return pgon_normal(P, p, d);
+    case RBG_SHAPE_ASPHERE: return asph_normal(P, p, d);
+    case RBG_SHAPE_WINSTON2D: return win_normal(P, false, p, d);
+    case RBG_SHAPE_WINSTONPOLY: return win_normal(P, true, p, d);
+  }
+  return v3(0, 0, 1);
+}
+
+template <> struct Csg<0> {
+  static RB_HD RB_NOINLINE bool contains(const DScene& sc, int sh, V3 p) { return prim_contains(sc, sc.shapes[sh], p); }
+  static RB_HD RB_NOINLINE double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) { sel = 0; return prim_dist_in(sc, sc.shapes[sh], p, d); }
+  static RB_HD RB_NOINLINE double dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
+    sel = 0;
+    return prim_dist_out(sc, sc.shapes[sh], p, d, step);
+  }
+  static RB_HD RB_NOINLINE V3 normal(const DScene& sc, int sh, V3 p, V3 d, int) { return prim_normal(sc, sc.shapes[sh], p, d); }
+};
+
+RB_HD inline V3 op_point(const DScene& sc, int m, V3 p) { return m < 0 ? p : to_local(sc.mats[m], p); }
+RB_HD inline V3 op_vec(const DScene& sc, int m, V3 d) { return m < 0 ? d : to_local_vec(sc.mats[m], d); }
+
+template <int DEPTH> RB_HD RB_NOINLINE bool Csg<DEPTH>::contains(const DScene& sc, int sh, V3 p) {
+  const DShape s = sc.shapes[sh];
+  if (s.type < RBG_SHAPE_UNION) return prim_contains(sc, s, p);
+  typedef Csg<DEPTH - 1> Sub;
+  bool l = Sub::contains(sc, s.left, op_point(sc, s.lmat, p));
+  if (s.type == RBG_SHAPE_UNION) return l || Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
+  if (!l) return false;
+  bool r = Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
+  return s.type == RBG_SHAPE_INTERSECTION ? r : !r;
+}
+
+template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) {
+  const DShape s = sc.shapes[sh];
+  sel = 0;
+  if (s.type < RBG_SHAPE_UNION) return prim_dist_in(sc, s, p, d);
+  typedef Csg<DEPTH - 1> Sub;
+  V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p), ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
+  int s1 = 0, s2 = 0;
+  if (s.type != RBG_SHAPE_UNION) {  // TGeoIntersection / TGeoSubtraction :: DistFromInside
+    double d1 = Sub::dist_in(sc, s.left, lp, ld, s1);
+    double d2 = s.type == RBG_SHAPE_INTERSECTION ? Sub::dist_in(sc, s.right, rp, rd, s2) : Sub::dist_out(sc, s.right, rp, rd, RB_BIG, s2);
+    if (d1 < d2) { sel = 1 | (s1 << 2); return d1; }
+    sel = 2 | (s2 << 2);
+    return d2;
+  }
+  // TGeoUnion::DistFromInside: leave whichever operand holds the point, continue through the other
+  bool in1 = Sub::contains(sc, s.left, lp), in2 = Sub::contains(sc, s.right, rp);
+  double d1 = 0, d2 = 0, snxt = 0;
+  if (in1) d1 = Sub::dist_in(sc, s.left, lp, ld, s1);
+  if (in2) d2 = Sub::dist_in(sc, s.right, rp, rd, s2);
+  if (!(in1 || in2)) {
+    d1 = Sub::dist_out(sc, s.left, lp, ld, RB_BIG, s1);
+    if (d1 < 2. * RB_TOL) {
+      double eps = d1 + RB_TOL;
+      in1 = true;
+      d1 = Sub::dist_in(sc, s.left, along(lp, ld, eps), ld, s1) + eps;
+    } else {
+      d2 = Sub::dist_out(sc, s.right, rp, rd, RB_BIG, s2);
+      if (d2 < 2. * RB_TOL) {
+        double eps = d2 + RB_TOL;
+        in2 = true;
+        d2 = Sub::dist_in(sc, s.right, along(rp, rd, eps), rd, s2) + eps;
+      }
+    }
+  }
+  V3 master = p;
+  for (int guard = 0; guard < 64 && (in1 || in2); guard++) {
+    if (in1 && (!in2 || d1 < d2)) {
+      snxt += d1;
+      sel = 1 | (s1 << 2);
+      in1 = false;
+      master = along(master, d, d1);
+      V3 q = op_point(sc, s.rmat, along(master, d, (1. + d1) * RB_TOL));
+      in2 = Sub::contains(sc, s.right, q);
+      if (!in2) return snxt;
+      d2 = Sub::dist_in(sc, s.right, q, rd, s2);
+      if (d2 < RB_TOL) return snxt;
+      d2 += (1. + d1) * RB_TOL;
+    } else {
+      snxt += d2;
+      sel = 2 | (s2 << 2);
+      in2 = false;
+      master = along(master, d, d2);
+      V3 q = op_point(sc, s.lmat, along(master, d, (1. + d2) * RB_TOL));
+      in1 = Sub::contains(sc, s.left, q);
+      if (!in1) return snxt;
+      d1 = Sub::dist_in(sc, s.left, q, ld, s1);
+      if (d1 < RB_TOL) return snxt;
+      d1 += (1. + d2) * RB_TOL;
+    }
+  }
+  return snxt;
+}
+
+template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
+  const DShape s = sc.shapes[sh];
+  sel = 0;
+  if (s.type < RBG_SHAPE_UNION) return prim_dist_out(sc, s, p, d, step);
+  typedef Csg<DEPTH - 1> Sub;
+  V3 ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
+  V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p);
+  int s1 = 0, s2 = 0;
+  if (s.type == RBG_SHAPE_UNION) {
+    double d1 = Sub::dist_out(sc, s.left, lp, ld, step, s1), d2 = Sub::dist_out(sc, s.right, rp, rd, step, s2);
+    if (d1 < d2) { sel = 1 | (s1 << 2); return d1; }
+    sel = 2 | (s2 << 2);
+    return d2;
+  }
+  V3 master = p;
+  if (s.type == RBG_SHAPE_INTERSECTION) {
+    bool inl = Sub::contains(sc, s.left, lp), inr = Sub::contains(sc, s.right, rp);
+    double snext = 0.0, d1, d2;
+    if (inl && inr) {
+      d1 = Sub::dist_in(sc, s.left, lp, ld, s1);
+      d2 = Sub::dist_in(sc, s.right, rp, rd, s2);
+      if (d1 < 1.E-3) inl = false;
+      if (d2 < 1.E-3) inr = false;
+      if (inl && inr) return snext;
+    }
+    for (int guard = 0; guard < 64; guard++) {
+      d1 = d2 = 0;
+      if (!inl) {
+        d1 = rb_max(Sub::dist_out(sc, s.left, lp, ld, RB_BIG, s1), RB_TOL);
+        if (d1 > 1E20) return RB_BIG;
+      }
+      if (!inr) {
+        d2 = rb_max(Sub::dist_out(sc, s.right, rp, rd, RB_BIG, s2), RB_TOL);
+        if (d2 > 1E20) return RB_BIG;
+      }
+      if (d1 > d2) {
+        snext += d1;
+        sel = 1 | (s1 << 2);
+        inl = true;
+        master = along(master, d, d1);
+        lp = op_point(sc, s.lmat, master);
+        rp = op_point(sc, s.rmat, master);
+        inr = Sub::contains(sc, s.right, along(rp, rd, RB_TOL));
+        if (inr) return snext;
+      } else {
+        snext += d2;
+        sel = 2 | (s2 << 2);
+        inr = true;
+        master = along(master, d, d2);
+        lp = op_point(sc, s.lmat, master);
+        rp = op_point(sc, s.rmat, master);
+        inl = Sub::contains(sc, s.left, along(lp, ld, RB_TOL));
+        if (inl) return snext;
+      }
+    }
+    return RB_BIG;
+  }
+  // TGeoSubtraction::DistFromOutside
+  bool inside = Sub::contains(sc, s.right, rp);
+  double snxt = 0., epsil = 0.;
+  for (int guard = 0; guard < 64; guard++) {
+    if (inside) {
+      double d1 = Sub::dist_in(sc, s.right, rp, rd, s2);
+      sel = 2 | (s2 << 2);
+      snxt += d1 + epsil;
+      master = along(master, d, d1 + 1E-8);
+      epsil = 1.E-8;
+      if (Sub::contains(sc, s.left, op_point(sc, s.lmat, master))) return snxt;
+    }
+    lp = op_point(sc, s.lmat, master);
+    double d2 = Sub::dist_out(sc, s.left, lp, ld, RB_BIG, s1);
+    if (d2 > 1E20) return RB_BIG;
+    rp = op_point(sc, s.rmat, master);
+    int s2b = 0;
+    double d1 = Sub::dist_out(sc, s.right, rp, rd, RB_BIG, s2b);
+    if (d2 < d1 - RB_TOL) {
+      sel = 1 | (s1 << 2);
+      return snxt + d2 + epsil;
+    }
+    snxt += d1 + epsil;
+    master = along(master, d, d1 + 1E-8);
+    epsil = 1.E-8;
+    rp = op_point(sc, s.rmat, master);
+    inside = true;
+  }
+  return RB_BIG;
+}
+
+template <int DEPTH> RB_HD RB_NOINLINE V3 Csg<DEPTH>::normal(const DScene& sc, int sh, V3 p, V3 d, int sel) {
+  const DShape s = sc.shapes[sh];
+  if (s.type < RBG_SHAPE_UNION) return prim_normal(sc, s, p, d);
+  typedef Csg<DEPTH - 1> Sub;
+  int side = sel & 3;
+  if (side == 0) {
+    bool inl = Sub::contains(sc, s.left, op_point(sc, s.lmat, p)), inr = Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
+    if (s.type == RBG_SHAPE_SUBTRACTION) side = inr ? 2 : 1;
+    else if (s.type == RBG_SHAPE_UNION) side = inl ? 1 : 2;
+    else side = inl ? 2 : 1;
+  }
+  int m = side == 1 ? s.lmat : s.rmat;
+  V3 ln = Sub::normal(sc, side == 1 ? s.left : s.right, op_point(sc, m, p), op_vec(sc, m, d), sel >> 2);
+  return m < 0 ? ln : to_master_vec(sc.mats[m], ln);
+}
+
+// ================================================================== flattened navigation
+struct RayReg {           // register-resident ray state
+  V3 p, d;
+  double t, lambda;
+  int cur;                // physical node containing the point, -1 = outside the top volume
+  int status, npoints, last_node;
+  uint32_t ndraw;
+  int on_boundary;
+};
+
+// first (lowest id = daughter order) child of `node` whose shape contains q; -1 if none
+template <int DEPTH> RB_HD inline int child_containing(const DScene& sc, int node, V3 q, int skip) {
+  const DNode& nd = sc.nodes[node];
+  int best = -1;
+  int i = nd.bvh_count > 0 ? nd.bvh_first : -1;
+  while (i >= 0) {
+    const DBvh& b = sc.bvh[i];
+    bool in = q.x >= b.lo[0] && q.x <= b.hi[0] && q.y >= b.lo[1] && q.y <= b.hi[1] && q.z >= b.lo[2] && q.z <= b.hi[2];
+    if (!in) { i = b.skip; continue; }
+    if (b.child >= 0) {
+      int c = b.child;
+      if (c != skip && (best < 0 || c < best)) {
+        const DNode& cn = sc.nodes[c];
+        if (Csg<DEPTH>::contains(sc, cn.shape, to_local(cn.g, q))) best = c;
+      }
+      i = b.skip;
+    } else i = i + 1;
+  }
+  return best;
+}
+// TGeoNavigator::SearchNode(downwards=false, skip) starting at `node`; returns the deepest node containing q or -1
+template <int DEPTH> RB_HD inline int search_node(const DScene& sc, int node, V3 q, int skip, bool check_current) {
+  if (check_current) {
+    while (true) {
+      if (node < 0) return -1;
+      const DNode& nd = sc.nodes[node];
+      bool inside = node == skip ? true : Csg<DEPTH>::contains(sc, nd.shape, to_local(nd.g, q));
+      if (inside) break;
+      skip = node;
+      node = nd.mother;
+    }
+  }
+  while (true) {
+    int c = child_containing<DEPTH>(sc, node, q, skip);
+    skip = -1;
+    if (c < 0) return node;
+    node = c;
+  }
+}
+
+struct StepOut {
+  double step;
+  int next;        // node now containing the point (-1 outside)
+  int crossed;     // node whose shape boundary was crossed (for FindNormal), -1 none
+  int sel;         // boolean-operand selection path of the crossed shape
+};
+
+RB_HD inline double locate_extra(const DScene& sc, int node, double step) {
+  double trmax = 1.;
+  if (node >= 0) {
+    const double* tr = sc.nodes[node].g.t;
+    trmax += fabs(tr[0]) + fabs(tr[1]) + fabs(tr[2]);
+  }
+  return 100. * (trmax + step) * RB_TOL;
+}
+
+// TGeoNavigator::FindNextBoundaryAndStep(Big) on the flattened scene
+template <int DEPTH> RB_HD inline StepOut next_boundary(const DScene& sc, RayReg& r, bool push_quirk) {
+  StepOut o;
+  o.crossed = -1;
+  o.sel = 0;
+  double extra = (r.on_boundary && push_quirk) ? RB_TOL : 0.0;
+  r.on_boundary = 0;
+  r.p = along(r.p, r.d, extra);
+  if (r.cur < 0) {
+    int sel = 0;
+    double s = Csg<DEPTH>::dist_out(sc, sc.top_shape, r.p, r.d, RB_BIG, sel);
+    if (s > 1e29) { o.step = RB_BIG; o.next = -1; return o; }
+    if (s <= 0) { s = 0.0; o.step = 0.0; r.p = along(r.p, r.d, -extra); }
+    else o.step = s + extra;
+    r.p = along(r.p, r.d, s);
+    r.on_boundary = 1;
+    o.crossed = 0;
+    o.sel = sel;
+    o.next = search_node<DEPTH>(sc, 0, along(r.p, r.d, locate_extra(sc, 0, o.step)), -1, false);
+    return o;
+  }
+  const DNode& cn = sc.nodes[r.cur];
+  int sel_exit = 0;
+  double s_exit = Csg<DEPTH>::dist_in(sc, cn.shape, to_local(cn.g, r.p), to_local_vec(cn.g, r.d), sel_exit);
+  if (s_exit <= RB_TOL) {
+    o.step = RB_TOL;
+    r.p = along(r.p, r.d, o.step);
+    r.on_boundary = 1;
+    o.crossed = r.cur;
+    o.sel = sel_exit;
+    if (cn.mother < 0) { o.next = -1; return o; }
+    o.next = search_node<DEPTH>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
+    return o;
+  }
+  double best = RB_BIG;
+  if (s_exit < best - RB_TOL) best = s_exit;
+  int enter = -1, esel = 0;
+  int i = cn.bvh_count > 0 ? cn.bvh_first : -1;
+  double idx = 1. / r.d.x, idy = 1. / r.d.y, idz = 1. / r.d.z;
+  while (i >= 0) {
+    const DBvh& b = sc.bvh[i];
+    // slab test against [0, best]
+    double t0 = (b.lo[0] - r.p.x) * idx, t1 = (b.hi[0] - r.p.x) * idx;
+    double tmin = rb_min(t0, t1), tmax = rb_max(t0, t1);
+    t0 = (b.lo[1] - r.p.y) * idy; t1 = (b.hi[1] - r.p.y) * idy;
+    tmin = rb_max(tmin, rb_min(t0, t1)); tmax = rb_min(tmax, rb_max(t0, t1));
+    t0 = (b.lo[2] - r.p.z) * idz; t1 = (b.hi[2] - r.p.z) * idz;
+    tmin = rb_max(tmin, rb_min(t0, t1)); tmax = rb_min(tmax, rb_max(t0, t1));
+    bool hit = tmax >= rb_max(tmin, 0.0) && tmin < best;
+    if (!hit) { i = b.skip; continue; }
+    if (b.child >= 0) {
+      const DNode& dn = sc.nodes[b.child];
+      int sel = 0;
+      double s = Csg<DEPTH>::dist_out(sc, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), best, sel);
+      if (s < best - RB_TOL) { best = s; enter = b.child; esel = sel; }
+      i = b.skip;
+    } else i = i + 1;
+  }
+  r.p = along(r.p, r.d, best);
+  o.step = best + extra;
+  r.on_boundary = 1;
+  if (enter >= 0) {
+    o.crossed = enter;
+    o.sel = esel;
+    o.next = search_node<DEPTH>(sc, enter, along(r.p, r.d, locate_extra(sc, enter, o.step)), -1, false);
+    return o;
+  }
+  o.crossed = r.cur;
+  o.sel = sel_exit;
+  if (cn.mother < 0) { o.next = -1; return o; }
+  o.next = search_node<DEPTH>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
+  return o;
+}
+
+// ================================================================== physics
+RB_HD inline int find_border(const DScene& sc, int vol1, int vol2) {
+  if (vol1 < 0) return -1;
+  const rbg_volume& v = sc.volumes[vol1];
+  for (int i = 0; i < v.nborders; i++)
+    if (sc.borders[v.first_border + i].vol2 == vol2) return v.first_border + i;
+  return -1;
+}
+
+struct Hit {       // context of one boundary interaction
+  int cur_vol, next_vol, next_node, border;
+  int crossed, sel;
+  double step;
+};
+
+template <int DEPTH> RB_HD inline V3 geometric_normal(const DScene& sc, const RayReg& r, const Hit& h, V3 dir) {
+  if (h.crossed < 0) return v3(0, 0, 1);
+  const DNode& nd = sc.nodes[h.crossed];
+  V3 ln = Csg<DEPTH>::normal(sc, nd.shape, to_local(nd.g, r.p), to_local_vec(nd.g, dir), h.sel);
+  return to_master_vec(nd.g, ln);
+}
+
+// AOpticsManager::GetFacetNormal — geometric normal, optionally perturbed by Gaussian micro-facets
+template <int DEPTH> RB_HD inline V3 facet_normal(const DScene& sc, const RayReg& r, const Hit& h, Philox& g) {
+  V3 n = geometric_normal<DEPTH>(sc, r, h, r.d);
+  if (h.border < 0) return n;
+  const rbg_border& c = sc.borders[h.border];
+  if (c.lambertian || c.sigma == 0) return n;
+  double sigma = c.sigma, f_max = rb_min(1., 4. * sigma);
+  V3 fn;
+  for (int guard = 0; guard < 100000; guard++) {
+    double alpha;
+    do {
+      alpha = rng_gaus(g, 0, sigma);
+    } while (f_max * rng_uniform(g) > sin(alpha) || alpha >= RB_PI / 2);
+    double phi = 2 * RB_PI * rng_uniform(g);
+    double sa = sin(alpha), ca = cos(alpha), px = sa * cos(phi), py = sa * sin(phi), pz = ca;
+    double up = n.x * n.x + n.y * n.y;  // TVector3::RotateUz(n)
+    if (up != 0) {
+      up = sqrt(up);
+      fn = v3((n.x * n.z * px - n.y * py + n.x * up * pz) / up, (n.y * n.z * px + n.x * py + n.y * up * pz) / up, (n.z * n.z * px - px + n.z * up * pz) / up);
+    } else if (n.z < 0.) fn = v3(-px, py, -pz);
+    else fn = v3(px, py, pz);
+    if (dot(r.d, fn) > 0.0) break;
+  }
+  return fn;
+}
+
+RB_HD inline double mirror_reflectance(const DScene& sc, int vol, double lambda, double angle) {
+  int mi = sc.volumes[vol].mirror;
+  double ret = 1.0;
+  if (mi >= 0) {
+    const rbg_mirror& m = sc.mirrors[mi];
+    if (m.th2 >= 0) ret = th2_interp(sc, m.th2, lambda, angle);
+    else if (m.graph1d >= 0) ret = graph_eval(sc, m.graph1d, lambda);
+    else ret = m.constant;
+  }
+  return ret > 1 ? 1 : (ret < 0 ? 0 : ret);
+}
+
+RB_HD inline void add_point(RayReg& r, V3 p, double t) {
+  r.p = p;
+  r.t = t;
+  r.npoints++;
+}
+RB_HD inline void set_direction(RayReg& r, V3 d2) {
+  double mag = sqrt(dot(d2, d2));
+  if (mag > 0) r.d = (1. / mag) * d2;
+}
+
+// AOpticsManager::DoReflection.  `pos` is the boundary point; r.p still holds the segment start.
+template <int DEPTH> RB_HD inline void do_reflection(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1,
+                                                    Philox& g, const V3* normal_in) {
+  RayReg at = r;
+  at.p = pos;
+  V3 n = normal_in ? *normal_in : facet_normal<DEPTH>(sc, at, h, g);
+  V3 d1 = r.d;
+  double cos1 = dot(d1, n);
+  bool absorbed = false;
+  int next_type = h.next_vol < 0 ? RBG_NULL : sc.volumes[h.next_vol].type;
+  const rbg_border* c = h.border >= 0 ? &sc.borders[h.border] : nullptr;
+  if (next_type == RBG_MIRROR) {
+    double angle = rb_acos(cos1), ref, tr;
+    if (c && c->multilayer >= 0) tmm_mixed(sc, c->multilayer, angle, r.lambda, ref, tr);
+    else ref = mirror_reflectance(sc, h.next_vol, r.lambda, angle);
+    if (ref < rng_uniform(g)) { absorbed = true; r.status = RBG_ABSORB; }
+  }
+  V3 d2;
+  if (c && c->lambertian) {
+    double y = 0.5 * rng_uniform(g), theta = rb_asin(sqrt(2 * y)), phi = 2 * RB_PI * rng_uniform(g);
+    double perp = sqrt(n.x * n.x + n.y * n.y);
+    double theta_n = (n.x == 0 && n.y == 0 && n.z == 0 ? 0 : atan2(perp, n.z)) * 180. / RB_PI;
+    double phi_n = (n.x == 0 && n.y == 0 ? 0 : atan2(n.y, n.x)) * 180. / RB_PI;
+    double ph = (phi_n + 90) * RB_PI / 180., th = (theta_n + 180) * RB_PI / 180.;
+    double sp = sin(ph), cp = cos(ph), st = sin(th), ct = cos(th);
+    V3 v = v3(sin(theta) * cos(phi), sin(theta) * sin(phi), cos(theta));
+    d2 = v3(cp * v.x - ct * sp * v.y + st * sp * v.z, sp * v.x + ct * cp * v.y - st * cp * v.z, st * v.y + ct * v.z);
+  } else d2 = v3(d1.x - 2 * n.x * cos1, d1.y - 2 * n.y * cos1, d1.z - 2 * n.z * cos1);
+  if (!absorbed) set_direction(r, d2);
+  double t = r.t + h.step / (RB_C_CM / n1);
+  // nav->Step() backwards by 1e-6 (+1e-6 of ROOT's Step) and relocate; the recorded vertex is the stepped-back point
+  V3 back = along(pos, d1, -2e-6);
+  loc = search_node<DEPTH>(sc, h.next_node < 0 ? 0 : h.next_node, back, -1, true);
+  if (tp.quirks & RBG_QUIRK_STEPBACK) pos = back;
+  add_point(r, pos, t);
+  r.last_node = h.next_node;
+  r.on_boundary = 0;
+}
+
+// AOpticsManager::DoFresnel
+template <int DEPTH> RB_HD inline void do_fresnel(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1, double n2,
+                                                 double k2, Philox& g) {
+  RayReg at = r;
+  at.p = pos;
+  V3 n = facet_normal<DEPTH>(sc, at, h, g);
+  V3 d1 = r.d;
+  double cos1 = dot(d1, n), sin1 = sqrt(1 - cos1 * cos1), sin2 = n1 * sin1 / n2, cos2 = sqrt(1 - sin2 * sin2);
+  bool absorbed = false, decided = false;
+  const rbg_border* c = h.border >= 0 ? &sc.borders[h.border] : nullptr;
+  if (c && c->multilayer >= 0) {
+    double R, T;
+    tmm_mixed(sc, c->multilayer, rb_acos(cos1), r.lambda, R, T);
+    double rnd = rng_uniform(g);
+    if (rnd < R) { do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+    decided = true;
+    if (!(rnd < R + T)) absorbed = true;
+  }
+  if (!decided) {
+    if (sin2 > 1.) { do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+    if (!tp.disable_fresnel) {
+      double Rs, Rp;
+      if (k2 <= 0.) {
+        double e1s = n1 * cos1, e2s = n2 * cos2, e1p = n1 / cos1, e2p = n2 / cos2;
+        Rs = sqr((e1s - e2s) / (e1s + e2s));
+        Rp = sqr((e1p - e2p) / (e1p + e2p));
+      } else {
+        double x1S = n1 * cos1, x1P = n1 / cos1;
+        double u = sqr(n2) - sqr(k2) - sqr(n1 * sin1), v = 2 * n2 * k2, tmp = sqrt(sqr(u) + sqr(v));
+        double cosxi2 = sqrt(1 + u / tmp) / sqrt(2.), sinxi2 = sqrt(1 - u / tmp) / sqrt(2.);
+        double x2S = sqrt(tmp) * cosxi2, y2S = sqrt(tmp) * sinxi2;
+        tmp = sqr(x2S) + sqr(y2S);
+        double x2P = (2 * n2 * k2 * y2S + (sqr(n2) - sqr(k2)) * x2S) / tmp, y2P = (2 * n2 * k2 * x2S - (sqr(n2) - sqr(k2)) * y2S) / tmp;
+        Rs = (sqr(x1S - x2S) + sqr(y2S)) / (sqr(x1S + x2S) + sqr(y2S));
+        Rp = (sqr(x1P - x2P) + sqr(y2P)) / (sqr(x1P + x2P) + sqr(y2P));
+      }
+      if (rng_uniform(g) < (Rs + Rp) / 2.) { do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+    }
+  }
+  V3 d2 = d1;
+  if (sin1 != 0) {
+    double f = sin2 / sin1;
+    d2 = v3((d1.x - cos1 * n.x) * f + n.x * cos2, (d1.y - cos1 * n.y) * f + n.y * cos2, (d1.z - cos1 * n.z) * f + n.z * cos2);
+  }
+  add_point(r, pos, r.t + h.step / (RB_C_CM / n1));
+  r.last_node = h.next_node;
+  if (absorbed) r.status = RBG_ABSORB;
+  else set_direction(r, d2);
+}
+
+// One iteration of the while(ray->IsRunning()) loop, src/AOpticsManager.cxx:359-518
+template <int DEPTH> RB_HD inline void trace_step(const DScene& sc, const DTraceParams& tp, RayReg& r, Philox& g) {
+  V3 x1 = r.p;
+  double t1 = r.t;
+  int cur = r.cur;
+  int cur_vol = cur < 0 ? -1 : sc.nodes[cur].volume;
+  int typeCurrent = cur < 0 ? RBG_NULL : sc.nodes[cur].type;
+  RayReg nav = r;  // navigator copy: nav.p advances to the boundary, r.p stays at the segment start
+  StepOut so = next_boundary<DEPTH>(sc, nav, (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0);
+  r.on_boundary = nav.on_boundary;
+  Hit h;
+  h.cur_vol = cur_vol;
+  h.next_node = so.next;
+  h.next_vol = so.next < 0 ? -1 : sc.nodes[so.next].volume;
+  h.crossed = so.crossed;
+  h.sel = so.sel;
+  h.step = so.step;
+  h.border = find_border(sc, cur_vol, h.next_vol);
+  int typeNext = so.next < 0 ? RBG_NULL : sc.nodes[so.next].type;
+  V3 pos = nav.p;
+  int loc = so.next;
+  double lambda = r.lambda;
+  if (typeCurrent == RBG_LENS) {
+    double k = index_k(sc, sc.volumes[cur_vol].index, lambda);
+    if (k > 0) {
+      double abs = lambda / (4 * RB_PI * k);
+      if (abs > 0 && abs < 1e300) {
+        double abs_step = -abs * log(rng_uniform(g));
+        if (abs_step < so.step) {
+          double n1 = index_n(sc, sc.volumes[cur_vol].index, lambda);
+          add_point(r, along(x1, r.d, abs_step), t1 + abs_step / (RB_C_CM / n1));
+          r.last_node = so.next;
+          r.status = RBG_ABSORB;
+          r.cur = loc;
+          return;
+        }
+      }
+    }
+  }
+  bool curVac = typeCurrent == RBG_NULL || typeCurrent == RBG_OPT || typeCurrent == RBG_OTHER;
+  bool curLens = typeCurrent == RBG_LENS;
+  if ((curVac || curLens) && typeNext == RBG_MIRROR) {
+    double n1 = curLens ? index_n(sc, sc.volumes[cur_vol].index, lambda) : 1.;
+    do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, nullptr);
+  } else if (curVac && typeNext == RBG_LENS) {
+    int ix = sc.volumes[h.next_vol].index;
+    do_fresnel<DEPTH>(sc, tp, r, pos, loc, h, 1., index_n(sc, ix, lambda), index_k(sc, ix, lambda), g);
+  } else if ((curVac || curLens) && (typeNext == RBG_OBS || typeNext == RBG_FOCUS)) {
+    double speed = curLens ? RB_C_CM / index_n(sc, sc.volumes[cur_vol].index, lambda) : RB_C_CM;
+    add_point(r, pos, t1 + so.step / speed);
+    r.last_node = so.next;
+  } else if (curVac && (typeNext == RBG_OTHER || typeNext == RBG_OPT)) {
+    add_point(r, pos, t1 + so.step / RB_C_CM);
+    r.last_node = so.next;
+  } else if (curLens && typeNext == RBG_LENS) {
+    int i1 = sc.volumes[cur_vol].index, i2 = sc.volumes[h.next_vol].index;
+    do_fresnel<DEPTH>(sc, tp, r, pos, loc, h, index_n(sc, i1, lambda), index_n(sc, i2, lambda), index_k(sc, i2, lambda), g);
+  } else if (curLens && (typeNext == RBG_NULL || typeNext == RBG_OPT || typeNext == RBG_OTHER)) {
+    do_fresnel<DEPTH>(sc, tp, r, pos, loc, h, index_n(sc, sc.volumes[cur_vol].index, lambda), 1., 0., g);
+  }
+  // termination (evaluated after the interaction, src/AOpticsManager.cxx:485-513)
+  if (typeNext == RBG_NULL) {
+    add_point(r, pos, t1 + so.step / RB_C_CM);
+    r.last_node = so.next;
+    r.status = RBG_EXIT;
+  } else if (typeCurrent == RBG_FOCUS || typeCurrent == RBG_OBS || typeCurrent == RBG_MIRROR || typeNext == RBG_OBS) {
+    r.status = RBG_STOP;
+  } else if (typeNext == RBG_FOCUS) {
+    const rbg_volume& fv = sc.volumes[h.next_vol];
+    double qe = 1.;
+    if (fv.focal >= 0) {
+      const rbg_focal f = sc.focals[fv.focal];
+      double angle = 0.;
+      if (f.qe_angle >= 0) {
+        RayReg at = r;
+        at.p = pos;
+        V3 n = facet_normal<DEPTH>(sc, at, h, g);
+        angle = rb_acos(dot(r.d, n));
+      }
+      if (f.qe_lambda >= 0) qe = graph_eval(sc, f.qe_lambda, lambda);
+      if (f.qe_angle >= 0) qe *= graph_eval(sc, f.qe_angle, angle);
+    }
+    if (qe == 1 || rng_uniform(g) < qe) r.status = RBG_FOCUSED;
+    else r.status = RBG_STOP;
+  }
+  r.cur = loc;
+  if (r.status == RBG_RUN && r.npoints >= tp.limit) r.status = RBG_SUSPEND;
+}
+
+// locate the start point (InitTrack -> FindNode)
+template <int DEPTH> RB_HD inline int locate_start(const DScene& sc, V3 p) { return search_node<DEPTH>(sc, 0, p, -1, true); }
+
+#endif  // RB_DEVICE_CUH

@@ -1,0 +1,645 @@
+// rb_kernels.cu — sm_100a kernels and the C ABI (include/robast_b200.h) of the B200 tracer.
+//
+//  k_trace<DEPTH>   one thread per live ray; runs `max_steps` iterations of the reference's
+//                   while(ray->IsRunning()) loop (src/AOpticsManager.cxx:359-518) in registers.
+//                   FP64-pipe bound.  Replaces TGeoNavigator::FindNextBoundaryAndStep + DoReflection
+//                   + DoFresnel + GetFacetNormal and every TGeoShape::Dist*/ComputeNormal virtual call.
+//  k_compact        stable stream compaction of surviving ray indices between bounces: warp scan +
+//                   block scan + decoupled look-back across tiles (single pass, 4 B read + 4 B write
+//                   per live ray).  HBM bound.  Replaces the survivor test of the reference's while loop.
+//  k_shoot          ARayShooter generators on device (src/ARayShooter.cxx:122-460), 64 B/ray written.
+//  k_hist2d/k_moments  focal-plane reducers (TH2D fill, GetMean/GetRMS of the tutorials).
+//  k_tmm            AMultilayer::CoherentTMMMixed per (theta, lambda) pair.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rb_build.h"
+#include "rb_trace_kernel.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+static int g_profile = 0;
+struct ProfEvt { cudaEvent_t a, b; int kind; };
+static std::vector<ProfEvt> g_prof_events;
+static double g_prof_ms[2] = {0, 0};
+static long long g_prof_n[2] = {0, 0};
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string("cuda: ") + #call + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class F> static int guard(F f) {
+  try {
+    f();
+    return RBG_OK;
+  } catch (NotSupported& e) {
+    g_err = e.what();
+    return RBG_ENOTSUP;
+  } catch (Invalid& e) {
+    g_err = e.what();
+    return RBG_EINVAL;
+  } catch (std::bad_alloc&) {
+    g_err = "out of host memory";
+    return RBG_ENOMEM;
+  } catch (std::runtime_error& e) {
+    g_err = e.what();
+    return g_err.find("cuda") == 0 ? RBG_ECUDA : RBG_EINTERNAL;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return RBG_EINTERNAL;
+  } catch (...) {
+    g_err = "unknown exception";
+    return RBG_EINTERNAL;
+  }
+}
+
+struct ProfScope {
+  cudaStream_t st;
+  int kind;
+  ProfEvt e;
+  bool on;
+  ProfScope(cudaStream_t s, int k) : st(s), kind(k), on(g_profile != 0) {
+    if (on) {
+      cudaEventCreate(&e.a);
+      cudaEventCreate(&e.b);
+      e.kind = kind;
+      cudaEventRecord(e.a, st);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(e.b, st);
+      g_prof_events.push_back(e);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ kernels
+// ---- stream compaction (decoupled look-back)
+#define CP_THREADS 256
+#define CP_ITEMS 4
+#define CP_TILE (CP_THREADS * CP_ITEMS)
+__global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restrict__ live_in, int n_in, const int32_t* __restrict__ status,
+                                                       int32_t* __restrict__ live_out, int32_t* count_out, unsigned long long* tile_state,
+                                                       int32_t* tile_counter, int ntiles) {
+  __shared__ int s_tile, s_prefix;
+  __shared__ int s_warp[CP_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int base = tile * CP_TILE + tid * CP_ITEMS;
+  int idx[CP_ITEMS];
+  bool alive[CP_ITEMS];
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < CP_ITEMS; k++) {
+    int i = base + k;
+    alive[k] = false;
+    idx[k] = 0;
+    if (i < n_in) {
+      idx[k] = live_in ? live_in[i] : i;
+      alive[k] = status[idx[k]] == RBG_RUN;
+    }
+    cnt += alive[k] ? 1 : 0;
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < CP_THREADS / 32 ? s_warp[lane] : 0, w = v;
+#pragma unroll
+    for (int o = 1; o < CP_THREADS / 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
+    }
+    if (lane < CP_THREADS / 32) s_warp[lane] = w - v;  // exclusive warp offsets
+    if (lane == CP_THREADS / 32 - 1) {
+      int total = w, excl = 0;
+      volatile unsigned long long* ts = tile_state;
+      if (tile > 0) {
+        atomicExch(&tile_state[tile], (1ull << 32) | (unsigned)total);  // AGGREGATE
+        int j = tile - 1;
+        while (true) {
+          unsigned long long st = ts[j];
+          unsigned flag = (unsigned)(st >> 32);
+          if (flag == 0) continue;  // predecessor not published yet
+          excl += (int)(unsigned)st;
+          if (flag == 2) break;
+          j--;
+        }
+      }
+      atomicExch(&tile_state[tile], (2ull << 32) | (unsigned)(excl + total));  // INCLUSIVE PREFIX
+      s_prefix = excl;
+      if (tile == ntiles - 1) *count_out = excl + total;
+    }
+  }
+  __syncthreads();
+  int pos = s_prefix + s_warp[warp] + incl - cnt;
+#pragma unroll
+  for (int k = 0; k < CP_ITEMS; k++)
+    if (alive[k]) live_out[pos++] = idx[k];
+}
+
+// ---- ARayShooter on device
+__global__ void k_shoot(rbg_shoot_desc s, long long first, long long n, double* x, double* y, double* z, double* t, double* dx, double* dy, double* dz,
+                        double* lambda) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  unsigned long long id = (unsigned long long)(first + j);
+  Philox g;
+  g.k0 = (uint32_t)s.seed; g.k1 = (uint32_t)(s.seed >> 32);
+  g.id0 = (uint32_t)id; g.id1 = (uint32_t)(id >> 32);
+  g.ndraw = 0x40000000u;
+  double px = 0, py = 0;
+  if (s.kind == 0) {
+    long long i = (long long)id / s.ny, k = (long long)id % s.ny;
+    double deltax = s.nx == 1 ? s.dx / 2 : s.dx / (s.nx - 1), deltay = s.ny == 1 ? s.dy / 2 : s.dy / (s.ny - 1);
+    px = i * deltax - s.dx / 2;
+    py = k * deltay - s.dy / 2;
+  } else if (s.kind == 1) {
+    px = -s.dx / 2 + s.dx * rng_uniform(g);
+    py = -s.dy / 2 + s.dy * rng_uniform(g);
+  } else if (s.kind == 2) {
+    double rmax = s.dx;
+    do {
+      px = -rmax + 2 * rmax * rng_uniform(g);
+      py = -rmax + 2 * rmax * rng_uniform(g);
+    } while (sqrt(px * px + py * py) > rmax);
+  } else {
+    long long idx = (long long)id;
+    if (idx > 0) {
+      long long i = 0, acc = 1;
+      while (idx >= acc + (long long)s.ny * (i + 1)) { acc += (long long)s.ny * (i + 1); i++; }
+      long long k = idx - acc;
+      double rr = s.dx * (i + 1) / s.nx, phi = 2 * RB_PI / s.ny / (i + 1) * k;
+      px = rr * cos(phi);
+      py = rr * sin(phi);
+    }
+  }
+  // rot * (px,py,0) + tr ; dir = rot * dir, normalised
+  double qx = s.rot[0] * px + s.rot[1] * py, qy = s.rot[3] * px + s.rot[4] * py, qz = s.rot[6] * px + s.rot[7] * py;
+  double ndx = s.rot[0] * s.dir[0] + s.rot[1] * s.dir[1] + s.rot[2] * s.dir[2], ndy = s.rot[3] * s.dir[0] + s.rot[4] * s.dir[1] + s.rot[5] * s.dir[2],
+         ndz = s.rot[6] * s.dir[0] + s.rot[7] * s.dir[1] + s.rot[8] * s.dir[2];
+  double mag = sqrt(ndx * ndx + ndy * ndy + ndz * ndz);
+  if (mag > 0) { ndx /= mag; ndy /= mag; ndz /= mag; }
+  x[j] = s.tr[0] + qx; y[j] = s.tr[1] + qy; z[j] = s.tr[2] + qz; t[j] = 0;
+  dx[j] = ndx; dy[j] = ndy; dz[j] = ndz;
+  lambda[j] = s.lambda_min == s.lambda_max ? s.lambda_min : s.lambda_min + (s.lambda_max - s.lambda_min) * rng_uniform(g);
+}
+
+// ---- reducers
+#define HIST_SMEM_BINS 8192
+__global__ void k_hist2d(long long n, const double* __restrict__ x, const double* __restrict__ y, const int32_t* __restrict__ status, int sel, int nx,
+                         double xmin, double xmax, int ny, double ymin, double ymax, unsigned long long* hist, int use_smem) {
+  __shared__ unsigned int sh[HIST_SMEM_BINS];
+  int nb = nx * ny;
+  if (use_smem) {
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+  }
+  double sx = nx / (xmax - xmin), sy = ny / (ymax - ymin);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (status[i] != sel) continue;
+    double vx = x[i], vy = y[i];
+    if (vx < xmin || !(vx < xmax) || vy < ymin || !(vy < ymax)) continue;
+    int bx = (int)((vx - xmin) * sx), by = (int)((vy - ymin) * sy);
+    bx = bx >= nx ? nx - 1 : bx;
+    by = by >= ny ? ny - 1 : by;
+    if (use_smem) atomicAdd(&sh[bx + nx * by], 1u);
+    else atomicAdd(&hist[bx + nx * by], 1ull);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+      if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+  }
+}
+
+__global__ void k_moments(long long n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ t,
+                          const int32_t* __restrict__ status, int sel, double* moments, unsigned long long* counts) {
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  unsigned int c[6] = {0, 0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int s = status[i];
+    if (s >= 0 && s < 6) c[s]++;
+    if (s != sel) continue;
+    double vx = x[i], vy = y[i], vt = t[i];
+    acc[0] += 1; acc[1] += vx; acc[2] += vy; acc[3] += vx * vx; acc[4] += vy * vy; acc[5] += vt; acc[6] += vt * vt;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; k++)
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+    for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_down_sync(0xffffffffu, c[k], o);
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 7; k++)
+      if (acc[k] != 0) atomicAdd(&moments[k], acc[k]);
+    for (int k = 0; k < 6; k++)
+      if (c[k]) atomicAdd(&counts[k], (unsigned long long)c[k]);
+  }
+}
+
+__global__ void k_tmm(DScene sc, int ml, long long n, const double* __restrict__ theta, const double* __restrict__ lambda, double* R, double* T) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r, t;
+  tmm_mixed(sc, ml, theta[i], lambda[i], r, t);
+  R[i] = r;
+  T[i] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ host: scene
+struct rbg_scene {
+  int device = 0;
+  int depth = 0;
+  DScene d;
+  std::vector<void*> allocs;
+  std::vector<std::string> node_names;
+  // per-scene scratch for the wavefront loop and host staging
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* stage[3] = {nullptr, nullptr, nullptr};
+  size_t stage_bytes[3] = {0, 0, 0};
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  int32_t* d_count = nullptr;
+  int32_t* h_count = nullptr;  // pinned
+};
+
+template <class T> static const T* upload(rbg_scene* s, const std::vector<T>& v) {
+  if (v.empty()) return nullptr;
+  void* p = nullptr;
+  CK(cudaMalloc(&p, v.size() * sizeof(T)));
+  s->allocs.push_back(p);
+  CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return (const T*)p;
+}
+template <class T> static const T* upload(rbg_scene* s, const T* src, size_t n) {
+  if (!n || !src) return nullptr;
+  return upload(s, std::vector<T>(src, src + n));
+}
+
+static void scene_free(rbg_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->scratch) cudaFree(s->scratch);
+  for (int i = 0; i < 3; i++) {
+    if (s->stage[i]) cudaFree(s->stage[i]);
+    if (s->streams[i]) cudaStreamDestroy(s->streams[i]);
+  }
+  if (s->d_count) cudaFree(s->d_count);
+  if (s->h_count) cudaFreeHost(s->h_count);
+  delete s;
+}
+
+// ------------------------------------------------------------------------------------------------ host: trace driver
+static void launch_trace(int depth, const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init, int keep,
+                         cudaStream_t st) {
+  if (n <= 0) return;
+  ProfScope ps(st, 0);
+  int rc;
+  switch (depth) {
+    case 0: rc = rb_launch_trace_d0(sc, tp, R, live, n, init, keep, st); break;
+    case 1: rc = rb_launch_trace_d1(sc, tp, R, live, n, init, keep, st); break;
+    case 2: rc = rb_launch_trace_d2(sc, tp, R, live, n, init, keep, st); break;
+    case 3: rc = rb_launch_trace_d3(sc, tp, R, live, n, init, keep, st); break;
+    default: throw NotSupported("boolean composite nesting deeper than 3 is not supported");
+  }
+  g_launches++;
+  if (rc != 0) throw std::runtime_error(std::string("cuda: k_trace launch: ") + cudaGetErrorString((cudaError_t)rc));
+}
+
+static void ensure_scratch(rbg_scene* s, size_t bytes) {
+  if (bytes <= s->scratch_bytes) return;
+  if (s->scratch) CK(cudaFree(s->scratch));
+  s->scratch = nullptr;
+  s->scratch_bytes = 0;
+  CK(cudaMalloc(&s->scratch, bytes));
+  s->scratch_bytes = bytes;
+}
+
+// device-resident trace of n rays (n < 2^31) on stream st
+static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long long n, unsigned long long id_offset, cudaStream_t st, void* scratch,
+                         int32_t* d_count, int32_t* h_count) {
+  if (n <= 0) return;
+  if (n > 0x7fffff00LL) throw Invalid("at most 2^31-256 rays per call on the device path; shard the batch");
+  DTraceParams tp;
+  tp.limit = o->limit > 0 ? o->limit : 100;
+  tp.disable_fresnel = o->disable_fresnel;
+  tp.quirks = o->quirks;
+  tp.max_steps = o->steps_per_launch;
+  tp.seed = o->seed;
+  tp.ray_id_offset = id_offset;
+  if (tp.max_steps <= 0) {  // one launch, every ray runs to its terminal status in registers
+    R.cur = nullptr;
+    R.ndraw = nullptr;
+    launch_trace(s->depth, s->d, tp, R, nullptr, n, 1, 0, st);
+    return;
+  }
+  // wavefront: bounce kernel -> compaction of survivors -> next bounce
+  size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
+  char* base = (char*)scratch;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 255) & ~size_t(255); return p; };
+  R.cur = (int32_t*)take(n * 4);
+  R.ndraw = (uint32_t*)take(n * 4);
+  int32_t* liveA = (int32_t*)take(n * 4);
+  int32_t* liveB = (int32_t*)take(n * 4);
+  unsigned long long* tile_state = (unsigned long long*)take(ntile * 8);
+  int32_t* tile_counter = (int32_t*)take(256);
+  const int32_t* live = nullptr;
+  long long nlive = n;
+  int init = 1;
+  for (int iter = 0; nlive > 0; iter++) {
+    if (iter > 100000) throw std::runtime_error("wavefront did not terminate");
+    launch_trace(s->depth, s->d, tp, R, live, nlive, init, 1, st);
+    init = 0;
+    int tiles = (int)((nlive + CP_TILE - 1) / CP_TILE);
+    CK(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
+    CK(cudaMemsetAsync(tile_counter, 0, 4, st));
+    int32_t* out = (live == liveA) ? liveB : liveA;
+    {
+      ProfScope ps(st, 1);
+      k_compact<<<tiles, CP_THREADS, 0, st>>>(live, (int)nlive, R.status, out, d_count, tile_state, tile_counter, tiles);
+      g_launches++;
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(h_count, d_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nlive = *h_count;
+    live = out;
+  }
+}
+static size_t wavefront_scratch_bytes(long long n) {
+  size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
+  return 4 * ((size_t)n * 4 + 256) + ntile * 8 + 256 + 512;
+}
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int rbg_abi_version(void) { return RBG_ABI_VERSION; }
+const char* rbg_last_error(void) { return g_err.c_str(); }
+int rbg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int64_t rbg_launch_count(void) { return g_launches.load(); }
+int rbg_profile_enable(int on) {
+  g_profile = on;
+  return RBG_OK;
+}
+int rbg_profile_read(double* bounce_ms, int64_t* bounce_launches, double* compact_ms, int64_t* compact_launches) {
+  return guard([&] {
+    for (auto& e : g_prof_events) {
+      CK(cudaEventSynchronize(e.b));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e.a, e.b));
+      g_prof_ms[e.kind] += ms;
+      g_prof_n[e.kind]++;
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    g_prof_events.clear();
+    if (bounce_ms) *bounce_ms = g_prof_ms[0];
+    if (bounce_launches) *bounce_launches = g_prof_n[0];
+    if (compact_ms) *compact_ms = g_prof_ms[1];
+    if (compact_launches) *compact_launches = g_prof_n[1];
+    g_prof_ms[0] = g_prof_ms[1] = 0;
+    g_prof_n[0] = g_prof_n[1] = 0;
+  });
+}
+
+int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
+  rbg_scene* s = nullptr;
+  int rc = guard([&] {
+    if (!out) throw Invalid("null output handle");
+    *out = nullptr;
+    validate_desc(D);
+    int ndev = rbg_device_count();
+    if (ndev <= 0) throw std::runtime_error("cuda: no CUDA device available — the tracer has no CPU fallback");
+    if (device < 0 || device >= ndev) throw Invalid("bad device index");
+    SceneBuilder B;
+    B.D = D;
+    B.build_shapes();
+    if (D->top_volume >= 0) B.flatten(D->top_volume, mat_identity(), -1, 0, std::string(D->names + D->volumes[D->top_volume].name) + "_1");
+    int depth = scene_depth_needed(B);
+    if (depth > 3) throw NotSupported("boolean composite nesting deeper than 3 is not supported");
+    CK(cudaSetDevice(device));
+    s = new rbg_scene;
+    s->device = device;
+    s->depth = depth;
+    s->node_names = B.names;
+    memset(&s->d, 0, sizeof(s->d));
+    s->d.nodes = upload(s, B.nodes);
+    s->d.bvh = upload(s, B.bvh);
+    s->d.shapes = upload(s, B.shapes);
+    s->d.dpar = upload(s, B.dpar);
+    s->d.mats = upload(s, B.mats);
+    s->d.volumes = upload(s, D->volumes, D->nvolumes);
+    s->d.borders = upload(s, D->borders, D->nborders);
+    s->d.graphs = upload(s, D->graphs, D->ngraphs);
+    s->d.gx = upload(s, D->gx, D->ngpts);
+    s->d.gy = upload(s, D->gy, D->ngpts);
+    s->d.th2 = upload(s, D->th2, D->nth2);
+    s->d.th2v = upload(s, D->th2v, D->nth2v);
+    s->d.indices = upload(s, D->indices, D->nindices);
+    s->d.mirrors = upload(s, D->mirrors, D->nmirrors);
+    s->d.focals = upload(s, D->focals, D->nfocals);
+    s->d.multilayers = upload(s, D->multilayers, D->nmultilayers);
+    s->d.layers = upload(s, D->layers, D->nlayers);
+    s->d.nnodes = (int)B.nodes.size();
+    s->d.top_shape = D->top_volume >= 0 ? D->volumes[D->top_volume].shape : -1;
+    CK(cudaMalloc((void**)&s->d_count, 3 * sizeof(int32_t)));
+    CK(cudaMallocHost((void**)&s->h_count, 3 * sizeof(int32_t)));
+    // the CSG call chain is not inlined: give it stack
+    size_t want = 8192, have = 0;
+    CK(cudaDeviceGetLimit(&have, cudaLimitStackSize));
+    if (have < want) CK(cudaDeviceSetLimit(cudaLimitStackSize, want));
+    *out = s;
+    s = nullptr;
+  });
+  if (s) scene_free(s);
+  return rc;
+}
+
+int rbg_scene_destroy(rbg_scene* s) {
+  return guard([&] { scene_free(s); });
+}
+int rbg_scene_num_nodes(const rbg_scene* s) { return s ? (int)s->node_names.size() : 0; }
+const char* rbg_scene_node_name(const rbg_scene* s, int node) {
+  if (!s || node < 0 || node >= (int)s->node_names.size()) return "";
+  return s->node_names[node].c_str();
+}
+
+int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void* stream) {
+  return guard([&] {
+    if (!s || !o || !rays) throw Invalid("null argument");
+    if (s->d.top_shape < 0) throw Invalid("scene has no top volume");
+    if (rays->n <= 0) return;
+    if (!rays->x || !rays->y || !rays->z || !rays->t || !rays->dx || !rays->dy || !rays->dz || !rays->lambda || !rays->ox || !rays->oy || !rays->oz ||
+        !rays->ot || !rays->odx || !rays->ody || !rays->odz || !rays->status || !rays->last_node || !rays->npoints)
+      throw Invalid("null ray array");
+    CK(cudaSetDevice(s->device));
+    if (rays->on_device) {
+      cudaStream_t st = (cudaStream_t)stream;
+      DRays R;
+      R.x = rays->x; R.y = rays->y; R.z = rays->z; R.t = rays->t; R.dx = rays->dx; R.dy = rays->dy; R.dz = rays->dz; R.lambda = rays->lambda;
+      R.ox = rays->ox; R.oy = rays->oy; R.oz = rays->oz; R.ot = rays->ot; R.odx = rays->odx; R.ody = rays->ody; R.odz = rays->odz;
+      R.status = rays->status; R.last_node = rays->last_node; R.npoints = rays->npoints;
+      R.cur = nullptr; R.ndraw = nullptr;
+      if (o->steps_per_launch > 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
+      trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count);
+      return;
+    }
+    // host buffers: chunked H2D -> trace -> D2H, three chunks in flight on three streams
+    const long long CH = 1 << 22;
+    long long chunk = std::min<long long>(rays->n, CH);
+    size_t per_ray = 8 * 8 + 7 * 8 + 3 * 4;  // in + out
+    size_t bytes = (size_t)chunk * per_ray + 4096 + (o->steps_per_launch > 0 ? wavefront_scratch_bytes(chunk) : 0);
+    int nst = rays->n > chunk ? 3 : 1;
+    for (int k = 0; k < nst; k++) {
+      if (!s->streams[k]) CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
+      if (s->stage_bytes[k] < bytes) {
+        if (s->stage[k]) CK(cudaFree(s->stage[k]));
+        s->stage[k] = nullptr;
+        s->stage_bytes[k] = 0;
+        CK(cudaMalloc(&s->stage[k], bytes));
+        s->stage_bytes[k] = bytes;
+      }
+    }
+    int ci = 0;
+    for (long long b = 0; b < rays->n; b += chunk, ci++) {
+      long long m = std::min(chunk, rays->n - b);
+      int k = ci % nst;
+      cudaStream_t st = s->streams[k];
+      char* base = (char*)s->stage[k];
+      double* din[8];
+      double* dout[7];
+      int32_t* diout[3];
+      size_t off = 0;
+      for (int a = 0; a < 8; a++) { din[a] = (double*)(base + off); off += (size_t)chunk * 8; }
+      for (int a = 0; a < 7; a++) { dout[a] = (double*)(base + off); off += (size_t)chunk * 8; }
+      for (int a = 0; a < 3; a++) { diout[a] = (int32_t*)(base + off); off += (size_t)chunk * 4; }
+      off = (off + 255) & ~size_t(255);
+      const double* hin[8] = {rays->x, rays->y, rays->z, rays->t, rays->dx, rays->dy, rays->dz, rays->lambda};
+      double* hout[7] = {rays->ox, rays->oy, rays->oz, rays->ot, rays->odx, rays->ody, rays->odz};
+      int32_t* hiout[3] = {rays->status, rays->last_node, rays->npoints};
+      for (int a = 0; a < 8; a++) CK(cudaMemcpyAsync(din[a], hin[a] + b, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+      DRays R;
+      R.x = din[0]; R.y = din[1]; R.z = din[2]; R.t = din[3]; R.dx = din[4]; R.dy = din[5]; R.dz = din[6]; R.lambda = din[7];
+      R.ox = dout[0]; R.oy = dout[1]; R.oz = dout[2]; R.ot = dout[3]; R.odx = dout[4]; R.ody = dout[5]; R.odz = dout[6];
+      R.status = diout[0]; R.last_node = diout[1]; R.npoints = diout[2];
+      R.cur = nullptr; R.ndraw = nullptr;
+      trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + off, s->d_count + k, s->h_count + k);
+      for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(hout[a] + b, dout[a], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+      for (int a = 0; a < 3; a++) CK(cudaMemcpyAsync(hiout[a] + b, diout[a], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      if (ci + 1 >= nst) {  // before reusing a stage buffer, the chunk that used it must be done
+        // streams are in-order, so the next use of stream k is automatically serialised
+      }
+    }
+    for (int k = 0; k < nst; k++) CK(cudaStreamSynchronize(s->streams[k]));
+  });
+}
+
+int rbg_shoot(const rbg_shoot_desc* d, int64_t first, int64_t n, double* x, double* y, double* z, double* t, double* dx, double* dy, double* dz,
+              double* lambda, int device, void* stream) {
+  return guard([&] {
+    if (!d || n < 0) throw Invalid("bad argument");
+    if (d->kind < 0 || d->kind > 3) throw Invalid("unknown shooter kind");
+    if ((d->kind == 0 || d->kind == 3) && (d->nx < 1 || d->ny < 1)) throw Invalid("grid shooters need nx,ny >= 1");
+    if (n == 0) return;
+    CK(cudaSetDevice(device));
+    long long blocks = (n + 255) / 256;
+    k_shoot<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*d, first, n, x, y, z, t, dx, dy, dz, lambda);
+    g_launches++;
+    CK(cudaGetLastError());
+  });
+}
+
+int rbg_hist2d(int64_t n, const double* x, const double* y, const int32_t* status, int32_t sel, int32_t nx, double xmin, double xmax, int32_t ny,
+               double ymin, double ymax, unsigned long long* hist, int device, void* stream) {
+  return guard([&] {
+    if (nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin)) throw Invalid("bad histogram axes");
+    if (n <= 0) return;
+    CK(cudaSetDevice(device));
+    int use_smem = (long long)nx * ny <= HIST_SMEM_BINS;
+    int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    k_hist2d<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, x, y, status, sel, nx, xmin, xmax, ny, ymin, ymax, hist, use_smem);
+    g_launches++;
+    CK(cudaGetLastError());
+  });
+}
+
+int rbg_moments(int64_t n, const double* x, const double* y, const double* t, const int32_t* status, int32_t sel, double* moments, long long* counts,
+                int device, void* stream) {
+  return guard([&] {
+    if (n <= 0) return;
+    CK(cudaSetDevice(device));
+    int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    k_moments<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, x, y, t, status, sel, moments, (unsigned long long*)counts);
+    g_launches++;
+    CK(cudaGetLastError());
+  });
+}
+
+int rbg_tmm(rbg_scene* s, int ml, int64_t n, const double* theta, const double* lambda, double* refl, double* trans, void* stream) {
+  return guard([&] {
+    if (!s) throw Invalid("null scene");
+    if (n <= 0) return;
+    CK(cudaSetDevice(s->device));
+    long long blocks = (n + 127) / 128;
+    k_tmm<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(s->d, ml, n, theta, lambda, refl, trans);
+    g_launches++;
+    CK(cudaGetLastError());
+  });
+}
+
+int rbg_tmm_host(rbg_scene* s, int ml, int64_t n, const double* theta, const double* lambda, double* refl, double* trans) {
+  return guard([&] {
+    if (!s) throw Invalid("null scene");
+    if (n <= 0) return;
+    CK(cudaSetDevice(s->device));
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)n * 8 * 4));
+    try {
+      CK(cudaMemcpy(d, theta, (size_t)n * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d + n, lambda, (size_t)n * 8, cudaMemcpyHostToDevice));
+      long long blocks = (n + 127) / 128;
+      k_tmm<<<(unsigned)blocks, 128>>>(s->d, ml, n, d, d + n, d + 2 * n, d + 3 * n);
+      g_launches++;
+      CK(cudaGetLastError());
+      CK(cudaMemcpy(refl, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(trans, d + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cudaFree(d);
+      throw;
+    }
+    cudaFree(d);
+  });
+}
+
+}  // extern "C"

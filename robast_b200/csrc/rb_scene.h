@@ -1,0 +1,86 @@
+// rb_scene.h — device-resident scene tables (SoA-ish flat arrays) shared by host builder and kernels.
+// Layout in HBM (all read-only during a trace, a few kB .. few hundred kB, L1/L2 resident):
+//   nodes[]   : one entry per PHYSICAL placed node (flattened TGeo path, DFS pre-order, 0 = top):
+//               world->local rotation+translation, volume/shape/type ids, mother, BVH slice
+//   bvh[]     : threaded (stackless) BVH per mother node over its daughters' world AABBs
+//   shapes[], dpar[], mats[] : analytic shape parameters (+ derived constants), boolean operands
+//   volumes[], borders[], indices[], graphs, th2 tables, mirrors, focals, multilayers, layers
+#ifndef RB_SCENE_H
+#define RB_SCENE_H
+
+#include <stdint.h>
+
+#include "../../include/robast_b200.h"
+
+#if defined(__CUDACC__)
+#define RB_HD __host__ __device__
+#define RB_NOINLINE __noinline__
+#else
+#define RB_HD
+#define RB_NOINLINE __attribute__((noinline))
+#endif
+
+struct DMat {  // local -> master: m = r*l + t
+  double r[9];
+  double t[3];
+};
+
+struct DNode {
+  DMat g;            // node-local -> world
+  int32_t volume;    // id into volumes[]
+  int32_t shape;     // id into shapes[]
+  int32_t type;      // RBG_LENS ... RBG_OTHER
+  int32_t mother;    // physical id of the mother, -1 for top
+  int32_t bvh_first; // slice of bvh[] over this node's daughters (bvh_count == 0: no daughters)
+  int32_t bvh_count;
+  int32_t overlap;
+  int32_t pad;
+};
+
+struct DBvh {
+  double lo[3], hi[3];
+  int32_t child;     // >= 0: leaf holding this physical node id; -1: internal
+  int32_t skip;      // absolute index of the next BVH entry when this subtree is done/missed (-1 = end)
+};
+
+struct DShape {
+  int32_t type;
+  int32_t ipar;
+  int32_t left, right;
+  int32_t lmat, rmat;
+};
+
+struct DScene {
+  const DNode* nodes;
+  const DBvh* bvh;
+  const DShape* shapes;
+  const double* dpar;
+  const DMat* mats;
+  const rbg_volume* volumes;
+  const rbg_border* borders;
+  const rbg_graph* graphs;
+  const double* gx;
+  const double* gy;
+  const rbg_th2* th2;
+  const double* th2v;
+  const rbg_index* indices;
+  const rbg_mirror* mirrors;
+  const rbg_focal* focals;
+  const rbg_multilayer* multilayers;
+  const rbg_layer* layers;
+  int32_t nnodes;
+  int32_t top_shape;
+};
+
+#define RB_MAX_TMM_LAYERS 16
+
+struct DTraceParams {
+  int32_t limit;
+  int32_t disable_fresnel;
+  uint32_t quirks;
+  int32_t max_steps;     // boundary steps per launch (<=0: unbounded)
+  uint64_t seed;
+  uint64_t ray_id_offset;
+};
+
+#endif

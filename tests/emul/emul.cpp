@@ -1,0 +1,72 @@
+// emul.cpp — DEBUGGING AID FOR THE GPU-LESS BUILD BOX, NOT PART OF THE PRODUCT.
+// Compiles the device functions of robast_b200/csrc/rb_device.cuh for the host (RB_HD expands to
+// nothing under g++) and runs the per-ray loop of k_trace serially, so that the CUDA path's math can
+// be compared with the oracle before a GPU run.  Only tests/ build and load this library.
+#include <cstdio>
+#include <cstring>
+
+#include "../../robast_b200/csrc/rb_build.h"
+#include "../../robast_b200/csrc/rb_device.cuh"
+
+namespace {
+template <int DEPTH> void run(const DScene& sc, const DTraceParams& tp, const rbg_rays* R) {
+  for (long long idx = 0; idx < R->n; idx++) {
+    RayReg r;
+    r.lambda = R->lambda[idx];
+    r.p = v3(R->x[idx], R->y[idx], R->z[idx]);
+    r.t = R->t[idx];
+    V3 d = v3(R->dx[idx], R->dy[idx], R->dz[idx]);
+    double mag = sqrt(dot(d, d));
+    r.d = mag > 0 ? (1. / mag) * d : d;
+    r.status = RBG_RUN; r.npoints = 1; r.last_node = -1; r.ndraw = 0; r.on_boundary = 0;
+    r.cur = locate_start<DEPTH>(sc, r.p);
+    unsigned long long id = tp.ray_id_offset + (unsigned long long)idx;
+    Philox g;
+    g.k0 = (uint32_t)tp.seed; g.k1 = (uint32_t)(tp.seed >> 32); g.id0 = (uint32_t)id; g.id1 = (uint32_t)(id >> 32); g.ndraw = 0;
+    while (r.status == RBG_RUN) trace_step<DEPTH>(sc, tp, r, g);
+    R->ox[idx] = r.p.x; R->oy[idx] = r.p.y; R->oz[idx] = r.p.z; R->ot[idx] = r.t;
+    R->odx[idx] = r.d.x; R->ody[idx] = r.d.y; R->odz[idx] = r.d.z;
+    R->status[idx] = r.status; R->last_node[idx] = r.last_node; R->npoints[idx] = r.npoints;
+  }
+}
+}  // namespace
+
+extern "C" int emul_trace(const rbg_scene_desc* D, const rbg_trace_opts* o, const rbg_rays* R, int /*nthreads*/) {
+  try {
+    validate_desc(D);
+    SceneBuilder B;
+    B.D = D;
+    B.build_shapes();
+    B.flatten(D->top_volume, mat_identity(), -1, 0, "top_1");
+    DScene sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.nodes = B.nodes.data(); sc.bvh = B.bvh.data(); sc.shapes = B.shapes.data(); sc.dpar = B.dpar.data(); sc.mats = B.mats.data();
+    sc.volumes = D->volumes; sc.borders = D->borders; sc.graphs = D->graphs; sc.gx = D->gx; sc.gy = D->gy; sc.th2 = D->th2; sc.th2v = D->th2v;
+    sc.indices = D->indices; sc.mirrors = D->mirrors; sc.focals = D->focals; sc.multilayers = D->multilayers; sc.layers = D->layers;
+    sc.nnodes = (int)B.nodes.size();
+    sc.top_shape = D->volumes[D->top_volume].shape;
+    DTraceParams tp;
+    tp.limit = o->limit > 0 ? o->limit : 100; tp.disable_fresnel = o->disable_fresnel; tp.quirks = o->quirks; tp.max_steps = 0;
+    tp.seed = o->seed; tp.ray_id_offset = o->ray_id_offset;
+    switch (scene_depth_needed(B)) {
+      case 0: run<0>(sc, tp, R); break;
+      case 1: run<1>(sc, tp, R); break;
+      case 2: run<2>(sc, tp, R); break;
+      case 3: run<3>(sc, tp, R); break;
+      default: return RBG_ENOTSUP;
+    }
+    return RBG_OK;
+  } catch (std::exception& e) {
+    fprintf(stderr, "emul_trace: %s\n", e.what());
+    return RBG_EINTERNAL;
+  }
+}
+extern "C" int emul_tmm(const rbg_scene_desc* D, int ml, int pol, double th, double lam, double* R, double* T) {
+  DScene sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.graphs = D->graphs; sc.gx = D->gx; sc.gy = D->gy; sc.th2 = D->th2; sc.th2v = D->th2v; sc.indices = D->indices;
+  sc.multilayers = D->multilayers; sc.layers = D->layers;
+  if (pol == 2) tmm_mixed(sc, ml, th, lam, *R, *T);
+  else tmm_coherent(sc, ml, pol, th, lam, *R, *T);
+  return 0;
+}

@@ -1,0 +1,154 @@
+"""Test helpers: load the CPU oracle (checker) and the host emulation of the device code, build ray
+batches, and run a trace through a chosen backend on the same flat scene description."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT_DIR, "oracle", "_build", "liboracle.so")
+EMUL_SO = os.path.join(ROOT_DIR, "tests", "_build", "libemul.so")
+
+
+def _build(cmd, out, srcs):
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call(cmd, cwd=ROOT_DIR)
+
+
+def load_oracle():
+    srcs = [os.path.join(ROOT_DIR, "oracle", "oracle.cpp"), os.path.join(ROOT_DIR, "include", "robast_b200.h")]
+    _build(["make", "-s", "-C", "oracle"], ORACLE_SO, srcs)
+    import robast_b200 as R
+    lib = C.CDLL(ORACLE_SO)
+    lib.orc_trace.restype = C.c_int
+    lib.orc_trace.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.c_int]
+    lib.orc_tmm.restype = C.c_int
+    lib.orc_tmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for name in ("orc_index_n", "orc_index_k", "orc_index_abslen", "orc_graph_eval"):
+        f = getattr(lib, name)
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.orc_th2_interp.restype = C.c_double
+    lib.orc_th2_interp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.orc_uniform.restype = C.c_double
+    lib.orc_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.orc_shoot.restype = C.c_int
+    lib.orc_shoot.argtypes = [C.POINTER(R.rbg_shoot_desc), C.c_int64, C.c_int64] + [C.c_void_p] * 8
+    lib.orc_shape_contains.restype = C.c_int
+    lib.orc_shape_contains.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.orc_shape_dist.restype = C.c_double
+    lib.orc_shape_dist.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.orc_shape_normal.restype = C.c_int
+    lib.orc_shape_normal.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def load_emul():
+    srcs = [os.path.join(ROOT_DIR, "tests", "emul", "emul.cpp")] + [os.path.join(ROOT_DIR, "robast_b200", "csrc", f)
+                                                                    for f in ("rb_device.cuh", "rb_build.h", "rb_scene.h")]
+    _build(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", EMUL_SO, "tests/emul/emul.cpp"], EMUL_SO, srcs)
+    import robast_b200 as R
+    lib = C.CDLL(EMUL_SO)
+    lib.emul_trace.restype = C.c_int
+    lib.emul_trace.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.c_int]
+    lib.emul_tmm.restype = C.c_int
+    lib.emul_tmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    return lib
+
+
+def shoot_desc(params):
+    import robast_b200 as R
+    d = R.rbg_shoot_desc()
+    for k in ("kind", "nx", "ny", "dx", "dy", "lambda_min", "lambda_max", "seed"):
+        setattr(d, k, params[k])
+    for i in range(9):
+        d.rot[i] = params["rot"][i]
+    for i in range(3):
+        d.tr[i] = params["tr"][i]
+        d.dir[i] = params["dir"][i]
+    return d
+
+
+class Rays:
+    """Host SoA batch: inputs (n,8) columns x,y,z,t,dx,dy,dz,lambda and separate outputs."""
+
+    def __init__(self, inp):
+        inp = np.ascontiguousarray(np.asarray(inp, dtype=np.float64).T)  # (8, n)
+        self.inp = inp
+        self.n = inp.shape[1]
+        self.out = np.zeros((7, self.n))
+        self.iout = np.zeros((3, self.n), dtype=np.int32)
+
+    def struct(self):
+        import robast_b200 as R
+        r = R.rbg_rays()
+        r.n = self.n
+        r.on_device = 0
+        names = ["x", "y", "z", "t", "dx", "dy", "dz", "lambda_"]
+        for i, k in enumerate(names):
+            setattr(r, k, self.inp[i].ctypes.data)
+        for i, k in enumerate(["ox", "oy", "oz", "ot", "odx", "ody", "odz"]):
+            setattr(r, k, self.out[i].ctypes.data)
+        for i, k in enumerate(["status", "last_node", "npoints"]):
+            setattr(r, k, self.iout[i].ctypes.data)
+        return r
+
+    pos = property(lambda s: s.out[0:3].T)
+    time = property(lambda s: s.out[3])
+    dirs = property(lambda s: s.out[4:7].T)
+    status = property(lambda s: s.iout[0])
+    last_node = property(lambda s: s.iout[1])
+    npoints = property(lambda s: s.iout[2])
+
+
+def make_rays(oracle, params, first, n):
+    """generate a beam with the oracle's ARayShooter restatement (same Philox stream as rbg_shoot)"""
+    a = np.zeros((8, n))
+    d = shoot_desc(params)
+    rc = oracle.orc_shoot(C.byref(d), first, n, *[a[i].ctypes.data for i in range(8)])
+    assert rc == 0
+    return Rays(a.T)
+
+
+def opts(limit=100, disable_fresnel=0, quirks=3, steps_per_launch=0, seed=1234, ray_id_offset=0):
+    import robast_b200 as R
+    o = R.rbg_trace_opts()
+    o.limit, o.disable_fresnel, o.quirks, o.steps_per_launch, o.seed, o.ray_id_offset = limit, disable_fresnel, quirks, steps_per_launch, seed, ray_id_offset
+    return o
+
+
+def trace_with(fn, export, rays, o, nthreads=1):
+    r = rays.struct()
+    rc = fn(export.desc_ptr(), C.byref(o), C.byref(r), nthreads)
+    assert rc == 0, "trace backend returned %d" % rc
+    return rays
+
+
+def trace_gpu(export, rays, o, device=0):
+    """through the C ABI: rbg_scene_create + rbg_trace with host pointers"""
+    import robast_b200 as R
+    h = C.c_void_p()
+    R.check(R.rbg_scene_create(export.desc_ptr(), device, C.byref(h)))
+    try:
+        r = rays.struct()
+        R.check(R.rbg_trace(h, C.byref(o), C.byref(r), None))
+    finally:
+        R.rbg_scene_destroy(h)
+    return rays
+
+
+def compare(a, b, tol_pos=1e-7, tol_dir=1e-9, tol_time=1e-7 / 2.99792458e10):
+    """per-ray parity report between two traced batches"""
+    same_status = a.status == b.status
+    dpos = np.linalg.norm(a.pos - b.pos, axis=1)
+    cosang = np.clip(np.sum(a.dirs * b.dirs, axis=1), -1, 1)
+    cross = np.linalg.norm(np.cross(a.dirs, b.dirs), axis=1)
+    dang = np.arctan2(cross, cosang)
+    dt = np.abs(a.time - b.time)
+    ok = same_status & (dpos <= tol_pos) & (dang <= tol_dir) & (dt <= tol_time + 1e-12 * np.abs(a.time))
+    return dict(n=a.n, status_mismatch=int((~same_status).sum()), max_dpos=float(dpos[same_status].max() if same_status.any() else 0),
+                max_dang=float(dang[same_status].max() if same_status.any() else 0), max_dt=float(dt[same_status].max() if same_status.any() else 0),
+                npoints_mismatch=int((a.npoints != b.npoints).sum()), node_mismatch=int((a.last_node != b.last_node).sum()), bad=int((~ok).sum()))
