@@ -258,13 +258,10 @@ void coherent_tmm(const rbg_scene_desc* d, int ml, int pol /*0=S,1=P*/, double t
   const cplx j(0, 1);
   for (int i = 1; i < N - 1; i++) {
     cplx em = std::exp(-j * delta[i]), ep = std::exp(j * delta[i]);
-    // (1/t) * (diag * [[1,r],[r,1]])
-    cplx a00 = em * cplx(1, 0) + cplx(0, 0) * r_list[i], a01 = em * r_list[i] + cplx(0, 0) * cplx(1, 0);
-    cplx a10 = cplx(0, 0) * cplx(1, 0) + ep * r_list[i], a11 = cplx(0, 0) * r_list[i] + ep * cplx(1, 0);
-    // reference evaluates (1./t * D) * B : scale D first
+    // reference evaluates (1./t * D) * B with D = diag(e^{-i delta}, e^{i delta}), B = [[1,r],[r,1]]
     cplx s = 1. / t_list[i];
     cplx d00 = s * em, d11 = s * ep;
-    a00 = d00; a01 = d00 * r_list[i]; a10 = d11 * r_list[i]; a11 = d11;
+    cplx a00 = d00, a01 = d00 * r_list[i], a10 = d11 * r_list[i], a11 = d11;
     cplx n00 = m00 * a00 + m01 * a10, n01 = m00 * a01 + m01 * a11, n10 = m10 * a00 + m11 * a10, n11 = m10 * a01 + m11 * a11;
     m00 = n00; m01 = n01; m10 = n10; m11 = n11;
   }
@@ -1840,6 +1837,10 @@ int orc_trace(const rbg_scene_desc* desc, const rbg_trace_opts* opts, const rbg_
           RayState r;
           r.x[0] = rays->x[i]; r.x[1] = rays->y[i]; r.x[2] = rays->z[i]; r.x[3] = rays->t[i];
           r.d[0] = rays->dx[i]; r.d[1] = rays->dy[i]; r.d[2] = rays->dz[i];
+          {  // ARay's constructor normalises the direction (src/ARay.cxx:28-36, :210-223)
+            double mag = sqrt(dot3(r.d, r.d));
+            if (mag > 0) { r.d[0] /= mag; r.d[1] /= mag; r.d[2] /= mag; }
+          }
           r.lambda = rays->lambda[i];
           r.status = RBG_RUN; r.npoints = 1; r.last_node = -1;
           T.trace(r, opts->ray_id_offset + (uint64_t)i);

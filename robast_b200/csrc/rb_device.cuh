@@ -1364,13 +1364,15 @@ template <int DEPTH> RB_HD inline StepOut next_boundary(const DScene& sc, RayReg
     tmin = rb_max(tmin, rb_min(t0, t1)); tmax = rb_min(tmax, rb_max(t0, t1));
     t0 = (b.lo[2] - r.p.z) * idz; t1 = (b.hi[2] - r.p.z) * idz;
     tmin = rb_max(tmin, rb_min(t0, t1)); tmax = rb_min(tmax, rb_max(t0, t1));
-    bool hit = tmax >= rb_max(tmin, 0.0) && tmin < best;
+    bool hit = tmax >= rb_max(tmin, 0.0) && tmin <= best + 2 * RB_TOL;
     if (!hit) { i = b.skip; continue; }
     if (b.child >= 0) {
       const DNode& dn = sc.nodes[b.child];
       int sel = 0;
-      double s = Csg<DEPTH>::dist_out(sc, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), best, sel);
-      if (s < best - RB_TOL) { best = s; enter = b.child; esel = sel; }
+      double s = Csg<DEPTH>::dist_out(sc, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), best + 2 * RB_TOL, sel);
+      // TGeo scans daughters in order and keeps the first one within tolerance: on (near-)ties the
+      // lowest daughter index wins regardless of the BVH visiting order
+      if (s < best - RB_TOL || (enter >= 0 && b.child < enter && s <= best + RB_TOL)) { best = s; enter = b.child; esel = sel; }
       i = b.skip;
     } else i = i + 1;
   }

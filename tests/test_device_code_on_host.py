@@ -1,0 +1,65 @@
+"""CPU-side check of the CUDA path's per-ray math: robast_b200/csrc/rb_device.cuh compiled for the
+host (tests/emul) and compared with the oracle per ray on all five configs.  This is a development
+aid for the GPU-less box; the real parity tests (-m gpu) run the kernels through the C ABI."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import helpers as H
+import scenes
+from robast_b200 import configs
+
+CASES = [(1, 0.0, 101, {}), (1, 1.5, 61, {}), (2, 0.0, 81, {}), (2, 2.5, 81, {}), (3, 0.0, 101, {}), (3, 5.0, 81, {}),
+         (4, 0.0, 60, {}), (4, 0.1, 60, {}), (5, 0.0, 50, {}), (5, 25.0, 50, {}), (5, 38.0, 40, {})]
+
+
+@pytest.mark.parametrize("cfg,theta,nside,kw", CASES)
+def test_configs_match_oracle(oracle, emul, cfg, theta, nside, kw):
+    mgr, _keep = configs.BUILDERS[cfg](**kw)
+    ex = mgr.ExportScene()
+    beam = configs.beam(cfg, theta, n_side=nside if cfg <= 3 else None)
+    n = nside * nside
+    o = H.opts(disable_fresnel=1 if cfg == 2 else 0, seed=99)
+    ref = H.trace_with(oracle.orc_trace, ex, H.make_rays(oracle, beam, 0, n), o, nthreads=4)
+    got = H.trace_with(emul.emul_trace, ex, H.make_rays(oracle, beam, 0, n), o)
+    rep = H.compare(ref, got)
+    assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, rep
+
+
+def test_tmm_device_code_matches_oracle(R, oracle, emul):
+    import os
+    air = R.ARefractiveIndex(1., 0.)
+    sio2 = R.AFilmetrixDotCom(os.path.join(configs.DATA, "SiO2.nk.txt"))
+    al = R.AFilmetrixDotCom(os.path.join(configs.DATA, "Al.nk.txt"))
+    ml = R.AMultilayer(air, al)
+    ml.InsertLayer(sio2, 25.4e-7)
+    ex, mid = R.export_multilayer(ml)
+    worst = 0
+    for lam in np.linspace(250e-7, 950e-7, 15):
+        for th in np.linspace(0, 1.55, 12):
+            for pol in (0, 1, 2):
+                a, b, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+                oracle.orc_tmm(ex.desc_ptr(), mid, pol, th, lam, C.byref(a), C.byref(b))
+                emul.emul_tmm(ex.desc_ptr(), mid, pol, th, lam, C.byref(c), C.byref(d))
+                worst = max(worst, abs(a.value - c.value), abs(b.value - d.value))
+    assert worst < 1e-12
+
+
+def test_unit_scenes_match_oracle(R, oracle, emul):
+    mgr, _k = scenes.snell_slab(1.5)
+    th = math.radians(30)
+    for fn in (oracle.orc_trace, emul.emul_trace):
+        rays = H.Rays([[0, 0, 0.2, 0, math.sin(th), 0, -math.cos(th), 400e-7]])
+        H.trace_with(fn, mgr.ExportScene(), rays, H.opts(disable_fresnel=1))
+        assert abs(rays.dirs[0, 0] - math.sin(th) / 1.5) < 1e-12 and rays.status[0] == 3
+    mgr, _k = scenes.sphere_shell_mirror()
+    # 999 bounces between a convex and a concave sphere amplify rounding differences exponentially
+    # (dispersing billiard): the long run pins the count, a short run pins the per-ray agreement
+    rays = H.Rays([[0, 0, 0, 0, 0.3, 0.1, -1, 400e-7]])
+    H.trace_with(emul.emul_trace, mgr.ExportScene(), rays, H.opts(limit=1000))
+    assert rays.npoints[0] == 1000 and rays.status[0] == 4
+    got = H.trace_with(emul.emul_trace, mgr.ExportScene(), H.Rays([[0, 0, 0, 0, 0.3, 0.1, -1, 400e-7]]), H.opts(limit=12))
+    ref = H.trace_with(oracle.orc_trace, mgr.ExportScene(), H.Rays([[0, 0, 0, 0, 0.3, 0.1, -1, 400e-7]]), H.opts(limit=12))
+    assert got.npoints[0] == 12 and H.compare(ref, got)["bad"] == 0

@@ -1,0 +1,258 @@
+"""Pins the CPU oracle against the reference's own golden vectors (tutorials/unittest_robast.py)."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import scenes
+from robast_b200 import configs
+
+nm, um, mm, m = 1e-7, 1e-4, 0.1, 100.0
+deg = math.pi / 180
+
+
+def tmm(oracle, ml, pol, th, lam, export_fn=None):
+    import robast_b200 as R
+    ex, mid = R.export_multilayer(ml)
+    r, t = C.c_double(), C.c_double()
+    assert oracle.orc_tmm(ex.desc_ptr(), mid, pol, th, lam, C.byref(r), C.byref(t)) == 0
+    return r.value, t.value
+
+
+def basic_stack(R, reverse=False):  # unittest_robast.py:629-636
+    med1, med2, med3, med4 = R.ARefractiveIndex(1.), R.ARefractiveIndex(2., 4.), R.ARefractiveIndex(3., .3), R.ARefractiveIndex(1., .1)
+    if not reverse:
+        multi = R.AMultilayer(med1, med4)
+        multi.InsertLayer(med2, 2)
+        multi.InsertLayer(med3, 3)
+    else:
+        multi = R.AMultilayer(med4, med1)
+        multi.InsertLayer(med3, 3)
+        multi.InsertLayer(med2, 2)
+    return multi, [med1, med2, med3, med4]
+
+
+def test_kat_tmm_basic(R, oracle):  # unittest_robast.py:627-655 (tmm.tests.basic_test)
+    multi, _k = basic_stack(R)
+    rs, rp = 0.37273208839139516, 0.37016110373044969
+    ts, tp = 0.22604491247079261, 0.22824374314132009
+    r, t = tmm(oracle, multi, 0, 0.1, 100)
+    assert abs(r - rs) < 1e-12 and abs(t - ts) < 1e-12
+    r, t = tmm(oracle, multi, 1, 0.1, 100)
+    assert abs(r - rp) < 1e-12 and abs(t - tp) < 1e-12
+    r, t = tmm(oracle, multi, 2, 0.1, 100)
+    assert abs(r - (rs + rp) / 2) < 1e-12 and abs(t - (ts + tp) / 2) < 1e-12
+
+
+def test_kat_tmm_bare_interface_is_fresnel(R, oracle):
+    # two semi-infinite media: TMM must reduce to the Fresnel equations
+    a, b = R.ARefractiveIndex(1.), R.ARefractiveIndex(1.5)
+    ml = R.AMultilayer(a, b)
+    th = 30 * deg
+    th2 = math.asin(math.sin(th) / 1.5)
+    rs = ((math.cos(th) - 1.5 * math.cos(th2)) / (math.cos(th) + 1.5 * math.cos(th2))) ** 2
+    rp = ((1.5 * math.cos(th) - math.cos(th2)) / (1.5 * math.cos(th) + math.cos(th2))) ** 2
+    r, t = tmm(oracle, ml, 0, th, 500 * nm)
+    assert abs(r - rs) < 1e-14 and abs(r + t - 1) < 1e-14
+    r, t = tmm(oracle, ml, 1, th, 500 * nm)
+    assert abs(r - rp) < 1e-14 and abs(r + t - 1) < 1e-14
+
+
+def test_kat_tmm_table_matches_direct_at_bin_centre(R, oracle):  # unittest_robast.py:698-709, table built by the oracle
+    multi, _k = basic_stack(R)
+    r0, t0 = tmm(oracle, multi, 2, 45 * deg, 600)
+    h_r = R.TH2D("", "", 801, 199.5, 1000.5, 90, -0.5 * deg, 89.5 * deg)
+    for j in range(1, 91):
+        for i in range(1, 802):
+            lam, th = 199.5 + (i - 0.5), (-0.5 + (j - 0.5)) * deg
+            if abs(lam - 600) < 2 and abs(th - 45 * deg) < 2 * deg:
+                h_r.SetBinContent(i, j, tmm(oracle, multi, 2, th, lam)[0])
+    ex, hid = R.export_th2(h_r)
+    assert abs(oracle.orc_th2_interp(ex.desc_ptr(), hid, 600., 45 * deg) - r0) < 1e-7
+    assert abs(h_r.Interpolate(600., 45 * deg) - r0) < 1e-7  # host TH2 mirror agrees with the oracle's restatement
+
+
+def test_kat_sellmeier_nbk7(R, oracle):  # unittest_robast.py:530-561
+    nbk7 = R.ASellmeierFormula(1.03961212, 0.231792344, 1.01046945, 0.00600069867, 0.0200179144, 103.560653)
+    ex, iid = R.export_index(nbk7)
+    data = ((2325.4, 1.489210), (1970.1, 1.494950), (1529.6, 1.500910), (1060.0, 1.506690), (1014.0, 1.507310), (852.1, 1.509800),
+            (706.5, 1.512890), (656.3, 1.514320), (643.8, 1.514720), (632.8, 1.515090), (589.3, 1.516730), (587.6, 1.516800),
+            (546.1, 1.518720), (486.1, 1.522380), (480.0, 1.522830), (435.8, 1.526680), (404.7, 1.530240), (365.0, 1.536270),
+            (334.1, 1.542720), (312.6, 1.548620))
+    for wl, n in data:
+        assert abs(oracle.orc_index_n(ex.desc_ptr(), iid, wl * nm) - n) < 5e-5  # 4 decimal places, as the reference asserts
+        assert abs(nbk7.GetRefractiveIndex(wl * nm) - n) < 5e-5
+    assert abs(nbk7.GetAbbeNumber() - 64.17) < 0.05
+
+
+def test_kat_agf_nbk7(R, oracle):  # unittest_robast.py:524-528
+    schott = R.AGlassCatalog(os.path.join(configs.DATA, "nbk7.agf"))
+    r = schott.GetRefractiveIndex("N-BK7")
+    ex, iid = R.export_index(r)
+    assert abs(oracle.orc_index_n(ex.desc_ptr(), iid, 589.3 * nm) / 1.51680 - 1.) < 5e-5
+    assert abs(oracle.orc_index_k(ex.desc_ptr(), iid, 2325 * nm) - 4.2911e-6) < 5e-10
+    assert abs(r.GetExtinctionCoefficient(2325 * nm) - 4.2911e-6) < 5e-10
+
+
+def test_kat_tgraph_eval(R, oracle):  # unittest_robast.py:415-426, src/ARefractiveIndex.cxx:19-27
+    g = R.TGraph()
+    g.SetPoint(0, 400 * nm, 1.6)
+    g.SetPoint(1, 500 * nm, 1.5)
+    ex, gid = R.export_graph(g)
+    ev = lambda x: oracle.orc_graph_eval(ex.desc_ptr(), gid, x)
+    assert abs(ev(450 * nm) - 1.55) < 1e-15 and abs(g.Eval(450 * nm) - 1.55) < 1e-15
+    assert abs(ev(600 * nm) - 1.4) < 1e-12 and abs(ev(300 * nm) - 1.7) < 1e-12  # linear extrapolation
+    one = R.ARefractiveIndex(1.25, 0.5)
+    ex, iid = R.export_index(one)
+    assert oracle.orc_index_n(ex.desc_ptr(), iid, 123 * nm) == 1.25 and oracle.orc_index_k(ex.desc_ptr(), iid, 1.) == 0.5
+
+
+def test_kat_mixed_index(R, oracle):  # unittest_robast.py:612-625
+    a, b = R.ARefractiveIndex(1., 1.), R.ARefractiveIndex(2., 2.)
+    mixed = R.AMixedRefractiveIndex(a, b, 3, 7)
+    ex, iid = R.export_index(mixed)
+    assert abs(oracle.orc_index_n(ex.desc_ptr(), iid, 100 * nm) - 1.7) < 1e-15
+    assert abs(oracle.orc_index_k(ex.desc_ptr(), iid, 100 * nm) - 1.7) < 1e-15
+
+
+def test_kat_snell_slab(oracle):  # unittest_robast.py:428-468
+    mgr, _k = scenes.snell_slab(1.5)
+    th = 30 * deg
+    rays = H.Rays([[0, 0, 2 * mm, 0, math.sin(th), 0, -math.cos(th), 400 * nm]])
+    H.trace_with(oracle.orc_trace, mgr.ExportScene(), rays, H.opts(disable_fresnel=1))
+    assert abs(rays.dirs[0, 0] - math.sin(th) / 1.5) < 1e-12 and abs(rays.dirs[0, 1]) < 1e-15
+    assert rays.status[0] == 3  # focused on the box nested inside the lens
+
+
+def test_kat_limit_suspend(oracle):  # unittest_robast.py:390-413
+    mgr, _k = scenes.sphere_shell_mirror()
+    rays = H.Rays([[0, 0, 0, 0, 0, 0, -1, 400 * nm]])
+    H.trace_with(oracle.orc_trace, mgr.ExportScene(), rays, H.opts(limit=1000))
+    assert rays.npoints[0] == 1000 and rays.status[0] == 4
+
+
+def test_stat_fresnel_n3(R, oracle):  # unittest_robast.py:122-160
+    wl, absl, idx = 400 * nm, 1 * um, 3.
+    k = R.ARefractiveIndex.AbsorptionLengthToExtinctionCoefficient(absl, wl)
+    refidx = R.ARefractiveIndex(idx, k)
+    mgr, lens = scenes.lens_box(refidx)
+    N = 100000
+    rays = H.Rays(np.tile([0, 0, 0.8 * m, 0, 0, 0, -1, wl], (N, 1)))
+    H.trace_with(oracle.orc_trace, mgr.ExportScene(), rays, H.opts(seed=7), nthreads=4)
+    n = int((rays.status == 2).sum())
+    ref = (idx - 1) ** 2 / (idx + 1) ** 2
+    # k > 0 -> absorbing-medium Fresnel form; the reference's own 3 sigma window
+    assert (n - 3 * n ** 0.5) / N < ref * 1.002 and ref * 0.998 < (n + 3 * n ** 0.5) / N
+    assert int((rays.status == 5).sum()) + n == N
+
+
+def test_stat_absorption_length(R, oracle):  # unittest_robast.py:67-120
+    wl, absl = 400 * nm, 1 * mm
+    g_n, g_k = R.TGraph(), R.TGraph()
+    g_n.SetPoint(0, wl, 1)
+    g_k.SetPoint(0, wl, R.ARefractiveIndex.AbsorptionLengthToExtinctionCoefficient(absl, wl))
+    refidx = R.ARefractiveIndex()
+    refidx.SetRefractiveIndex(g_n)
+    refidx.SetExtinctionCoefficient(g_k)
+    mgr, lens = scenes.lens_box(refidx)
+    N = 20000
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(N, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    inp = np.zeros((N, 8))
+    inp[:, 4:7] = d
+    inp[:, 7] = wl
+    rays = H.Rays(inp)
+    H.trace_with(oracle.orc_trace, mgr.ExportScene(), rays, H.opts(seed=3), nthreads=4)
+    ab = rays.status == 5
+    assert ab.sum() == N  # 1 mm absorption length in a 1 m cube: nothing escapes
+    dist = np.linalg.norm(rays.pos[ab], axis=1)
+    assert abs(dist.mean() / absl - 1) < 3 / math.sqrt(N)
+
+
+def test_kat_parabola_focus_and_stepback_quirk(oracle):
+    mgr, _k = configs.simple_parabolic()
+    ex = mgr.ExportScene()
+    beam = configs.beam(1, 0.0, n_side=101)
+    ideal = H.make_rays(oracle, beam, 0, 101 * 101)
+    H.trace_with(oracle.orc_trace, ex, ideal, H.opts(quirks=2))
+    f = ideal.status == 3
+    assert f.sum() > 2000
+    assert np.abs(ideal.pos[f][:, :2]).max() < 1e-11 and np.abs(ideal.pos[f][:, 2] - 300.).max() < 1e-11
+    quirk = H.make_rays(oracle, beam, 0, 101 * 101)
+    H.trace_with(oracle.orc_trace, ex, quirk, H.opts(quirks=3))
+    assert (quirk.status == ideal.status).all()
+    # reflection vertex 2e-6 cm short along d1=(0,0,-1): the hit moves by 2e-6 * tan(2 alpha), tan(alpha) = r / 2F
+    r = np.hypot(quirk.inp[0][f], quirk.inp[1][f])
+    alpha = np.arctan(r / 600.)
+    shift = np.hypot(quirk.pos[f][:, 0], quirk.pos[f][:, 1])
+    assert np.abs(shift - 2e-6 * np.tan(2 * alpha)).max() < 1e-11
+    assert 1.0e-6 < shift.max() < 1.1e-6
+    # classes: r < 20.001 cm stops on obs1, 20.001 < r < 150 cm focuses, else exits at z = -10 m
+    r_all = np.hypot(quirk.inp[0], quirk.inp[1])
+    assert (quirk.status[r_all < 20.0] == 1).all() and (quirk.status[(r_all > 20.01) & (r_all < 149.99)] == 3).all()
+    ex_ = quirk.status == 2
+    assert (r_all[ex_] > 149.99).all() and np.abs(quirk.pos[ex_][:, 2] + 1000.).max() < 1e-9
+    # time of flight: path length / c
+    tof = quirk.time[f] * 2.99792458e10
+    assert np.abs(tof - (600. - r[...] ** 2 / 1200. + np.hypot(r, 300. - r ** 2 / 1200.))).max() < 1e-5
+
+
+def test_kat_davies_cotton_facets_aim_at_2f(R):  # SURVEY.md Appendix B sanity check of the Euler convention
+    mgr, _k = configs.davies_cotton()
+    ex = mgr.ExportScene()
+    n = 0
+    for i in range(ex.num_nodes()):
+        vol, mat, copy, ovl = ex.node(i)
+        if mat < 0 or i >= 88:
+            continue
+        rot, tr = ex.matrix(mat)
+        normal = np.array([rot[2], rot[5], rot[8]])  # facet local +z in the world
+        to_2f = np.array([0, 0, 3200.]) - np.array(tr)
+        to_2f /= np.linalg.norm(to_2f)
+        assert np.abs(normal - to_2f).max() < 1e-12
+        # no net spin: the local y axis stays in the plane spanned by z and the radial direction's normal
+        n += 1
+    assert n == 88
+
+
+def test_kat_shooter_grids(R, oracle):  # src/ARayShooter.cxx:122-183,401-452
+    arr = R.ARayShooter.Square(400 * nm, 90., 4)
+    c = arr.columns()
+    assert arr.GetN() == 16
+    assert np.allclose(c["x"][:5], [-45, -45, -45, -45, -15]) and np.allclose(c["y"][:5], [-45, -15, 15, 45, -45])  # x-major order
+    assert np.allclose(c["dz"], 1)
+    circ = R.ARayShooter.Circle(400 * nm, 100., 3, 6)
+    assert circ.GetN() == 1 + 6 + 12 + 18
+    # the oracle's Philox shooter reproduces the same grid
+    b = dict(kind=0, nx=4, ny=4, dx=90., dy=90., lambda_min=400 * nm, lambda_max=400 * nm, rot=[1, 0, 0, 0, 1, 0, 0, 0, 1], tr=[0, 0, 0], dir=[0, 0, 1], seed=1)
+    rays = H.make_rays(oracle, b, 0, 16)
+    assert np.allclose(rays.inp[0], c["x"]) and np.allclose(rays.inp[1], c["y"])
+    b.update(kind=3, nx=3, ny=6, dx=100.)
+    rays = H.make_rays(oracle, b, 0, 37)
+    cc = circ.columns()
+    assert np.allclose(rays.inp[0], cc["x"], atol=1e-12) and np.allclose(rays.inp[1], cc["y"], atol=1e-12)
+
+
+def test_winston_cone_cutoff(oracle):  # closed-form property of a Winston cone: acceptance asin(R2/R1) = 30 deg
+    mgr, _k = configs.hex_winston_cone(rings=0, coating="ideal")
+    ex = mgr.ExportScene()
+    frac = {}
+    for th in (0., 15., 45.):
+        rays = H.make_rays(oracle, configs.beam(5, th, n_side=30 * mm), 0, 4000)
+        H.trace_with(oracle.orc_trace, ex, rays, H.opts(), nthreads=4)
+        frac[th] = (rays.status == 3).mean()
+    assert frac[0.] > 0.98 and frac[15.] > 0.9 and frac[45.] == 0.0
+
+
+def test_schmidt_cassegrain_design_spot(oracle):  # the Zemax sample design focuses d-line light to a few-micron spot
+    mgr, _k = configs.schmidt_cassegrain(disable_fresnel=True)
+    b = configs.beam(4, 0.0)
+    b["lambda_min"] = b["lambda_max"] = 587.6 * nm
+    rays = H.make_rays(oracle, b, 0, 5000)
+    H.trace_with(oracle.orc_trace, mgr.ExportScene(), rays, H.opts(disable_fresnel=1), nthreads=4)
+    f = rays.status == 3
+    assert f.sum() > 3000 and rays.pos[f][:, :2].std(0).max() < 5e-4  # < 5 um rms
