@@ -111,6 +111,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--steps-per-launch", type=int, default=int(os.environ.get("RB_STEPS_PER_LAUNCH", "0")))
+    ap.add_argument("--n-side", type=int, default=N_SIDE, help="grid side per field angle (profiling runs only; the bench metric uses 3334)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -139,7 +140,8 @@ def main():
     export = mgr.ExportScene()
     scene = C.c_void_p()
     R.check(R.rbg_scene_create(export.desc_ptr(), local, C.byref(scene)))
-    n = N_SIDE * N_SIDE
+    nside = args.n_side
+    n = nside * nside
     nang = len(ANGLES)
     stream = torch.cuda.current_stream().cuda_stream
     # this rank's field angles: the 0..4 deg sweep refined by the rank (weak scaling, geometry replicated)
@@ -148,7 +150,7 @@ def main():
     out = torch.empty((7, n), dtype=torch.float64, device=dev)
     iout = torch.empty((3, n), dtype=torch.int32, device=dev)
     for k, th in enumerate(my_angles):
-        d = H.shoot_desc(configs.beam(2, th, n_side=N_SIDE))
+        d = H.shoot_desc(configs.beam(2, th, n_side=nside))
         R.check(R.rbg_shoot(C.byref(d), 0, n, *[inp[k, i].data_ptr() for i in range(8)], local, stream))
     hist = torch.zeros((nang, 200 * 200), dtype=torch.int64, device=dev)
     mom = torch.zeros((nang, 8), dtype=torch.float64, device=dev)
