@@ -286,7 +286,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     kernel_ms = bm.value / max(1, bn.value)
     achieved = (BYTES_IN + BYTES_OUT) * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
-    roof = {"bound": "hbm", "kernel": "k_trace<1>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
+    roof = {"bound": "hbm", "kernel": "k_trace<%s>" % R.rbg_scene_kernel_variant(scene).decode(), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
             "traffic": None, "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback", "algorithmic_bytes_per_ray": BYTES_IN + BYTES_OUT,
             "kernel_ms_per_launch": kernel_ms, "kernel_launches": bn.value, "kernel_share_of_step": bm.value / ms if ms else None,
             "note": "k_trace is FP64-pipe bound, not HBM bound: see profiles/ for sm__inst_executed_pipe_fp64 and DESIGN.md"}

@@ -179,7 +179,7 @@ typedef struct {
   int32_t limit;            /* fLimit (SetLimit), default 100; <=0 -> 100 */
   int32_t disable_fresnel;  /* DisableFresnelReflection */
   uint32_t quirks;          /* RBG_QUIRK_* */
-  int32_t steps_per_launch; /* wavefront granularity: boundary steps per bounce kernel; <=0 = until done */
+  int32_t steps_per_launch; /* wavefront granularity: boundary steps per bounce kernel; 0 = auto, <0 = until done (one launch) */
   uint64_t seed;            /* Philox key */
   uint64_t ray_id_offset;   /* global index of ray 0 (multi-GPU sharding keeps streams independent of G) */
 } rbg_trace_opts;
@@ -212,6 +212,8 @@ int rbg_scene_create(const rbg_scene_desc* desc, int device, rbg_scene** out);
 int rbg_scene_destroy(rbg_scene* scene);
 /* physical (flattened) node table: count, and "<volname>_<copyNo>" name of node i (ROOT naming) */
 int rbg_scene_num_nodes(const rbg_scene* scene);
+/* name of the k_trace instantiation selected for this scene (scene-specialised or generic_dN) */
+const char* rbg_scene_kernel_variant(const rbg_scene* scene);
 const char* rbg_scene_node_name(const rbg_scene* scene, int node);
 
 /* TraceNonSequential over a ray batch (src/AOpticsManager.cxx:335-520,523-587).

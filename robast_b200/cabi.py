@@ -42,6 +42,7 @@ rbg_scene_create = _proto("rbg_scene_create", C.c_int, [C.c_void_p, C.c_int, C.P
 rbg_scene_destroy = _proto("rbg_scene_destroy", C.c_int, [C.c_void_p])
 rbg_scene_num_nodes = _proto("rbg_scene_num_nodes", C.c_int, [C.c_void_p])
 rbg_scene_node_name = _proto("rbg_scene_node_name", C.c_char_p, [C.c_void_p, C.c_int])
+rbg_scene_kernel_variant = _proto("rbg_scene_kernel_variant", C.c_char_p, [C.c_void_p])
 rbg_trace = _proto("rbg_trace", C.c_int, [C.c_void_p, C.POINTER(rbg_trace_opts), C.POINTER(rbg_rays), C.c_void_p])
 rbg_launch_count = _proto("rbg_launch_count", C.c_int64, [])
 rbg_profile_enable = _proto("rbg_profile_enable", C.c_int, [C.c_int])
@@ -53,7 +54,7 @@ rbg_tmm = _proto("rbg_tmm", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, 
 rbg_tmm_host = _proto("rbg_tmm_host", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp])
 
 ABI_SYMBOLS = ["rbg_abi_version", "rbg_last_error", "rbg_device_count", "rbg_scene_create", "rbg_scene_destroy",
-               "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_trace", "rbg_launch_count", "rbg_profile_enable",
+               "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_scene_kernel_variant", "rbg_trace", "rbg_launch_count", "rbg_profile_enable",
                "rbg_profile_read", "rbg_shoot", "rbg_hist2d", "rbg_moments", "rbg_tmm", "rbg_tmm_host"]
 
 

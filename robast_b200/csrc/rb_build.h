@@ -12,6 +12,8 @@
 
 #include "rb_scene.h"
 
+namespace {  // internal linkage: this header is compiled into more than one shared object
+
 struct NotSupported : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
@@ -211,8 +213,11 @@ struct SceneBuilder {
     bvh.push_back(DBvh());
     Box b = box_empty();
     for (int i = lo; i < hi; i++) { box_add(b, items[i].second.lo); box_add(b, items[i].second.hi); }
-    memcpy(bvh[me].lo, b.lo, sizeof(b.lo));
-    memcpy(bvh[me].hi, b.hi, sizeof(b.hi));
+    for (int k = 0; k < 3; k++) {  // outward rounding + padding that covers the fp32 error of the slab test
+      double pad = 2e-3 + 4e-7 * std::max(fabs(b.lo[k]), fabs(b.hi[k]));
+      bvh[me].lo[k] = std::nextafterf((float)(b.lo[k] - pad), -INFINITY);
+      bvh[me].hi[k] = std::nextafterf((float)(b.hi[k] + pad), INFINITY);
+    }
     if (hi - lo == 1) {
       bvh[me].child = items[lo].first;
     } else {
@@ -253,6 +258,23 @@ struct SceneBuilder {
   }
 };
 
+// compile-time features a scene needs from the bounce kernel (see RB_PH_* / RB_SBIT in rb_device.cuh)
+static void scene_features_needed(const rbg_scene_desc* D, unsigned& shapes, unsigned& phys) {
+  shapes = phys = 0;
+  for (int i = 0; i < D->nshapes; i++) shapes |= 1u << D->shapes[i].type;
+  for (int i = 0; i < D->nvolumes; i++) {
+    if (D->volumes[i].type == RBG_LENS) phys |= 1u;
+    if (D->volumes[i].focal >= 0) phys |= 16u;
+  }
+  for (int i = 0; i < D->nborders; i++) {
+    if (D->borders[i].multilayer >= 0) phys |= 2u;
+    if (D->borders[i].sigma != 0) phys |= 4u;
+    if (D->borders[i].lambertian) phys |= 8u;
+  }
+  for (int i = 0; i < D->nmirrors; i++)
+    if (D->mirrors[i].graph1d >= 0 || D->mirrors[i].th2 >= 0) phys |= 32u;
+}
+
 static int scene_depth_needed(const SceneBuilder& B) {
   int d = 0;
   for (int v : B.shape_depth) d = std::max(d, v);
@@ -278,4 +300,5 @@ static void validate_desc(const rbg_scene_desc* D) {
     if (D->mirrors[i].graph2d >= 0) throw NotSupported("TGraph2D mirror reflectance is not supported on the device path");
 }
 
+}  // namespace
 #endif

@@ -21,6 +21,26 @@
 
 #include "rb_scene.h"
 
+// compile-time feature masks: a scene-specialised instantiation only carries the shapes / physics it needs
+// (the generic kernel overflows the instruction cache, profiles/r1a_k_trace_ncu_summary.md)
+#define RB_SBIT(t) (1u << (t))
+#define RB_SHAPES_ALL 0xffffu
+#define RB_PH_LENS 1u        /* ALens: Snell/Fresnel, bulk absorption, n(lambda) */
+#define RB_PH_MULTILAYER 2u  /* AMultilayer on a border (TMM or table) */
+#define RB_PH_ROUGH 4u       /* Gaussian facet roughness */
+#define RB_PH_LAMBERT 8u     /* Lambertian border */
+#define RB_PH_QE 16u         /* AFocalSurface QE graphs */
+#define RB_PH_MIRROR_TABLE 32u /* AMirror reflectance != constant */
+#define RB_PH_ALL 0xffu
+template <int D, unsigned S, unsigned P, int MINB = 1, int STEP_THREADS = 512, int STEP_MINB = 2> struct TraceCfg {
+  static constexpr int depth = D;
+  static constexpr unsigned shapes = S;
+  static constexpr unsigned phys = P;
+  static constexpr int min_blocks = MINB;            // k_trace: __launch_bounds__(128, MINB) (register cap)
+  static constexpr int step_threads = STEP_THREADS;  // k_step: block size and min resident blocks per SM
+  static constexpr int step_min_blocks = STEP_MINB;
+};
+
 #define RB_BIG 1e30
 #define RB_TOL 1e-10
 #define RB_PI 3.14159265358979323846
@@ -457,7 +477,7 @@ RB_HD inline V3 tube_normal(const double* P, V3 p, V3 d) {
   double r = sqrt(p.x * p.x + p.y * p.y);
   double s0 = fabs(P[2] - fabs(p.z)), s1 = P[0] > 1e-10 ? fabs(r - P[0]) : RB_BIG, s2 = fabs(P[1] - r);
   if (s0 <= s1 && s0 <= s2) return v3(0, 0, d.z >= 0 ? 1 : -1);
-  double phi = rb_atan2(p.y, p.x), nx = cos(phi), ny = sin(phi);
+  double nx = r > 0 ? p.x / r : 1., ny = r > 0 ? p.y / r : 0.;  // (cos phi, sin phi) of phi = atan2(y, x)
   if (nx * d.x + ny * d.y < 0) { nx = -nx; ny = -ny; }
   return v3(nx, ny, 0);
 }
@@ -485,8 +505,8 @@ RB_HD inline double para_surface(const double* P, V3 p, V3 d, bool in) {
     double dist = 0.5 * (sum + i * sone * delta);
     if (dist < 0) continue;
     if (dist < 1.E-8) {
-      double talf = -2. * fa * sqrt(rsq), phi = rb_atan2(p.y, p.x);
-      double ndotd = talf * (cos(phi) * d.x + sin(phi) * d.y) + d.z;
+      double rr = sqrt(rsq), talf = -2. * fa * rr;
+      double ndotd = (rr > 0 ? talf * (p.x * d.x + p.y * d.y) / rr : talf * d.x) + d.z;
       if (!in) ndotd = -ndotd;
       if (ndotd < 0) return dist;
     } else return dist;
@@ -517,8 +537,9 @@ RB_HD inline V3 para_normal(const double* P, V3 p, V3 d) {
   if ((fabs(p.z) - P[2]) > -1E-5) return v3(0, 0, d.z >= 0 ? 1. : -1.);
   double safz = P[2] - fabs(p.z), r = sqrt(p.x * p.x + p.y * p.y), safr = fabs(r - sqrt((p.z - P[4]) / P[3]));
   if (safz < safr) return v3(0, 0, d.z >= 0 ? 1. : -1.);
-  double talf = -2. * P[3] * r, calf = 1. / sqrt(1. + talf * talf), salf = talf * calf, phi = rb_atan2(p.y, p.x);
-  V3 n = v3(salf * cos(phi), salf * sin(phi), calf);
+  double talf = -2. * P[3] * r, calf = 1. / sqrt(1. + talf * talf), salf = talf * calf;
+  double cph = r > 0 ? p.x / r : 1., sph = r > 0 ? p.y / r : 0.;
+  V3 n = v3(salf * cph, salf * sph, calf);
   if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
   return n;
 }
@@ -818,7 +839,7 @@ RB_HD inline double asph_dist_out(const double* P, V3 p, V3 d, double step) {
   return asph_dist4(P, p, d);
 }
 RB_HD inline V3 asph_normal(const double* P, V3 p, V3 d) {
-  double r = sqrt(p.x * p.x + p.y * p.y), phi = atan2(p.y, p.x);
+  double r = sqrt(p.x * p.x + p.y * p.y);
   double best = P[6] > 0 ? fabs(r - P[6]) : RB_BIG, f, df = 0;
   int which = 0;
   double s = fabs(r - P[7]);
@@ -833,7 +854,7 @@ RB_HD inline V3 asph_normal(const double* P, V3 p, V3 d) {
   if (which < 2) nx = 1;
   else if (dfs == 0) nz = 1;
   else { double inv = 1. / sqrt(1 + dfs * dfs); nx = dfs * inv; nz = -inv; }
-  V3 n = v3(nx * cos(phi), nx * sin(phi), nz);
+  V3 n = r > 0 ? v3(nx * p.x / r, nx * p.y / r, nz) : v3(nx, 0, nz);  // RotateZ(atan2(y, x))
   if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
   return n;
 }
@@ -995,102 +1016,102 @@ RB_HD inline V3 win_normal(const double* P, bool poly, V3 p, V3 d) {
 
 // ================================================================== shape dispatch, boolean composites
 // DEPTH = remaining boolean nesting levels compiled in (scene build picks the instantiation).
-template <int DEPTH> struct Csg {
+template <int DEPTH, unsigned SM> struct Csg {
   static RB_HD RB_NOINLINE bool contains(const DScene& sc, int sh, V3 p);
   static RB_HD RB_NOINLINE double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel);
   static RB_HD RB_NOINLINE double dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel);
   static RB_HD RB_NOINLINE V3 normal(const DScene& sc, int sh, V3 p, V3 d, int sel);
 };
 
-RB_HD inline bool prim_contains(const DScene& sc, const DShape& s, V3 p) {
+template <unsigned SM> RB_HD inline bool prim_contains(const DScene& sc, const DShape& s, V3 p) {
   const double* P = sc.dpar + s.ipar;
   switch (s.type) {
-    case RBG_SHAPE_BBOX: return bbox_contains(P, p);
-    case RBG_SHAPE_TUBE: return tube_contains(P, p);
-    case RBG_SHAPE_SPHERE: return sphere_contains(P, p);
-    case RBG_SHAPE_PARABOLOID: return para_contains(P, p);
-    case RBG_SHAPE_PGON: return pgon_contains(P, p);
-    case RBG_SHAPE_ASPHERE: return asph_contains(P, p);
-    case RBG_SHAPE_WINSTON2D: return win_contains(P, false, p);
-    case RBG_SHAPE_WINSTONPOLY: return win_contains(P, true, p);
+    case RBG_SHAPE_BBOX: if constexpr ((SM & RB_SBIT(RBG_SHAPE_BBOX)) != 0) return bbox_contains(P, p); else break;
+    case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_contains(P, p); else break;
+    case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_contains(P, p); else break;
+    case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_contains(P, p); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_contains(P, p); else break;
+    case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_contains(P, p); else break;
+    case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_contains(P, false, p); else break;
+    case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_contains(P, true, p); else break;
   }
   return false;
 }
-RB_HD inline double prim_dist_in(const DScene& sc, const DShape& s, V3 p, V3 d) {
+template <unsigned SM> RB_HD inline double prim_dist_in(const DScene& sc, const DShape& s, V3 p, V3 d) {
   const double* P = sc.dpar + s.ipar;
   switch (s.type) {
-    case RBG_SHAPE_BBOX: return bbox_dist_in(P, p, d);
-    case RBG_SHAPE_TUBE: return tube_dist_in(P[0], P[1], P[2], p, d);
-    case RBG_SHAPE_SPHERE: return sphere_dist(P, p, d, true);
-    case RBG_SHAPE_PARABOLOID: return para_dist_in(P, p, d);
-    case RBG_SHAPE_PGON: return pgon_dist_in(P, p, d);
-    case RBG_SHAPE_ASPHERE: return asph_dist4(P, p, d);
-    case RBG_SHAPE_WINSTON2D: return win_dist_in(P, false, p, d);
-    case RBG_SHAPE_WINSTONPOLY: return win_dist_in(P, true, p, d);
+    case RBG_SHAPE_BBOX: if constexpr ((SM & RB_SBIT(RBG_SHAPE_BBOX)) != 0) return bbox_dist_in(P, p, d); else break;
+    case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_dist_in(P[0], P[1], P[2], p, d); else break;
+    case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_dist(P, p, d, true); else break;
+    case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_dist_in(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_dist_in(P, p, d); else break;
+    case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist4(P, p, d); else break;
+    case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_in(P, false, p, d); else break;
+    case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_in(P, true, p, d); else break;
   }
   return RB_BIG;
 }
-RB_HD inline double prim_dist_out(const DScene& sc, const DShape& s, V3 p, V3 d, double step) {
+template <unsigned SM> RB_HD inline double prim_dist_out(const DScene& sc, const DShape& s, V3 p, V3 d, double step) {
   const double* P = sc.dpar + s.ipar;
   switch (s.type) {
-    case RBG_SHAPE_BBOX: return bbox_dist_out(P, p, d, step);
-    case RBG_SHAPE_TUBE: return tube_dist_out(P[0], P[1], P[2], p, d);
-    case RBG_SHAPE_SPHERE: return sphere_dist(P, p, d, false);
-    case RBG_SHAPE_PARABOLOID: return para_dist_out(P, p, d);
-    case RBG_SHAPE_PGON: return pgon_dist_out(P, p, d);
-    case RBG_SHAPE_ASPHERE: return asph_dist_out(P, p, d, step);
-    case RBG_SHAPE_WINSTON2D: return win_dist_out(P, false, p, d);
-    case RBG_SHAPE_WINSTONPOLY: return win_dist_out(P, true, p, d);
+    case RBG_SHAPE_BBOX: if constexpr ((SM & RB_SBIT(RBG_SHAPE_BBOX)) != 0) return bbox_dist_out(P, p, d, step); else break;
+    case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_dist_out(P[0], P[1], P[2], p, d); else break;
+    case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_dist(P, p, d, false); else break;
+    case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_dist_out(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_dist_out(P, p, d); else break;
+    case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist_out(P, p, d, step); else break;
+    case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_out(P, false, p, d); else break;
+    case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_out(P, true, p, d); else break;
   }
   return RB_BIG;
 }
-RB_HD inline V3 prim_normal(const DScene& sc, const DShape& s, V3 p, V3 d) {
+template <unsigned SM> RB_HD inline V3 prim_normal(const DScene& sc, const DShape& s, V3 p, V3 d) {
   const double* P = sc.dpar + s.ipar;
   switch (s.type) {
-    case RBG_SHAPE_BBOX: return bbox_normal(P, p, d);
-    case RBG_SHAPE_TUBE: return tube_normal(P, p, d);
-    case RBG_SHAPE_SPHERE: return sphere_normal(P, p, d);
-    case RBG_SHAPE_PARABOLOID: return para_normal(P, p, d);
-    case RBG_SHAPE_PGON: return pgon_normal(P, p, d);
-    case RBG_SHAPE_ASPHERE: return asph_normal(P, p, d);
-    case RBG_SHAPE_WINSTON2D: return win_normal(P, false, p, d);
-    case RBG_SHAPE_WINSTONPOLY: return win_normal(P, true, p, d);
+    case RBG_SHAPE_BBOX: if constexpr ((SM & RB_SBIT(RBG_SHAPE_BBOX)) != 0) return bbox_normal(P, p, d); else break;
+    case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_normal(P, p, d); else break;
+    case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_normal(P, p, d); else break;
+    case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_normal(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_normal(P, p, d); else break;
+    case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_normal(P, p, d); else break;
+    case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_normal(P, false, p, d); else break;
+    case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_normal(P, true, p, d); else break;
   }
   return v3(0, 0, 1);
 }
 
-template <> struct Csg<0> {
-  static RB_HD RB_NOINLINE bool contains(const DScene& sc, int sh, V3 p) { return prim_contains(sc, sc.shapes[sh], p); }
-  static RB_HD RB_NOINLINE double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) { sel = 0; return prim_dist_in(sc, sc.shapes[sh], p, d); }
+template <unsigned SM> struct Csg<0, SM> {
+  static RB_HD RB_NOINLINE bool contains(const DScene& sc, int sh, V3 p) { return prim_contains<SM>(sc, sc.shapes[sh], p); }
+  static RB_HD RB_NOINLINE double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) { sel = 0; return prim_dist_in<SM>(sc, sc.shapes[sh], p, d); }
   static RB_HD RB_NOINLINE double dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
     sel = 0;
-    return prim_dist_out(sc, sc.shapes[sh], p, d, step);
+    return prim_dist_out<SM>(sc, sc.shapes[sh], p, d, step);
   }
-  static RB_HD RB_NOINLINE V3 normal(const DScene& sc, int sh, V3 p, V3 d, int) { return prim_normal(sc, sc.shapes[sh], p, d); }
+  static RB_HD RB_NOINLINE V3 normal(const DScene& sc, int sh, V3 p, V3 d, int) { return prim_normal<SM>(sc, sc.shapes[sh], p, d); }
 };
 
 RB_HD inline V3 op_point(const DScene& sc, int m, V3 p) { return m < 0 ? p : to_local(sc.mats[m], p); }
 RB_HD inline V3 op_vec(const DScene& sc, int m, V3 d) { return m < 0 ? d : to_local_vec(sc.mats[m], d); }
 
-template <int DEPTH> RB_HD RB_NOINLINE bool Csg<DEPTH>::contains(const DScene& sc, int sh, V3 p) {
+template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE bool Csg<DEPTH, SM>::contains(const DScene& sc, int sh, V3 p) {
   const DShape s = sc.shapes[sh];
-  if (s.type < RBG_SHAPE_UNION) return prim_contains(sc, s, p);
-  typedef Csg<DEPTH - 1> Sub;
+  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::contains(sc, sh, p);  // one shared copy of the primitive code
+  typedef Csg<DEPTH - 1, SM> Sub;
   bool l = Sub::contains(sc, s.left, op_point(sc, s.lmat, p));
-  if (s.type == RBG_SHAPE_UNION) return l || Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
+  if ((SM & RB_SBIT(RBG_SHAPE_UNION)) != 0 && s.type == RBG_SHAPE_UNION) return l || Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
   if (!l) return false;
   bool r = Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
   return s.type == RBG_SHAPE_INTERSECTION ? r : !r;
 }
 
-template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) {
+template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE double Csg<DEPTH, SM>::dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) {
   const DShape s = sc.shapes[sh];
   sel = 0;
-  if (s.type < RBG_SHAPE_UNION) return prim_dist_in(sc, s, p, d);
-  typedef Csg<DEPTH - 1> Sub;
+  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::dist_in(sc, sh, p, d, sel);
+  typedef Csg<DEPTH - 1, SM> Sub;
   V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p), ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
   int s1 = 0, s2 = 0;
-  if (s.type != RBG_SHAPE_UNION) {  // TGeoIntersection / TGeoSubtraction :: DistFromInside
+  if ((SM & RB_SBIT(RBG_SHAPE_UNION)) == 0 || s.type != RBG_SHAPE_UNION) {  // TGeoIntersection / TGeoSubtraction :: DistFromInside
     double d1 = Sub::dist_in(sc, s.left, lp, ld, s1);
     double d2 = s.type == RBG_SHAPE_INTERSECTION ? Sub::dist_in(sc, s.right, rp, rd, s2) : Sub::dist_out(sc, s.right, rp, rd, RB_BIG, s2);
     if (d1 < d2) { sel = 1 | (s1 << 2); return d1; }
@@ -1146,22 +1167,22 @@ template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_in(const DScene& 
   return snxt;
 }
 
-template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
+template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE double Csg<DEPTH, SM>::dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
   const DShape s = sc.shapes[sh];
   sel = 0;
-  if (s.type < RBG_SHAPE_UNION) return prim_dist_out(sc, s, p, d, step);
-  typedef Csg<DEPTH - 1> Sub;
+  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::dist_out(sc, sh, p, d, step, sel);
+  typedef Csg<DEPTH - 1, SM> Sub;
   V3 ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
   V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p);
   int s1 = 0, s2 = 0;
-  if (s.type == RBG_SHAPE_UNION) {
+  if ((SM & RB_SBIT(RBG_SHAPE_UNION)) != 0 && s.type == RBG_SHAPE_UNION) {
     double d1 = Sub::dist_out(sc, s.left, lp, ld, step, s1), d2 = Sub::dist_out(sc, s.right, rp, rd, step, s2);
     if (d1 < d2) { sel = 1 | (s1 << 2); return d1; }
     sel = 2 | (s2 << 2);
     return d2;
   }
   V3 master = p;
-  if (s.type == RBG_SHAPE_INTERSECTION) {
+  if ((SM & RB_SBIT(RBG_SHAPE_INTERSECTION)) != 0 && s.type == RBG_SHAPE_INTERSECTION) {
     bool inl = Sub::contains(sc, s.left, lp), inr = Sub::contains(sc, s.right, rp);
     double snext = 0.0, d1, d2;
     if (inl && inr) {
@@ -1171,13 +1192,19 @@ template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_out(const DScene&
       if (d2 < 1.E-3) inr = false;
       if (inl && inr) return snext;
     }
+    // either operand missing means no hit: try the cheaper primitive first (same result, fewer instructions)
+    const bool right_first = sc.shapes[s.right].type < sc.shapes[s.left].type && sc.shapes[s.left].type < RBG_SHAPE_UNION ? false : sc.shapes[s.right].type != RBG_SHAPE_SPHERE;
     for (int guard = 0; guard < 64; guard++) {
       d1 = d2 = 0;
+      if (right_first && !inr) {
+        d2 = rb_max(Sub::dist_out(sc, s.right, rp, rd, RB_BIG, s2), RB_TOL);
+        if (d2 > 1E20) return RB_BIG;
+      }
       if (!inl) {
         d1 = rb_max(Sub::dist_out(sc, s.left, lp, ld, RB_BIG, s1), RB_TOL);
         if (d1 > 1E20) return RB_BIG;
       }
-      if (!inr) {
+      if (!right_first && !inr) {
         d2 = rb_max(Sub::dist_out(sc, s.right, rp, rd, RB_BIG, s2), RB_TOL);
         if (d2 > 1E20) return RB_BIG;
       }
@@ -1204,6 +1231,7 @@ template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_out(const DScene&
     return RB_BIG;
   }
   // TGeoSubtraction::DistFromOutside
+  if ((SM & RB_SBIT(RBG_SHAPE_SUBTRACTION)) == 0) return RB_BIG;
   bool inside = Sub::contains(sc, s.right, rp);
   double snxt = 0., epsil = 0.;
   for (int guard = 0; guard < 64; guard++) {
@@ -1234,10 +1262,10 @@ template <int DEPTH> RB_HD RB_NOINLINE double Csg<DEPTH>::dist_out(const DScene&
   return RB_BIG;
 }
 
-template <int DEPTH> RB_HD RB_NOINLINE V3 Csg<DEPTH>::normal(const DScene& sc, int sh, V3 p, V3 d, int sel) {
+template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE V3 Csg<DEPTH, SM>::normal(const DScene& sc, int sh, V3 p, V3 d, int sel) {
   const DShape s = sc.shapes[sh];
-  if (s.type < RBG_SHAPE_UNION) return prim_normal(sc, s, p, d);
-  typedef Csg<DEPTH - 1> Sub;
+  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::normal(sc, sh, p, d, 0);
+  typedef Csg<DEPTH - 1, SM> Sub;
   int side = sel & 3;
   if (side == 0) {
     bool inl = Sub::contains(sc, s.left, op_point(sc, s.lmat, p)), inr = Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
@@ -1261,19 +1289,20 @@ struct RayReg {           // register-resident ray state
 };
 
 // first (lowest id = daughter order) child of `node` whose shape contains q; -1 if none
-template <int DEPTH> RB_HD inline int child_containing(const DScene& sc, int node, V3 q, int skip) {
+template <class K> RB_HD inline int child_containing(const DScene& sc, int node, V3 q, int skip) {
   const DNode& nd = sc.nodes[node];
   int best = -1;
   int i = nd.bvh_count > 0 ? nd.bvh_first : -1;
+  const float qx = (float)q.x, qy = (float)q.y, qz = (float)q.z;  // boxes are padded for this rounding
   while (i >= 0) {
     const DBvh& b = sc.bvh[i];
-    bool in = q.x >= b.lo[0] && q.x <= b.hi[0] && q.y >= b.lo[1] && q.y <= b.hi[1] && q.z >= b.lo[2] && q.z <= b.hi[2];
+    bool in = qx >= b.lo[0] && qx <= b.hi[0] && qy >= b.lo[1] && qy <= b.hi[1] && qz >= b.lo[2] && qz <= b.hi[2];
     if (!in) { i = b.skip; continue; }
     if (b.child >= 0) {
       int c = b.child;
       if (c != skip && (best < 0 || c < best)) {
         const DNode& cn = sc.nodes[c];
-        if (Csg<DEPTH>::contains(sc, cn.shape, to_local(cn.g, q))) best = c;
+        if (Csg<K::depth, K::shapes>::contains(sc, cn.shape, to_local(cn.g, q))) best = c;
       }
       i = b.skip;
     } else i = i + 1;
@@ -1281,30 +1310,34 @@ template <int DEPTH> RB_HD inline int child_containing(const DScene& sc, int nod
   return best;
 }
 // TGeoNavigator::SearchNode(downwards=false, skip) starting at `node`; returns the deepest node containing q or -1
-template <int DEPTH> RB_HD inline int search_node(const DScene& sc, int node, V3 q, int skip, bool check_current) {
+template <class K> RB_HD inline int search_node(const DScene& sc, int node, V3 q, int skip, bool check_current) {
   if (check_current) {
     while (true) {
       if (node < 0) return -1;
       const DNode& nd = sc.nodes[node];
-      bool inside = node == skip ? true : Csg<DEPTH>::contains(sc, nd.shape, to_local(nd.g, q));
+      bool inside = node == skip ? true : Csg<K::depth, K::shapes>::contains(sc, nd.shape, to_local(nd.g, q));
       if (inside) break;
       skip = node;
       node = nd.mother;
     }
   }
   while (true) {
-    int c = child_containing<DEPTH>(sc, node, q, skip);
+    int c = child_containing<K>(sc, node, q, skip);
     skip = -1;
     if (c < 0) return node;
     node = c;
   }
 }
 
+#define RB_MAXVIS 12
 struct StepOut {
   double step;
   int next;        // node now containing the point (-1 outside)
   int crossed;     // node whose shape boundary was crossed (for FindNormal), -1 none
   int sel;         // boolean-operand selection path of the crossed shape
+  int from;        // node the step started in (-1 outside)
+  int nvis;        // daughters of `from` whose padded AABB the ray touched before the boundary; -1 = not recorded
+  int vis[RB_MAXVIS];
 };
 
 RB_HD inline double locate_extra(const DScene& sc, int node, double step) {
@@ -1317,79 +1350,135 @@ RB_HD inline double locate_extra(const DScene& sc, int node, double step) {
 }
 
 // TGeoNavigator::FindNextBoundaryAndStep(Big) on the flattened scene
-template <int DEPTH> RB_HD inline StepOut next_boundary(const DScene& sc, RayReg& r, bool push_quirk) {
+// ---- one TGeoNavigator::FindNextBoundaryAndStep, split into phases so that the block-lock-step kernel can
+// put a barrier between them (all warps of an SM then execute the same code region: instruction-cache reuse)
+struct NavStep {
   StepOut o;
+  double extra, best, s_exit;
+  int sel_exit, enter, esel;
+  int mode;      // 0 = finished in nb_begin, 1 = daughters to examine
+  int bvh_next;  // >= 0: traversal stopped because o.vis was full; resume here after evaluating the batch
+};
+
+// phase A: boundary push, outside-world entry, DistFromInside of the current shape
+template <class K> RB_HD inline void nb_begin(const DScene& sc, RayReg& r, bool push_quirk, NavStep& st) {
+  StepOut& o = st.o;
   o.crossed = -1;
   o.sel = 0;
+  o.from = r.cur;
+  o.nvis = -1;
+  st.mode = 0;
+  st.bvh_next = -1;
+  st.enter = -1;
+  st.esel = 0;
   double extra = (r.on_boundary && push_quirk) ? RB_TOL : 0.0;
+  st.extra = extra;
   r.on_boundary = 0;
   r.p = along(r.p, r.d, extra);
   if (r.cur < 0) {
     int sel = 0;
-    double s = Csg<DEPTH>::dist_out(sc, sc.top_shape, r.p, r.d, RB_BIG, sel);
-    if (s > 1e29) { o.step = RB_BIG; o.next = -1; return o; }
+    double s = Csg<K::depth, K::shapes>::dist_out(sc, sc.top_shape, r.p, r.d, RB_BIG, sel);
+    if (s > 1e29) { o.step = RB_BIG; o.next = -1; return; }
     if (s <= 0) { s = 0.0; o.step = 0.0; r.p = along(r.p, r.d, -extra); }
     else o.step = s + extra;
     r.p = along(r.p, r.d, s);
     r.on_boundary = 1;
     o.crossed = 0;
     o.sel = sel;
-    o.next = search_node<DEPTH>(sc, 0, along(r.p, r.d, locate_extra(sc, 0, o.step)), -1, false);
-    return o;
+    o.next = search_node<K>(sc, 0, along(r.p, r.d, locate_extra(sc, 0, o.step)), -1, false);
+    return;
   }
   const DNode& cn = sc.nodes[r.cur];
-  int sel_exit = 0;
-  double s_exit = Csg<DEPTH>::dist_in(sc, cn.shape, to_local(cn.g, r.p), to_local_vec(cn.g, r.d), sel_exit);
-  if (s_exit <= RB_TOL) {
+  st.sel_exit = 0;
+  st.s_exit = Csg<K::depth, K::shapes>::dist_in(sc, cn.shape, to_local(cn.g, r.p), to_local_vec(cn.g, r.d), st.sel_exit);
+  if (st.s_exit <= RB_TOL) {
     o.step = RB_TOL;
     r.p = along(r.p, r.d, o.step);
     r.on_boundary = 1;
     o.crossed = r.cur;
-    o.sel = sel_exit;
-    if (cn.mother < 0) { o.next = -1; return o; }
-    o.next = search_node<DEPTH>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
-    return o;
+    o.sel = st.sel_exit;
+    if (cn.mother < 0) { o.next = -1; return; }
+    o.next = search_node<K>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
+    return;
   }
-  double best = RB_BIG;
-  if (s_exit < best - RB_TOL) best = s_exit;
-  int enter = -1, esel = 0;
-  int i = cn.bvh_count > 0 ? cn.bvh_first : -1;
-  double idx = 1. / r.d.x, idy = 1. / r.d.y, idz = 1. / r.d.z;
-  while (i >= 0) {
+  st.best = RB_BIG;
+  if (st.s_exit < st.best - RB_TOL) st.best = st.s_exit;
+  st.mode = 1;
+  o.nvis = 0;
+  st.bvh_next = cn.bvh_count > 0 ? cn.bvh_first : -1;
+}
+
+// phase B: threaded-BVH walk over the daughters of the current node; only collects candidates (postponed leaf
+// intersection).  fp32 slab test against padded boxes: one FFMA per plane, FMNMX min/max.
+template <class K> RB_HD inline void nb_collect(const DScene& sc, const RayReg& r, NavStep& st) {
+  StepOut& o = st.o;
+  int i = st.bvh_next;
+  if (st.mode != 1 || i < 0) { st.bvh_next = -1; return; }
+  const float ix = (float)(1. / r.d.x), iy = (float)(1. / r.d.y), iz = (float)(1. / r.d.z);
+  const float ox = -(float)r.p.x * ix, oy = -(float)r.p.y * iy, oz = -(float)r.p.z * iz;
+  const bool px = isfinite(ix) && isfinite(ox), py = isfinite(iy) && isfinite(oy), pz = isfinite(iz) && isfinite(oz);
+  const float fx = (float)r.p.x, fy = (float)r.p.y, fz = (float)r.p.z;
+  const float bestf = st.best > 1e29 ? 3.0e38f : (float)st.best * 1.000001f + 1e-3f;
+  while (i >= 0 && o.nvis < RB_MAXVIS) {
     const DBvh& b = sc.bvh[i];
-    // slab test against [0, best]
-    double t0 = (b.lo[0] - r.p.x) * idx, t1 = (b.hi[0] - r.p.x) * idx;
-    double tmin = rb_min(t0, t1), tmax = rb_max(t0, t1);
-    t0 = (b.lo[1] - r.p.y) * idy; t1 = (b.hi[1] - r.p.y) * idy;
-    tmin = rb_max(tmin, rb_min(t0, t1)); tmax = rb_min(tmax, rb_max(t0, t1));
-    t0 = (b.lo[2] - r.p.z) * idz; t1 = (b.hi[2] - r.p.z) * idz;
-    tmin = rb_max(tmin, rb_min(t0, t1)); tmax = rb_min(tmax, rb_max(t0, t1));
-    bool hit = tmax >= rb_max(tmin, 0.0) && tmin <= best + 2 * RB_TOL;
+    float tmin = 0.f, tmax = bestf;
+    bool hit = true;
+    if (px) { float t0 = fmaf(b.lo[0], ix, ox), t1 = fmaf(b.hi[0], ix, ox); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
+    else hit = hit && fx >= b.lo[0] && fx <= b.hi[0];
+    if (py) { float t0 = fmaf(b.lo[1], iy, oy), t1 = fmaf(b.hi[1], iy, oy); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
+    else hit = hit && fy >= b.lo[1] && fy <= b.hi[1];
+    if (pz) { float t0 = fmaf(b.lo[2], iz, oz), t1 = fmaf(b.hi[2], iz, oz); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
+    else hit = hit && fz >= b.lo[2] && fz <= b.hi[2];
+    hit = hit && tmin <= tmax * 1.000002f + 1e-4f;
     if (!hit) { i = b.skip; continue; }
-    if (b.child >= 0) {
-      const DNode& dn = sc.nodes[b.child];
-      int sel = 0;
-      double s = Csg<DEPTH>::dist_out(sc, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), best + 2 * RB_TOL, sel);
-      // TGeo scans daughters in order and keeps the first one within tolerance: on (near-)ties the
-      // lowest daughter index wins regardless of the BVH visiting order
-      if (s < best - RB_TOL || (enter >= 0 && b.child < enter && s <= best + RB_TOL)) { best = s; enter = b.child; esel = sel; }
-      i = b.skip;
-    } else i = i + 1;
+    if (b.child >= 0) { o.vis[o.nvis++] = b.child; i = b.skip; }
+    else i = i + 1;
   }
-  r.p = along(r.p, r.d, best);
-  o.step = best + extra;
+  st.bvh_next = i;  // >= 0 only if the candidate buffer filled up
+}
+
+// phase C: DistFromOutside of candidate k.  TGeo scans daughters in order and keeps the first one within
+// tolerance: on (near-)ties the lowest daughter index wins regardless of the visiting order.
+template <class K> RB_HD inline void nb_eval(const DScene& sc, const RayReg& r, NavStep& st, int k) {
+  int c = st.o.vis[k];
+  const DNode& dn = sc.nodes[c];
+  int sel = 0;
+  double s = Csg<K::depth, K::shapes>::dist_out(sc, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), st.best + 2 * RB_TOL, sel);
+  if (s < st.best - RB_TOL || (st.enter >= 0 && c < st.enter && s <= st.best + RB_TOL)) { st.best = s; st.enter = c; st.esel = sel; }
+}
+
+// phase D: move to the boundary and locate the node behind it (CrossBoundaryAndLocate)
+template <class K> RB_HD inline void nb_finish(const DScene& sc, RayReg& r, NavStep& st) {
+  if (st.mode != 1) return;
+  StepOut& o = st.o;
+  const DNode& cn = sc.nodes[r.cur];
+  r.p = along(r.p, r.d, st.best);
+  o.step = st.best + st.extra;
   r.on_boundary = 1;
-  if (enter >= 0) {
-    o.crossed = enter;
-    o.sel = esel;
-    o.next = search_node<DEPTH>(sc, enter, along(r.p, r.d, locate_extra(sc, enter, o.step)), -1, false);
-    return o;
+  if (st.enter >= 0) {
+    o.crossed = st.enter;
+    o.sel = st.esel;
+    o.next = search_node<K>(sc, st.enter, along(r.p, r.d, locate_extra(sc, st.enter, o.step)), -1, false);
+    return;
   }
   o.crossed = r.cur;
-  o.sel = sel_exit;
-  if (cn.mother < 0) { o.next = -1; return o; }
-  o.next = search_node<DEPTH>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
-  return o;
+  o.sel = st.sel_exit;
+  if (cn.mother < 0) { o.next = -1; return; }
+  o.next = search_node<K>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
+}
+
+// the phases run back to back for one thread (per-ray loop kernel, host emulation)
+template <class K> RB_HD inline void next_boundary(const DScene& sc, RayReg& r, bool push_quirk, NavStep& st) {
+  nb_begin<K>(sc, r, push_quirk, st);
+  bool overflow = false;
+  while (st.mode == 1 && st.bvh_next >= 0) {
+    if (st.o.nvis >= RB_MAXVIS) { st.o.nvis = 0; overflow = true; }  // more than RB_MAXVIS candidates: process in batches
+    int first = st.o.nvis;
+    nb_collect<K>(sc, r, st);
+    for (int k = first; k < st.o.nvis; k++) nb_eval<K>(sc, r, st, k);
+  }
+  if (overflow) st.o.nvis = -1;  // the visited list is incomplete: relocate_back must not rely on it
+  nb_finish<K>(sc, r, st);
 }
 
 // ================================================================== physics
@@ -1405,18 +1494,20 @@ struct Hit {       // context of one boundary interaction
   int cur_vol, next_vol, next_node, border;
   int crossed, sel;
   double step;
+  const StepOut* so;
 };
 
-template <int DEPTH> RB_HD inline V3 geometric_normal(const DScene& sc, const RayReg& r, const Hit& h, V3 dir) {
+template <class K> RB_HD inline V3 geometric_normal(const DScene& sc, const RayReg& r, const Hit& h, V3 dir) {
   if (h.crossed < 0) return v3(0, 0, 1);
   const DNode& nd = sc.nodes[h.crossed];
-  V3 ln = Csg<DEPTH>::normal(sc, nd.shape, to_local(nd.g, r.p), to_local_vec(nd.g, dir), h.sel);
+  V3 ln = Csg<K::depth, K::shapes>::normal(sc, nd.shape, to_local(nd.g, r.p), to_local_vec(nd.g, dir), h.sel);
   return to_master_vec(nd.g, ln);
 }
 
 // AOpticsManager::GetFacetNormal — geometric normal, optionally perturbed by Gaussian micro-facets
-template <int DEPTH> RB_HD inline V3 facet_normal(const DScene& sc, const RayReg& r, const Hit& h, Philox& g) {
-  V3 n = geometric_normal<DEPTH>(sc, r, h, r.d);
+template <class K> RB_HD inline V3 facet_normal(const DScene& sc, const RayReg& r, const Hit& h, Philox& g) {
+  V3 n = geometric_normal<K>(sc, r, h, r.d);
+  if constexpr ((K::phys & RB_PH_ROUGH) == 0) return n;
   if (h.border < 0) return n;
   const rbg_border& c = sc.borders[h.border];
   if (c.lambertian || c.sigma == 0) return n;
@@ -1462,25 +1553,66 @@ RB_HD inline void set_direction(RayReg& r, V3 d2) {
   if (mag > 0) r.d = (1. / mag) * d2;
 }
 
+// Navigator state after DoReflection's backward Step(): TGeoNavigator::FindNode() from the entered node at
+// `back` = boundary - 2e-6 d1.  Common case (a daughter of the start node was entered): `back` lies on the ray
+// just before the boundary, so any sibling containing it had its AABB touched by this step's traversal and is in
+// so.vis — no second BVH walk is needed.  Everything else takes the generic SearchNode path.
+template <class K> RB_HD inline int relocate_back(const DScene& sc, const Hit& h, V3 back) {
+  const StepOut& so = *h.so;
+  typedef Csg<K::depth, K::shapes> G;
+  if (so.nvis >= 0 && so.from >= 0 && so.next >= 0 && so.next == so.crossed && sc.nodes[so.next].mother == so.from && so.step > 4e-6) {
+    const DNode& en = sc.nodes[so.next];
+    if (G::contains(sc, en.shape, to_local(en.g, back))) return search_node<K>(sc, so.next, back, -1, false);
+    const DNode& fn = sc.nodes[so.from];
+    if (G::contains(sc, fn.shape, to_local(fn.g, back))) {
+      int best = -1;
+      for (int k = 0; k < so.nvis; k++) {
+        int c = so.vis[k];
+        if (c == so.next || (best >= 0 && c > best)) continue;
+        const DNode& cn = sc.nodes[c];
+        if (G::contains(sc, cn.shape, to_local(cn.g, back))) best = c;
+      }
+      return best < 0 ? so.from : search_node<K>(sc, best, back, -1, false);
+    }
+  }
+  return search_node<K>(sc, h.next_node < 0 ? 0 : h.next_node, back, -1, true);
+}
+
 // AOpticsManager::DoReflection.  `pos` is the boundary point; r.p still holds the segment start.
-template <int DEPTH> RB_HD inline void do_reflection(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1,
+template <class K> RB_HD inline void do_reflection(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1,
                                                     Philox& g, const V3* normal_in) {
   RayReg at = r;
   at.p = pos;
-  V3 n = normal_in ? *normal_in : facet_normal<DEPTH>(sc, at, h, g);
+  V3 n = normal_in ? *normal_in : facet_normal<K>(sc, at, h, g);
   V3 d1 = r.d;
   double cos1 = dot(d1, n);
   bool absorbed = false;
   int next_type = h.next_vol < 0 ? RBG_NULL : sc.volumes[h.next_vol].type;
   const rbg_border* c = h.border >= 0 ? &sc.borders[h.border] : nullptr;
   if (next_type == RBG_MIRROR) {
-    double angle = rb_acos(cos1), ref, tr;
-    if (c && c->multilayer >= 0) tmm_mixed(sc, c->multilayer, angle, r.lambda, ref, tr);
-    else ref = mirror_reflectance(sc, h.next_vol, r.lambda, angle);
-    if (ref < rng_uniform(g)) { absorbed = true; r.status = RBG_ABSORB; }
+    double ref = 1.0;
+    bool have = false;
+    if constexpr ((K::phys & RB_PH_MULTILAYER) != 0) {
+      if (c && c->multilayer >= 0) {
+        double tr;
+        tmm_mixed(sc, c->multilayer, rb_acos(cos1), r.lambda, ref, tr);
+        have = true;
+      }
+    }
+    if (!have) {
+      if constexpr ((K::phys & RB_PH_MIRROR_TABLE) != 0) ref = mirror_reflectance(sc, h.next_vol, r.lambda, rb_acos(cos1));
+      else {
+        int mi = sc.volumes[h.next_vol].mirror;
+        ref = mi >= 0 ? sc.mirrors[mi].constant : 1.0;
+        ref = ref > 1 ? 1 : (ref < 0 ? 0 : ref);
+      }
+    }
+    if (ref < rng_uniform(g)) { absorbed = true; r.status = RBG_ABSORB; }  // the reference always draws here
   }
   V3 d2;
-  if (c && c->lambertian) {
+  bool lamb = false;
+  if constexpr ((K::phys & RB_PH_LAMBERT) != 0) lamb = c && c->lambertian;
+  if (lamb) {
     double y = 0.5 * rng_uniform(g), theta = rb_asin(sqrt(2 * y)), phi = 2 * RB_PI * rng_uniform(g);
     double perp = sqrt(n.x * n.x + n.y * n.y);
     double theta_n = (n.x == 0 && n.y == 0 && n.z == 0 ? 0 : atan2(perp, n.z)) * 180. / RB_PI;
@@ -1494,7 +1626,7 @@ template <int DEPTH> RB_HD inline void do_reflection(const DScene& sc, const DTr
   double t = r.t + h.step / (RB_C_CM / n1);
   // nav->Step() backwards by 1e-6 (+1e-6 of ROOT's Step) and relocate; the recorded vertex is the stepped-back point
   V3 back = along(pos, d1, -2e-6);
-  loc = search_node<DEPTH>(sc, h.next_node < 0 ? 0 : h.next_node, back, -1, true);
+  loc = relocate_back<K>(sc, h, back);
   if (tp.quirks & RBG_QUIRK_STEPBACK) pos = back;
   add_point(r, pos, t);
   r.last_node = h.next_node;
@@ -1502,25 +1634,27 @@ template <int DEPTH> RB_HD inline void do_reflection(const DScene& sc, const DTr
 }
 
 // AOpticsManager::DoFresnel
-template <int DEPTH> RB_HD inline void do_fresnel(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1, double n2,
+template <class K> RB_HD inline void do_fresnel(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1, double n2,
                                                  double k2, Philox& g) {
   RayReg at = r;
   at.p = pos;
-  V3 n = facet_normal<DEPTH>(sc, at, h, g);
+  V3 n = facet_normal<K>(sc, at, h, g);
   V3 d1 = r.d;
   double cos1 = dot(d1, n), sin1 = sqrt(1 - cos1 * cos1), sin2 = n1 * sin1 / n2, cos2 = sqrt(1 - sin2 * sin2);
   bool absorbed = false, decided = false;
   const rbg_border* c = h.border >= 0 ? &sc.borders[h.border] : nullptr;
-  if (c && c->multilayer >= 0) {
-    double R, T;
-    tmm_mixed(sc, c->multilayer, rb_acos(cos1), r.lambda, R, T);
-    double rnd = rng_uniform(g);
-    if (rnd < R) { do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
-    decided = true;
-    if (!(rnd < R + T)) absorbed = true;
+  if constexpr ((K::phys & RB_PH_MULTILAYER) != 0) {
+    if (c && c->multilayer >= 0) {
+      double R, T;
+      tmm_mixed(sc, c->multilayer, rb_acos(cos1), r.lambda, R, T);
+      double rnd = rng_uniform(g);
+      if (rnd < R) { do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+      decided = true;
+      if (!(rnd < R + T)) absorbed = true;
+    }
   }
   if (!decided) {
-    if (sin2 > 1.) { do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+    if (sin2 > 1.) { do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
     if (!tp.disable_fresnel) {
       double Rs, Rp;
       if (k2 <= 0.) {
@@ -1537,7 +1671,7 @@ template <int DEPTH> RB_HD inline void do_fresnel(const DScene& sc, const DTrace
         Rs = (sqr(x1S - x2S) + sqr(y2S)) / (sqr(x1S + x2S) + sqr(y2S));
         Rp = (sqr(x1P - x2P) + sqr(y2P)) / (sqr(x1P + x2P) + sqr(y2P));
       }
-      if (rng_uniform(g) < (Rs + Rp) / 2.) { do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+      if (rng_uniform(g) < (Rs + Rp) / 2.) { do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
     }
   }
   V3 d2 = d1;
@@ -1552,14 +1686,13 @@ template <int DEPTH> RB_HD inline void do_fresnel(const DScene& sc, const DTrace
 }
 
 // One iteration of the while(ray->IsRunning()) loop, src/AOpticsManager.cxx:359-518
-template <int DEPTH> RB_HD inline void trace_step(const DScene& sc, const DTraceParams& tp, RayReg& r, Philox& g) {
+// (the interaction / termination half; `nav` is the navigator copy whose point sits on the boundary, `so` the step record)
+template <class K> RB_HD inline void trace_shade(const DScene& sc, const DTraceParams& tp, RayReg& r, const RayReg& nav, const StepOut& so, Philox& g) {
   V3 x1 = r.p;
   double t1 = r.t;
   int cur = r.cur;
   int cur_vol = cur < 0 ? -1 : sc.nodes[cur].volume;
   int typeCurrent = cur < 0 ? RBG_NULL : sc.nodes[cur].type;
-  RayReg nav = r;  // navigator copy: nav.p advances to the boundary, r.p stays at the segment start
-  StepOut so = next_boundary<DEPTH>(sc, nav, (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0);
   r.on_boundary = nav.on_boundary;
   Hit h;
   h.cur_vol = cur_vol;
@@ -1568,12 +1701,14 @@ template <int DEPTH> RB_HD inline void trace_step(const DScene& sc, const DTrace
   h.crossed = so.crossed;
   h.sel = so.sel;
   h.step = so.step;
+  h.so = &so;
   h.border = find_border(sc, cur_vol, h.next_vol);
   int typeNext = so.next < 0 ? RBG_NULL : sc.nodes[so.next].type;
   V3 pos = nav.p;
   int loc = so.next;
   double lambda = r.lambda;
-  if (typeCurrent == RBG_LENS) {
+  constexpr bool kLens = (K::phys & RB_PH_LENS) != 0;  // without ALens volumes every lens branch is dead code
+  if (kLens && typeCurrent == RBG_LENS) {
     double k = index_k(sc, sc.volumes[cur_vol].index, lambda);
     if (k > 0) {
       double abs = lambda / (4 * RB_PI * k);
@@ -1591,25 +1726,29 @@ template <int DEPTH> RB_HD inline void trace_step(const DScene& sc, const DTrace
     }
   }
   bool curVac = typeCurrent == RBG_NULL || typeCurrent == RBG_OPT || typeCurrent == RBG_OTHER;
-  bool curLens = typeCurrent == RBG_LENS;
+  bool curLens = kLens && typeCurrent == RBG_LENS;
   if ((curVac || curLens) && typeNext == RBG_MIRROR) {
-    double n1 = curLens ? index_n(sc, sc.volumes[cur_vol].index, lambda) : 1.;
-    do_reflection<DEPTH>(sc, tp, r, pos, loc, h, n1, g, nullptr);
-  } else if (curVac && typeNext == RBG_LENS) {
-    int ix = sc.volumes[h.next_vol].index;
-    do_fresnel<DEPTH>(sc, tp, r, pos, loc, h, 1., index_n(sc, ix, lambda), index_k(sc, ix, lambda), g);
+    double n1 = 1.;
+    if constexpr (kLens) n1 = curLens ? index_n(sc, sc.volumes[cur_vol].index, lambda) : 1.;
+    do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, nullptr);
   } else if ((curVac || curLens) && (typeNext == RBG_OBS || typeNext == RBG_FOCUS)) {
-    double speed = curLens ? RB_C_CM / index_n(sc, sc.volumes[cur_vol].index, lambda) : RB_C_CM;
+    double speed = RB_C_CM;
+    if constexpr (kLens) speed = curLens ? RB_C_CM / index_n(sc, sc.volumes[cur_vol].index, lambda) : RB_C_CM;
     add_point(r, pos, t1 + so.step / speed);
     r.last_node = so.next;
   } else if (curVac && (typeNext == RBG_OTHER || typeNext == RBG_OPT)) {
     add_point(r, pos, t1 + so.step / RB_C_CM);
     r.last_node = so.next;
-  } else if (curLens && typeNext == RBG_LENS) {
-    int i1 = sc.volumes[cur_vol].index, i2 = sc.volumes[h.next_vol].index;
-    do_fresnel<DEPTH>(sc, tp, r, pos, loc, h, index_n(sc, i1, lambda), index_n(sc, i2, lambda), index_k(sc, i2, lambda), g);
-  } else if (curLens && (typeNext == RBG_NULL || typeNext == RBG_OPT || typeNext == RBG_OTHER)) {
-    do_fresnel<DEPTH>(sc, tp, r, pos, loc, h, index_n(sc, sc.volumes[cur_vol].index, lambda), 1., 0., g);
+  } else if constexpr (kLens) {
+    if (curVac && typeNext == RBG_LENS) {
+      int ix = sc.volumes[h.next_vol].index;
+      do_fresnel<K>(sc, tp, r, pos, loc, h, 1., index_n(sc, ix, lambda), index_k(sc, ix, lambda), g);
+    } else if (curLens && typeNext == RBG_LENS) {
+      int i1 = sc.volumes[cur_vol].index, i2 = sc.volumes[h.next_vol].index;
+      do_fresnel<K>(sc, tp, r, pos, loc, h, index_n(sc, i1, lambda), index_n(sc, i2, lambda), index_k(sc, i2, lambda), g);
+    } else if (curLens && (typeNext == RBG_NULL || typeNext == RBG_OPT || typeNext == RBG_OTHER)) {
+      do_fresnel<K>(sc, tp, r, pos, loc, h, index_n(sc, sc.volumes[cur_vol].index, lambda), 1., 0., g);
+    }
   }
   // termination (evaluated after the interaction, src/AOpticsManager.cxx:485-513)
   if (typeNext == RBG_NULL) {
@@ -1621,13 +1760,13 @@ template <int DEPTH> RB_HD inline void trace_step(const DScene& sc, const DTrace
   } else if (typeNext == RBG_FOCUS) {
     const rbg_volume& fv = sc.volumes[h.next_vol];
     double qe = 1.;
-    if (fv.focal >= 0) {
+    if constexpr ((K::phys & RB_PH_QE) != 0) if (fv.focal >= 0) {
       const rbg_focal f = sc.focals[fv.focal];
       double angle = 0.;
       if (f.qe_angle >= 0) {
         RayReg at = r;
         at.p = pos;
-        V3 n = facet_normal<DEPTH>(sc, at, h, g);
+        V3 n = facet_normal<K>(sc, at, h, g);
         angle = rb_acos(dot(r.d, n));
       }
       if (f.qe_lambda >= 0) qe = graph_eval(sc, f.qe_lambda, lambda);
@@ -1640,7 +1779,14 @@ template <int DEPTH> RB_HD inline void trace_step(const DScene& sc, const DTrace
   if (r.status == RBG_RUN && r.npoints >= tp.limit) r.status = RBG_SUSPEND;
 }
 
+template <class K> RB_HD inline void trace_step(const DScene& sc, const DTraceParams& tp, RayReg& r, Philox& g) {
+  RayReg nav = r;  // navigator copy: nav.p advances to the boundary, r.p stays at the segment start
+  NavStep st;
+  next_boundary<K>(sc, nav, (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0, st);
+  trace_shade<K>(sc, tp, r, nav, st.o, g);
+}
+
 // locate the start point (InitTrack -> FindNode)
-template <int DEPTH> RB_HD inline int locate_start(const DScene& sc, V3 p) { return search_node<DEPTH>(sc, 0, p, -1, true); }
+template <class K> RB_HD inline int locate_start(const DScene& sc, V3 p) { return search_node<K>(sc, 0, p, -1, true); }
 
 #endif  // RB_DEVICE_CUH

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <stdexcept>
@@ -23,7 +24,7 @@
 #include <vector>
 
 #include "rb_build.h"
-#include "rb_trace_kernel.cuh"
+#include "rb_variants.h"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -271,6 +272,7 @@ __global__ void k_tmm(DScene sc, int ml, long long n, const double* __restrict__
 struct rbg_scene {
   int device = 0;
   int depth = 0;
+  const rb_variant* variant = nullptr;
   DScene d;
   std::vector<void*> allocs;
   std::vector<std::string> node_names;
@@ -312,18 +314,29 @@ static void scene_free(rbg_scene* s) {
 }
 
 // ------------------------------------------------------------------------------------------------ host: trace driver
-static void launch_trace(int depth, const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init, int keep,
-                         cudaStream_t st) {
+static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys) {
+  const char* force = getenv("RB_FORCE_GENERIC");
+  const rb_variant* best = nullptr;
+  int best_cost = 1 << 30;
+  if (const char* want = getenv("RB_VARIANT"))  // experiments: force a named (compatible) instantiation
+    for (const rb_variant* v : rb_variants)
+      if (!strcmp(v->name, want) && v->depth >= depth && !(shapes & ~v->shapes) && !(phys & ~v->phys)) return v;
+  for (const rb_variant* v : rb_variants) {
+    if (v->depth < depth || (shapes & ~v->shapes) || (phys & ~v->phys)) continue;
+    if (force && force[0] == '1' && v->shapes != RB_SHAPES_ALL) continue;
+    int cost = __builtin_popcount(v->shapes) + __builtin_popcount(v->phys) + 4 * (v->depth - depth);
+    if (cost < best_cost) { best_cost = cost; best = v; }
+  }
+  if (!best) throw NotSupported("boolean composite nesting deeper than 3 is not supported");
+  return best;
+}
+static void launch_trace(const rb_variant* v, const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init,
+                         int keep, cudaStream_t st) {
   if (n <= 0) return;
   ProfScope ps(st, 0);
-  int rc;
-  switch (depth) {
-    case 0: rc = rb_launch_trace_d0(sc, tp, R, live, n, init, keep, st); break;
-    case 1: rc = rb_launch_trace_d1(sc, tp, R, live, n, init, keep, st); break;
-    case 2: rc = rb_launch_trace_d2(sc, tp, R, live, n, init, keep, st); break;
-    case 3: rc = rb_launch_trace_d3(sc, tp, R, live, n, init, keep, st); break;
-    default: throw NotSupported("boolean composite nesting deeper than 3 is not supported");
-  }
+  static const bool no_lockstep = getenv("RB_NO_LOCKSTEP") != nullptr;
+  // wavefront launches of exactly one boundary step use the block-lock-step kernel
+  int rc = (tp.max_steps == 1 && keep && !no_lockstep) ? v->launch_step(sc, tp, R, live, n, init, keep, st) : v->launch(sc, tp, R, live, n, init, keep, st);
   g_launches++;
   if (rc != 0) throw std::runtime_error(std::string("cuda: k_trace launch: ") + cudaGetErrorString((cudaError_t)rc));
 }
@@ -346,13 +359,15 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   tp.limit = o->limit > 0 ? o->limit : 100;
   tp.disable_fresnel = o->disable_fresnel;
   tp.quirks = o->quirks;
-  tp.max_steps = o->steps_per_launch;
+  // steps_per_launch: > 0 as given; 0 = auto (wavefront with one boundary step per bounce kernel for large
+  // batches, where compaction pays for itself; a single launch for small ones); < 0 = single launch
+  tp.max_steps = o->steps_per_launch > 0 ? o->steps_per_launch : (o->steps_per_launch == 0 && n >= 262144 ? 1 : 0);
   tp.seed = o->seed;
   tp.ray_id_offset = id_offset;
   if (tp.max_steps <= 0) {  // one launch, every ray runs to its terminal status in registers
     R.cur = nullptr;
     R.ndraw = nullptr;
-    launch_trace(s->depth, s->d, tp, R, nullptr, n, 1, 0, st);
+    launch_trace(s->variant, s->d, tp, R, nullptr, n, 1, 0, st);
     return;
   }
   // wavefront: bounce kernel -> compaction of survivors -> next bounce
@@ -371,7 +386,7 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   int init = 1;
   for (int iter = 0; nlive > 0; iter++) {
     if (iter > 100000) throw std::runtime_error("wavefront did not terminate");
-    launch_trace(s->depth, s->d, tp, R, live, nlive, init, 1, st);
+    launch_trace(s->variant, s->d, tp, R, live, nlive, init, 1, st);
     init = 0;
     int tiles = (int)((nlive + CP_TILE - 1) / CP_TILE);
     CK(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
@@ -395,6 +410,7 @@ static size_t wavefront_scratch_bytes(long long n) {
 }
 
 // ================================================================================================ C ABI
+#pragma GCC visibility push(default)
 extern "C" {
 
 int rbg_abi_version(void) { return RBG_ABI_VERSION; }
@@ -452,6 +468,9 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     s = new rbg_scene;
     s->device = device;
     s->depth = depth;
+    unsigned need_shapes = 0, need_phys = 0;
+    scene_features_needed(D, need_shapes, need_phys);
+    s->variant = pick_variant(depth, need_shapes, need_phys);
     s->node_names = B.names;
     memset(&s->d, 0, sizeof(s->d));
     s->d.nodes = upload(s, B.nodes);
@@ -490,6 +509,7 @@ int rbg_scene_destroy(rbg_scene* s) {
   return guard([&] { scene_free(s); });
 }
 int rbg_scene_num_nodes(const rbg_scene* s) { return s ? (int)s->node_names.size() : 0; }
+const char* rbg_scene_kernel_variant(const rbg_scene* s) { return s && s->variant ? s->variant->name : ""; }
 const char* rbg_scene_node_name(const rbg_scene* s, int node) {
   if (!s || node < 0 || node >= (int)s->node_names.size()) return "";
   return s->node_names[node].c_str();
@@ -511,7 +531,7 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
       R.ox = rays->ox; R.oy = rays->oy; R.oz = rays->oz; R.ot = rays->ot; R.odx = rays->odx; R.ody = rays->ody; R.odz = rays->odz;
       R.status = rays->status; R.last_node = rays->last_node; R.npoints = rays->npoints;
       R.cur = nullptr; R.ndraw = nullptr;
-      if (o->steps_per_launch > 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
+      if (o->steps_per_launch >= 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
       trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count);
       return;
     }
@@ -519,7 +539,7 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
     const long long CH = 1 << 22;
     long long chunk = std::min<long long>(rays->n, CH);
     size_t per_ray = 8 * 8 + 7 * 8 + 3 * 4;  // in + out
-    size_t bytes = (size_t)chunk * per_ray + 4096 + (o->steps_per_launch > 0 ? wavefront_scratch_bytes(chunk) : 0);
+    size_t bytes = (size_t)chunk * per_ray + 4096 + (o->steps_per_launch >= 0 ? wavefront_scratch_bytes(chunk) : 0);
     int nst = rays->n > chunk ? 3 : 1;
     for (int k = 0; k < nst; k++) {
       if (!s->streams[k]) CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
@@ -643,3 +663,4 @@ int rbg_tmm_host(rbg_scene* s, int ml, int64_t n, const double* theta, const dou
 }
 
 }  // extern "C"
+#pragma GCC visibility pop

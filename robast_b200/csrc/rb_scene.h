@@ -37,8 +37,8 @@ struct DNode {
   int32_t pad;
 };
 
-struct DBvh {
-  double lo[3], hi[3];
+struct DBvh {   // 32 B; boxes are fp32, rounded outwards and padded, traversal is fp32-conservative
+  float lo[3], hi[3];
   int32_t child;     // >= 0: leaf holding this physical node id; -1: internal
   int32_t skip;      // absolute index of the next BVH entry when this subtree is done/missed (-1 = end)
 };

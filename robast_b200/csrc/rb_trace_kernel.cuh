@@ -16,13 +16,7 @@ struct DRays {
 
 #define TRACE_THREADS 128
 
-template <int DEPTH>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, DTraceParams tp, DRays R, const int32_t* __restrict__ live, long long n, int init,
-                                                        int keep_state) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  long long idx = live ? (long long)live[i] : i;
-  RayReg r;
+template <class K> __device__ inline void load_ray(const DScene& sc, const DTraceParams& tp, const DRays& R, long long idx, int init, RayReg& r, Philox& g) {
   r.lambda = R.lambda[idx];
   if (init) {
     r.p = v3(R.x[idx], R.y[idx], R.z[idx]);
@@ -35,7 +29,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, DTraceParams
     r.last_node = -1;
     r.ndraw = 0;
     r.on_boundary = 0;
-    r.cur = locate_start<DEPTH>(sc, r.p);
+    r.cur = locate_start<K>(sc, r.p);
   } else {
     r.p = v3(R.ox[idx], R.oy[idx], R.oz[idx]);
     r.t = R.ot[idx];
@@ -49,17 +43,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, DTraceParams
     r.cur = R.cur[idx];
   }
   unsigned long long id = tp.ray_id_offset + (unsigned long long)idx;
-  Philox g;
   g.k0 = (uint32_t)tp.seed;
   g.k1 = (uint32_t)(tp.seed >> 32);
   g.id0 = (uint32_t)id;
   g.id1 = (uint32_t)(id >> 32);
   g.ndraw = r.ndraw;
-  int steps = 0;
-  while (r.status == RBG_RUN && (tp.max_steps <= 0 || steps < tp.max_steps)) {
-    trace_step<DEPTH>(sc, tp, r, g);
-    steps++;
-  }
+}
+__device__ inline void store_ray(const DRays& R, long long idx, const RayReg& r, const Philox& g, int keep_state) {
   R.ox[idx] = r.p.x; R.oy[idx] = r.p.y; R.oz[idx] = r.p.z; R.ot[idx] = r.t;
   R.odx[idx] = r.d.x; R.ody[idx] = r.d.y; R.odz[idx] = r.d.z;
   R.status[idx] = r.status;
@@ -71,19 +61,96 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, DTraceParams
   }
 }
 
-
-// returns the cudaGetLastError() code of the launch
-#define RB_DECLARE_TRACE_LAUNCH(N)                                                                                                 \
-  int rb_launch_trace_d##N(const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init, \
-                           int keep, cudaStream_t st)
-RB_DECLARE_TRACE_LAUNCH(0);
-RB_DECLARE_TRACE_LAUNCH(1);
-RB_DECLARE_TRACE_LAUNCH(2);
-RB_DECLARE_TRACE_LAUNCH(3);
-#define RB_DEFINE_TRACE_LAUNCH(N)                                                                        \
-  RB_DECLARE_TRACE_LAUNCH(N) {                                                                           \
-    long long blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;                                          \
-    k_trace<N><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(sc, tp, R, live, n, init, keep);              \
-    return (int)cudaGetLastError();                                                                      \
+// ---- per-ray loop kernel: `max_steps` boundary steps per launch (<= 0: until the ray terminates)
+template <class K>
+__global__ void __launch_bounds__(TRACE_THREADS, K::min_blocks) k_trace(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
+                                                                        const __grid_constant__ DRays R, const int32_t* __restrict__ live, long long n,
+                                                                        int init, int keep_state) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long idx = live ? (long long)live[i] : i;
+  RayReg r;
+  Philox g;
+  load_ray<K>(sc, tp, R, idx, init, r, g);
+  int steps = 0;
+  while (r.status == RBG_RUN && (tp.max_steps <= 0 || steps < tp.max_steps)) {
+    trace_step<K>(sc, tp, r, g);
+    steps++;
   }
+  store_ray(R, idx, r, g, keep_state);
+}
+
+// ---- wavefront bounce kernel: exactly one boundary step per live ray, executed in block-wide lock step.
+// The phases of the step (DistFromInside / BVH walk / candidate DistFromOutside / relocation / interaction) are
+// separated by barriers so that all warps of a block run the same code region at the same time: the per-SM
+// instruction cache is then shared instead of thrashed (profiles/r1d: icc hit rate 58 %, L1.5 saturated by
+// instruction requests without this).  Idle lanes of the last block shadow the last ray and store nothing.
+template <class K>
+__global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
+                                                                              const __grid_constant__ DRays R, const int32_t* __restrict__ live,
+                                                                              long long n, int init) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  long long idx = live ? (long long)live[i] : i;
+  RayReg r;
+  Philox g;
+  load_ray<K>(sc, tp, R, idx, init, r, g);
+  __syncthreads();
+  const bool run = r.status == RBG_RUN;
+  const bool push = (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0;
+  RayReg nav = r;
+  NavStep st;
+  st.mode = 0;
+  st.bvh_next = -1;
+  st.o.nvis = -1;
+  if (run) nb_begin<K>(sc, nav, push, st);
+  bool overflow = false;
+  while (true) {
+    const bool want = run && st.mode == 1 && st.bvh_next >= 0;
+    if (!__syncthreads_or(want)) break;
+    int first = 0;
+    if (want) {
+      if (st.o.nvis >= RB_MAXVIS) { st.o.nvis = 0; overflow = true; }
+      first = st.o.nvis;
+      nb_collect<K>(sc, nav, st);
+    }
+    for (int k = 0;; k++) {
+      const bool more = want && first + k < st.o.nvis;
+      if (!__syncthreads_or(more)) break;
+      if (more) nb_eval<K>(sc, nav, st, first + k);
+    }
+  }
+  if (overflow) st.o.nvis = -1;
+  if (run) nb_finish<K>(sc, nav, st);
+  __syncthreads();
+  if (run) trace_shade<K>(sc, tp, r, nav, st.o, g);
+  if (active) store_ray(R, idx, r, g, 1);
+}
+
+// Launch entry points per compiled variant (each variant in its own translation unit so they build in parallel).
+typedef int (*rb_launch_fn)(const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init, int keep,
+                            cudaStream_t st);
+struct rb_variant {
+  const char* name;
+  int depth;
+  unsigned shapes, phys;
+  rb_launch_fn launch;       // k_trace: per-ray loop
+  rb_launch_fn launch_step;  // k_step : one lock-step boundary step (wavefront)
+};
+#define RB_DEFINE_TRACE_VARIANT(NAME, D, S, P, MB, STH, SMB)                                                                          \
+  typedef TraceCfg<D, S, P, MB, STH, SMB> rb_cfg_##NAME;                                                                              \
+  int rb_launch_trace_##NAME(const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init,   \
+                             int keep, cudaStream_t st) {                                                                            \
+    long long blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;                                                                      \
+    k_trace<rb_cfg_##NAME><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(sc, tp, R, live, n, init, keep);                              \
+    return (int)cudaGetLastError();                                                                                                  \
+  }                                                                                                                                  \
+  int rb_launch_step_##NAME(const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init,    \
+                            int, cudaStream_t st) {                                                                                  \
+    long long blocks = (n + STH - 1) / STH;                                                                                          \
+    k_step<rb_cfg_##NAME><<<(unsigned)blocks, STH, 0, st>>>(sc, tp, R, live, n, init);                                               \
+    return (int)cudaGetLastError();                                                                                                  \
+  }                                                                                                                                  \
+  extern const rb_variant rb_variant_##NAME = {#NAME, D, S, P, rb_launch_trace_##NAME, rb_launch_step_##NAME};
 #endif

@@ -9,7 +9,7 @@
 #include "../../robast_b200/csrc/rb_device.cuh"
 
 namespace {
-template <int DEPTH> void run(const DScene& sc, const DTraceParams& tp, const rbg_rays* R) {
+template <class K> void run(const DScene& sc, const DTraceParams& tp, const rbg_rays* R) {
   for (long long idx = 0; idx < R->n; idx++) {
     RayReg r;
     r.lambda = R->lambda[idx];
@@ -19,11 +19,11 @@ template <int DEPTH> void run(const DScene& sc, const DTraceParams& tp, const rb
     double mag = sqrt(dot(d, d));
     r.d = mag > 0 ? (1. / mag) * d : d;
     r.status = RBG_RUN; r.npoints = 1; r.last_node = -1; r.ndraw = 0; r.on_boundary = 0;
-    r.cur = locate_start<DEPTH>(sc, r.p);
+    r.cur = locate_start<K>(sc, r.p);
     unsigned long long id = tp.ray_id_offset + (unsigned long long)idx;
     Philox g;
     g.k0 = (uint32_t)tp.seed; g.k1 = (uint32_t)(tp.seed >> 32); g.id0 = (uint32_t)id; g.id1 = (uint32_t)(id >> 32); g.ndraw = 0;
-    while (r.status == RBG_RUN) trace_step<DEPTH>(sc, tp, r, g);
+    while (r.status == RBG_RUN) trace_step<K>(sc, tp, r, g);
     R->ox[idx] = r.p.x; R->oy[idx] = r.p.y; R->oz[idx] = r.p.z; R->ot[idx] = r.t;
     R->odx[idx] = r.d.x; R->ody[idx] = r.d.y; R->odz[idx] = r.d.z;
     R->status[idx] = r.status; R->last_node[idx] = r.last_node; R->npoints[idx] = r.npoints;
@@ -31,7 +31,7 @@ template <int DEPTH> void run(const DScene& sc, const DTraceParams& tp, const rb
 }
 }  // namespace
 
-extern "C" int emul_trace(const rbg_scene_desc* D, const rbg_trace_opts* o, const rbg_rays* R, int /*nthreads*/) {
+extern "C" __attribute__((visibility("default"))) int emul_trace(const rbg_scene_desc* D, const rbg_trace_opts* o, const rbg_rays* R, int /*nthreads*/) {
   try {
     validate_desc(D);
     SceneBuilder B;
@@ -49,10 +49,10 @@ extern "C" int emul_trace(const rbg_scene_desc* D, const rbg_trace_opts* o, cons
     tp.limit = o->limit > 0 ? o->limit : 100; tp.disable_fresnel = o->disable_fresnel; tp.quirks = o->quirks; tp.max_steps = 0;
     tp.seed = o->seed; tp.ray_id_offset = o->ray_id_offset;
     switch (scene_depth_needed(B)) {
-      case 0: run<0>(sc, tp, R); break;
-      case 1: run<1>(sc, tp, R); break;
-      case 2: run<2>(sc, tp, R); break;
-      case 3: run<3>(sc, tp, R); break;
+      case 0: run<TraceCfg<0, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
+      case 1: run<TraceCfg<1, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
+      case 2: run<TraceCfg<2, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
+      case 3: run<TraceCfg<3, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
       default: return RBG_ENOTSUP;
     }
     return RBG_OK;
@@ -61,7 +61,7 @@ extern "C" int emul_trace(const rbg_scene_desc* D, const rbg_trace_opts* o, cons
     return RBG_EINTERNAL;
   }
 }
-extern "C" int emul_tmm(const rbg_scene_desc* D, int ml, int pol, double th, double lam, double* R, double* T) {
+extern "C" __attribute__((visibility("default"))) int emul_tmm(const rbg_scene_desc* D, int ml, int pol, double th, double lam, double* R, double* T) {
   DScene sc;
   memset(&sc, 0, sizeof(sc));
   sc.graphs = D->graphs; sc.gx = D->gx; sc.gy = D->gy; sc.th2 = D->th2; sc.th2v = D->th2v; sc.indices = D->indices;

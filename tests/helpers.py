@@ -49,7 +49,7 @@ def load_oracle():
 def load_emul():
     srcs = [os.path.join(ROOT_DIR, "tests", "emul", "emul.cpp")] + [os.path.join(ROOT_DIR, "robast_b200", "csrc", f)
                                                                     for f in ("rb_device.cuh", "rb_build.h", "rb_scene.h")]
-    _build(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", EMUL_SO, "tests/emul/emul.cpp"], EMUL_SO, srcs)
+    _build(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", EMUL_SO, "tests/emul/emul.cpp"], EMUL_SO, srcs)
     import robast_b200 as R
     lib = C.CDLL(EMUL_SO)
     lib.emul_trace.restype = C.c_int
