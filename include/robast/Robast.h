@@ -698,7 +698,7 @@ class ARay : public TObject {
   void GetLastPoint(Double_t* x) const { memcpy(x, fLast, sizeof(fLast)); }
   const Double_t* GetFirstPoint() const { return fFirst; }
   const Double_t* GetLastPoint() const { return fLast; }
-  const Double_t* GetPoint(Int_t i) const { return i == 0 ? fFirst : (i == fNpoints - 1 ? fLast : nullptr); }
+  const Double_t* GetPoint(Int_t i) const { return i == fNpoints - 1 ? fLast : fFirst; }  // intermediate vertices are not kept
   Int_t GetNpoints() const { return fNpoints; }
   Double_t GetLambda() const { return fLambda; }
   void SetLambda(Double_t l) { fLambda = l; }
@@ -716,6 +716,8 @@ class ARay : public TObject {
   TObject* FindNodeStartWith(const char* name) const {
     return (fNodeHistory.GetEntries() && strncmp(fLastNode.GetName(), name, strlen(name)) == 0) ? (TObject*)&fLastNode : nullptr;
   }
+  // node history keeps only the last node: index 0 if it matches, else -1
+  Int_t FindNodeNumberStartWith(const char* name) const { return FindNodeStartWith(name) ? 0 : -1; }
   void SetLineWidth(Int_t) {}
   void SetLineColor(Int_t) {}
   TPolyLine3D* MakePolyLine3D() const;

@@ -786,8 +786,14 @@ struct TThread {
 };
 
 // ---------------------------------------------------------------------------- TGraph / TGraph2D
+struct TAxisStub {  // display-only axis handle
+  void SetTitle(const char*) {}
+  void SetLimits(Double_t, Double_t) {}
+  void SetRangeUser(Double_t, Double_t) {}
+};
 class TGraph : public TNamed {
   std::vector<Double_t> fX, fY;
+  TAxisStub fAxis;
 
  public:
   TGraph() {}
@@ -826,6 +832,9 @@ class TGraph : public TNamed {
   void SetLineStyle(Int_t) {}
   void SetMarkerStyle(Int_t) {}
   void SetLineColor(Int_t) {}
+  TAxisStub* GetXaxis() { return &fAxis; }
+  TAxisStub* GetYaxis() { return &fAxis; }
+  void SetTitle(const char* t) override { TNamed::SetTitle(t); }
 };
 
 class TGraph2D : public TNamed {

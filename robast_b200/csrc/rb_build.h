@@ -222,21 +222,37 @@ struct SceneBuilder {
       bvh[me].child = items[lo].first;
     } else {
       bvh[me].child = -1;
-      int axis = 0;
-      double ext = -1;
-      for (int k = 0; k < 3; k++) {
-        double clo = 1e300, chi = -1e300;
-        for (int i = lo; i < hi; i++) {
-          double c = 0.5 * (items[i].second.lo[k] + items[i].second.hi[k]);
-          clo = std::min(clo, c);
-          chi = std::max(chi, c);
+      // surface-area heuristic, exact sweep over the three axes (N is at most a few thousand)
+      auto area = [](const Box& x) {
+        double dx = x.hi[0] - x.lo[0], dy = x.hi[1] - x.lo[1], dz = x.hi[2] - x.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+      };
+      int best_axis = -1, best_split = -1;
+      double best_cost = 1e300;
+      std::vector<double> right_area(hi - lo);
+      for (int axis = 0; axis < 3; axis++) {
+        std::sort(items.begin() + lo, items.begin() + hi, [axis](const std::pair<int, Box>& p, const std::pair<int, Box>& q) {
+          return p.second.lo[axis] + p.second.hi[axis] < q.second.lo[axis] + q.second.hi[axis];
+        });
+        Box acc = box_empty();
+        for (int i = hi - 1; i > lo; i--) {
+          box_add(acc, items[i].second.lo);
+          box_add(acc, items[i].second.hi);
+          right_area[i - lo] = area(acc);
         }
-        if (chi - clo > ext) { ext = chi - clo; axis = k; }
+        acc = box_empty();
+        for (int i = lo; i < hi - 1; i++) {
+          box_add(acc, items[i].second.lo);
+          box_add(acc, items[i].second.hi);
+          double cost = area(acc) * (i - lo + 1) + right_area[i + 1 - lo] * (hi - i - 1);
+          if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i + 1; }
+        }
       }
-      int mid = (lo + hi) / 2;
-      std::nth_element(items.begin() + lo, items.begin() + mid, items.begin() + hi, [axis](const std::pair<int, Box>& a, const std::pair<int, Box>& c) {
-        return a.second.lo[axis] + a.second.hi[axis] < c.second.lo[axis] + c.second.hi[axis];
+      int axis = best_axis;
+      std::sort(items.begin() + lo, items.begin() + hi, [axis](const std::pair<int, Box>& p, const std::pair<int, Box>& q) {
+        return p.second.lo[axis] + p.second.hi[axis] < q.second.lo[axis] + q.second.hi[axis];
       });
+      int mid = best_split;
       bvh_rec(items, lo, mid);
       bvh_rec(items, mid, hi);
     }

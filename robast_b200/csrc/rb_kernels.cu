@@ -88,34 +88,56 @@ struct ProfScope {
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
-// ---- stream compaction (decoupled look-back)
+// ---- stream compaction (single pass, decoupled look-back, stable)
+// One tile = 256 threads x 16 rays, blocked so that every thread reads 64 contiguous bytes (4 x 128-bit loads).
+// Tile prefixes are published as (flag << 32 | value) words; warp 0 looks back over 32 predecessor tiles at a time.
 #define CP_THREADS 256
-#define CP_ITEMS 4
+#define CP_ITEMS 16
 #define CP_TILE (CP_THREADS * CP_ITEMS)
 __global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restrict__ live_in, int n_in, const int32_t* __restrict__ status,
                                                        int32_t* __restrict__ live_out, int32_t* count_out, unsigned long long* tile_state,
-                                                       int32_t* tile_counter, int ntiles) {
+                                                       int32_t* tile_counter, int ntiles, int vec_ok) {
   __shared__ int s_tile, s_prefix;
   __shared__ int s_warp[CP_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1);
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1);  // tiles are numbered in the order they start: no deadlock in the look-back
   __syncthreads();
   const int tile = s_tile;
   const int base = tile * CP_TILE + tid * CP_ITEMS;
   int idx[CP_ITEMS];
-  bool alive[CP_ITEMS];
-  int cnt = 0;
+  unsigned alive = 0;
+  if (vec_ok && base + CP_ITEMS <= n_in) {  // 128-bit loads need 16-byte aligned arrays
+    int st[CP_ITEMS];
+    if (live_in) {
 #pragma unroll
-  for (int k = 0; k < CP_ITEMS; k++) {
-    int i = base + k;
-    alive[k] = false;
-    idx[k] = 0;
-    if (i < n_in) {
-      idx[k] = live_in ? live_in[i] : i;
-      alive[k] = status[idx[k]] == RBG_RUN;
+      for (int k = 0; k < CP_ITEMS; k += 4) {
+        int4 v = *reinterpret_cast<const int4*>(live_in + base + k);
+        idx[k] = v.x; idx[k + 1] = v.y; idx[k + 2] = v.z; idx[k + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < CP_ITEMS; k++) st[k] = status[idx[k]];
+    } else {
+#pragma unroll
+      for (int k = 0; k < CP_ITEMS; k += 4) {
+        int4 v = *reinterpret_cast<const int4*>(status + base + k);
+        st[k] = v.x; st[k + 1] = v.y; st[k + 2] = v.z; st[k + 3] = v.w;
+        idx[k] = base + k; idx[k + 1] = base + k + 1; idx[k + 2] = base + k + 2; idx[k + 3] = base + k + 3;
+      }
     }
-    cnt += alive[k] ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) alive |= (st[k] == RBG_RUN ? 1u : 0u) << k;
+  } else {
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) {
+      int i = base + k;
+      idx[k] = 0;
+      if (i < n_in) {
+        idx[k] = live_in ? live_in[i] : i;
+        alive |= (status[idx[k]] == RBG_RUN ? 1u : 0u) << k;
+      }
+    }
   }
+  const int cnt = __popc(alive);
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -132,21 +154,27 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restric
       if (lane >= o) w += u;
     }
     if (lane < CP_THREADS / 32) s_warp[lane] = w - v;  // exclusive warp offsets
-    if (lane == CP_THREADS / 32 - 1) {
-      int total = w, excl = 0;
-      volatile unsigned long long* ts = tile_state;
-      if (tile > 0) {
-        atomicExch(&tile_state[tile], (1ull << 32) | (unsigned)total);  // AGGREGATE
-        int j = tile - 1;
-        while (true) {
-          unsigned long long st = ts[j];
-          unsigned flag = (unsigned)(st >> 32);
-          if (flag == 0) continue;  // predecessor not published yet
-          excl += (int)(unsigned)st;
-          if (flag == 2) break;
-          j--;
-        }
-      }
+    const int total = __shfl_sync(0xffffffffu, w, CP_THREADS / 32 - 1);
+    if (lane == 0 && tile > 0) atomicExch(&tile_state[tile], (1ull << 32) | (unsigned)total);  // AGGREGATE
+    int excl = 0;
+    volatile unsigned long long* ts = tile_state;
+    for (int j0 = tile - 1; j0 >= 0; j0 -= 32) {  // warp-parallel look-back, 32 predecessors per round
+      int j = j0 - lane;
+      unsigned long long stw = 0;
+      unsigned flag;
+      do {
+        stw = j >= 0 ? ts[j] : (2ull << 32);
+        flag = (unsigned)(stw >> 32);
+      } while (__any_sync(0xffffffffu, flag == 0));
+      unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2);
+      int upto = incl_mask ? __ffs(incl_mask) - 1 : 31;  // nearest predecessor that already holds an inclusive prefix
+      int contrib = lane <= upto ? (int)(unsigned)stw : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      excl += contrib;
+      if (incl_mask) break;
+    }
+    if (lane == 0) {
       atomicExch(&tile_state[tile], (2ull << 32) | (unsigned)(excl + total));  // INCLUSIVE PREFIX
       s_prefix = excl;
       if (tile == ntiles - 1) *count_out = excl + total;
@@ -156,7 +184,7 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restric
   int pos = s_prefix + s_warp[warp] + incl - cnt;
 #pragma unroll
   for (int k = 0; k < CP_ITEMS; k++)
-    if (alive[k]) live_out[pos++] = idx[k];
+    if (alive & (1u << k)) live_out[pos++] = idx[k];
 }
 
 // ---- ARayShooter on device
@@ -394,7 +422,8 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     int32_t* out = (live == liveA) ? liveB : liveA;
     {
       ProfScope ps(st, 1);
-      k_compact<<<tiles, CP_THREADS, 0, st>>>(live, (int)nlive, R.status, out, d_count, tile_state, tile_counter, tiles);
+      k_compact<<<tiles, CP_THREADS, 0, st>>>(live, (int)nlive, R.status, out, d_count, tile_state, tile_counter, tiles,
+                                              (reinterpret_cast<uintptr_t>(R.status) & 15) == 0);
       g_launches++;
       CK(cudaGetLastError());
     }

@@ -115,11 +115,9 @@ __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(co
       first = st.o.nvis;
       nb_collect<K>(sc, nav, st);
     }
-    for (int k = 0;; k++) {
-      const bool more = want && first + k < st.o.nvis;
-      if (!__syncthreads_or(more)) break;
-      if (more) nb_eval<K>(sc, nav, st, first + k);
-    }
+    __syncthreads();  // all warps enter the shape code together; inside the phase they run unsynchronised
+    if (want)
+      for (int k = first; k < st.o.nvis; k++) nb_eval<K>(sc, nav, st, k);
   }
   if (overflow) st.o.nvis = -1;
   if (run) nb_finish<K>(sc, nav, st);
