@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(co
   RayReg r;
   Philox g;
   load_ray<K>(sc, tp, R, idx, init, r, g);
+  // a ray shot from outside the top volume first has to enter it (no daughters to examine, no interaction
+  // besides AddPoint): take that step here instead of spending a whole bounce launch on it
+  if (init && r.cur < 0 && r.status == RBG_RUN) trace_step<K>(sc, tp, r, g);
   __syncthreads();
   const bool run = r.status == RBG_RUN;
   const bool push = (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0;
