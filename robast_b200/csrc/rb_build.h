@@ -147,8 +147,14 @@ struct SceneBuilder {
         case RBG_SHAPE_WINSTON2D:
         case RBG_SHAPE_WINSTONPOLY: {
           double r1 = P[0], r2 = P[1], theta = asin(r2 / r1), dz = (r1 + r2) / tan(theta) / 2., f = r2 * (1 + sin(theta));
-          double v[8] = {r1, r2, P[2], theta, dz, f, cos(theta), sin(theta)};
-          dpar.insert(dpar.end(), v, v + 8);
+          int npoly = s.type == RBG_SHAPE_WINSTONPOLY ? std::max(3, (int)P[2]) : 0;
+          double v[10] = {r1, r2, s.type == RBG_SHAPE_WINSTONPOLY ? (double)npoly : P[2], theta, dz, f, cos(theta), sin(theta), tan(theta),
+                          npoly ? tan(M_PI / npoly) : 0.};
+          dpar.insert(dpar.end(), v, v + 10);
+          for (int k = 0; k < npoly; k++) {  // face azimuths k 2pi/N
+            dpar.push_back(cos(k * 2 * M_PI / npoly));
+            dpar.push_back(sin(k * 2 * M_PI / npoly));
+          }
           if (s.type == RBG_SHAPE_WINSTON2D) setbox(r1, P[2], -dz, dz);
           else {
             double R = r1 / cos(M_PI / std::max(3, (int)P[2]));

@@ -875,45 +875,61 @@ RB_HD inline bool win_dRdZ(const double* P, double z, double& out) {
   out = (-da1 + (a1 * da1 - 2 * da0 * a2) / sqrt(a1 * a1 - 4 * a0 * a2)) / (2 * a2);
   return true;
 }
-// intersection with the tilted parabola of the face at azimuth phi (cphi,sphi), accepted within |azimuth| <= open/2
-RB_HD inline double win_parabola(const double* P, V3 pt, V3 dir, double cphi, double sphi, double open) {
+// P (device layout): r1,r2,(dy|npoly),theta,dz,f,cos(theta),sin(theta),tan(theta),tan(pi/npoly), npoly x (cos,sin) of the face azimuths
+// Intersection with the tilted parabola of the face at azimuth phi (cphi,sphi).  Same algebra as the reference's
+// DistToParabola, with the trigonometry removed: tan(atan2(pz,px) - theta) = (pz - px tan(theta)) / (px + pz tan(theta)),
+// and the azimuth window |atan2(yc,xc)| <= open/2 becomes |yc| <= xc tan(open/2) (xc >= r2 > 0; for open = pi it is
+// always true).  wtan < 0 means "no window".
+RB_HD inline double win_parabola(const double* P, V3 pt, V3 dir, double cphi, double sphi, double wtan) {
   double x = cphi * pt.x + sphi * pt.y, y = -sphi * pt.x + cphi * pt.y, z = pt.z;
   double px = cphi * dir.x + sphi * dir.y, py = -sphi * dir.x + cphi * dir.y, pz = dir.z;
   if (px == 0 && pz == 0) return RB_BIG;
-  double r1 = P[0], r2 = P[1], theta = P[3], DZ = P[4], f = P[5], cost = P[6], sint = P[7];
+  double r1 = P[0], r2 = P[1], DZ = P[4], f = P[5], cost = P[6], sint = P[7], tant = P[8];
   double X = cost * (x + r2) + (z + DZ) * sint, Z = -sint * (x + r2) + (z + DZ) * cost + f;
-  double tanA = tan(rb_atan2(pz, px) - theta);
+  double tanA = (pz - px * tant) / (px + pz * tant);
   double tmp = tanA * tanA - (X * tanA - Z) / f;
   if (tmp < 0) return RB_BIG;
   double Xc[2];
   if (DZ * 2 / fabs(tanA) < RB_TOL) { Xc[0] = X; Xc[1] = X; }
   else { double sq = sqrt(tmp); Xc[0] = 2 * f * (tanA + sq); Xc[1] = 2 * f * (tanA - sq); }
+  // the transverse coordinate follows the better conditioned of py/pz, py/px (reference :375-394)
+  double apx = fabs(px), apy = fabs(py), apz = fabs(pz);
+  bool use_z = (apx <= apz && apy <= apz) ? true : ((apy <= apx && apz <= apx) ? false : apx < 1e-5);
+  double slope = use_z ? py / pz : py / px;
   double best = RB_BIG;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     double Zc = Xc[k] * Xc[k] / 4. / f;
-    double xc = cost * Xc[k] - sint * (Zc - f) - r2, zc = sint * Xc[k] + cost * (Zc - f) - DZ, yc;
-    if (fabs(px) <= fabs(pz) && fabs(py) <= fabs(pz)) yc = y + (zc - z) * py / pz;
-    else if (fabs(py) <= fabs(px) && fabs(pz) <= fabs(px)) yc = y + (xc - x) * py / px;
-    else yc = y + (fabs(px) < 1e-5 ? (zc - z) * py / pz : (xc - x) * py / px);
-    double ddx = xc - x, ddy = yc - y, ddz = zc - z;
+    double xc = cost * Xc[k] - sint * (Zc - f) - r2, zc = sint * Xc[k] + cost * (Zc - f) - DZ;
+    double ddx = xc - x, ddz = zc - z;
+    double ddy = (use_z ? ddz : ddx) * slope, yc = y + ddy;
     if (xc < r2 || r1 < xc || zc < -DZ || DZ < zc || ddx * px + ddz * pz < 0) continue;
-    if (fabs(rb_atan2(yc, xc)) <= open / 2.) best = rb_min(best, sqrt(ddx * ddx + ddy * ddy + ddz * ddz));
+    if (wtan < 0 || fabs(yc) <= xc * wtan) best = rb_min(best, sqrt(ddx * ddx + ddy * ddy + ddz * ddz));
   }
   return best;
 }
-RB_HD inline bool win_inside_polygon(int n, double x, double y, double r) {
-  double th = rb_atan2(y, x), w = RB_PI / n;
-  while (th > w) th -= 2 * w;
-  while (th < -w) th += 2 * w;
-  return !(sqrt(x * x + y * y) * cos(th) > r);
+// largest projection of (x,y) on the face normals = rho cos(folded azimuth) of the reference's InsidePolygon
+RB_HD inline double win_face_proj(const double* P, double x, double y, int& kbest) {
+  int n = (int)P[2];
+  const double* cs = P + 10;
+  double m = -RB_BIG;
+  kbest = 0;
+  for (int k = 0; k < n; k++) {
+    double pr = x * cs[2 * k] + y * cs[2 * k + 1];
+    if (pr > m) { m = pr; kbest = k; }
+  }
+  return m;
+}
+RB_HD inline bool win_inside_polygon(const double* P, double x, double y, double r) {
+  int k;
+  return !(win_face_proj(P, x, y, k) > r);
 }
 RB_HD inline bool win_contains(const double* P, bool poly, V3 p) {
   double r;
   if (poly) {
     if (fabs(p.z) > P[4]) return false;
     if (!win_R(P, p.z, r)) return false;
-    return win_inside_polygon((int)P[2], p.x, p.y, r);
+    return win_inside_polygon(P, p.x, p.y, r);
   }
   if (fabs(p.y) > P[2] || fabs(p.z) > P[4]) return false;
   if (!win_R(P, p.z, r)) return false;
@@ -925,35 +941,31 @@ RB_HD inline double win_dist_in(const double* P, bool poly, V3 p, V3 d) {
   else if (d.z > 0) best = (P[4] - p.z) / d.z;
   if (poly) {
     int n = (int)P[2];
-    for (int i = 0; i < n; i++) {
-      double ph = i * 2 * RB_PI / n;
-      best = rb_min(best, win_parabola(P, p, d, cos(ph), sin(ph), RB_PI));
-    }
+    const double* cs = P + 10;
+    for (int i = 0; i < n; i++) best = rb_min(best, win_parabola(P, p, d, cs[2 * i], cs[2 * i + 1], -1.));
     return best;
   }
   if (d.y < 0) best = rb_min(best, -(p.y + P[2]) / d.y);
   else if (d.y > 0) best = rb_min(best, (P[2] - p.y) / d.y);
-  best = rb_min(best, win_parabola(P, p, d, 1., 0., RB_PI));
-  return rb_min(best, win_parabola(P, p, d, cos(RB_PI), sin(RB_PI), RB_PI));
+  best = rb_min(best, win_parabola(P, p, d, 1., 0., -1.));
+  return rb_min(best, win_parabola(P, p, d, -1., 0., -1.));
 }
 RB_HD inline double win_dist_out(const double* P, bool poly, V3 p, V3 d) {
   double DZ = P[4];
   if (poly) {
     int n = (int)P[2];
+    const double* cs = P + 10;
     if (p.z <= -DZ) {
       if (d.z <= 0) return RB_BIG;
       double s = -(DZ + p.z) / d.z;
-      if (win_inside_polygon(n, p.x + s * d.x, p.y + s * d.y, P[1])) return s;
+      if (win_inside_polygon(P, p.x + s * d.x, p.y + s * d.y, P[1])) return s;
     } else if (p.z >= DZ) {
       if (d.z >= 0) return RB_BIG;
       double s = (DZ - p.z) / d.z;
-      if (win_inside_polygon(n, p.x + s * d.x, p.y + s * d.y, P[0])) return s;
+      if (win_inside_polygon(P, p.x + s * d.x, p.y + s * d.y, P[0])) return s;
     }
     double best = RB_BIG;
-    for (int i = 0; i < n; i++) {
-      double ph = i * 2 * RB_PI / n;
-      best = rb_min(best, win_parabola(P, p, d, cos(ph), sin(ph), 2 * RB_PI / n));
-    }
+    for (int i = 0; i < n; i++) best = rb_min(best, win_parabola(P, p, d, cs[2 * i], cs[2 * i + 1], P[9]));
     return best;
   }
   double DY = P[2], r;
@@ -975,9 +987,9 @@ RB_HD inline double win_dist_out(const double* P, bool poly, V3 p, V3 d) {
     double s = (DY - p.y) / d.y, xn = p.x + s * d.x, zn = p.z + s * d.z;
     if (fabs(zn) <= DZ && win_R(P, zn, r) && fabs(xn) <= r) return s;
   }
-  double s0 = win_parabola(P, p, d, 1., 0., RB_PI);
+  double s0 = win_parabola(P, p, d, 1., 0., -1.);
   if (!(fabs(p.y + s0 * d.y) <= DY)) s0 = RB_BIG;
-  double s1 = win_parabola(P, p, d, cos(RB_PI), sin(RB_PI), RB_PI);
+  double s1 = win_parabola(P, p, d, -1., 0., -1.);
   if (!(fabs(p.y + s1 * d.y) <= DY)) s1 = RB_BIG;
   return rb_min(s0, s1);
 }
@@ -985,19 +997,15 @@ RB_HD inline V3 win_normal(const double* P, bool poly, V3 p, V3 d) {
   double r, dr = 0;
   V3 n;
   if (poly) {
-    int np = (int)P[2];
-    double w = RB_PI / np, s0 = fabs(fabs(P[4]) - fabs(p.z));
-    double phi = rb_atan2(p.y, p.x);
-    while (phi > w) phi -= 2 * w;
-    while (phi < -w) phi += 2 * w;
-    double s1 = win_R(P, p.z, r) ? fabs(r - sqrt(p.x * p.x + p.y * p.y) * cos(phi)) : RB_BIG;
+    const double* cs = P + 10;
+    int k;
+    double proj = win_face_proj(P, p.x, p.y, k);
+    double s0 = fabs(fabs(P[4]) - fabs(p.z));
+    double s1 = win_R(P, p.z, r) ? fabs(r - proj) : RB_BIG;
     if (!(s1 < s0)) n = v3(0, 0, 1);
     else {
-      phi = rb_atan2(p.y, p.x);
-      if (phi < -w) phi += 2 * RB_PI;
-      int k = (int)floor((phi + w) / (2 * w));
       win_dRdZ(P, p.z, dr);
-      n = v3(cos(k * 2 * w), sin(k * 2 * w), -dr);
+      n = v3(cs[2 * k], cs[2 * k + 1], -dr);
     }
   } else {
     double s0 = fabs(fabs(P[2]) - fabs(p.y)), s1 = fabs(fabs(P[4]) - fabs(p.z)), s2 = win_R(P, p.z, r) ? fabs(r - fabs(p.x)) : RB_BIG;

@@ -412,8 +412,15 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   const int32_t* live = nullptr;
   long long nlive = n;
   int init = 1;
+  const long long tail = std::max<long long>(4096, n / 512);  // survivors below this finish in one per-ray-loop launch
   for (int iter = 0; nlive > 0; iter++) {
     if (iter > 100000) throw std::runtime_error("wavefront did not terminate");
+    if (iter > 0 && nlive <= tail) {
+      DTraceParams tl = tp;
+      tl.max_steps = 0;
+      launch_trace(s->variant, s->d, tl, R, live, nlive, 0, 1, st);
+      break;
+    }
     launch_trace(s->variant, s->d, tp, R, live, nlive, init, 1, st);
     init = 0;
     int tiles = (int)((nlive + CP_TILE - 1) / CP_TILE);
