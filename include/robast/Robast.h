@@ -624,6 +624,14 @@ class AMirror : public AOpticalComponent {
   void SetReflectance(std::shared_ptr<TGraph> ref) { fReflectance1D = ref; }
   void SetReflectance(std::shared_ptr<TGraph2D> ref) { fReflectance2D = ref; }
   void SetReflectance(std::shared_ptr<TH2> ref) { fReflectanceTH2 = ref; }
+  // src/AMirror.cxx:39-60: priority TGraph2D > TH2 > TGraph > constant, clamped to [0, 1]
+  Double_t GetReflectance(Double_t lambda, Double_t angle) const {
+    Double_t ret = fReflectance;
+    if (fReflectance2D) ret = fReflectance2D->Interpolate(lambda, angle);
+    else if (fReflectanceTH2) ret = fReflectanceTH2->Interpolate(lambda, angle);
+    else if (fReflectance1D) ret = fReflectance1D->Eval(lambda);
+    return ret > 1 ? 1 : (ret < 0 ? 0 : ret);
+  }
   Double_t GetConstantReflectance() const { return fReflectance; }
   std::shared_ptr<TGraph> GetReflectance1D() const { return fReflectance1D; }
   std::shared_ptr<TGraph2D> GetReflectance2D() const { return fReflectance2D; }
@@ -1000,6 +1008,9 @@ struct ASceneExport {
   std::vector<rbg_focal> focals;
   std::vector<rbg_multilayer> multilayers;
   std::vector<rbg_layer> layers;
+  std::vector<rbg_graph2d> graph2ds;
+  std::vector<int32_t> tri;
+  std::vector<double> g2x, g2y, g2z;
   std::vector<char> names;
   rbg_scene_desc desc;
 
@@ -1010,6 +1021,7 @@ struct ASceneExport {
   std::map<const TH2*, int> th2_id;
   std::map<const ARefractiveIndex*, int> index_id;
   std::map<const AMultilayer*, int> multilayer_id;
+  std::map<const TGraph2D*, int> graph2d_id;
 
   int AddMatrix(const TGeoMatrix* m) {
     if (!m || m->IsIdentity()) return -1;
@@ -1151,6 +1163,22 @@ struct ASceneExport {
     indices.push_back(r);
     return index_id[x] = (int)indices.size() - 1;
   }
+  int AddGraph2D(const TGraph2D* g) {  // baked to its Delaunay triangle list (TGraph2D::Interpolate)
+    if (!g) return -1;
+    auto it = graph2d_id.find(g);
+    if (it != graph2d_id.end()) return it->second;
+    const std::vector<Int_t>& t = g->GetTriangles();
+    rbg_graph2d r;
+    r.first_tri = (int32_t)(tri.size() / 3);
+    r.ntri = (int32_t)(t.size() / 3);
+    int32_t base = (int32_t)g2x.size();
+    for (Int_t v : t) tri.push_back(base + v);
+    g2x.insert(g2x.end(), g->GetX(), g->GetX() + g->GetN());
+    g2y.insert(g2y.end(), g->GetY(), g->GetY() + g->GetN());
+    g2z.insert(g2z.end(), g->GetZ(), g->GetZ() + g->GetN());
+    graph2ds.push_back(r);
+    return graph2d_id[g] = (int)graph2ds.size() - 1;
+  }
   int AddMultilayer(const AMultilayer* m) {
     if (!m) return -1;
     auto it = multilayer_id.find(m);
@@ -1188,8 +1216,13 @@ struct ASceneExport {
     RB_SET(volumes, nvolumes, volumes) RB_SET(borders, nborders, borders) RB_SET(graphs, ngraphs, graphs) RB_SET(gx, ngpts, gx)
     RB_SET(th2, nth2, th2) RB_SET(th2v, nth2v, th2v) RB_SET(indices, nindices, indices) RB_SET(mirrors, nmirrors, mirrors)
     RB_SET(focals, nfocals, focals) RB_SET(multilayers, nmultilayers, multilayers) RB_SET(layers, nlayers, layers) RB_SET(names, nnames, names)
+    RB_SET(graph2d, ngraph2d, graph2ds) RB_SET(g2x, ng2pts, g2x)
 #undef RB_SET
     desc.gy = gy.empty() ? nullptr : gy.data();
+    desc.ntri = (int32_t)(tri.size() / 3);
+    desc.tri = tri.empty() ? nullptr : tri.data();
+    desc.g2y = g2y.empty() ? nullptr : g2y.data();
+    desc.g2z = g2z.empty() ? nullptr : g2z.data();
   }
   void BuildFromTop(const TGeoVolume* topv) {
     std::vector<const TGeoVolume*> order;
@@ -1208,12 +1241,11 @@ struct ASceneExport {
       names.insert(names.end(), nm, nm + strlen(nm) + 1);
       if (auto* l = dynamic_cast<const ALens*>(v)) r.index = AddIndex(l->GetIndex().get());
       if (auto* m = dynamic_cast<const AMirror*>(v)) {
-        if (m->GetReflectance2D()) throw std::runtime_error("AMirror: TGraph2D reflectance is not supported by the device path yet");
         rbg_mirror mm;
         mm.constant = m->GetConstantReflectance();
         mm.graph1d = AddGraph(m->GetReflectance1D().get());
         mm.th2 = AddTH2(m->GetReflectanceTH2().get());
-        mm.graph2d = -1; mm.pad = 0;
+        mm.graph2d = AddGraph2D(m->GetReflectance2D().get()); mm.pad = 0;
         mirrors.push_back(mm);
         r.mirror = (int)mirrors.size() - 1;
       }
@@ -1268,7 +1300,6 @@ inline void AMultilayer::DeviceTMM(Int_t n, const Double_t* th, const Double_t* 
 // reference include/AOpticsManager.h:38-105, src/AOpticsManager.cxx:27-49,304-332,523-594
 class AOpticsManager : public TGeoManager {
  public:
-  typedef std::function<int(const rbg_scene_desc*, const rbg_trace_opts*, const rbg_rays*)> TraceFn;
 
  private:
   Int_t fLimit = 100;
@@ -1280,7 +1311,6 @@ class AOpticsManager : public TGeoManager {
   rbg_scene* fScene = nullptr;
   std::string fSceneKey;
   std::shared_ptr<std::vector<std::string>> fNodeNames;
-  TraceFn fTraceFn;  // test hook (tests/ plug the CPU oracle here); empty = CUDA library
 
   static std::string Key(const ASceneExport& e) {
     std::string k;
@@ -1334,7 +1364,6 @@ class AOpticsManager : public TGeoManager {
   void SetSeed(ULong64_t seed) { fSeed = seed; fRayCounter = 0; }
   void SetQuirks(UInt_t q) { fQuirks = q; }
   void SetDevice(Int_t d) { fDevice = d; }
-  void SetTraceFunction(TraceFn f) { fTraceFn = f; }
   std::shared_ptr<ASceneExport> ExportScene() const {
     if (!fTopVolume) throw std::runtime_error("AOpticsManager: no top volume");
     auto e = std::make_shared<ASceneExport>();
@@ -1388,11 +1417,7 @@ class AOpticsManager : public TGeoManager {
     opts.ray_id_offset = fRayCounter;
     fRayCounter += n;
     int rc;
-    if (fTraceFn) {
-      rc = fTraceFn(&ex->desc, &opts, &r);
-      if (rc != RBG_OK) throw std::runtime_error("AOpticsManager::TraceNonSequential: trace hook failed");
-      fNodeNames.reset();
-    } else {
+    {  // the CUDA library is the only trace path: no CPU fallback, no pluggable tracer
       std::string key = Key(*ex);
       if (!fScene || key != fSceneKey) {
         if (fScene) rbg_scene_destroy(fScene);

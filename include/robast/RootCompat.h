@@ -837,19 +837,106 @@ class TGraph : public TNamed {
   void SetTitle(const char* t) override { TNamed::SetTitle(t); }
 };
 
+// TGraph2D::Interpolate = linear interpolation over the Delaunay triangulation of the (x, y) points, which ROOT
+// builds on coordinates normalised to the data range (TGraphDelaunay / ROOT::Math::Delaunay2D); outside the convex
+// hull it returns 0 (TGraph2D's default fZout).  The triangulation is done here, on the host, by Bowyer-Watson
+// insertion; the exporter ships the triangle list to the device (rbg_graph2d).
 class TGraph2D : public TNamed {
   std::vector<Double_t> fX, fY, fZ;
+  mutable std::vector<Int_t> fTri;  // 3 vertex ids per triangle
+  mutable Bool_t fTriValid = kFALSE;
+
+  void Triangulate() const {
+    fTri.clear();
+    fTriValid = kTRUE;
+    const Int_t n = GetN();
+    if (n < 3) return;
+    Double_t xmin = fX[0], xmax = fX[0], ymin = fY[0], ymax = fY[0];
+    for (Int_t i = 1; i < n; i++) {
+      xmin = std::min(xmin, fX[i]); xmax = std::max(xmax, fX[i]);
+      ymin = std::min(ymin, fY[i]); ymax = std::max(ymax, fY[i]);
+    }
+    const Double_t sx = xmax > xmin ? 1. / (xmax - xmin) : 1., sy = ymax > ymin ? 1. / (ymax - ymin) : 1.;
+    std::vector<Double_t> px(n + 3), py(n + 3);
+    for (Int_t i = 0; i < n; i++) { px[i] = (fX[i] - xmin) * sx; py[i] = (fY[i] - ymin) * sy; }
+    px[n] = -1000.; py[n] = -1000.; px[n + 1] = 1001.; py[n + 1] = -1000.; px[n + 2] = 0.5; py[n + 2] = 2000.;  // super-triangle
+    struct T { Int_t v[3]; };
+    std::vector<T> tris;
+    tris.push_back(T{{n, n + 1, n + 2}});
+    auto orient = [&](Int_t a, Int_t b, Int_t c) { return (px[b] - px[a]) * (py[c] - py[a]) - (py[b] - py[a]) * (px[c] - px[a]); };
+    auto in_circle = [&](const T& t, Int_t p) {  // strictly inside the circumcircle of the (counter-clockwise) triangle
+      Double_t ax = px[t.v[0]] - px[p], ay = py[t.v[0]] - py[p], bx = px[t.v[1]] - px[p], by = py[t.v[1]] - py[p], cx = px[t.v[2]] - px[p],
+               cy = py[t.v[2]] - py[p];
+      Double_t det = (ax * ax + ay * ay) * (bx * cy - cx * by) - (bx * bx + by * by) * (ax * cy - cx * ay) + (cx * cx + cy * cy) * (ax * by - bx * ay);
+      return det > 1e-14;
+    };
+    for (Int_t p = 0; p < n; p++) {
+      Bool_t dup = kFALSE;
+      for (Int_t q = 0; q < p && !dup; q++) dup = px[q] == px[p] && py[q] == py[p];
+      if (dup) continue;
+      std::vector<T> keep;
+      std::vector<std::pair<Int_t, Int_t>> edges;
+      for (const T& t : tris) {
+        if (in_circle(t, p)) {
+          for (int e = 0; e < 3; e++) edges.emplace_back(t.v[e], t.v[(e + 1) % 3]);
+        } else keep.push_back(t);
+      }
+      if (edges.empty()) {  // on a circumcircle of every neighbour (degenerate): fall back to the containing triangle
+        for (size_t k = 0; k < keep.size(); k++) {
+          const T t = keep[k];
+          if (orient(t.v[0], t.v[1], p) >= 0 && orient(t.v[1], t.v[2], p) >= 0 && orient(t.v[2], t.v[0], p) >= 0) {
+            for (int e = 0; e < 3; e++) edges.emplace_back(t.v[e], t.v[(e + 1) % 3]);
+            keep.erase(keep.begin() + k);
+            break;
+          }
+        }
+      }
+      for (size_t i = 0; i < edges.size(); i++) {  // boundary of the cavity = edges that appear once
+        Bool_t shared = kFALSE;
+        for (size_t j = 0; j < edges.size() && !shared; j++)
+          shared = i != j && edges[i].first == edges[j].second && edges[i].second == edges[j].first;
+        if (shared) continue;
+        T t{{edges[i].first, edges[i].second, p}};
+        if (orient(t.v[0], t.v[1], t.v[2]) < 0) std::swap(t.v[0], t.v[1]);
+        if (orient(t.v[0], t.v[1], t.v[2]) > 0) keep.push_back(t);
+      }
+      tris.swap(keep);
+    }
+    for (const T& t : tris)
+      if (t.v[0] < n && t.v[1] < n && t.v[2] < n) { fTri.push_back(t.v[0]); fTri.push_back(t.v[1]); fTri.push_back(t.v[2]); }
+  }
 
  public:
   TGraph2D() {}
+  TGraph2D(Int_t n, const Double_t* x, const Double_t* y, const Double_t* z) : fX(x, x + n), fY(y, y + n), fZ(z, z + n) {}
   void SetPoint(Int_t i, Double_t x, Double_t y, Double_t z) {
     if (i >= (Int_t)fX.size()) { fX.resize(i + 1); fY.resize(i + 1); fZ.resize(i + 1); }
     fX[i] = x; fY[i] = y; fZ[i] = z;
+    fTriValid = kFALSE;
   }
+  void AddPoint(Double_t x, Double_t y, Double_t z) { SetPoint(GetN(), x, y, z); }
   Int_t GetN() const { return (Int_t)fX.size(); }
   const Double_t* GetX() const { return fX.data(); }
   const Double_t* GetY() const { return fY.data(); }
   const Double_t* GetZ() const { return fZ.data(); }
+  const std::vector<Int_t>& GetTriangles() const {
+    if (!fTriValid) Triangulate();
+    return fTri;
+  }
+  // same arithmetic as the device/oracle evaluation of rbg_graph2d: first triangle (in list order) whose three
+  // barycentric coordinates are >= -1e-9, linear interpolation inside it, 0 outside the hull
+  Double_t Interpolate(Double_t x, Double_t y) const {
+    const std::vector<Int_t>& t = GetTriangles();
+    for (size_t k = 0; k + 2 < t.size(); k += 3) {
+      Double_t x0 = fX[t[k]], y0 = fY[t[k]], x1 = fX[t[k + 1]], y1 = fY[t[k + 1]], x2 = fX[t[k + 2]], y2 = fY[t[k + 2]];
+      Double_t den = (y1 - y2) * (x0 - x2) + (x2 - x1) * (y0 - y2);
+      if (den == 0) continue;
+      Double_t l0 = ((y1 - y2) * (x - x2) + (x2 - x1) * (y - y2)) / den, l1 = ((y2 - y0) * (x - x2) + (x0 - x2) * (y - y2)) / den, l2 = 1. - l0 - l1;
+      if (l0 < -1e-9 || l1 < -1e-9 || l2 < -1e-9) continue;
+      return l0 * fZ[t[k]] + l1 * fZ[t[k + 1]] + l2 * fZ[t[k + 2]];
+    }
+    return 0.;
+  }
 };
 
 // ---------------------------------------------------------------------------- histograms

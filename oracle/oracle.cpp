@@ -174,6 +174,32 @@ double th2_interp(const rbg_scene_desc* d, int h, double x, double y) {
          1.0 * q22 / dd * (x - x1) * (y - y1);
 }
 
+// TGraph2D::Interpolate (src/AMirror.cxx:47): ROOT interpolates linearly inside the Delaunay triangle that holds
+// (x, y) and returns 0 outside the convex hull.  The triangle list comes with the scene description (the host layer
+// triangulates, include/robast/RootCompat.h); the plane through the three vertices is evaluated here in the
+// point-normal form z = z0 - (nx (x-x0) + ny (y-y0)) / nz, after a same-side test against each edge.
+double graph2d_interp(const rbg_scene_desc* d, int g, double x, double y) {
+  const rbg_graph2d& G = d->graph2d[g];
+  for (int k = 0; k < G.ntri; k++) {
+    const int32_t* t = d->tri + 3 * (G.first_tri + k);
+    double X[3], Y[3], Z[3];
+    for (int i = 0; i < 3; i++) { X[i] = d->g2x[t[i]]; Y[i] = d->g2y[t[i]]; Z[i] = d->g2z[t[i]]; }
+    double area2 = (X[1] - X[0]) * (Y[2] - Y[0]) - (X[2] - X[0]) * (Y[1] - Y[0]);
+    if (area2 == 0) continue;
+    bool inside = true;
+    for (int i = 0; i < 3 && inside; i++) {  // signed area of (edge i, point) relative to the triangle's own orientation
+      int a = (i + 1) % 3, b = (i + 2) % 3;
+      double w = ((X[a] - x) * (Y[b] - y) - (X[b] - x) * (Y[a] - y)) / area2;
+      if (w < -1e-9) inside = false;
+    }
+    if (!inside) continue;
+    double ux = X[1] - X[0], uy = Y[1] - Y[0], uz = Z[1] - Z[0], vx = X[2] - X[0], vy = Y[2] - Y[0], vz = Z[2] - Z[0];
+    double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    return Z[0] - (nx * (x - X[0]) + ny * (y - Y[0])) / nz;
+  }
+  return 0.;
+}
+
 // ================================================================== refractive indices
 // include/ARefractiveIndex.h:36-65, src/ASellmeierFormula.cxx:46-54, src/ASchottFormula.cxx:43-55,
 // src/ACauchyFormula.cxx:40-46, include/AMixedRefractiveIndex.h:36-45
@@ -1607,7 +1633,8 @@ struct Tracer {
     double ret = 1.0;
     if (v.mirror >= 0) {
       const rbg_mirror& m = S.d->mirrors[v.mirror];
-      if (m.th2 >= 0) ret = th2_interp(S.d, m.th2, lambda, angle);
+      if (m.graph2d >= 0) ret = graph2d_interp(S.d, m.graph2d, lambda, angle);
+      else if (m.th2 >= 0) ret = th2_interp(S.d, m.th2, lambda, angle);
       else if (m.graph1d >= 0) ret = graph_eval(S.d, m.graph1d, lambda);
       else ret = m.constant;
     }
@@ -1878,6 +1905,7 @@ double orc_index_k(const rbg_scene_desc* desc, int id, double lambda) { return i
 double orc_index_abslen(const rbg_scene_desc* desc, int id, double lambda) { return index_abslen(desc, id, lambda); }
 double orc_graph_eval(const rbg_scene_desc* desc, int g, double x) { return graph_eval(desc, g, x); }
 double orc_th2_interp(const rbg_scene_desc* desc, int h, double x, double y) { return th2_interp(desc, h, x, y); }
+double orc_graph2d_interp(const rbg_scene_desc* desc, int g, double x, double y) { return graph2d_interp(desc, g, x, y); }
 
 // shape-level entry points (local frame) for shape parity tests
 int orc_shape_contains(const rbg_scene_desc* desc, int shape, const double* p) {

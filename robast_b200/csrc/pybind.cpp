@@ -15,7 +15,6 @@ template <class T> using Raw = std::unique_ptr<T, py::nodelete>;
 static py::array_t<double> view_d(std::vector<double>& v, py::object owner) { return py::array_t<double>({(py::ssize_t)v.size()}, {sizeof(double)}, v.data(), owner); }
 static py::array_t<int32_t> view_i(std::vector<int32_t>& v, py::object owner) { return py::array_t<int32_t>({(py::ssize_t)v.size()}, {sizeof(int32_t)}, v.data(), owner); }
 
-typedef int (*oracle_trace_fn)(const rbg_scene_desc*, const rbg_trace_opts*, const rbg_rays*, int);
 
 PYBIND11_MODULE(_robast, m) {
   m.doc() = "robast_b200 host layer (ROOT-compat subset + ROBAST classes) over the CUDA C ABI";
@@ -128,7 +127,8 @@ PYBIND11_MODULE(_robast, m) {
   py::class_<TGraph, std::shared_ptr<TGraph>>(m, "TGraph")
       .def(py::init<>())
       .def("SetPoint", &TGraph::SetPoint).def("GetN", &TGraph::GetN).def("Eval", &TGraph::Eval);
-  py::class_<TGraph2D, std::shared_ptr<TGraph2D>>(m, "TGraph2D").def(py::init<>()).def("SetPoint", &TGraph2D::SetPoint).def("GetN", &TGraph2D::GetN);
+  py::class_<TGraph2D, std::shared_ptr<TGraph2D>>(m, "TGraph2D").def(py::init<>()).def("SetPoint", &TGraph2D::SetPoint).def("GetN", &TGraph2D::GetN)
+      .def("Interpolate", &TGraph2D::Interpolate).def("GetTriangles", [](const TGraph2D& g) { return g.GetTriangles(); });
   py::class_<TH1, std::shared_ptr<TH1>>(m, "TH1").def("GetEntries", &TH1::GetEntries);
   py::class_<TH1D, TH1, std::shared_ptr<TH1D>>(m, "TH1D")
       .def(py::init<const char*, const char*, int, double, double>())
@@ -188,7 +188,8 @@ PYBIND11_MODULE(_robast, m) {
       .def("SetReflectance", (void(AMirror::*)(double)) & AMirror::SetReflectance)
       .def("SetReflectance", (void(AMirror::*)(std::shared_ptr<TGraph>)) & AMirror::SetReflectance)
       .def("SetReflectance", (void(AMirror::*)(std::shared_ptr<TH2>)) & AMirror::SetReflectance)
-      .def("SetReflectance", (void(AMirror::*)(std::shared_ptr<TGraph2D>)) & AMirror::SetReflectance);
+      .def("SetReflectance", (void(AMirror::*)(std::shared_ptr<TGraph2D>)) & AMirror::SetReflectance)
+      .def("GetReflectance", &AMirror::GetReflectance);
   py::class_<AFocalSurface, AOpticalComponent, Raw<AFocalSurface>>(m, "AFocalSurface")
       .def(py::init<const char*, const TGeoShape*>())
       .def("SetQuantumEfficiency", [](AFocalSurface& f, std::shared_ptr<TGraph> g) { f.SetQuantumEfficiency(g.get()); }, py::keep_alive<1, 2>())
@@ -311,12 +312,6 @@ PYBIND11_MODULE(_robast, m) {
       .def("SetLimit", &AOpticsManager::SetLimit).def("GetLimit", &AOpticsManager::GetLimit)
       .def("SetSeed", &AOpticsManager::SetSeed).def("SetQuirks", &AOpticsManager::SetQuirks).def("SetDevice", &AOpticsManager::SetDevice)
       .def("ExportScene", &AOpticsManager::ExportScene)
-      // tests only: route the trace through a CPU oracle entry point (address of orc_trace obtained via ctypes)
-      .def("SetOracleTraceFunction", [](AOpticsManager& mg, uintptr_t addr, int nthreads) {
-        if (!addr) { mg.SetTraceFunction(nullptr); return; }
-        oracle_trace_fn f = (oracle_trace_fn)addr;
-        mg.SetTraceFunction([f, nthreads](const rbg_scene_desc* d, const rbg_trace_opts* o, const rbg_rays* r) { return f(d, o, r, nthreads); });
-      })
       .def("TraceNonSequential", [](AOpticsManager& mg, ARayArray& a) { py::gil_scoped_release rel; mg.TraceNonSequential(a); })
       .def("TraceNonSequential", [](AOpticsManager& mg, ARay& r) { mg.TraceNonSequential(r); });
 }

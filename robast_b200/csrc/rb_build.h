@@ -294,7 +294,7 @@ static void scene_features_needed(const rbg_scene_desc* D, unsigned& shapes, uns
     if (D->borders[i].lambertian) phys |= 8u;
   }
   for (int i = 0; i < D->nmirrors; i++)
-    if (D->mirrors[i].graph1d >= 0 || D->mirrors[i].th2 >= 0) phys |= 32u;
+    if (D->mirrors[i].graph1d >= 0 || D->mirrors[i].th2 >= 0 || D->mirrors[i].graph2d >= 0) phys |= 32u;
 }
 
 static int scene_depth_needed(const SceneBuilder& B) {
@@ -319,7 +319,13 @@ static void validate_desc(const rbg_scene_desc* D) {
     if (m.n < 2 || m.n > RB_MAX_TMM_LAYERS * 64 || m.first < 0 || m.first + m.n > D->nlayers) throw Invalid("bad multilayer");
   }
   for (int i = 0; i < D->nmirrors; i++)
-    if (D->mirrors[i].graph2d >= 0) throw NotSupported("TGraph2D mirror reflectance is not supported on the device path");
+    if (D->mirrors[i].graph2d >= D->ngraph2d) throw Invalid("mirror with bad TGraph2D id");
+  for (int i = 0; i < D->ngraph2d; i++) {
+    const rbg_graph2d& g = D->graph2d[i];
+    if (g.first_tri < 0 || g.ntri < 0 || g.first_tri + g.ntri > D->ntri) throw Invalid("bad TGraph2D triangle slice");
+  }
+  for (int i = 0; i < 3 * D->ntri; i++)
+    if (D->tri[i] < 0 || D->tri[i] >= D->ng2pts) throw Invalid("TGraph2D triangle vertex out of range");
 }
 
 }  // namespace

@@ -153,6 +153,22 @@ RB_HD inline double th2_interp(const DScene& sc, int h, double x, double y) {
          1.0 * q22 / dd * (x - x1) * (y - y1);
 }
 
+// TGraph2D::Interpolate on the Delaunay triangle list baked by the exporter: the first triangle (list order) whose
+// barycentric coordinates are all >= -1e-9 interpolates linearly; outside the convex hull the value is 0 (fZout)
+RB_HD inline double graph2d_interp(const DScene& sc, int g, double x, double y) {
+  const rbg_graph2d G = sc.graph2d[g];
+  for (int k = 0; k < G.ntri; k++) {
+    const int32_t* t = sc.tri + 3 * (G.first_tri + k);
+    double x0 = sc.g2x[t[0]], y0 = sc.g2y[t[0]], x1 = sc.g2x[t[1]], y1 = sc.g2y[t[1]], x2 = sc.g2x[t[2]], y2 = sc.g2y[t[2]];
+    double den = (y1 - y2) * (x0 - x2) + (x2 - x1) * (y0 - y2);
+    if (den == 0) continue;
+    double l0 = ((y1 - y2) * (x - x2) + (x2 - x1) * (y - y2)) / den, l1 = ((y2 - y0) * (x - x2) + (x0 - x2) * (y - y2)) / den, l2 = 1. - l0 - l1;
+    if (l0 < -1e-9 || l1 < -1e-9 || l2 < -1e-9) continue;
+    return l0 * sc.g2z[t[0]] + l1 * sc.g2z[t[1]] + l2 * sc.g2z[t[2]];
+  }
+  return 0.;
+}
+
 // ================================================================== refractive index n(λ), k(λ)
 RB_HD inline double index_k1(const DScene& sc, int id, double lambda) {
   if (id < 0) return 0.;
@@ -314,29 +330,21 @@ RB_HD inline void tmm_mixed(const DScene& sc, int ml, double th, double lam, dou
 }
 
 // ================================================================== primitive shapes
-// Small fixed-capacity candidate list: crossing parameters of all bounding surfaces of a
-// non-convex primitive; intervals between sorted candidates are classified by Contains().
-#define RB_MAXC 12
-struct Cands {
-  double t[RB_MAXC];
-  int n;
-};
-RB_HD inline void cand_add(Cands& c, double t) {
-  if (!(t > 1e-11) || t > 1e29 || c.n >= RB_MAXC) return;
-  int i = c.n++;
-  while (i > 0 && c.t[i - 1] > t) { c.t[i] = c.t[i - 1]; i--; }
-  c.t[i] = t;
-}
-RB_HD inline void cand_quadratic(Cands& c, double A, double B, double C) {
+// Crossing parameters of all bounding surfaces of a non-convex primitive; the intervals between consecutive
+// candidates are classified by Contains().  The candidates stay in registers (fixed slots, RB_BIG = unused) and are
+// visited in ascending order by repeated selection of the smallest one above the last — no sorted array in local memory.
+RB_HD inline double cand_ok(double t) { return (t > 1e-11 && t <= 1e29) ? t : RB_BIG; }
+RB_HD inline void cand_quadratic(double A, double B, double C, double& t0, double& t1) {
+  t0 = t1 = RB_BIG;
   if (fabs(A) < 1e-300 || fabs(A) < 1e-14 * fabs(B)) {
-    if (B != 0) cand_add(c, -C / B);
+    if (B != 0) t0 = cand_ok(-C / B);
     return;
   }
   double disc = B * B - 4 * A * C;
   if (disc < 0) return;
   double s = sqrt(disc), q = -0.5 * (B + (B >= 0 ? s : -s));
-  cand_add(c, q / A);
-  if (q != 0) cand_add(c, C / q);
+  t0 = cand_ok(q / A);
+  if (q != 0) t1 = cand_ok(C / q);
 }
 
 // ---- TGeoBBox  P: dx,dy,dz,ox,oy,oz
@@ -564,30 +572,35 @@ RB_HD inline bool sphere_contains(const double* P, V3 p) {
   return true;
 }
 RB_HD inline double sphere_dist(const double* P, V3 p, V3 d, bool from_inside) {
-  Cands c;
-  c.n = 0;
+  double c[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) c[k] = RB_BIG;
   double a = dot(d, d), b = 2 * dot(p, d), pp = dot(p, p);
-  if (P[0] > 0) cand_quadratic(c, a, b, pp - P[0] * P[0]);
-  cand_quadratic(c, a, b, pp - P[1] * P[1]);
+  if (P[0] > 0) cand_quadratic(a, b, pp - P[0] * P[0], c[0], c[1]);
+  cand_quadratic(a, b, pp - P[1] * P[1], c[2], c[3]);
   int flags = (int)P[14];
   double dxy = d.x * d.x + d.y * d.y, pdxy = p.x * d.x + p.y * d.y, pxy = p.x * p.x + p.y * p.y;
   if (flags & 1) {
     double c2 = P[6] * P[6], s2 = P[7] * P[7];
-    cand_quadratic(c, dxy * c2 - d.z * d.z * s2, 2 * (pdxy * c2 - p.z * d.z * s2), pxy * c2 - p.z * p.z * s2);
+    cand_quadratic(dxy * c2 - d.z * d.z * s2, 2 * (pdxy * c2 - p.z * d.z * s2), pxy * c2 - p.z * p.z * s2, c[4], c[5]);
   }
   if (flags & 2) {
     double c2 = P[8] * P[8], s2 = P[9] * P[9];
-    cand_quadratic(c, dxy * c2 - d.z * d.z * s2, 2 * (pdxy * c2 - p.z * d.z * s2), pxy * c2 - p.z * p.z * s2);
+    cand_quadratic(dxy * c2 - d.z * d.z * s2, 2 * (pdxy * c2 - p.z * d.z * s2), pxy * c2 - p.z * p.z * s2, c[6], c[7]);
   }
   if (flags & 4) {
     double den = d.y * P[10] - d.x * P[11];
-    if (den != 0) cand_add(c, -(p.y * P[10] - p.x * P[11]) / den);
+    if (den != 0) c[8] = cand_ok(-(p.y * P[10] - p.x * P[11]) / den);
     den = d.y * P[12] - d.x * P[13];
-    if (den != 0) cand_add(c, -(p.y * P[12] - p.x * P[13]) / den);
+    if (den != 0) c[9] = cand_ok(-(p.y * P[12] - p.x * P[13]) / den);
   }
-  double prev = 0;
-  for (int i = 0; i < c.n; i++) {
-    double t = c.t[i];
+  double prev = 0, last = 0;
+  for (int it = 0; it < 10; it++) {
+    double t = RB_BIG;
+#pragma unroll
+    for (int k = 0; k < 10; k++) t = (c[k] > last && c[k] < t) ? c[k] : t;
+    if (t > 1e29) break;
+    last = t;
     if (t - prev < 1e-12) { prev = t; continue; }
     bool in = sphere_contains(P, along(p, d, 0.5 * (prev + t)));
     if (from_inside ? !in : in) return prev;
@@ -1544,7 +1557,8 @@ RB_HD inline double mirror_reflectance(const DScene& sc, int vol, double lambda,
   double ret = 1.0;
   if (mi >= 0) {
     const rbg_mirror& m = sc.mirrors[mi];
-    if (m.th2 >= 0) ret = th2_interp(sc, m.th2, lambda, angle);
+    if (m.graph2d >= 0) ret = graph2d_interp(sc, m.graph2d, lambda, angle);
+    else if (m.th2 >= 0) ret = th2_interp(sc, m.th2, lambda, angle);
     else if (m.graph1d >= 0) ret = graph_eval(sc, m.graph1d, lambda);
     else ret = m.constant;
   }

@@ -18,9 +18,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rb_build.h"
@@ -32,6 +35,7 @@ static std::atomic<long long> g_launches{0};
 static int g_profile = 0;
 struct ProfEvt { cudaEvent_t a, b; int kind; };
 static std::vector<ProfEvt> g_prof_events;
+static std::mutex g_prof_mutex;
 static double g_prof_ms[2] = {0, 0};
 static long long g_prof_n[2] = {0, 0};
 
@@ -82,6 +86,7 @@ struct ProfScope {
   ~ProfScope() {
     if (on) {
       cudaEventRecord(e.b, st);
+      std::lock_guard<std::mutex> lk(g_prof_mutex);
       g_prof_events.push_back(e);
     }
   }
@@ -297,6 +302,7 @@ __global__ void k_tmm(DScene sc, int ml, long long n, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ host: scene
+#define RB_HOST_STREAMS 4  // chunks in flight on the host-buffer path of rbg_trace (one worker thread + stream + stage each)
 struct rbg_scene {
   int device = 0;
   int depth = 0;
@@ -307,9 +313,9 @@ struct rbg_scene {
   // per-scene scratch for the wavefront loop and host staging
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
-  void* stage[3] = {nullptr, nullptr, nullptr};
-  size_t stage_bytes[3] = {0, 0, 0};
-  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  void* stage[RB_HOST_STREAMS] = {};
+  size_t stage_bytes[RB_HOST_STREAMS] = {};
+  cudaStream_t streams[RB_HOST_STREAMS] = {};
   int32_t* d_count = nullptr;
   int32_t* h_count = nullptr;  // pinned
 };
@@ -332,7 +338,7 @@ static void scene_free(rbg_scene* s) {
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
   if (s->scratch) cudaFree(s->scratch);
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < RB_HOST_STREAMS; i++) {
     if (s->stage[i]) cudaFree(s->stage[i]);
     if (s->streams[i]) cudaStreamDestroy(s->streams[i]);
   }
@@ -342,13 +348,21 @@ static void scene_free(rbg_scene* s) {
 }
 
 // ------------------------------------------------------------------------------------------------ host: trace driver
+#ifdef RB_EXPERIMENTS
+extern const rb_variant* const rb_x_variants[];
+#endif
 static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys) {
   const char* force = getenv("RB_FORCE_GENERIC");
   const rb_variant* best = nullptr;
   int best_cost = 1 << 30;
-  if (const char* want = getenv("RB_VARIANT"))  // experiments: force a named (compatible) instantiation
+  if (const char* want = getenv("RB_VARIANT")) {  // experiments: force a named (compatible) instantiation
     for (const rb_variant* v : rb_variants)
       if (!strcmp(v->name, want) && v->depth >= depth && !(shapes & ~v->shapes) && !(phys & ~v->phys)) return v;
+#ifdef RB_EXPERIMENTS
+    for (const rb_variant* const* pv = rb_x_variants; *pv; pv++)
+      if (!strcmp((*pv)->name, want) && (*pv)->depth >= depth && !(shapes & ~(*pv)->shapes) && !(phys & ~(*pv)->phys)) return *pv;
+#endif
+  }
   for (const rb_variant* v : rb_variants) {
     if (v->depth < depth || (shapes & ~v->shapes) || (phys & ~v->phys)) continue;
     if (force && force[0] == '1' && v->shapes != RB_SHAPES_ALL) continue;
@@ -526,10 +540,15 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     s->d.focals = upload(s, D->focals, D->nfocals);
     s->d.multilayers = upload(s, D->multilayers, D->nmultilayers);
     s->d.layers = upload(s, D->layers, D->nlayers);
+    s->d.graph2d = upload(s, D->graph2d, D->ngraph2d);
+    s->d.tri = upload(s, D->tri, 3 * (size_t)D->ntri);
+    s->d.g2x = upload(s, D->g2x, D->ng2pts);
+    s->d.g2y = upload(s, D->g2y, D->ng2pts);
+    s->d.g2z = upload(s, D->g2z, D->ng2pts);
     s->d.nnodes = (int)B.nodes.size();
     s->d.top_shape = D->top_volume >= 0 ? D->volumes[D->top_volume].shape : -1;
-    CK(cudaMalloc((void**)&s->d_count, 3 * sizeof(int32_t)));
-    CK(cudaMallocHost((void**)&s->h_count, 3 * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&s->d_count, RB_HOST_STREAMS * sizeof(int32_t)));
+    CK(cudaMallocHost((void**)&s->h_count, RB_HOST_STREAMS * sizeof(int32_t)));
     // the CSG call chain is not inlined: give it stack
     size_t want = 8192, have = 0;
     CK(cudaDeviceGetLimit(&have, cudaLimitStackSize));
@@ -571,12 +590,37 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
       trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count);
       return;
     }
-    // host buffers: chunked H2D -> trace -> D2H, three chunks in flight on three streams
-    const long long CH = 1 << 22;
+    // host buffers: chunked H2D -> trace -> D2H.  Up to RB_HOST_STREAMS chunks are in flight, each on its own stream
+    // with its own stage buffer, driven by its own host thread: the wavefront loop reads the survivor count back
+    // after every bounce, and that wait must not keep the other chunks' copies from being enqueued.  In steady state
+    // the H2D of chunk c+1, the bounce kernels of chunk c and the D2H of chunk c-1 overlap (PCIe is full duplex).
+    // chunk size: small enough that a 1e7-ray call has a steady state (H2D, kernels and D2H of different chunks
+    // overlapping), large enough that a bounce launch still fills the 148 SMs many times over
+    static const long long CH = getenv("RB_HOST_CHUNK") ? std::max(4096LL, atoll(getenv("RB_HOST_CHUNK"))) : (1LL << 20);
     long long chunk = std::min<long long>(rays->n, CH);
     size_t per_ray = 8 * 8 + 7 * 8 + 3 * 4;  // in + out
     size_t bytes = (size_t)chunk * per_ray + 4096 + (o->steps_per_launch >= 0 ? wavefront_scratch_bytes(chunk) : 0);
-    int nst = rays->n > chunk ? 3 : 1;
+    // chunk list: sizes ramp up from chunk/8 at the start and down again at the end, so that the un-overlapped
+    // pipeline fill (first H2D) and drain (last D2H) of the call are short
+    std::vector<std::pair<long long, long long>> chunks;  // (first ray, count)
+    {
+      long long head = 0, tail = rays->n;
+      std::vector<std::pair<long long, long long>> back;
+      for (long long sz = std::max<long long>(chunk / 8, 65536); sz < chunk && tail - head > 4 * chunk; sz *= 2) {
+        chunks.emplace_back(head, sz);
+        head += sz;
+        back.emplace_back(tail - sz, sz);
+        tail -= sz;
+      }
+      while (head < tail) {
+        long long m = std::min(chunk, tail - head);
+        chunks.emplace_back(head, m);
+        head += m;
+      }
+      chunks.insert(chunks.end(), back.rbegin(), back.rend());
+    }
+    long long nchunks = (long long)chunks.size();
+    int nst = (int)std::min<long long>(nchunks, RB_HOST_STREAMS);
     for (int k = 0; k < nst; k++) {
       if (!s->streams[k]) CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
       if (s->stage_bytes[k] < bytes) {
@@ -587,37 +631,57 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
         s->stage_bytes[k] = bytes;
       }
     }
-    int ci = 0;
-    for (long long b = 0; b < rays->n; b += chunk, ci++) {
-      long long m = std::min(chunk, rays->n - b);
-      int k = ci % nst;
+    auto work = [&](int k) {
+      CK(cudaSetDevice(s->device));
       cudaStream_t st = s->streams[k];
       char* base = (char*)s->stage[k];
-      double* din[8];
-      double* dout[7];
-      int32_t* diout[3];
-      size_t off = 0;
-      for (int a = 0; a < 8; a++) { din[a] = (double*)(base + off); off += (size_t)chunk * 8; }
-      for (int a = 0; a < 7; a++) { dout[a] = (double*)(base + off); off += (size_t)chunk * 8; }
-      for (int a = 0; a < 3; a++) { diout[a] = (int32_t*)(base + off); off += (size_t)chunk * 4; }
-      off = (off + 255) & ~size_t(255);
-      const double* hin[8] = {rays->x, rays->y, rays->z, rays->t, rays->dx, rays->dy, rays->dz, rays->lambda};
-      double* hout[7] = {rays->ox, rays->oy, rays->oz, rays->ot, rays->odx, rays->ody, rays->odz};
-      int32_t* hiout[3] = {rays->status, rays->last_node, rays->npoints};
-      for (int a = 0; a < 8; a++) CK(cudaMemcpyAsync(din[a], hin[a] + b, (size_t)m * 8, cudaMemcpyHostToDevice, st));
-      DRays R;
-      R.x = din[0]; R.y = din[1]; R.z = din[2]; R.t = din[3]; R.dx = din[4]; R.dy = din[5]; R.dz = din[6]; R.lambda = din[7];
-      R.ox = dout[0]; R.oy = dout[1]; R.oz = dout[2]; R.ot = dout[3]; R.odx = dout[4]; R.ody = dout[5]; R.odz = dout[6];
-      R.status = diout[0]; R.last_node = diout[1]; R.npoints = diout[2];
-      R.cur = nullptr; R.ndraw = nullptr;
-      trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + off, s->d_count + k, s->h_count + k);
-      for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(hout[a] + b, dout[a], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-      for (int a = 0; a < 3; a++) CK(cudaMemcpyAsync(hiout[a] + b, diout[a], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-      if (ci + 1 >= nst) {  // before reusing a stage buffer, the chunk that used it must be done
-        // streams are in-order, so the next use of stream k is automatically serialised
+      for (long long ci = k; ci < nchunks; ci += nst) {
+        long long b = chunks[ci].first, m = chunks[ci].second;
+        double* din[8];
+        double* dout[7];
+        int32_t* diout[3];
+        size_t off = 0;
+        for (int a = 0; a < 8; a++) { din[a] = (double*)(base + off); off += (size_t)chunk * 8; }
+        for (int a = 0; a < 7; a++) { dout[a] = (double*)(base + off); off += (size_t)chunk * 8; }
+        for (int a = 0; a < 3; a++) { diout[a] = (int32_t*)(base + off); off += (size_t)chunk * 4; }
+        off = (off + 255) & ~size_t(255);
+        const double* hin[8] = {rays->x, rays->y, rays->z, rays->t, rays->dx, rays->dy, rays->dz, rays->lambda};
+        double* hout[7] = {rays->ox, rays->oy, rays->oz, rays->ot, rays->odx, rays->ody, rays->odz};
+        int32_t* hiout[3] = {rays->status, rays->last_node, rays->npoints};
+        for (int a = 0; a < 8; a++) CK(cudaMemcpyAsync(din[a], hin[a] + b, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        DRays R;
+        R.x = din[0]; R.y = din[1]; R.z = din[2]; R.t = din[3]; R.dx = din[4]; R.dy = din[5]; R.dz = din[6]; R.lambda = din[7];
+        R.ox = dout[0]; R.oy = dout[1]; R.oz = dout[2]; R.ot = dout[3]; R.odx = dout[4]; R.ody = dout[5]; R.odz = dout[6];
+        R.status = diout[0]; R.last_node = diout[1]; R.npoints = diout[2];
+        R.cur = nullptr; R.ndraw = nullptr;
+        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + off, s->d_count + k, s->h_count + k);
+        // the stream is in-order: the next chunk's H2D into this stage buffer waits for these copies
+        for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(hout[a] + b, dout[a], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+        for (int a = 0; a < 3; a++) CK(cudaMemcpyAsync(hiout[a] + b, diout[a], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      }
+      CK(cudaStreamSynchronize(st));
+    };
+    if (nst == 1) {
+      work(0);
+      return;
+    }
+    std::exception_ptr errs[RB_HOST_STREAMS];
+    std::vector<std::thread> workers;
+    for (int k = 0; k < nst; k++)
+      workers.emplace_back([&, k] {
+        try {
+          work(k);
+        } catch (...) {
+          errs[k] = std::current_exception();
+        }
+      });
+    for (auto& w : workers) w.join();
+    for (int k = 0; k < nst; k++) {
+      if (errs[k]) {
+        for (int j = 0; j < nst; j++) cudaStreamSynchronize(s->streams[j]);
+        std::rethrow_exception(errs[k]);
       }
     }
-    for (int k = 0; k < nst; k++) CK(cudaStreamSynchronize(s->streams[k]));
   });
 }
 

@@ -68,6 +68,11 @@ struct DScene {
   const rbg_focal* focals;
   const rbg_multilayer* multilayers;
   const rbg_layer* layers;
+  const rbg_graph2d* graph2d;
+  const int32_t* tri;
+  const double* g2x;
+  const double* g2y;
+  const double* g2z;
   int32_t nnodes;
   int32_t top_shape;
 };

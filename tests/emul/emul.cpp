@@ -43,6 +43,7 @@ extern "C" __attribute__((visibility("default"))) int emul_trace(const rbg_scene
     sc.nodes = B.nodes.data(); sc.bvh = B.bvh.data(); sc.shapes = B.shapes.data(); sc.dpar = B.dpar.data(); sc.mats = B.mats.data();
     sc.volumes = D->volumes; sc.borders = D->borders; sc.graphs = D->graphs; sc.gx = D->gx; sc.gy = D->gy; sc.th2 = D->th2; sc.th2v = D->th2v;
     sc.indices = D->indices; sc.mirrors = D->mirrors; sc.focals = D->focals; sc.multilayers = D->multilayers; sc.layers = D->layers;
+    sc.graph2d = D->graph2d; sc.tri = D->tri; sc.g2x = D->g2x; sc.g2y = D->g2y; sc.g2z = D->g2z;
     sc.nnodes = (int)B.nodes.size();
     sc.top_shape = D->volumes[D->top_volume].shape;
     DTraceParams tp;

@@ -33,6 +33,8 @@ def load_oracle():
         f.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.orc_th2_interp.restype = C.c_double
     lib.orc_th2_interp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.orc_graph2d_interp.restype = C.c_double
+    lib.orc_graph2d_interp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
     lib.orc_uniform.restype = C.c_double
     lib.orc_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     lib.orc_shoot.restype = C.c_int

@@ -63,3 +63,23 @@ def test_unit_scenes_match_oracle(R, oracle, emul):
     got = H.trace_with(emul.emul_trace, mgr.ExportScene(), H.Rays([[0, 0, 0, 0, 0.3, 0.1, -1, 400e-7]]), H.opts(limit=12))
     ref = H.trace_with(oracle.orc_trace, mgr.ExportScene(), H.Rays([[0, 0, 0, 0, 0.3, 0.1, -1, 400e-7]]), H.opts(limit=12))
     assert got.npoints[0] == 12 and H.compare(ref, got)["bad"] == 0
+
+
+def test_tgraph2d_mirror_device_code_matches_oracle(R, oracle, emul):
+    g = R.TGraph2D()
+    for i, (lam, th, v) in enumerate(((300e-7, 0., 0.0), (300e-7, math.pi / 2, 0.3), (500e-7, 0., 0.7), (500e-7, math.pi / 2, 1.0), (420e-7, 0.7, 0.9))):
+        g.SetPoint(i, lam, th, v)
+    mgr, mirror, keep = scenes.mirror_box_with_border(reflectance=g)
+    rng = np.random.default_rng(5)
+    n = 4000
+    inp = np.zeros((n, 8))
+    inp[:, 2] = 51.
+    ang = rng.random(n) * 1.4
+    inp[:, 4], inp[:, 6], inp[:, 7] = np.sin(ang), -np.cos(ang), 300e-7 + 200e-7 * rng.random(n)
+    ex = mgr.ExportScene()
+    ref = H.trace_with(oracle.orc_trace, ex, H.Rays(inp), H.opts(seed=3))
+    got = H.trace_with(emul.emul_trace, ex, H.Rays(inp), H.opts(seed=3))
+    rep = H.compare(ref, got)
+    assert rep["bad"] == 0 and rep["status_mismatch"] == 0, rep
+    frac = (got.status == 2).mean()
+    assert 0.3 < frac < 0.9

@@ -171,6 +171,27 @@ def test_reference_style_unit_tests_on_gpu(R):
     assert nf + ns == 90000 and abs(nf / 90000. - 0.5) < 3 * math.sqrt(0.25 / 90000)
 
 
+def test_mirror_tgraph2d_reflectance(R, oracle):
+    """unittest_robast.py:218-246: TGraph2D reflectance 0.5 at (400 nm, 45 deg); GPU vs oracle per ray + the reference's 3-sigma test"""
+    nm, deg = 1e-7, math.pi / 180.
+    g = R.TGraph2D()
+    g.SetPoint(0, 300 * nm, 0 * deg, 0.0)
+    g.SetPoint(1, 300 * nm, 90 * deg, 0.3)
+    g.SetPoint(2, 500 * nm, 0 * deg, 0.7)
+    g.SetPoint(3, 500 * nm, 90 * deg, 1.0)
+    mgr, mirror, keep = scenes.mirror_box_with_border(reflectance=g)
+    N = 100000
+    inp = np.tile([0, 0, 51., 0, math.sqrt(2.), 0, -math.sqrt(2.), 400 * nm], (N, 1))
+    ex = mgr.ExportScene()
+    ref = H.trace_with(oracle.orc_trace, ex, H.Rays(inp), H.opts(seed=21), nthreads=4)
+    got = H.trace_gpu(ex, H.Rays(inp), H.opts(seed=21))
+    rep = H.compare(ref, got)
+    assert rep["bad"] == 0 and rep["status_mismatch"] == 0, rep
+    n = int((got.status == R.RBG_EXIT).sum())
+    assert (n - 3 * n ** 0.5) / N < 0.5 < (n + 3 * n ** 0.5) / N
+    assert int((got.status == R.RBG_ABSORB).sum()) + n == N
+
+
 def test_roughness_and_lambertian_statistics(R, oracle):
     """unittest_robast.py:333-388 (reflected direction spread = 2 sigma) and :782-850 (Lambertian) on the GPU vs the oracle"""
     sigma = math.radians(1.0)

@@ -256,3 +256,60 @@ def test_schmidt_cassegrain_design_spot(oracle):  # the Zemax sample design focu
     H.trace_with(oracle.orc_trace, mgr.ExportScene(), rays, H.opts(disable_fresnel=1), nthreads=4)
     f = rays.status == 3
     assert f.sum() > 3000 and rays.pos[f][:, :2].std(0).max() < 5e-4  # < 5 um rms
+
+
+def test_kat_tgraph2d_interpolate(R, oracle):  # unittest_robast.py:220-229: 0.5 at (400 nm, 45 deg); src/AMirror.cxx:46-47
+    deg = math.pi / 180.
+    g = R.TGraph2D()
+    g.SetPoint(0, 300 * nm, 0 * deg, 0.0)
+    g.SetPoint(1, 300 * nm, 90 * deg, 0.3)
+    g.SetPoint(2, 500 * nm, 0 * deg, 0.7)
+    g.SetPoint(3, 500 * nm, 90 * deg, 1.0)
+    assert len(g.GetTriangles()) == 6  # two triangles over the rectangle
+    assert abs(g.Interpolate(400 * nm, 45 * deg) - 0.5) < 1e-12
+    mirror = R.AMirror("mirror", R.TGeoBBox("mirrorbox", 50., 50., 50.))
+    mirror.SetReflectance(g)
+    assert abs(mirror.GetReflectance(400 * nm, 45 * deg) - 0.5) < 1e-3  # the reference asserts 3 places
+    assert mirror.GetReflectance(800 * nm, 45 * deg) == 0.0  # outside the convex hull: TGraph2D returns 0
+    mgr, mirror, keep = scenes.mirror_box_with_border(reflectance=g)
+    ex = mgr.ExportScene()
+    for lam, th in ((400 * nm, 45 * deg), (310 * nm, 80 * deg), (499 * nm, 1 * deg), (300 * nm, 90 * deg), (600 * nm, 0.2)):
+        assert abs(oracle.orc_graph2d_interp(ex.desc_ptr(), 0, lam, th) - g.Interpolate(lam, th)) < 1e-13
+
+
+def test_tgraph2d_delaunay_properties(R, oracle):
+    """scattered points: the triangulation covers the convex hull exactly once, satisfies the empty-circumcircle
+    property on the normalised coordinates ROOT triangulates in, and reproduces a plane exactly"""
+    rng = np.random.default_rng(3)
+    n = 60
+    x, y = 3e-5 + 4e-5 * rng.random(n), 1.5 * rng.random(n)  # wavelengths (cm) and angles (rad): very different scales
+    f = lambda a, b: 0.2 + 3000. * a + 0.25 * b
+    g = R.TGraph2D()
+    for i in range(n):
+        g.SetPoint(i, x[i], y[i], f(x[i], y[i]))
+    tri = np.asarray(g.GetTriangles()).reshape(-1, 3)
+    xn, yn = (x - x.min()) / (x.max() - x.min()), (y - y.min()) / (y.max() - y.min())
+    from scipy.spatial import ConvexHull
+    hull = ConvexHull(np.c_[xn, yn])
+    area = 0.5 * np.abs((xn[tri[:, 1]] - xn[tri[:, 0]]) * (yn[tri[:, 2]] - yn[tri[:, 0]]) - (xn[tri[:, 2]] - xn[tri[:, 0]]) * (yn[tri[:, 1]] - yn[tri[:, 0]]))
+    assert abs(area.sum() - hull.volume) < 1e-9 and len(tri) == 2 * n - 2 - len(hull.vertices)
+    for a, b, c in tri:  # empty circumcircle
+        ax, ay, bx, by, cx, cy = xn[a], yn[a], xn[b], yn[b], xn[c], yn[c]
+        d = 2 * (ax * (by - cy) + bx * (cy - ay) + cx * (ay - by))
+        ux = ((ax * ax + ay * ay) * (by - cy) + (bx * bx + by * by) * (cy - ay) + (cx * cx + cy * cy) * (ay - by)) / d
+        uy = ((ax * ax + ay * ay) * (cx - bx) + (bx * bx + by * by) * (ax - cx) + (cx * cx + cy * cy) * (bx - ax)) / d
+        r2 = (ax - ux) ** 2 + (ay - uy) ** 2
+        others = np.ones(n, bool)
+        others[[a, b, c]] = False
+        assert ((xn[others] - ux) ** 2 + (yn[others] - uy) ** 2 > r2 * (1 - 1e-9)).all()
+    mirror = R.AMirror("mirror", R.TGeoBBox("mirrorbox", 50., 50., 50.))
+    mirror.SetReflectance(g)
+    mgr = scenes.make_the_world()
+    mgr.GetTopVolume().AddNode(mirror, 1)
+    mgr.CloseGeometry()
+    ex = mgr.ExportScene()
+    for k in range(200):
+        a, b = 3e-5 + 4e-5 * rng.random(), 1.5 * rng.random()
+        v = g.Interpolate(a, b)
+        assert abs(oracle.orc_graph2d_interp(ex.desc_ptr(), 0, a, b) - v) < 1e-12
+        assert v == 0.0 or abs(v - f(a, b)) < 1e-12
