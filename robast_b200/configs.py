@@ -205,6 +205,42 @@ def hex_winston_cone(rings=2, coating="multilayer", precalc=False):
     return mgr, keep
 
 
+# ----------------------------------------------------------------------------- HexOkumuraCone.C:34-83 (mode 1) and a round variant
+def okumura_cone(kind="pgon", nz=100):
+    """single Bezier-profile light guide: kind='pgon' = hex-hex Okumura cone (AGeoBezierPgon, HexOkumuraCone.C:63-68),
+    kind='pcon' = its round counterpart (AGeoBezierPcon); ideal mirror, flat PMT just below the exit aperture."""
+    rin, rout = 20 * mm, 10 * mm
+    mgr = R.AOpticsManager("manager", "HexOkumuraCone")
+    world = R.AOpticalComponent("world", R.TGeoBBox("worldbox", 10 * cm, 10 * cm, 10 * cm))
+    mgr.SetTopVolume(world)
+    rot30 = R.TGeoRotation("rot30", 30, 0, 0)
+    rot30.RegisterYourself()
+    dz = R.AGeoWinstonConePoly("hexWin", rin, rout, 6).GetDZ()
+    if kind == "pgon":
+        outer = R.TGeoPgon("pgon", 0, 360, 6, 4)
+        inner = R.AGeoBezierPgon("hexBez", 0, 360, 6, nz, rin, rout, dz)
+        expr = "pgon:rot30 - hexBez:rot30"
+        pmt_shape = R.TGeoPgon("pgonPMT", 0, 360, 6, 2)
+    else:
+        outer = R.TGeoPcon("pgon", 0, 360, 4)
+        inner = R.AGeoBezierPcon("hexBez", 0, 360, nz, rin, rout, dz)
+        expr = "pgon - hexBez"
+        pmt_shape = R.TGeoPcon("pgonPMT", 0, 360, 2)
+    outer.DefineSection(0, -dz * 0.9999, 0, rout * 1.1)
+    outer.DefineSection(1, -dz * 0.5, 0, rin * 0.9)
+    outer.DefineSection(2, -dz * 0., 0, rin * 1.001)
+    outer.DefineSection(3, dz * 0.9999, 0, rin * 1.001)
+    inner.SetControlPoints(0.39, 0.18, 0.87, 0.36)
+    cone_mirror = R.AMirror("coneMirror", R.TGeoCompositeShape("coneComp1", expr))
+    world.AddNode(cone_mirror, 1)
+    pmt_shape.DefineSection(0, -dz - 0.01 * mm, 0, rout * 1.01)
+    pmt_shape.DefineSection(1, -dz, 0, rout * 1.01)
+    pmt = R.AFocalSurface("pmt", pmt_shape)
+    world.AddNode(pmt, 1, rot30)
+    mgr.CloseGeometry()
+    return mgr, [outer, inner, pmt_shape]
+
+
 # ----------------------------------------------------------------------------- beams
 def beam(cfg, theta_deg=0.0, n_side=None):
     """rbg_shoot_desc parameters (dict) of the configuration's synthetic beam."""

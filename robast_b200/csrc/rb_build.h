@@ -137,7 +137,20 @@ struct SceneBuilder {
           setbox(R, R, P[4], P[4 + 3 * (nz - 1)]);
           break;
         }
-        case RBG_SHAPE_PCON: throw NotSupported("TGeoPcon is not supported on the device path yet");
+        case RBG_SHAPE_PCON: {  // device layout = the polygon's with nedges = 0: phi1,dphi,0,nz, nz x (z,rmin,rmax)
+          int nz = (int)P[2];
+          if (fabs(P[1] - 360.) > 1e-9) throw NotSupported("TGeoPcon with dphi != 360 is not supported on the device path");
+          if (nz < 2) throw Invalid("TGeoPcon needs nz >= 2");
+          double rmx = 0;
+          for (int k = 0; k < nz; k++) {
+            if (P[3 + 3 * k + 1] > 0) throw NotSupported("TGeoPcon with rmin > 0 is not supported on the device path");
+            rmx = std::max(rmx, P[3 + 3 * k + 2]);
+          }
+          dpar.push_back(P[0]); dpar.push_back(P[1]); dpar.push_back(0.); dpar.push_back((double)nz);
+          dpar.insert(dpar.end(), P + 3, P + 3 + 3 * nz);
+          setbox(rmx, rmx, P[3], P[3 + 3 * (nz - 1)]);
+          break;
+        }
         case RBG_SHAPE_ASPHERE: {
           int n1 = (int)P[8], n2 = (int)P[9];
           dpar.insert(dpar.end(), P, P + 12 + n1 + n2);

@@ -633,22 +633,29 @@ RB_HD inline V3 sphere_normal(const double* P, V3 p, V3 d) {
   return n;
 }
 
-// ---- TGeoPgon (rmin == 0, full 360 deg; enforced at scene build)
-// P: phi1,dphi,nedges,nz, nz x (z,rmin,rmax), nedges x (cos,sin) of the edge-centre azimuths.
-// The solid is a stack of convex slabs: each slab is clipped analytically (2 z planes + nedges side
-// planes); no trigonometry per ray.
-RB_HD inline double pgon_proj_max(const double* P, V3 p) {
+// ---- TGeoPgon / TGeoPcon (rmin == 0, full 360 deg; enforced at scene build)
+// P: phi1,dphi,nedges,nz, nz x (z,rmin,rmax), nedges x (cos,sin) of the edge-centre azimuths; a polycone is stored
+// with nedges = 0 (CONE = true: the radial measure is sqrt(x^2+y^2) instead of the largest edge projection).
+// The solid is a stack of convex slabs: each slab is clipped analytically (2 z planes + nedges side planes, or one
+// cone frustum); no trigonometry per ray.
+template <bool CONE> RB_HD inline double poly_radius(const double* P, V3 p, int& eb) {
+  eb = 0;
+  if (CONE) return sqrt(p.x * p.x + p.y * p.y);
   int ne = (int)P[2], nz = (int)P[3];
   const double* cs = P + 4 + 3 * nz;
   double m = -RB_BIG;
-  for (int e = 0; e < ne; e++) m = rb_max(m, p.x * cs[2 * e] + p.y * cs[2 * e + 1]);
+  for (int e = 0; e < ne; e++) {
+    double pr = p.x * cs[2 * e] + p.y * cs[2 * e + 1];
+    if (pr > m) { m = pr; eb = e; }
+  }
   return m;
 }
-RB_HD inline bool pgon_contains(const double* P, V3 p) {
+template <bool CONE> RB_HD inline bool poly_contains(const double* P, V3 p) {
   int nz = (int)P[3];
   const double* sec = P + 4;
   if (p.z < sec[0] || p.z > sec[3 * (nz - 1)]) return false;
-  double r = pgon_proj_max(P, p);
+  int eb;
+  double r = poly_radius<CONE>(P, p, eb);
   int iz = 0;
   for (int i = 1; i < nz; i++)
     if (sec[3 * i] <= p.z) iz = i;
@@ -659,7 +666,7 @@ RB_HD inline bool pgon_contains(const double* P, V3 p) {
   return !(r > rmax);
 }
 // ray interval inside slab k; returns false if empty
-RB_HD inline bool pgon_slab(const double* P, int k, V3 p, V3 d, double& tin, double& tout) {
+template <bool CONE> RB_HD inline bool poly_slab(const double* P, int k, V3 p, V3 d, double& tin, double& tout) {
   int ne = (int)P[2], nz = (int)P[3];
   const double* sec = P + 4;
   const double* cs = P + 4 + 3 * nz;
@@ -673,6 +680,26 @@ RB_HD inline bool pgon_slab(const double* P, int k, V3 p, V3 d, double& tin, dou
     tout = rb_max(ta, tb);
   } else if (p.z < z0 || p.z > z1) return false;
   double s = (r1 - r0) / dz, base = r0 + (p.z - z0) * s;
+  if (CONE) {
+    // inside the frustum: f(t) = |xy(t)|^2 - (base + s dz t)^2 <= 0 on the nappe with non-negative radius, which is
+    // the only one the z slab can reach (r0, r1 >= 0)
+    double g = s * d.z, A = d.x * d.x + d.y * d.y - g * g, B = 2 * (p.x * d.x + p.y * d.y - base * g), C = p.x * p.x + p.y * p.y - base * base;
+    if (fabs(A) < 1e-14 * (d.x * d.x + d.y * d.y + g * g)) {  // parallel to a generator: f is linear
+      if (B > 0) tout = rb_min(tout, -C / B);
+      else if (B < 0) tin = rb_max(tin, -C / B);
+      else if (C > 0) return false;
+      return tin < tout;
+    }
+    double disc = B * B - 4 * A * C;
+    if (disc < 0) return false;  // (A < 0 cannot have disc < 0: the line would cross the axis plane inside both nappes)
+    double sq = sqrt(disc), q = -0.5 * (B + (B >= 0 ? sq : -sq));
+    double ta = q / A, tb = q != 0 ? C / q : ta;
+    double t1 = rb_min(ta, tb), t2 = rb_max(ta, tb);
+    if (A > 0) { tin = rb_max(tin, t1); tout = rb_min(tout, t2); }
+    else if (g > 0) tin = rb_max(tin, t2);
+    else tout = rb_min(tout, t1);
+    return tin < tout;
+  }
   for (int e = 0; e < ne; e++) {
     // half-space: x c + y s - (r0 + (z - z0) s) <= 0
     double f0 = p.x * cs[2 * e] + p.y * cs[2 * e + 1] - base, fd = d.x * cs[2 * e] + d.y * cs[2 * e + 1] - s * d.z;
@@ -682,12 +709,12 @@ RB_HD inline bool pgon_slab(const double* P, int k, V3 p, V3 d, double& tin, dou
   }
   return tin < tout;
 }
-RB_HD inline double pgon_dist_out(const double* P, V3 p, V3 d) {
+template <bool CONE> RB_HD inline double poly_dist_out(const double* P, V3 p, V3 d) {
   int nz = (int)P[3];
   double best = RB_BIG;
   for (int k = 0; k + 1 < nz; k++) {
     double tin, tout;
-    if (!pgon_slab(P, k, p, d, tin, tout)) continue;
+    if (!poly_slab<CONE>(P, k, p, d, tin, tout)) continue;
     if (tout <= 1e-11) continue;
     double t = tin > 0 ? tin : 0.0;
     if (tout - t < 1e-12) continue;
@@ -695,30 +722,29 @@ RB_HD inline double pgon_dist_out(const double* P, V3 p, V3 d) {
   }
   return best;
 }
-RB_HD inline double pgon_dist_in(const double* P, V3 p, V3 d) {
+template <bool CONE> RB_HD inline double poly_dist_in(const double* P, V3 p, V3 d) {
   int nz = (int)P[3];
   double cur = 0;
   for (int iter = 0; iter < nz; iter++) {
     bool advanced = false;
     for (int k = 0; k + 1 < nz; k++) {
       double tin, tout;
-      if (!pgon_slab(P, k, p, d, tin, tout)) continue;
+      if (!poly_slab<CONE>(P, k, p, d, tin, tout)) continue;
       if (tin <= cur + 1e-9 && tout > cur + 1e-9) { cur = tout; advanced = true; }
     }
     if (!advanced) break;
   }
   return cur;
 }
-RB_HD inline V3 pgon_normal(const double* P, V3 p, V3 d) {
-  int ne = (int)P[2], nz = (int)P[3];
+template <bool CONE> RB_HD inline V3 poly_normal(const double* P, V3 p, V3 d) {
+  int nz = (int)P[3];
   const double* sec = P + 4;
   const double* cs = P + 4 + 3 * nz;
   int eb = 0;
-  double r = -RB_BIG;
-  for (int e = 0; e < ne; e++) {
-    double pr = p.x * cs[2 * e] + p.y * cs[2 * e + 1];
-    if (pr > r) { r = pr; eb = e; }
-  }
+  double r = poly_radius<CONE>(P, p, eb);
+  double ux, uy;  // outward radial unit vector of the lateral face
+  if (CONE) { ux = r > 0 ? p.x / r : 1.; uy = r > 0 ? p.y / r : 0.; }
+  else { ux = cs[2 * eb]; uy = cs[2 * eb + 1]; }
   double best = RB_BIG;
   V3 n = v3(0, 0, 1);
   for (int i = 0; i < nz; i++) {
@@ -733,7 +759,7 @@ RB_HD inline V3 pgon_normal(const double* P, V3 p, V3 d) {
     if (dz < 1e-8 || p.z < z0 - 1e-6 || p.z > z1 + 1e-6) continue;
     double s = (sec[3 * (k + 1) + 2] - sec[3 * k + 2]) / dz, rr = sec[3 * k + 2] + (p.z - z0) * s, nn = sqrt(1 + s * s);
     double dist = fabs(r - rr) / nn;
-    if (dist < best) { best = dist; n = v3(cs[2 * eb] / nn, cs[2 * eb + 1] / nn, -s / nn); }
+    if (dist < best) { best = dist; n = v3(ux / nn, uy / nn, -s / nn); }
   }
   if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
   return n;
@@ -1051,7 +1077,8 @@ template <unsigned SM> RB_HD inline bool prim_contains(const DScene& sc, const D
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_contains(P, p); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_contains(P, p); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_contains(P, p); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_contains(P, p); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_contains<false>(P, p); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_contains<true>(P, p); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_contains(P, p); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_contains(P, false, p); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_contains(P, true, p); else break;
@@ -1065,7 +1092,8 @@ template <unsigned SM> RB_HD inline double prim_dist_in(const DScene& sc, const 
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_dist_in(P[0], P[1], P[2], p, d); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_dist(P, p, d, true); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_dist_in(P, p, d); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_dist_in(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_dist_in<false>(P, p, d); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_dist_in<true>(P, p, d); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist4(P, p, d); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_in(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_in(P, true, p, d); else break;
@@ -1079,7 +1107,8 @@ template <unsigned SM> RB_HD inline double prim_dist_out(const DScene& sc, const
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_dist_out(P[0], P[1], P[2], p, d); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_dist(P, p, d, false); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_dist_out(P, p, d); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_dist_out(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_dist_out<false>(P, p, d); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_dist_out<true>(P, p, d); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist_out(P, p, d, step); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_out(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_out(P, true, p, d); else break;
@@ -1093,7 +1122,8 @@ template <unsigned SM> RB_HD inline V3 prim_normal(const DScene& sc, const DShap
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_normal(P, p, d); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_normal(P, p, d); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_normal(P, p, d); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return pgon_normal(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_normal<false>(P, p, d); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_normal<true>(P, p, d); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_normal(P, p, d); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_normal(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_normal(P, true, p, d); else break;

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restric
     if (lane == 0) {
       atomicExch(&tile_state[tile], (2ull << 32) | (unsigned)(excl + total));  // INCLUSIVE PREFIX
       s_prefix = excl;
-      if (tile == ntiles - 1) *count_out = excl + total;
+      if (tile == ntiles - 1) { *count_out = excl + total; __threadfence_system(); }
     }
   }
   __syncthreads();
@@ -302,7 +302,7 @@ __global__ void k_tmm(DScene sc, int ml, long long n, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ host: scene
-#define RB_HOST_STREAMS 4  // chunks in flight on the host-buffer path of rbg_trace (one worker thread + stream + stage each)
+#define RB_HOST_STREAMS 8  // chunks in flight on the host-buffer path of rbg_trace (one worker thread + stream + stage each)
 struct rbg_scene {
   int device = 0;
   int depth = 0;
@@ -443,12 +443,13 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     int32_t* out = (live == liveA) ? liveB : liveA;
     {
       ProfScope ps(st, 1);
-      k_compact<<<tiles, CP_THREADS, 0, st>>>(live, (int)nlive, R.status, out, d_count, tile_state, tile_counter, tiles,
+      // the survivor count is written straight into pinned host memory (UVA-mapped): a 4-byte cudaMemcpyAsync would
+      // queue behind the other chunks' multi-MB result copies on the D2H copy engine and stall every bounce
+      k_compact<<<tiles, CP_THREADS, 0, st>>>(live, (int)nlive, R.status, out, h_count, tile_state, tile_counter, tiles,
                                               (reinterpret_cast<uintptr_t>(R.status) & 15) == 0);
       g_launches++;
       CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(h_count, d_count, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     nlive = *h_count;
     live = out;
@@ -620,7 +621,8 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
       chunks.insert(chunks.end(), back.rbegin(), back.rend());
     }
     long long nchunks = (long long)chunks.size();
-    int nst = (int)std::min<long long>(nchunks, RB_HOST_STREAMS);
+    static const int max_streams = getenv("RB_HOST_NSTREAMS") ? std::min(RB_HOST_STREAMS, std::max(1, atoi(getenv("RB_HOST_NSTREAMS")))) : 6;
+    int nst = (int)std::min<long long>(nchunks, max_streams);
     for (int k = 0; k < nst; k++) {
       if (!s->streams[k]) CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
       if (s->stage_bytes[k] < bytes) {

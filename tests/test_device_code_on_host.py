@@ -83,3 +83,20 @@ def test_tgraph2d_mirror_device_code_matches_oracle(R, oracle, emul):
     assert rep["bad"] == 0 and rep["status_mismatch"] == 0, rep
     frac = (got.status == 2).mean()
     assert 0.3 < frac < 0.9
+
+
+@pytest.mark.parametrize("kind,theta", [("pgon", 0.0), ("pgon", 22.0), ("pcon", 0.0), ("pcon", 18.0), ("pcon", 35.0)])
+def test_bezier_cones_match_oracle(oracle, emul, kind, theta):
+    """HexOkumuraCone.C mode 1 (AGeoBezierPgon, 100 sections) and its round AGeoBezierPcon counterpart: the device code's
+    convex-slab polygon/cone intersection against the oracle's candidate/Contains restatement of TGeoPgon/TGeoPcon"""
+    mgr, _keep = configs.okumura_cone(kind)
+    ex = mgr.ExportScene()
+    beam = configs.beam(5, theta, n_side=6.0)
+    n = 3000
+    o = H.opts(seed=7)
+    ref = H.trace_with(oracle.orc_trace, ex, H.make_rays(oracle, beam, 0, n), o, nthreads=4)
+    got = H.trace_with(emul.emul_trace, ex, H.make_rays(oracle, beam, 0, n), o)
+    rep = H.compare(ref, got)
+    assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, rep
+    frac = (got.status == 3).mean()
+    assert (frac > 0.05) if theta < 25 else (frac < 0.05)  # inside / outside the ~30 deg acceptance of the guide

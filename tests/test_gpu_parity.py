@@ -47,6 +47,20 @@ def test_precalculated_tmm_table_config5(oracle):
     assert rep["bad"] == 0 and rep["status_mismatch"] == 0, rep
 
 
+@pytest.mark.parametrize("kind,theta,steps", [("pgon", 0.0, 0), ("pgon", 20.0, 1), ("pcon", 0.0, 0), ("pcon", 15.0, 1), ("pcon", 33.0, 0)])
+def test_bezier_cone_parity(R, oracle, kind, theta, steps):
+    """HexOkumuraCone.C mode 1 (AGeoBezierPgon, 100 z sections) and the round AGeoBezierPcon variant (TGeoPcon on device)"""
+    mgr, _keep = configs.okumura_cone(kind)
+    ex = mgr.ExportScene()
+    beam = configs.beam(5, theta, n_side=6.0)
+    n = 20000
+    o = H.opts(seed=77, steps_per_launch=steps)
+    ref = H.trace_with(oracle.orc_trace, ex, H.make_rays(oracle, beam, 0, n), o, nthreads=os.cpu_count() or 4)
+    got = H.trace_gpu(ex, H.make_rays(oracle, beam, 0, n), o)
+    rep = H.compare(ref, got)
+    assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, rep
+
+
 def test_empty_and_ragged_batches(R, oracle):
     mgr, _ = configs.simple_parabolic()
     ex = mgr.ExportScene()
