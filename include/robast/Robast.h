@@ -683,6 +683,8 @@ class ARay : public TObject {
   Int_t fId;
   TObjArray fNodeHistory;
   TNamed fLastNode;
+  std::vector<Double_t> fHist;    // recorded polyline, 4 per point (x, y, z, t), point 0 = start; empty = not recorded
+  std::vector<TNamed> fNodeObjs;  // node-history entries of the recorded points ("<volume>_<copyNo>")
 
  public:
   ARay(Int_t id, Double_t lambda, Double_t x, Double_t y, Double_t z, Double_t t, Double_t nx, Double_t ny, Double_t nz) : fLambda(lambda), fId(id) {
@@ -706,7 +708,19 @@ class ARay : public TObject {
   void GetLastPoint(Double_t* x) const { memcpy(x, fLast, sizeof(fLast)); }
   const Double_t* GetFirstPoint() const { return fFirst; }
   const Double_t* GetLastPoint() const { return fLast; }
-  const Double_t* GetPoint(Int_t i) const { return i == fNpoints - 1 ? fLast : fFirst; }  // intermediate vertices are not kept
+  // TGeoTrack::GetPoint: vertex i of the polyline.  Intermediate vertices exist when the trace recorded a history
+  // (AOpticsManager::SetHistoryDepth; on by default for small batches); otherwise only the first and last are kept.
+  const Double_t* GetPoint(Int_t i) const {
+    if (i >= 0 && (size_t)(4 * i + 3) < fHist.size()) return &fHist[4 * i];
+    return i == fNpoints - 1 ? fLast : fFirst;
+  }
+  Int_t GetPoint(Int_t i, Double_t& x, Double_t& y, Double_t& z, Double_t& t) const {
+    if (i < 0 || i >= fNpoints) return -1;
+    const Double_t* p = GetPoint(i);
+    x = p[0]; y = p[1]; z = p[2]; t = p[3];
+    return i;
+  }
+  Int_t GetNrecorded() const { return (Int_t)(fHist.size() / 4); }
   Int_t GetNpoints() const { return fNpoints; }
   Double_t GetLambda() const { return fLambda; }
   void SetLambda(Double_t l) { fLambda = l; }
@@ -721,11 +735,19 @@ class ARay : public TObject {
   }
   const TObjArray* GetNodeHistory() const { return &fNodeHistory; }
   const char* GetLastNodeName() const { return fLastNode.GetName(); }
+  // src/ARay.cxx:42-63: first node-history entry whose name starts with `name` (entry n belongs to point n + 1).
+  // Without a recorded history the list holds the last node only.
   TObject* FindNodeStartWith(const char* name) const {
-    return (fNodeHistory.GetEntries() && strncmp(fLastNode.GetName(), name, strlen(name)) == 0) ? (TObject*)&fLastNode : nullptr;
+    Int_t i = FindNodeNumberStartWith(name);
+    return i < 0 ? nullptr : fNodeHistory.At(i);
   }
-  // node history keeps only the last node: index 0 if it matches, else -1
-  Int_t FindNodeNumberStartWith(const char* name) const { return FindNodeStartWith(name) ? 0 : -1; }
+  Int_t FindNodeNumberStartWith(const char* name) const {
+    for (Int_t i = 0; i <= fNodeHistory.GetLast(); i++) {
+      TObject* node = fNodeHistory.At(i);
+      if (node && strncmp(node->GetName(), name, strlen(name)) == 0) return i;
+    }
+    return -1;
+  }
   void SetLineWidth(Int_t) {}
   void SetLineColor(Int_t) {}
   TPolyLine3D* MakePolyLine3D() const;
@@ -736,9 +758,25 @@ class ARay : public TObject {
     fStatus = status;
     fNpoints = npoints;
     fNodeHistory.Clear();
+    fHist.clear();
+    fNodeObjs.clear();
     if (last_node) {
       fLastNode.SetName(last_node);
       fNodeHistory.Add(&fLastNode);
+    }
+  }
+  // recorded polyline of the last trace: npts points (x, y, z, t each) and the node entered with points 1..npts-1
+  void SetHistory(const Double_t* pts, Int_t npts, const int32_t* nodes, const std::vector<std::string>* names) {
+    fHist.assign(pts, pts + 4 * (size_t)npts);
+    fNodeHistory.Clear();
+    fNodeObjs.clear();
+    fNodeObjs.resize(npts > 1 ? npts - 1 : 0);
+    for (Int_t k = 1; k < npts; k++) {
+      int32_t id = nodes[k];
+      if (names && id >= 0 && id < (int32_t)names->size()) {
+        fNodeObjs[k - 1].SetName((*names)[id].c_str());
+        fNodeHistory.Add(&fNodeObjs[k - 1]);
+      } else fNodeHistory.Add(nullptr);  // left the world: the reference adds a null node
     }
   }
 };
@@ -777,7 +815,27 @@ class ARayArray : public TObject {
     std::vector<Double_t> x0, y0, z0, t0, x, y, z, t, dx, dy, dz, lambda;
     std::vector<int32_t> status, npoints, last_node;
     std::vector<ARay*> obj;  // lazily created ARay views (owned)
+    // optional polyline record, ray-major: ray i owns hpts[4*hist_depth*i ...] (x,y,z,t per point), hnode[hist_depth*i ...]
+    // and hcount[i] valid points (0 = none)
+    int32_t hist_depth = 0;
+    std::vector<Double_t> hpts;
+    std::vector<int32_t> hnode, hcount;
     size_t size() const { return x.size(); }
+    void EnsureHistory(int32_t depth) {  // (re)shape the record to `depth` points per ray, keeping what fits
+      if (depth == hist_depth && hcount.size() == size()) return;
+      std::vector<Double_t> np((size_t)4 * depth * size(), 0.);
+      std::vector<int32_t> nn((size_t)depth * size(), -1), nc(size(), 0);
+      for (size_t i = 0; i < hcount.size() && i < size(); i++) {
+        int32_t c = std::min(hcount[i], depth);
+        nc[i] = c;
+        for (int32_t k = 0; k < c; k++) {
+          for (int a = 0; a < 4; a++) np[4 * ((size_t)depth * i + k) + a] = hpts[4 * ((size_t)hist_depth * i + k) + a];
+          nn[(size_t)depth * i + k] = hnode[(size_t)hist_depth * i + k];
+        }
+      }
+      hpts.swap(np); hnode.swap(nn); hcount.swap(nc);
+      hist_depth = depth;
+    }
   };
 
  private:
@@ -795,6 +853,8 @@ class ARayArray : public TObject {
       const char* nn = nullptr;
       if (fNodeNames && fT.last_node[i] >= 0 && fT.last_node[i] < (int32_t)fNodeNames->size()) nn = (*fNodeNames)[fT.last_node[i]].c_str();
       fT.obj[i]->SetTraced(last, dir, fT.status[i], fT.npoints[i], nn);
+      if (fT.hist_depth > 0 && i < fT.hcount.size() && fT.hcount[i] > 0)
+        fT.obj[i]->SetHistory(&fT.hpts[4 * (size_t)fT.hist_depth * i], fT.hcount[i], &fT.hnode[(size_t)fT.hist_depth * i], fNodeNames.get());
       fBucket[fT.status[i]].Add(fT.obj[i]);
     }
     fViewsValid = kTRUE;
@@ -828,6 +888,11 @@ class ARayArray : public TObject {
     fT.dx.push_back(dx); fT.dy.push_back(dy); fT.dz.push_back(dz); fT.lambda.push_back(lambda);
     fT.status.push_back(RBG_RUN); fT.npoints.push_back(1); fT.last_node.push_back(-1);
     fT.obj.push_back(nullptr);
+    if (fT.hist_depth > 0) {
+      fT.hpts.resize(4 * (size_t)fT.hist_depth * fT.size(), 0.);
+      fT.hnode.resize((size_t)fT.hist_depth * fT.size(), -1);
+      fT.hcount.resize(fT.size(), 0);
+    }
     fViewsValid = kFALSE;
   }
   void Reserve(size_t n) {
@@ -840,9 +905,16 @@ class ARayArray : public TObject {
     if (!array) return;
     Table& o = array->fT;
     static const int order[6] = {RBG_ABSORB, RBG_EXIT, RBG_FOCUSED, RBG_RUN, RBG_STOP, RBG_SUSPEND};
+    const int32_t depth = std::max(fT.hist_depth, o.hist_depth);
+    if (depth > 0) { fT.EnsureHistory(depth); o.EnsureHistory(depth); }
     for (int s : order)
       for (size_t i = 0; i < o.size(); i++) {
         if (o.status[i] != s) continue;
+        if (depth > 0) {
+          fT.hpts.insert(fT.hpts.end(), o.hpts.begin() + 4 * (size_t)depth * i, o.hpts.begin() + 4 * (size_t)depth * (i + 1));
+          fT.hnode.insert(fT.hnode.end(), o.hnode.begin() + (size_t)depth * i, o.hnode.begin() + (size_t)depth * (i + 1));
+          fT.hcount.push_back(o.hcount[i]);
+        }
         fT.x0.push_back(o.x0[i]); fT.y0.push_back(o.y0[i]); fT.z0.push_back(o.z0[i]); fT.t0.push_back(o.t0[i]);
         fT.x.push_back(o.x[i]); fT.y.push_back(o.y[i]); fT.z.push_back(o.z[i]); fT.t.push_back(o.t[i]);
         fT.dx.push_back(o.dx[i]); fT.dy.push_back(o.dy[i]); fT.dz.push_back(o.dz[i]); fT.lambda.push_back(o.lambda[i]);
@@ -1308,6 +1380,7 @@ class AOpticsManager : public TGeoManager {
   ULong64_t fSeed = 20180601ULL;
   ULong64_t fRayCounter = 0;  // global ray index so that successive calls use fresh random streams
   Int_t fDevice = 0;
+  Int_t fHistoryDepth = -1;  // < 0: automatic (see SetHistoryDepth)
   rbg_scene* fScene = nullptr;
   std::string fSceneKey;
   std::shared_ptr<std::vector<std::string>> fNodeNames;
@@ -1364,6 +1437,11 @@ class AOpticsManager : public TGeoManager {
   void SetSeed(ULong64_t seed) { fSeed = seed; fRayCounter = 0; }
   void SetQuirks(UInt_t q) { fQuirks = q; }
   void SetDevice(Int_t d) { fDevice = d; }
+  // polyline record (ARay::GetPoint(i), node history): points kept per ray.  < 0 = automatic: min(limit, 16) points
+  // for batches below 262144 rays (the reference always keeps every point; large batches keep first/last only
+  // unless a depth is requested here), 0 = never.
+  void SetHistoryDepth(Int_t n) { fHistoryDepth = n; }
+  Int_t GetHistoryDepth() const { return fHistoryDepth; }
   std::shared_ptr<ASceneExport> ExportScene() const {
     if (!fTopVolume) throw std::runtime_error("AOpticsManager: no top volume");
     auto e = std::make_shared<ASceneExport>();
@@ -1428,8 +1506,36 @@ class AOpticsManager : public TGeoManager {
         fNodeNames = std::make_shared<std::vector<std::string>>();
         for (int i = 0; i < rbg_scene_num_nodes(fScene); i++) fNodeNames->push_back(rbg_scene_node_name(fScene, i));
       }
-      rc = rbg_trace(fScene, &opts, &r, nullptr);
+      int32_t depth = fHistoryDepth >= 0 ? fHistoryDepth : (n < 262144 ? std::min<Int_t>(fLimit, 16) : 0);
+      std::vector<Double_t> hbuf;
+      std::vector<int32_t> hnbuf;
+      rbg_history hist;
+      memset(&hist, 0, sizeof(hist));
+      if (depth > 0) {
+        hbuf.resize((size_t)4 * depth * n);
+        hnbuf.assign((size_t)depth * n, -1);
+        hist.max_points = depth;
+        hist.hx = hbuf.data(); hist.hy = hbuf.data() + (size_t)depth * n; hist.hz = hbuf.data() + (size_t)2 * depth * n;
+        hist.ht = hbuf.data() + (size_t)3 * depth * n;
+        hist.hnode = hnbuf.data();
+      }
+      rc = rbg_trace_history(fScene, &opts, &r, depth > 0 ? &hist : nullptr, nullptr);
       if (rc != RBG_OK) throw std::runtime_error(std::string("AOpticsManager::TraceNonSequential: ") + rbg_last_error());
+      if (depth > 0) {  // point-major device layout -> ray-major table rows
+        T.EnsureHistory(std::max(depth, T.hist_depth));
+        const int32_t D = T.hist_depth;
+        for (size_t j = 0; j < n; j++) {
+          size_t i = run[j];
+          int32_t c = std::min<int32_t>(icol[2][j], depth);
+          T.hcount[i] = c;
+          for (int32_t k = 0; k < c; k++) {
+            size_t src = (size_t)k * n + j, dst = (size_t)D * i + k;
+            T.hpts[4 * dst] = hist.hx[src]; T.hpts[4 * dst + 1] = hist.hy[src]; T.hpts[4 * dst + 2] = hist.hz[src]; T.hpts[4 * dst + 3] = hist.ht[src];
+            T.hnode[dst] = hist.hnode[src];
+          }
+        }
+      } else if (T.hist_depth > 0)
+        for (size_t j = 0; j < n; j++) T.hcount[run[j]] = 0;
     }
     if (!contiguous)
       for (size_t j = 0; j < n; j++) {
@@ -1452,7 +1558,9 @@ class AOpticsManager : public TGeoManager {
     const ARayArray::Table& T = tmp.GetTable();
     Double_t last[4] = {T.x[0], T.y[0], T.z[0], T.t[0]}, dir[3] = {T.dx[0], T.dy[0], T.dz[0]};
     const char* nn = (fNodeNames && T.last_node[0] >= 0) ? (*fNodeNames)[T.last_node[0]].c_str() : nullptr;
+    const bool fresh = ray.GetNpoints() == 1;
     ray.SetTraced(last, dir, T.status[0], ray.GetNpoints() + T.npoints[0] - 1, nn);
+    if (fresh && T.hist_depth > 0 && T.hcount[0] > 0) ray.SetHistory(&T.hpts[0], T.hcount[0], &T.hnode[0], fNodeNames.get());
   }
   void TraceNonSequential(ARay* ray) { TraceNonSequential(*ray); }
   void TraceNonSequential(TObjArray* array) {

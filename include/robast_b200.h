@@ -222,6 +222,21 @@ const char* rbg_scene_node_name(const rbg_scene* scene, int node);
  * pointers the work is enqueued on `stream` and the call returns without synchronising. */
 int rbg_trace(rbg_scene* scene, const rbg_trace_opts* opts, const rbg_rays* rays, void* stream);
 
+/* Optional polyline record of every ray (ARay's TGeoTrack points and node history, reference
+ * include/ARay.h:24-68, src/ARay.cxx:66-71): point k of ray i is written to h?[k*n + i], k = 0 is the
+ * start point; hnode holds the placed-node id recorded by ARay::AddNode with point k (-1 for k = 0).
+ * Rays keep at most max_points points (rays->npoints still counts all of them); entries k >= npoints are
+ * left untouched.  Same residency as the ray arrays (host or device).  A trace with a history runs as one
+ * per-ray-loop launch per chunk (no wavefront compaction); it is opt-in and not part of the rays/s metric. */
+typedef struct {
+  int32_t max_points;
+  int32_t pad;
+  double *hx, *hy, *hz, *ht;
+  int32_t* hnode;
+} rbg_history;
+int rbg_trace_history(rbg_scene* scene, const rbg_trace_opts* opts, const rbg_rays* rays,
+                      const rbg_history* history, void* stream);
+
 /* kernel-launch counter for the calling process (bench.py reports it as gpu_launches) */
 int64_t rbg_launch_count(void);
 /* timing of the dominant kernel: enable, then read accumulated ms and launch count of bounce kernels */
@@ -229,7 +244,9 @@ int rbg_profile_enable(int on);
 int rbg_profile_read(double* bounce_ms, int64_t* bounce_launches, double* compact_ms, int64_t* compact_launches);
 
 /* ARayShooter on device (src/ARayShooter.cxx:122-460): fills device SoA x..lambda for n rays.
- * kind: 0 Rectangle(grid nx*ny, x-major), 1 RandomRectangle, 2 RandomCircle, 3 Circle(nr,nphi).
+ * kind: 0 Rectangle(grid nx*ny, x-major), 1 RandomRectangle, 2 RandomCircle, 3 Circle(nr,nphi),
+ * 4 RandomCone (point source at tr aimed at the disc of radius dx at z=dy, rotated), 5 RandomSphere
+ * (isotropic point source at tr), 6 RandomSphericalCone (point source, uniform within dx DEGREES of rot*z).
  * rot (9, row major) and tr (3) may be NULL; dir (3) NULL = (0,0,1).  lambda_min==lambda_max
  * gives a monochromatic beam, else uniform per ray.  `first` is the global index of the first
  * ray generated (sharding / chunking). */

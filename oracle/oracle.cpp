@@ -1642,9 +1642,17 @@ struct Tracer {
     ret = ret < 0 ? 0 : ret;
     return ret;
   }
+  // ARay keeps every point (TGeoTrack::AddPoint) and every node (ARay::AddNode, include/ARay.h:35) of the current ray
+  std::vector<double> track;  // x,y,z,t per point; the caller seeds it with the start point
+  std::vector<int> nodes;     // one entry per AddNode call
   void add_point(RayState& r, const double* p, double t) {
     r.x[0] = p[0]; r.x[1] = p[1]; r.x[2] = p[2]; r.x[3] = t;
     r.npoints++;
+    track.insert(track.end(), {p[0], p[1], p[2], t});
+  }
+  void add_node(RayState& r, int node) {
+    r.last_node = node;
+    nodes.push_back(node);
   }
   // src/AOpticsManager.cxx:170-247
   void do_reflection(double n1, RayState& r, int cur_vol, int next_vol, int next_phys, const double* normal_in) {
@@ -1700,7 +1708,7 @@ struct Tracer {
     nav.D[0] = r.d[0]; nav.D[1] = r.d[1]; nav.D[2] = r.d[2];
     if (absorbed) { nav.D[0] = d2[0]; nav.D[1] = d2[1]; nav.D[2] = d2[2]; }
     add_point(r, nav.P, t);
-    r.last_node = next_phys;
+    add_node(r, next_phys);
   }
   // src/AOpticsManager.cxx:52-167
   void do_fresnel(double n1, double n2, double k2, RayState& r, int cur_vol, int next_vol, int next_phys) {
@@ -1751,7 +1759,7 @@ struct Tracer {
     double speed = kC / n1;
     double t = r.x[3] + step / speed;
     add_point(r, nav.P, t);
-    r.last_node = next_phys;
+    add_node(r, next_phys);
     if (absorbed) r.status = RBG_ABSORB;
     else {
       double mag = sqrt(dot3(d2, d2));
@@ -1785,7 +1793,7 @@ struct Tracer {
             double n1 = lens_n(cur_vol, lambda), speed = kC / n1;
             double x2[3] = {x1[0] + abs_step * d1[0], x1[1] + abs_step * d1[1], x1[2] + abs_step * d1[2]};
             add_point(r, x2, x1[3] + abs_step / speed);
-            r.last_node = next_phys;
+            add_node(r, next_phys);
             r.status = RBG_ABSORB;
             continue;
           }
@@ -1800,10 +1808,10 @@ struct Tracer {
       } else if ((curVac || typeCurrent == RBG_LENS) && (typeNext == RBG_OBS || typeNext == RBG_FOCUS)) {  // :442-457
         double speed = typeCurrent == RBG_LENS ? kC / lens_n(cur_vol, lambda) : kC;
         add_point(r, nav.P, x1[3] + step / speed);
-        r.last_node = next_phys;
+        add_node(r, next_phys);
       } else if (curVac && (typeNext == RBG_OTHER || typeNext == RBG_OPT)) {  // :458-466
         add_point(r, nav.P, x1[3] + step / kC);
-        r.last_node = next_phys;
+        add_node(r, next_phys);
       } else if (typeCurrent == RBG_LENS && typeNext == RBG_LENS) {  // :467-474
         do_fresnel(lens_n(cur_vol, lambda), lens_n(next_vol, lambda), lens_k(next_vol, lambda), r, cur_vol, next_vol, next_phys);
       } else if (typeCurrent == RBG_LENS && (typeNext == RBG_NULL || typeNext == RBG_OPT || typeNext == RBG_OTHER)) {  // :475-482
@@ -1811,7 +1819,7 @@ struct Tracer {
       }
       if (typeNext == RBG_NULL) {  // :485-491
         add_point(r, nav.P, x1[3] + step / kC);
-        r.last_node = next_phys;
+        add_node(r, next_phys);
         r.status = RBG_EXIT;
       } else if (typeCurrent == RBG_FOCUS || typeCurrent == RBG_OBS || typeCurrent == RBG_MIRROR || typeNext == RBG_OBS) {
         r.status = RBG_STOP;
@@ -1847,7 +1855,12 @@ void check_desc(const rbg_scene_desc* d) {
 extern "C" {
 
 // TraceNonSequential over a host SoA batch; nthreads contiguous chunks like src/AOpticsManager.cxx:529-568
+int orc_trace_history(const rbg_scene_desc* desc, const rbg_trace_opts* opts, const rbg_rays* rays, const rbg_history* hist, int nthreads);
 int orc_trace(const rbg_scene_desc* desc, const rbg_trace_opts* opts, const rbg_rays* rays, int nthreads) {
+  return orc_trace_history(desc, opts, rays, nullptr, nthreads);
+}
+// same, also returning each ray's polyline and node history in the layout of rbg_history (point k of ray i at k*n + i)
+int orc_trace_history(const rbg_scene_desc* desc, const rbg_trace_opts* opts, const rbg_rays* rays, const rbg_history* hist, int nthreads) {
   try {
     check_desc(desc);
     if (rays->on_device) return RBG_EINVAL;
@@ -1870,7 +1883,17 @@ int orc_trace(const rbg_scene_desc* desc, const rbg_trace_opts* opts, const rbg_
           }
           r.lambda = rays->lambda[i];
           r.status = RBG_RUN; r.npoints = 1; r.last_node = -1;
+          T.track.assign(r.x, r.x + 4);
+          T.nodes.clear();
           T.trace(r, opts->ray_id_offset + (uint64_t)i);
+          if (hist && hist->max_points > 0) {
+            if ((int)T.track.size() != 4 * r.npoints || (int)T.nodes.size() != r.npoints - 1) throw std::runtime_error("AddPoint/AddNode out of step");
+            for (int k = 0; k < r.npoints && k < hist->max_points; k++) {
+              int64_t o = (int64_t)k * n + i;
+              hist->hx[o] = T.track[4 * k]; hist->hy[o] = T.track[4 * k + 1]; hist->hz[o] = T.track[4 * k + 2]; hist->ht[o] = T.track[4 * k + 3];
+              hist->hnode[o] = k == 0 ? -1 : T.nodes[k - 1];
+            }
+          }
           rays->ox[i] = r.x[0]; rays->oy[i] = r.x[1]; rays->oz[i] = r.x[2]; rays->ot[i] = r.x[3];
           rays->odx[i] = r.d[0]; rays->ody[i] = r.d[1]; rays->odz[i] = r.d[2];
           rays->status[i] = r.status; rays->last_node[i] = r.last_node; rays->npoints[i] = r.npoints;
@@ -1950,6 +1973,39 @@ int orc_shoot(const rbg_shoot_desc* s, int64_t first, int64_t n, double* x, doub
     r.id[0] = (uint32_t)id; r.id[1] = (uint32_t)(id >> 32);
     r.ndraw = 0x40000000u;  // shooter draws live in their own counter range
     double p[3] = {0, 0, 0};
+    if (s->kind >= 4 && s->kind <= 6) {  // src/ARayShooter.cxx:240-392: point sources at tr
+      double v[3], w[3];
+      if (s->kind == 4) {  // RandomCone(lambda, r = dx, d = dy, n, rot, tr)
+        double rr = s->dx;
+        do {
+          p[0] = -rr + 2 * rr * r.uniform();
+          p[1] = -rr + 2 * rr * r.uniform();
+        } while (p[0] * p[0] + p[1] * p[1] > rr * rr);
+        p[2] = s->dy;
+        l2mv(rot, p, v);
+      } else if (s->kind == 5) {  // RandomSphere: TRandom::Sphere(x, y, z, 1)
+        double a = 0, b = 0, r2 = 1;
+        while (r2 > 0.25) {
+          a = r.uniform() - 0.5;
+          b = r.uniform() - 0.5;
+          r2 = a * a + b * b;
+        }
+        double scale = 8.0 * sqrt(0.25 - r2);
+        v[0] = a * scale; v[1] = b * scale; v[2] = -1. + 8.0 * r2;
+      } else {  // RandomSphericalCone(lambda, n, theta = dx deg, rot, tr)
+        double c0 = cos(s->dx * kPi / 180.), ran = c0 + (1. - c0) * r.uniform(), th = acos(std::min(1., std::max(-1., ran))), phi = 2 * kPi * r.uniform();
+        double l[3] = {sin(th) * cos(phi), sin(th) * sin(phi), cos(th)};
+        l2mv(rot, l, v);
+      }
+      double vm = sqrt(dot3(v, v));
+      if (vm > 0) { v[0] /= vm; v[1] /= vm; v[2] /= vm; }
+      double zero[3] = {0, 0, 0};
+      l2m(tr, zero, w);
+      x[j] = w[0]; y[j] = w[1]; z[j] = w[2]; t[j] = 0;
+      dx[j] = v[0]; dy[j] = v[1]; dz[j] = v[2];
+      lambda[j] = s->lambda_min == s->lambda_max ? s->lambda_min : s->lambda_min + (s->lambda_max - s->lambda_min) * r.uniform();
+      continue;
+    }
     if (s->kind == 0) {
       int64_t i = (int64_t)id / s->ny, k = (int64_t)id % s->ny;
       double deltax = s->nx == 1 ? s->dx / 2 : s->dx / (s->nx - 1), deltay = s->ny == 1 ? s->dy / 2 : s->dy / (s->ny - 1);

@@ -22,6 +22,10 @@ class rbg_rays(C.Structure):
                             "ox", "oy", "oz", "ot", "odx", "ody", "odz", "status", "last_node", "npoints")]
 
 
+class rbg_history(C.Structure):
+    _fields_ = [("max_points", C.c_int32), ("pad", C.c_int32)] + [(k, _dp) for k in ("hx", "hy", "hz", "ht", "hnode")]
+
+
 class rbg_shoot_desc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("pad", C.c_int32),
                 ("dx", C.c_double), ("dy", C.c_double), ("lambda_min", C.c_double), ("lambda_max", C.c_double),
@@ -44,6 +48,7 @@ rbg_scene_num_nodes = _proto("rbg_scene_num_nodes", C.c_int, [C.c_void_p])
 rbg_scene_node_name = _proto("rbg_scene_node_name", C.c_char_p, [C.c_void_p, C.c_int])
 rbg_scene_kernel_variant = _proto("rbg_scene_kernel_variant", C.c_char_p, [C.c_void_p])
 rbg_trace = _proto("rbg_trace", C.c_int, [C.c_void_p, C.POINTER(rbg_trace_opts), C.POINTER(rbg_rays), C.c_void_p])
+rbg_trace_history = _proto("rbg_trace_history", C.c_int, [C.c_void_p, C.POINTER(rbg_trace_opts), C.POINTER(rbg_rays), C.POINTER(rbg_history), C.c_void_p])
 rbg_launch_count = _proto("rbg_launch_count", C.c_int64, [])
 rbg_profile_enable = _proto("rbg_profile_enable", C.c_int, [C.c_int])
 rbg_profile_read = _proto("rbg_profile_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)])
@@ -54,7 +59,7 @@ rbg_tmm = _proto("rbg_tmm", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, 
 rbg_tmm_host = _proto("rbg_tmm_host", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp])
 
 ABI_SYMBOLS = ["rbg_abi_version", "rbg_last_error", "rbg_device_count", "rbg_scene_create", "rbg_scene_destroy",
-               "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_scene_kernel_variant", "rbg_trace", "rbg_launch_count", "rbg_profile_enable",
+               "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_scene_kernel_variant", "rbg_trace", "rbg_trace_history", "rbg_launch_count", "rbg_profile_enable",
                "rbg_profile_read", "rbg_shoot", "rbg_hist2d", "rbg_moments", "rbg_tmm", "rbg_tmm_host"]
 
 

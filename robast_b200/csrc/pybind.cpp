@@ -209,6 +209,15 @@ PYBIND11_MODULE(_robast, m) {
       .def("GetFirstPoint", [](const ARay& r) { return std::vector<double>(r.GetFirstPoint(), r.GetFirstPoint() + 4); })
       .def("GetNpoints", &ARay::GetNpoints).def("GetLambda", &ARay::GetLambda).def("GetStatus", &ARay::GetStatus)
       .def("GetLastNodeName", &ARay::GetLastNodeName)
+      .def("GetPoint", [](const ARay& r, int i) { const double* p = r.GetPoint(i); return std::vector<double>(p, p + 4); })
+      .def("GetNrecorded", &ARay::GetNrecorded)
+      .def("FindNodeNumberStartWith", &ARay::FindNodeNumberStartWith)
+      .def("GetNodeHistoryNames", [](const ARay& r) {
+        std::vector<std::string> v;
+        const TObjArray* h = r.GetNodeHistory();
+        for (Int_t i = 0; i <= h->GetLast(); i++) v.push_back(h->At(i) ? h->At(i)->GetName() : "");
+        return v;
+      })
       .def("IsAbsorbed", &ARay::IsAbsorbed).def("IsExited", &ARay::IsExited).def("IsFocused", &ARay::IsFocused).def("IsRunning", &ARay::IsRunning)
       .def("IsStopped", &ARay::IsStopped).def("IsSuspended", &ARay::IsSuspended);
   py::class_<ARayArray>(m, "ARayArray")
@@ -311,6 +320,7 @@ PYBIND11_MODULE(_robast, m) {
       .def("DisableFresnelReflection", &AOpticsManager::DisableFresnelReflection)
       .def("SetLimit", &AOpticsManager::SetLimit).def("GetLimit", &AOpticsManager::GetLimit)
       .def("SetSeed", &AOpticsManager::SetSeed).def("SetQuirks", &AOpticsManager::SetQuirks).def("SetDevice", &AOpticsManager::SetDevice)
+      .def("SetHistoryDepth", &AOpticsManager::SetHistoryDepth).def("GetHistoryDepth", &AOpticsManager::GetHistoryDepth)
       .def("ExportScene", &AOpticsManager::ExportScene)
       .def("TraceNonSequential", [](AOpticsManager& mg, ARayArray& a) { py::gil_scoped_release rel; mg.TraceNonSequential(a); })
       .def("TraceNonSequential", [](AOpticsManager& mg, ARay& r) { mg.TraceNonSequential(r); });

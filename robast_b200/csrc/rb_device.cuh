@@ -680,7 +680,7 @@ template <bool CONE> RB_HD inline bool poly_slab(const double* P, int k, V3 p, V
     tout = rb_max(ta, tb);
   } else if (p.z < z0 || p.z > z1) return false;
   double s = (r1 - r0) / dz, base = r0 + (p.z - z0) * s;
-  if (CONE) {
+  if constexpr (CONE) {
     // inside the frustum: f(t) = |xy(t)|^2 - (base + s dz t)^2 <= 0 on the nappe with non-negative radius, which is
     // the only one the z slab can reach (r0, r1 >= 0)
     double g = s * d.z, A = d.x * d.x + d.y * d.y - g * g, B = 2 * (p.x * d.x + p.y * d.y - base * g), C = p.x * p.x + p.y * p.y - base * base;
@@ -699,15 +699,16 @@ template <bool CONE> RB_HD inline bool poly_slab(const double* P, int k, V3 p, V
     else if (g > 0) tin = rb_max(tin, t2);
     else tout = rb_min(tout, t1);
     return tin < tout;
+  } else {
+    for (int e = 0; e < ne; e++) {
+      // half-space: x c + y s - (r0 + (z - z0) s) <= 0
+      double f0 = p.x * cs[2 * e] + p.y * cs[2 * e + 1] - base, fd = d.x * cs[2 * e] + d.y * cs[2 * e + 1] - s * d.z;
+      if (fd > 0) tout = rb_min(tout, -f0 / fd);
+      else if (fd < 0) tin = rb_max(tin, -f0 / fd);
+      else if (f0 > 0) return false;
+    }
+    return tin < tout;
   }
-  for (int e = 0; e < ne; e++) {
-    // half-space: x c + y s - (r0 + (z - z0) s) <= 0
-    double f0 = p.x * cs[2 * e] + p.y * cs[2 * e + 1] - base, fd = d.x * cs[2 * e] + d.y * cs[2 * e + 1] - s * d.z;
-    if (fd > 0) tout = rb_min(tout, -f0 / fd);
-    else if (fd < 0) tin = rb_max(tin, -f0 / fd);
-    else if (f0 > 0) return false;
-  }
-  return tin < tout;
 }
 template <bool CONE> RB_HD inline double poly_dist_out(const double* P, V3 p, V3 d) {
   int nz = (int)P[3];
@@ -1541,11 +1542,24 @@ RB_HD inline int find_border(const DScene& sc, int vol1, int vol2) {
   return -1;
 }
 
+// optional per-ray polyline record (ARay's TGeoTrack points + node history, include/ARay.h:24-68): point k of ray
+// `idx` lives at [k * stride + idx]; points beyond max_points are dropped.  Null sink = keep the last point only.
+struct DHist {
+  double *x, *y, *z, *t;
+  int32_t* node;
+  long long stride;
+  int32_t max_points;
+};
+struct HistSink {
+  const DHist* h;
+  long long idx;
+};
 struct Hit {       // context of one boundary interaction
   int cur_vol, next_vol, next_node, border;
   int crossed, sel;
   double step;
   const StepOut* so;
+  const HistSink* hs;
 };
 
 template <class K> RB_HD inline V3 geometric_normal(const DScene& sc, const RayReg& r, const Hit& h, V3 dir) {
@@ -1595,9 +1609,16 @@ RB_HD inline double mirror_reflectance(const DScene& sc, int vol, double lambda,
   return ret > 1 ? 1 : (ret < 0 ? 0 : ret);
 }
 
-RB_HD inline void add_point(RayReg& r, V3 p, double t) {
+// ARay::AddPoint + AddNode
+RB_HD inline void add_point(RayReg& r, V3 p, double t, int node, const HistSink* hs) {
   r.p = p;
   r.t = t;
+  r.last_node = node;
+  if (hs && r.npoints < hs->h->max_points) {
+    long long o = (long long)r.npoints * hs->h->stride + hs->idx;
+    hs->h->x[o] = p.x; hs->h->y[o] = p.y; hs->h->z[o] = p.z; hs->h->t[o] = t;
+    hs->h->node[o] = node;
+  }
   r.npoints++;
 }
 RB_HD inline void set_direction(RayReg& r, V3 d2) {
@@ -1680,8 +1701,7 @@ template <class K> RB_HD inline void do_reflection(const DScene& sc, const DTrac
   V3 back = along(pos, d1, -2e-6);
   loc = relocate_back<K>(sc, h, back);
   if (tp.quirks & RBG_QUIRK_STEPBACK) pos = back;
-  add_point(r, pos, t);
-  r.last_node = h.next_node;
+  add_point(r, pos, t, h.next_node, h.hs);
   r.on_boundary = 0;
 }
 
@@ -1731,15 +1751,15 @@ template <class K> RB_HD inline void do_fresnel(const DScene& sc, const DTracePa
     double f = sin2 / sin1;
     d2 = v3((d1.x - cos1 * n.x) * f + n.x * cos2, (d1.y - cos1 * n.y) * f + n.y * cos2, (d1.z - cos1 * n.z) * f + n.z * cos2);
   }
-  add_point(r, pos, r.t + h.step / (RB_C_CM / n1));
-  r.last_node = h.next_node;
+  add_point(r, pos, r.t + h.step / (RB_C_CM / n1), h.next_node, h.hs);
   if (absorbed) r.status = RBG_ABSORB;
   else set_direction(r, d2);
 }
 
 // One iteration of the while(ray->IsRunning()) loop, src/AOpticsManager.cxx:359-518
 // (the interaction / termination half; `nav` is the navigator copy whose point sits on the boundary, `so` the step record)
-template <class K> RB_HD inline void trace_shade(const DScene& sc, const DTraceParams& tp, RayReg& r, const RayReg& nav, const StepOut& so, Philox& g) {
+template <class K>
+RB_HD inline void trace_shade(const DScene& sc, const DTraceParams& tp, RayReg& r, const RayReg& nav, const StepOut& so, Philox& g, const HistSink* hs = nullptr) {
   V3 x1 = r.p;
   double t1 = r.t;
   int cur = r.cur;
@@ -1754,6 +1774,7 @@ template <class K> RB_HD inline void trace_shade(const DScene& sc, const DTraceP
   h.sel = so.sel;
   h.step = so.step;
   h.so = &so;
+  h.hs = hs;
   h.border = find_border(sc, cur_vol, h.next_vol);
   int typeNext = so.next < 0 ? RBG_NULL : sc.nodes[so.next].type;
   V3 pos = nav.p;
@@ -1768,8 +1789,7 @@ template <class K> RB_HD inline void trace_shade(const DScene& sc, const DTraceP
         double abs_step = -abs * log(rng_uniform(g));
         if (abs_step < so.step) {
           double n1 = index_n(sc, sc.volumes[cur_vol].index, lambda);
-          add_point(r, along(x1, r.d, abs_step), t1 + abs_step / (RB_C_CM / n1));
-          r.last_node = so.next;
+          add_point(r, along(x1, r.d, abs_step), t1 + abs_step / (RB_C_CM / n1), so.next, hs);
           r.status = RBG_ABSORB;
           r.cur = loc;
           return;
@@ -1786,11 +1806,9 @@ template <class K> RB_HD inline void trace_shade(const DScene& sc, const DTraceP
   } else if ((curVac || curLens) && (typeNext == RBG_OBS || typeNext == RBG_FOCUS)) {
     double speed = RB_C_CM;
     if constexpr (kLens) speed = curLens ? RB_C_CM / index_n(sc, sc.volumes[cur_vol].index, lambda) : RB_C_CM;
-    add_point(r, pos, t1 + so.step / speed);
-    r.last_node = so.next;
+    add_point(r, pos, t1 + so.step / speed, so.next, hs);
   } else if (curVac && (typeNext == RBG_OTHER || typeNext == RBG_OPT)) {
-    add_point(r, pos, t1 + so.step / RB_C_CM);
-    r.last_node = so.next;
+    add_point(r, pos, t1 + so.step / RB_C_CM, so.next, hs);
   } else if constexpr (kLens) {
     if (curVac && typeNext == RBG_LENS) {
       int ix = sc.volumes[h.next_vol].index;
@@ -1804,8 +1822,7 @@ template <class K> RB_HD inline void trace_shade(const DScene& sc, const DTraceP
   }
   // termination (evaluated after the interaction, src/AOpticsManager.cxx:485-513)
   if (typeNext == RBG_NULL) {
-    add_point(r, pos, t1 + so.step / RB_C_CM);
-    r.last_node = so.next;
+    add_point(r, pos, t1 + so.step / RB_C_CM, so.next, hs);
     r.status = RBG_EXIT;
   } else if (typeCurrent == RBG_FOCUS || typeCurrent == RBG_OBS || typeCurrent == RBG_MIRROR || typeNext == RBG_OBS) {
     r.status = RBG_STOP;
@@ -1831,11 +1848,11 @@ template <class K> RB_HD inline void trace_shade(const DScene& sc, const DTraceP
   if (r.status == RBG_RUN && r.npoints >= tp.limit) r.status = RBG_SUSPEND;
 }
 
-template <class K> RB_HD inline void trace_step(const DScene& sc, const DTraceParams& tp, RayReg& r, Philox& g) {
+template <class K> RB_HD inline void trace_step(const DScene& sc, const DTraceParams& tp, RayReg& r, Philox& g, const HistSink* hs = nullptr) {
   RayReg nav = r;  // navigator copy: nav.p advances to the boundary, r.p stays at the segment start
   NavStep st;
   next_boundary<K>(sc, nav, (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0, st);
-  trace_shade<K>(sc, tp, r, nav, st.o, g);
+  trace_shade<K>(sc, tp, r, nav, st.o, g, hs);
 }
 
 // locate the start point (InitTrack -> FindNode)

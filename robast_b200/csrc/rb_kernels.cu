@@ -203,6 +203,40 @@ __global__ void k_shoot(rbg_shoot_desc s, long long first, long long n, double* 
   g.id0 = (uint32_t)id; g.id1 = (uint32_t)(id >> 32);
   g.ndraw = 0x40000000u;
   double px = 0, py = 0;
+  if (s.kind >= 4) {  // point sources at tr: RandomCone / RandomSphere / RandomSphericalCone (src/ARayShooter.cxx:240-392)
+    double vx, vy, vz;
+    if (s.kind == 4) {  // aimed at a random point of the disc of radius dx at z = dy, rotated
+      double r = s.dx;
+      do {
+        px = -r + 2 * r * rng_uniform(g);
+        py = -r + 2 * r * rng_uniform(g);
+      } while (px * px + py * py > r * r);
+      vx = s.rot[0] * px + s.rot[1] * py + s.rot[2] * s.dy;
+      vy = s.rot[3] * px + s.rot[4] * py + s.rot[5] * s.dy;
+      vz = s.rot[6] * px + s.rot[7] * py + s.rot[8] * s.dy;
+    } else if (s.kind == 5) {  // TRandom::Sphere (isotropic)
+      double a, b, r2;
+      do {
+        a = rng_uniform(g) - 0.5;
+        b = rng_uniform(g) - 0.5;
+        r2 = a * a + b * b;
+      } while (r2 > 0.25);
+      double scale = 8.0 * sqrt(0.25 - r2);
+      vx = a * scale; vy = b * scale; vz = -1. + 8.0 * r2;
+    } else {  // uniform in solid angle within dx degrees of +z, rotated
+      double c0 = cos(s.dx * RB_PI / 180.), ran = c0 + (1. - c0) * rng_uniform(g), th = rb_acos(ran), phi = 2 * RB_PI * rng_uniform(g);
+      double lx = sin(th) * cos(phi), ly = sin(th) * sin(phi), lz = cos(th);
+      vx = s.rot[0] * lx + s.rot[1] * ly + s.rot[2] * lz;
+      vy = s.rot[3] * lx + s.rot[4] * ly + s.rot[5] * lz;
+      vz = s.rot[6] * lx + s.rot[7] * ly + s.rot[8] * lz;
+    }
+    double mag = sqrt(vx * vx + vy * vy + vz * vz);  // ARay's constructor normalises the direction
+    if (mag > 0) { vx /= mag; vy /= mag; vz /= mag; }
+    x[j] = s.tr[0]; y[j] = s.tr[1]; z[j] = s.tr[2]; t[j] = 0;
+    dx[j] = vx; dy[j] = vy; dz[j] = vz;
+    lambda[j] = s.lambda_min == s.lambda_max ? s.lambda_min : s.lambda_min + (s.lambda_max - s.lambda_min) * rng_uniform(g);
+    return;
+  }
   if (s.kind == 0) {
     long long i = (long long)id / s.ny, k = (long long)id % s.ny;
     double deltax = s.nx == 1 ? s.dx / 2 : s.dx / (s.nx - 1), deltay = s.ny == 1 ? s.dy / 2 : s.dy / (s.ny - 1);
@@ -404,6 +438,7 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   // steps_per_launch: > 0 as given; 0 = auto (wavefront with one boundary step per bounce kernel for large
   // batches, where compaction pays for itself; a single launch for small ones); < 0 = single launch
   tp.max_steps = o->steps_per_launch > 0 ? o->steps_per_launch : (o->steps_per_launch == 0 && n >= 262144 ? 1 : 0);
+  if (R.hist.x) tp.max_steps = 0;  // the polyline record is written by the per-ray loop kernel only
   tp.seed = o->seed;
   tp.ray_id_offset = id_offset;
   if (tp.max_steps <= 0) {  // one launch, every ray runs to its terminal status in registers
@@ -571,9 +606,14 @@ const char* rbg_scene_node_name(const rbg_scene* s, int node) {
   return s->node_names[node].c_str();
 }
 
-int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void* stream) {
+int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void* stream) { return rbg_trace_history(s, o, rays, nullptr, stream); }
+
+int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, const rbg_history* hist, void* stream) {
   return guard([&] {
     if (!s || !o || !rays) throw Invalid("null argument");
+    const int hpts = hist ? hist->max_points : 0;
+    if (hpts < 0) throw Invalid("negative history depth");
+    if (hpts > 0 && (!hist->hx || !hist->hy || !hist->hz || !hist->ht || !hist->hnode)) throw Invalid("null history array");
     if (s->d.top_shape < 0) throw Invalid("scene has no top volume");
     if (rays->n <= 0) return;
     if (!rays->x || !rays->y || !rays->z || !rays->t || !rays->dx || !rays->dy || !rays->dz || !rays->lambda || !rays->ox || !rays->oy || !rays->oz ||
@@ -587,7 +627,13 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
       R.ox = rays->ox; R.oy = rays->oy; R.oz = rays->oz; R.ot = rays->ot; R.odx = rays->odx; R.ody = rays->ody; R.odz = rays->odz;
       R.status = rays->status; R.last_node = rays->last_node; R.npoints = rays->npoints;
       R.cur = nullptr; R.ndraw = nullptr;
-      if (o->steps_per_launch >= 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
+      memset(&R.hist, 0, sizeof(R.hist));
+      if (hpts > 0) {
+        R.hist.x = hist->hx; R.hist.y = hist->hy; R.hist.z = hist->hz; R.hist.t = hist->ht; R.hist.node = hist->hnode;
+        R.hist.stride = rays->n;
+        R.hist.max_points = hpts;
+      }
+      if (o->steps_per_launch >= 0 && hpts == 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
       trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count);
       return;
     }
@@ -600,7 +646,7 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
     static const long long CH = getenv("RB_HOST_CHUNK") ? std::max(4096LL, atoll(getenv("RB_HOST_CHUNK"))) : (1LL << 20);
     long long chunk = std::min<long long>(rays->n, CH);
     size_t per_ray = 8 * 8 + 7 * 8 + 3 * 4;  // in + out
-    size_t bytes = (size_t)chunk * per_ray + 4096 + (o->steps_per_launch >= 0 ? wavefront_scratch_bytes(chunk) : 0);
+    size_t bytes = (size_t)chunk * per_ray + 4096 + (o->steps_per_launch >= 0 ? wavefront_scratch_bytes(chunk) : 0) + (size_t)chunk * hpts * 36 + 1024;
     // chunk list: sizes ramp up from chunk/8 at the start and down again at the end, so that the un-overlapped
     // pipeline fill (first H2D) and drain (last D2H) of the call are short
     std::vector<std::pair<long long, long long>> chunks;  // (first ray, count)
@@ -656,7 +702,24 @@ int rbg_trace(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* rays, void*
         R.ox = dout[0]; R.oy = dout[1]; R.oz = dout[2]; R.ot = dout[3]; R.odx = dout[4]; R.ody = dout[5]; R.odz = dout[6];
         R.status = diout[0]; R.last_node = diout[1]; R.npoints = diout[2];
         R.cur = nullptr; R.ndraw = nullptr;
-        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + off, s->d_count + k, s->h_count + k);
+        memset(&R.hist, 0, sizeof(R.hist));
+        size_t scratch_off = off;
+        if (hpts > 0) {  // history stage: 4 double planes + 1 int plane of hpts x chunk, placed after the wavefront scratch
+          char* hb = base + off + ((o->steps_per_launch >= 0 ? wavefront_scratch_bytes(chunk) : 0) + 255) / 256 * 256;
+          size_t plane = (size_t)chunk * hpts * 8;
+          R.hist.x = (double*)hb; R.hist.y = (double*)(hb + plane); R.hist.z = (double*)(hb + 2 * plane); R.hist.t = (double*)(hb + 3 * plane);
+          R.hist.node = (int32_t*)(hb + 4 * plane);
+          R.hist.stride = chunk;
+          R.hist.max_points = hpts;
+        }
+        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + scratch_off, s->d_count + k, s->h_count + k);
+        if (hpts > 0) {
+          double* hd[4] = {hist->hx, hist->hy, hist->hz, hist->ht};
+          double* dd[4] = {R.hist.x, R.hist.y, R.hist.z, R.hist.t};
+          for (int a = 0; a < 4; a++)
+            CK(cudaMemcpy2DAsync(hd[a] + b, (size_t)rays->n * 8, dd[a], (size_t)chunk * 8, (size_t)m * 8, hpts, cudaMemcpyDeviceToHost, st));
+          CK(cudaMemcpy2DAsync(hist->hnode + b, (size_t)rays->n * 4, R.hist.node, (size_t)chunk * 4, (size_t)m * 4, hpts, cudaMemcpyDeviceToHost, st));
+        }
         // the stream is in-order: the next chunk's H2D into this stage buffer waits for these copies
         for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(hout[a] + b, dout[a], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
         for (int a = 0; a < 3; a++) CK(cudaMemcpyAsync(hiout[a] + b, diout[a], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
@@ -691,7 +754,7 @@ int rbg_shoot(const rbg_shoot_desc* d, int64_t first, int64_t n, double* x, doub
               double* lambda, int device, void* stream) {
   return guard([&] {
     if (!d || n < 0) throw Invalid("bad argument");
-    if (d->kind < 0 || d->kind > 3) throw Invalid("unknown shooter kind");
+    if (d->kind < 0 || d->kind > 6) throw Invalid("unknown shooter kind");
     if ((d->kind == 0 || d->kind == 3) && (d->nx < 1 || d->ny < 1)) throw Invalid("grid shooters need nx,ny >= 1");
     if (n == 0) return;
     CK(cudaSetDevice(device));

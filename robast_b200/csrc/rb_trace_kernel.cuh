@@ -12,6 +12,7 @@ struct DRays {
   int32_t *status, *last_node, *npoints;
   int32_t* cur;     // scratch (multi-launch only)
   uint32_t* ndraw;  // scratch: bit31 = on_boundary, low bits = draw counter
+  DHist hist;       // optional polyline record (hist.x == nullptr: off); per-ray loop kernel only
 };
 
 #define TRACE_THREADS 128
@@ -72,9 +73,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, K::min_blocks) k_trace(const __
   RayReg r;
   Philox g;
   load_ray<K>(sc, tp, R, idx, init, r, g);
+  HistSink sink;
+  sink.h = &R.hist;
+  sink.idx = idx;
+  const HistSink* hs = R.hist.x ? &sink : nullptr;
+  if (hs && init && R.hist.max_points > 0) {  // point 0 = the start point (no node entry)
+    R.hist.x[idx] = r.p.x; R.hist.y[idx] = r.p.y; R.hist.z[idx] = r.p.z; R.hist.t[idx] = r.t;
+    R.hist.node[idx] = -1;
+  }
   int steps = 0;
   while (r.status == RBG_RUN && (tp.max_steps <= 0 || steps < tp.max_steps)) {
-    trace_step<K>(sc, tp, r, g);
+    trace_step<K>(sc, tp, r, g, hs);
     steps++;
   }
   store_ray(R, idx, r, g, keep_state);

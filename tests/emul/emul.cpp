@@ -9,7 +9,14 @@
 #include "../../robast_b200/csrc/rb_device.cuh"
 
 namespace {
-template <class K> void run(const DScene& sc, const DTraceParams& tp, const rbg_rays* R) {
+template <class K> void run(const DScene& sc, const DTraceParams& tp, const rbg_rays* R, const rbg_history* H) {
+  DHist dh;
+  memset(&dh, 0, sizeof(dh));
+  if (H && H->max_points > 0) {
+    dh.x = H->hx; dh.y = H->hy; dh.z = H->hz; dh.t = H->ht; dh.node = H->hnode;
+    dh.stride = R->n;
+    dh.max_points = H->max_points;
+  }
   for (long long idx = 0; idx < R->n; idx++) {
     RayReg r;
     r.lambda = R->lambda[idx];
@@ -23,7 +30,12 @@ template <class K> void run(const DScene& sc, const DTraceParams& tp, const rbg_
     unsigned long long id = tp.ray_id_offset + (unsigned long long)idx;
     Philox g;
     g.k0 = (uint32_t)tp.seed; g.k1 = (uint32_t)(tp.seed >> 32); g.id0 = (uint32_t)id; g.id1 = (uint32_t)(id >> 32); g.ndraw = 0;
-    while (r.status == RBG_RUN) trace_step<K>(sc, tp, r, g);
+    HistSink sink;
+    sink.h = &dh;
+    sink.idx = idx;
+    const HistSink* hs = dh.x ? &sink : nullptr;
+    if (hs) { dh.x[idx] = r.p.x; dh.y[idx] = r.p.y; dh.z[idx] = r.p.z; dh.t[idx] = r.t; dh.node[idx] = -1; }
+    while (r.status == RBG_RUN) trace_step<K>(sc, tp, r, g, hs);
     R->ox[idx] = r.p.x; R->oy[idx] = r.p.y; R->oz[idx] = r.p.z; R->ot[idx] = r.t;
     R->odx[idx] = r.d.x; R->ody[idx] = r.d.y; R->odz[idx] = r.d.z;
     R->status[idx] = r.status; R->last_node[idx] = r.last_node; R->npoints[idx] = r.npoints;
@@ -31,7 +43,13 @@ template <class K> void run(const DScene& sc, const DTraceParams& tp, const rbg_
 }
 }  // namespace
 
-extern "C" __attribute__((visibility("default"))) int emul_trace(const rbg_scene_desc* D, const rbg_trace_opts* o, const rbg_rays* R, int /*nthreads*/) {
+extern "C" __attribute__((visibility("default"))) int emul_trace_history(const rbg_scene_desc* D, const rbg_trace_opts* o, const rbg_rays* R,
+                                                                         const rbg_history* H, int nthreads);
+extern "C" __attribute__((visibility("default"))) int emul_trace(const rbg_scene_desc* D, const rbg_trace_opts* o, const rbg_rays* R, int nthreads) {
+  return emul_trace_history(D, o, R, nullptr, nthreads);
+}
+extern "C" __attribute__((visibility("default"))) int emul_trace_history(const rbg_scene_desc* D, const rbg_trace_opts* o, const rbg_rays* R,
+                                                                         const rbg_history* H, int /*nthreads*/) {
   try {
     validate_desc(D);
     SceneBuilder B;
@@ -50,10 +68,10 @@ extern "C" __attribute__((visibility("default"))) int emul_trace(const rbg_scene
     tp.limit = o->limit > 0 ? o->limit : 100; tp.disable_fresnel = o->disable_fresnel; tp.quirks = o->quirks; tp.max_steps = 0;
     tp.seed = o->seed; tp.ray_id_offset = o->ray_id_offset;
     switch (scene_depth_needed(B)) {
-      case 0: run<TraceCfg<0, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
-      case 1: run<TraceCfg<1, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
-      case 2: run<TraceCfg<2, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
-      case 3: run<TraceCfg<3, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R); break;
+      case 0: run<TraceCfg<0, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
+      case 1: run<TraceCfg<1, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
+      case 2: run<TraceCfg<2, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
+      case 3: run<TraceCfg<3, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
       default: return RBG_ENOTSUP;
     }
     return RBG_OK;

@@ -25,6 +25,8 @@ def load_oracle():
     lib = C.CDLL(ORACLE_SO)
     lib.orc_trace.restype = C.c_int
     lib.orc_trace.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.c_int]
+    lib.orc_trace_history.restype = C.c_int
+    lib.orc_trace_history.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.POINTER(R.rbg_history), C.c_int]
     lib.orc_tmm.restype = C.c_int
     lib.orc_tmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in ("orc_index_n", "orc_index_k", "orc_index_abslen", "orc_graph_eval"):
@@ -56,6 +58,8 @@ def load_emul():
     lib = C.CDLL(EMUL_SO)
     lib.emul_trace.restype = C.c_int
     lib.emul_trace.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.c_int]
+    lib.emul_trace_history.restype = C.c_int
+    lib.emul_trace_history.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.POINTER(R.rbg_history), C.c_int]
     lib.emul_tmm.restype = C.c_int
     lib.emul_tmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return lib
@@ -104,6 +108,58 @@ class Rays:
     status = property(lambda s: s.iout[0])
     last_node = property(lambda s: s.iout[1])
     npoints = property(lambda s: s.iout[2])
+
+
+class History:
+    """polyline record in the layout of rbg_history: pts[a, k, i] = coordinate a (x,y,z,t) of point k of ray i"""
+
+    def __init__(self, n, depth):
+        self.n, self.depth = n, depth
+        self.pts = np.full((4, depth, n), np.nan)
+        self.node = np.full((depth, n), -99, dtype=np.int32)
+
+    def struct(self):
+        import robast_b200 as R
+        h = R.rbg_history()
+        h.max_points = self.depth
+        for a, k in enumerate(["hx", "hy", "hz", "ht"]):
+            setattr(h, k, self.pts[a].ctypes.data)
+        h.hnode = self.node.ctypes.data
+        return h
+
+
+def compare_history(ha, hb, npoints, tol_pos=1e-7, tol_time=1e-7 / 2.99792458e10):
+    """recorded points k < min(npoints, depth) of every ray agree (positions, times, node ids)"""
+    bad = 0
+    for k in range(ha.depth):
+        m = npoints > k
+        if not m.any():
+            break
+        dp = np.linalg.norm(ha.pts[:3, k, m] - hb.pts[:3, k, m], axis=0)
+        dt = np.abs(ha.pts[3, k, m] - hb.pts[3, k, m])
+        bad += int(((dp > tol_pos) | (dt > tol_time + 1e-12 * np.abs(ha.pts[3, k, m])) | (ha.node[k, m] != hb.node[k, m])).sum())
+    return bad
+
+
+def trace_history_with(fn, export, rays, o, depth, nthreads=1):
+    h = History(rays.n, depth)
+    r, hs = rays.struct(), h.struct()
+    rc = fn(export.desc_ptr(), C.byref(o), C.byref(r), C.byref(hs), nthreads)
+    assert rc == 0, "trace backend returned %d" % rc
+    return h
+
+
+def trace_history_gpu(export, rays, o, depth, device=0):
+    import robast_b200 as R
+    hnd = C.c_void_p()
+    R.check(R.rbg_scene_create(export.desc_ptr(), device, C.byref(hnd)))
+    h = History(rays.n, depth)
+    try:
+        r, hs = rays.struct(), h.struct()
+        R.check(R.rbg_trace_history(hnd, C.byref(o), C.byref(r), C.byref(hs), None))
+    finally:
+        R.rbg_scene_destroy(hnd)
+    return h
 
 
 def make_rays(oracle, params, first, n):

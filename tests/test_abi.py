@@ -27,6 +27,7 @@ def test_struct_layouts_match_header(R):
     assert ctypes.sizeof(R.rbg_trace_opts) == 32
     assert ctypes.sizeof(R.rbg_rays) == 16 + 18 * 8
     assert ctypes.sizeof(R.rbg_shoot_desc) == 16 + 4 * 8 + 15 * 8 + 8
+    assert ctypes.sizeof(R.rbg_history) == 8 + 5 * 8
 
 
 def test_no_gpu_fails_loudly(R):

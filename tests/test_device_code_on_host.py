@@ -100,3 +100,24 @@ def test_bezier_cones_match_oracle(oracle, emul, kind, theta):
     assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, rep
     frac = (got.status == 3).mean()
     assert (frac > 0.05) if theta < 25 else (frac < 0.05)  # inside / outside the ~30 deg acceptance of the guide
+
+
+@pytest.mark.parametrize("cfg,theta,n,kw", [(4, 0.05, 2500, {}), (5, 18.0, 2500, {"rings": 1}), (2, 1.0, 2500, {})])
+def test_polyline_history_matches_oracle(oracle, emul, cfg, theta, n, kw):
+    """ARay's full polyline + node history (include/ARay.h:24-68): every AddPoint/AddNode of the device code against the oracle's"""
+    mgr, _keep = configs.BUILDERS[cfg](**kw)
+    ex = mgr.ExportScene()
+    beam = configs.beam(cfg, theta, n_side=50 if cfg <= 3 else (12.0 if cfg == 5 else None))
+    o = H.opts(disable_fresnel=1 if cfg == 2 else 0, seed=17)
+    ra, rb = H.make_rays(oracle, beam, 0, n), H.make_rays(oracle, beam, 0, n)
+    ha = H.trace_history_with(oracle.orc_trace_history, ex, ra, o, 12, nthreads=4)
+    hb = H.trace_history_with(emul.emul_trace_history, ex, rb, o, 12)
+    assert H.compare(ra, rb)["bad"] == 0 and (ra.npoints == rb.npoints).all()
+    assert H.compare_history(ha, hb, ra.npoints) == 0
+    # the record is consistent with the plain outputs: point 0 = start, last recorded point = last point, node = last node
+    k = np.minimum(rb.npoints, 12) - 1
+    idx = np.arange(n)
+    full = rb.npoints <= 12
+    assert np.allclose(hb.pts[:3, 0, :], rb.inp[:3]) and (hb.node[0] == -1).all()
+    assert np.allclose(hb.pts[:3, k, idx][:, full], rb.out[:3][:, full], atol=0) and (hb.node[k, idx][full & (rb.npoints > 1)] == rb.last_node[full & (rb.npoints > 1)]).all()
+    assert rb.npoints.max() >= 3

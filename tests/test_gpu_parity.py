@@ -241,6 +241,18 @@ def test_shooter_and_reducers(R, oracle):
         torch.cuda.synchronize()
         got = buf.cpu().numpy()
         assert np.abs(got - host.inp).max() < 1e-12, cfg
+    # point-source generators (RandomCone / RandomSphere / RandomSphericalCone, src/ARayShooter.cxx:240-392)
+    rot = [0.36, 0.48, -0.8, -0.8, 0.6, 0., 0.48, 0.64, 0.6]
+    for kind, a, b in ((4, 45., 10.), (5, 0., 0.), (6, 25., 0.)):
+        params = dict(kind=kind, nx=1, ny=1, dx=a, dy=b, lambda_min=3e-5, lambda_max=7e-5, rot=rot, tr=[1., -2., 3.], dir=[0, 0, 1], seed=9)
+        n = 20000
+        host = H.make_rays(oracle, params, 7, n)
+        d = H.shoot_desc(params)
+        buf = torch.zeros((8, n), dtype=torch.float64, device=dev)
+        R.check(R.rbg_shoot(C.byref(d), 7, n, *[buf[i].data_ptr() for i in range(8)], 0, None))
+        torch.cuda.synchronize()
+        got = buf.cpu().numpy()
+        assert np.abs(got - host.inp).max() < 1e-12, kind
     # hist2d + moments against numpy
     n = 200000
     g = torch.Generator(device="cpu").manual_seed(0)
@@ -341,3 +353,47 @@ def test_full_size_properties_config1(R):
     # mirror symmetry of the grid: statuses are symmetric under x -> -x
     grid = st.reshape(1000, 1000)
     assert (grid == grid[::-1, :]).all() and (grid == grid[:, ::-1]).all()
+
+
+@pytest.mark.parametrize("cfg,theta,n,kw", [(4, 0.05, 30000, {}), (5, 18.0, 30000, {"rings": 1}), (2, 1.0, 40000, {})])
+def test_polyline_history_parity(R, oracle, cfg, theta, n, kw):
+    """rbg_trace_history: every recorded point / node of every ray against the oracle's AddPoint/AddNode record"""
+    mgr, _keep = configs.BUILDERS[cfg](**kw)
+    ex = mgr.ExportScene()
+    beam = configs.beam(cfg, theta, n_side=200 if cfg <= 3 else (12.0 if cfg == 5 else None))
+    o = H.opts(disable_fresnel=1 if cfg == 2 else 0, seed=17)
+    ra, rb = H.make_rays(oracle, beam, 0, n), H.make_rays(oracle, beam, 0, n)
+    ha = H.trace_history_with(oracle.orc_trace_history, ex, ra, o, 10, nthreads=os.cpu_count() or 4)
+    hb = H.trace_history_gpu(ex, rb, o, 10)
+    rep = H.compare(ra, rb)
+    assert rep["bad"] == 0 and rep["npoints_mismatch"] == 0, rep
+    assert H.compare_history(ha, hb, ra.npoints) == 0
+    # a history does not change the plain result
+    rc = H.trace_gpu(ex, H.make_rays(oracle, beam, 0, n), o)
+    assert (rc.out == rb.out).all() and (rc.iout == rb.iout).all()
+
+
+def test_history_through_mirror_classes(R):
+    """tutorials/DaviesCotton.C:219-231: FindNodeNumberStartWith("mirror") + GetPoint(n); unittest_robast.py:833-834 node names"""
+    mgr, _keep = configs.davies_cotton()
+    mgr.DisableFresnelReflection(True)
+    rays = R.ARayShooter.Square(400e-7, 1400., 60, None, R.TGeoTranslation("t", 0, 0, 3200.), R.TVector3(0, 0, -1))
+    mgr.TraceNonSequential(rays)
+    foc = rays.GetFocused()
+    assert foc.GetLast() + 1 > 500
+    for j in range(0, foc.GetLast() + 1, 37):
+        ray = foc.At(j)
+        assert ray.GetNpoints() == 3 and ray.GetNrecorded() == 3
+        names = ray.GetNodeHistoryNames()
+        assert len(names) == 2 and names[0].startswith("mirror") and names[1].startswith("focal")
+        nmir = ray.FindNodeNumberStartWith("mirror")
+        assert nmir == 0
+        p0, p1, p2 = ray.GetPoint(0), ray.GetPoint(nmir + 1), ray.GetPoint(2)
+        assert p0[2] == 3200. and abs(p1[0] - p0[0]) < 1e-9 and p1[2] < 200. and list(p2) == list(ray.GetLastPoint())
+        assert abs(math.hypot(p1[0], p1[1]) - math.hypot(p0[0], p0[1])) < 1e-9  # the vertical ray meets the dish right below its start
+    ex0 = rays.GetExited().At(0)
+    assert ex0.GetNodeHistoryNames()[-1] == ""  # left the world: null node entry, like the reference
+    mgr.SetHistoryDepth(0)
+    rays = R.ARayShooter.Square(400e-7, 1400., 20, None, R.TGeoTranslation("t", 0, 0, 3200.), R.TVector3(0, 0, -1))
+    mgr.TraceNonSequential(rays)
+    assert rays.GetFocused().At(0).GetNrecorded() == 0

@@ -237,6 +237,35 @@ def test_kat_shooter_grids(R, oracle):  # src/ARayShooter.cxx:122-183,401-452
     assert np.allclose(rays.inp[0], cc["x"], atol=1e-12) and np.allclose(rays.inp[1], cc["y"], atol=1e-12)
 
 
+def test_point_source_shooters(R, oracle):  # src/ARayShooter.cxx:240-392
+    base = dict(nx=1, ny=1, lambda_min=400 * nm, lambda_max=400 * nm, rot=[1, 0, 0, 0, 1, 0, 0, 0, 1], tr=[1., 2., 3.], dir=[0, 0, 1], seed=5)
+    n = 40000
+    cone = H.make_rays(oracle, dict(base, kind=4, dx=45., dy=10.), 0, n).inp   # RandomCone(r = 45, d = 10)
+    sph = H.make_rays(oracle, dict(base, kind=5, dx=0., dy=0.), 0, n).inp      # RandomSphere
+    scone = H.make_rays(oracle, dict(base, kind=6, dx=25., dy=0.), 0, n).inp   # RandomSphericalCone(theta = 25 deg)
+    for a in (cone, sph, scone):
+        assert np.allclose(a[0], 1.) and np.allclose(a[1], 2.) and np.allclose(a[2], 3.) and np.allclose(a[3], 0.)
+        assert np.allclose(a[4] ** 2 + a[5] ** 2 + a[6] ** 2, 1., atol=1e-14)
+    # RandomCone: the aim points d/dz * (dx, dy) fill the disc of radius r uniformly
+    gx, gy = 10. * cone[4] / cone[6], 10. * cone[5] / cone[6]
+    rr = np.hypot(gx, gy)
+    assert rr.max() <= 45. * (1 + 1e-12) and abs((rr < 45. / math.sqrt(2)).mean() - 0.5) < 3 * 0.5 / math.sqrt(n)
+    # RandomSphere: isotropic -> each component uniform in [-1, 1]
+    for k in (4, 5, 6):
+        assert abs(sph[k].mean()) < 4 / math.sqrt(3 * n) and abs((sph[k] ** 2).mean() - 1. / 3.) < 0.01
+    # RandomSphericalCone: cos(theta) uniform in [cos 25 deg, 1], phi uniform
+    c0 = math.cos(math.radians(25.))
+    assert scone[6].min() >= c0 - 1e-12 and abs(scone[6].mean() - (1 + c0) / 2) < 4 * (1 - c0) / math.sqrt(12 * n)
+    assert abs(np.arctan2(scone[5], scone[4]).mean()) < 4 * math.pi / math.sqrt(3 * n)
+    # the host-side generators of the mirror classes have the same geometry (they draw from gRandom instead of Philox)
+    arr = R.ARayShooter.RandomSphericalCone(400 * nm, 2000, 25.)
+    c = arr.columns()
+    assert c["dz"].min() >= c0 - 1e-12 and np.allclose(c["dx"] ** 2 + c["dy"] ** 2 + c["dz"] ** 2, 1.)
+    arr = R.ARayShooter.RandomCone(400 * nm, 45., 10., 2000)
+    c = arr.columns()
+    assert (10. * np.hypot(c["dx"], c["dy"]) / c["dz"]).max() <= 45. * (1 + 1e-12)
+
+
 def test_winston_cone_cutoff(oracle):  # closed-form property of a Winston cone: acceptance asin(R2/R1) = 30 deg
     mgr, _k = configs.hex_winston_cone(rings=0, coating="ideal")
     ex = mgr.ExportScene()
