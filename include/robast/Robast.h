@@ -721,6 +721,7 @@ class ARay : public TObject {
     return i;
   }
   Int_t GetNrecorded() const { return (Int_t)(fHist.size() / 4); }
+  Int_t GetNnodesRecorded() const { return (Int_t)fNodeObjs.size(); }  // node-history slots, a trailing null (world exit) included
   Int_t GetNpoints() const { return fNpoints; }
   Double_t GetLambda() const { return fLambda; }
   void SetLambda(Double_t l) { fLambda = l; }

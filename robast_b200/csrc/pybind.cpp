@@ -215,7 +215,8 @@ PYBIND11_MODULE(_robast, m) {
       .def("GetNodeHistoryNames", [](const ARay& r) {
         std::vector<std::string> v;
         const TObjArray* h = r.GetNodeHistory();
-        for (Int_t i = 0; i <= h->GetLast(); i++) v.push_back(h->At(i) ? h->At(i)->GetName() : "");
+        Int_t n = std::max(h->GetLast() + 1, r.GetNnodesRecorded());
+        for (Int_t i = 0; i < n; i++) v.push_back(h->At(i) ? h->At(i)->GetName() : "");
         return v;
       })
       .def("IsAbsorbed", &ARay::IsAbsorbed).def("IsExited", &ARay::IsExited).def("IsFocused", &ARay::IsFocused).def("IsRunning", &ARay::IsRunning)

@@ -383,12 +383,14 @@ def test_history_through_mirror_classes(R):
     assert foc.GetLast() + 1 > 500
     for j in range(0, foc.GetLast() + 1, 37):
         ray = foc.At(j)
-        assert ray.GetNpoints() == 3 and ray.GetNrecorded() == 3
+        npts = ray.GetNpoints()
+        assert npts >= 3 and ray.GetNrecorded() == npts, (npts, ray.GetNrecorded())
         names = ray.GetNodeHistoryNames()
-        assert len(names) == 2 and names[0].startswith("mirror") and names[1].startswith("focal")
+        # the beam starts above the world box: world entry, facet, focal plane
+        assert names == ["world_1", names[1], "focalPlane_1"] and names[1].startswith("mirror_"), names
         nmir = ray.FindNodeNumberStartWith("mirror")
-        assert nmir == 0
-        p0, p1, p2 = ray.GetPoint(0), ray.GetPoint(nmir + 1), ray.GetPoint(2)
+        assert nmir == 1 and ray.FindNodeNumberStartWith("nothing") == -1
+        p0, p1, p2 = ray.GetPoint(0), ray.GetPoint(nmir + 1), ray.GetPoint(npts - 1)
         assert p0[2] == 3200. and abs(p1[0] - p0[0]) < 1e-9 and p1[2] < 200. and list(p2) == list(ray.GetLastPoint())
         assert abs(math.hypot(p1[0], p1[1]) - math.hypot(p0[0], p0[1])) < 1e-9  # the vertical ray meets the dish right below its start
     ex0 = rays.GetExited().At(0)
