@@ -153,6 +153,9 @@ def main():
         d = H.shoot_desc(configs.beam(2, th, n_side=nside))
         R.check(R.rbg_shoot(C.byref(d), 0, n, *[inp[k, i].data_ptr() for i in range(8)], local, stream))
     hist = torch.zeros((nang, 200 * 200), dtype=torch.int64, device=dev)
+    hstats = torch.zeros((nang, 5), dtype=torch.float64, device=dev)
+    d80 = torch.zeros((nang, 3), dtype=torch.float64, device=dev)
+    d80_all = torch.zeros((world * nang, 3), dtype=torch.float64, device=dev)
     mom = torch.zeros((nang, 8), dtype=torch.float64, device=dev)
     cnt = torch.zeros((nang, 6), dtype=torch.int64, device=dev)
     opts = H.opts(disable_fresnel=1, steps_per_launch=args.steps_per_launch, seed=20180601)
@@ -172,18 +175,25 @@ def main():
 
     def step():
         hist.zero_()
+        hstats.zero_()
         mom.zero_()
         cnt.zero_()
         for k in range(nang):
             opts.ray_id_offset = (rank * nang + k) * n
             R.check(R.rbg_trace(scene, C.byref(opts), C.byref(structs[k]), stream))
-            cx = 1600. * math.tan(math.radians(my_angles[k]))  # PSF window of DaviesCotton.C:210 (mm) around the nominal image
-            R.check(R.rbg_hist2d(n, out[0].data_ptr(), out[1].data_ptr(), iout[0].data_ptr(), R.RBG_FOCUSED, 200, cx - 4., cx + 10., 200, -7., 7., hist[k].data_ptr(), local, stream))
+            # PSF histogram in image-centred coordinates (window of DaviesCotton.C:210, cm): every angle shares one binning,
+            # so the histograms of all ranks stack and the nine D80 searches run as one launch
+            cx = 1600. * math.tan(math.radians(my_angles[k]))
+            R.check(R.rbg_hist2d_stats(n, out[0].data_ptr(), out[1].data_ptr(), iout[0].data_ptr(), R.RBG_FOCUSED, cx, 0., 200, -4., 10., 200, -7., 7.,
+                                       hist[k].data_ptr(), hstats[k].data_ptr(), local, stream))
             R.check(R.rbg_moments(n, out[0].data_ptr(), out[1].data_ptr(), out[3].data_ptr(), iout[0].data_ptr(), R.RBG_FOCUSED, mom[k].data_ptr(), cnt[k].data_ptr(), local, stream))
+        # D80 of each of this rank's field angles (AGeoUtil::ContainmentRadius), then the cross-rank reductions
+        R.check(R.rbg_containment_radius(nang, hist.data_ptr(), 200, -4., 10., 200, -7., 7., hstats.data_ptr(), 0.8, d80.data_ptr(), local, stream))
         if dist is not None:
             dist.all_reduce(hist)
             dist.all_reduce(mom)
             dist.all_reduce(cnt)
+            dist.all_gather_into_tensor(d80_all, d80)
 
     def barrier():
         if dist is not None:
@@ -258,8 +268,14 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        # untimed verification: the host-buffer path returns the same status counts as the device-resident path
+        host_counts = torch.zeros(6, dtype=torch.int64)
+        for k in range(nang):
+            opts.ray_id_offset = (rank * nang + k) * n
+            R.check(R.rbg_trace(scene, C.byref(opts), C.byref(hs[k]), None))
+            host_counts += torch.bincount(hiout[0].to(torch.int64), minlength=6)
         e2e = {"value": rays_per_step * ksteps / float(dt.item()), "unit": "rays/s", "h2d_bytes_per_step": BYTES_IN * n * nang, "d2h_bytes_per_step": BYTES_OUT * n * nang,
-               "steps": ksteps, "focused_check": int((hiout[0] == R.RBG_FOCUSED).sum().item())}
+               "steps": ksteps, "status_counts_match_device_path": bool((host_counts == cnt.sum(0).cpu()).all().item()) if world == 1 else None}
         del hin, hout, hiout
 
     # ---- CPU baseline (rank 0, N=1): the oracle on all host threads, bounded sample
@@ -285,17 +301,29 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     kernel_ms = bm.value / max(1, bn.value)
-    achieved = (BYTES_IN + BYTES_OUT) * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
-    roof = {"bound": "hbm", "kernel": "k_trace<%s>" % R.rbg_scene_kernel_variant(scene).decode(), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-            "traffic": None, "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback", "algorithmic_bytes_per_ray": BYTES_IN + BYTES_OUT,
+    # one bounce launch processes the live rays of one field angle; per TraceNonSequential pass the algorithmic bytes are
+    # 132 B/ray (64 in + 68 out), and the bounce kernel runs `launches per pass` times per pass
+    passes = args.steps * nang
+    achieved = (BYTES_IN + BYTES_OUT) * n * passes / (bm.value * 1e-3) / 1e9 if bm.value > 0 else None
+    variant = R.rbg_scene_kernel_variant(scene).decode()
+    roof = {"bound": "hbm", "kernel": "k_step<%s> (wavefront bounce kernel; k_trace<%s> finishes the tail)" % (variant, variant), "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
+            "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "of fallback", "algorithmic_bytes_per_ray": BYTES_IN + BYTES_OUT,
+            "algorithmic_bytes_per_pass": (BYTES_IN + BYTES_OUT) * n, "bounce_ms_per_pass": bm.value / passes, "bounce_launches_per_pass": bn.value / passes,
             "kernel_ms_per_launch": kernel_ms, "kernel_launches": bn.value, "kernel_share_of_step": bm.value / ms if ms else None,
-            "note": "k_trace is FP64-pipe bound, not HBM bound: see profiles/ for sm__inst_executed_pipe_fp64 and DESIGN.md"}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_k_trace.json")
-    if os.path.exists(traffic_file):
+            "compact": {"ms_per_launch": cm_.value / max(1, cn.value), "launches": cn.value, "share_of_step": cm_.value / ms if ms else None},
+            "note": "achieved = 132 B/ray x rays of a pass / summed CUDA-event time of that pass's bounce launches. The bounce kernel is bound by FP64/"
+                    "instruction issue, not HBM: see roofline.fp64 and profiles/"}
+    for fn, key in (("traffic_k_step.json", "traffic"),):
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            roof[key] = json.load(open(os.path.join(ROOT, "profiles", fn))).get("dram_bytes_per_pass")
         except Exception:
             pass
+    try:
+        fp = json.load(open(os.path.join(ROOT, "profiles", "fp64_roofline.json")))
+        roof["fp64"] = fp
+    except Exception:
+        pass
 
     if rank == 0:
         print(json.dumps({
@@ -305,7 +333,7 @@ def main():
                        "rays_per_step_per_gpu": n * nang, "rays_per_step": rays_per_step, "l2_policy": "inputs (711 MB per batch) larger than L2, no flush",
                        "steps_per_launch": args.steps_per_launch, "parallelism": "rays sharded over %d GPU(s), geometry replicated" % world},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks_summary(samples),
-            "check": {"focused_fraction": focused_frac, "status_counts": counts},
+            "check": {"focused_fraction": focused_frac, "status_counts": counts, "d80_cm_by_angle": [round(v, 4) for v in d80[:, 0].cpu().numpy().tolist()]},
         }))
     R.rbg_scene_destroy(scene)
     if dist is not None:

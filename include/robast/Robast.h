@@ -466,6 +466,20 @@ inline void MakePointToPointBBox(const char* name, const TVector3& v1, const TVe
   (*combi)->SetName(Form("%scombi", name));
   (*combi)->RegisterYourself();
 }
+// reference src/AGeoUtil.cxx:198-308: radius and centre of the circle containing `fraction` of the histogram (D80 for
+// fraction = 0.8).  Runs on the GPU (rbg_containment_radius_host: one block, the reference's search step for step).
+inline void ContainmentRadius(TH2* h2, Double_t fraction, Double_t& r, Double_t& x, Double_t& y, Int_t device = 0) {
+  const Int_t nx = h2->GetNbinsX(), ny = h2->GetNbinsY();
+  std::vector<Double_t> bins((size_t)nx * ny);
+  for (Int_t j = 1; j <= ny; j++)
+    for (Int_t i = 1; i <= nx; i++) bins[(i - 1) + (size_t)nx * (j - 1)] = h2->GetBinContent(i, j);
+  Double_t stats[5], out[3];
+  h2->GetStats5(stats);
+  if (rbg_containment_radius_host(bins.data(), nx, h2->GetXaxis()->GetXmin(), h2->GetXaxis()->GetXmax(), ny, h2->GetYaxis()->GetXmin(),
+                                  h2->GetYaxis()->GetXmax(), stats, fraction, out, device) != RBG_OK)
+    throw std::runtime_error(std::string("AGeoUtil::ContainmentRadius: ") + rbg_last_error());
+  r = out[0]; x = out[1]; y = out[2];
+}
 }  // namespace AGeoUtil
 
 // ============================================================================ multilayer (description; TMM runs on device)

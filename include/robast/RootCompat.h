@@ -1047,6 +1047,8 @@ class TH2 : public TH1 {
     return std::sqrt(std::fabs(s2 - m * m));
   }
   Double_t GetRMS(Int_t axis = 1) const { return GetStdDev(axis); }
+  // sum w, wx, wy, wx^2, wy^2 of the in-range fills (ROOT's fTsumw...), for the device reducers
+  void GetStats5(Double_t* s) const { s[0] = fSw; s[1] = fSwx; s[2] = fSwy; s[3] = fSwx2; s[4] = fSwy2; }
   Double_t Integral() const {
     Double_t s = 0;
     for (Int_t j = 1; j <= fYaxis.fN; j++)

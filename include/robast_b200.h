@@ -271,6 +271,24 @@ int rbg_shoot(const rbg_shoot_desc* d, int64_t first, int64_t n, double* x, doub
 int rbg_hist2d(int64_t n, const double* x, const double* y, const int32_t* status, int32_t sel,
                int32_t nx, double xmin, double xmax, int32_t ny, double ymin, double ymax,
                unsigned long long* hist, int device, void* stream);
+/* rbg_hist2d of (x - x0, y - y0) that also accumulates the TH2 statistics of the in-range fills into
+ * stats[5] (device): Σw, Σx', Σy', Σx'², Σy'² of the shifted coordinates — what TH2::GetMean/GetStdDev use.
+ * stats may be NULL.  The origin shift lets the PSFs of several field angles share one binning. */
+int rbg_hist2d_stats(int64_t n, const double* x, const double* y, const int32_t* status, int32_t sel,
+                     double x0, double y0, int32_t nx, double xmin, double xmax, int32_t ny, double ymin,
+                     double ymax, unsigned long long* hist, double* stats, int device, void* stream);
+/* AGeoUtil::ContainmentRadius (reference src/AGeoUtil.cxx:18-42,198-308; D80 of the tutorials, e.g.
+ * tutorials/MST.C:231-281) on `nhist` device-resident histograms of identical binning: hist
+ * (nhist x nx*ny uint64, bin (i,j) at i + nx*j, as written by rbg_hist2d), stats (nhist x 5 doubles
+ * from rbg_hist2d_stats), out (nhist x 3 doubles: radius, centre x, centre y). One block per histogram. */
+int rbg_containment_radius(int32_t nhist, const unsigned long long* hist, int32_t nx, double xmin,
+                           double xmax, int32_t ny, double ymin, double ymax, const double* stats,
+                           double fraction, double* out, int device, void* stream);
+/* same for ONE host histogram with double bin contents (what AGeoUtil::ContainmentRadius(TH2*) binds);
+ * bins, stats and out are host pointers; copies inside, synchronous */
+int rbg_containment_radius_host(const double* bins, int32_t nx, double xmin, double xmax, int32_t ny,
+                                double ymin, double ymax, const double* stats, double fraction,
+                                double* out, int device);
 int rbg_moments(int64_t n, const double* x, const double* y, const double* t, const int32_t* status,
                 int32_t sel, double* moments, long long* counts, int device, void* stream);
 

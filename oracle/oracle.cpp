@@ -1930,6 +1930,79 @@ double orc_graph_eval(const rbg_scene_desc* desc, int g, double x) { return grap
 double orc_th2_interp(const rbg_scene_desc* desc, int h, double x, double y) { return th2_interp(desc, h, x, y); }
 double orc_graph2d_interp(const rbg_scene_desc* desc, int g, double x, double y) { return graph2d_interp(desc, g, x, y); }
 
+// AGeoUtil::ContainmentRadius, src/AGeoUtil.cxx:18-42 (SumInRadius) and :198-308, on a flat histogram: bins[i + nx*j]
+// = content of bin (i+1, j+1), stats = {sum w, sum x, sum y, sum x^2, sum y^2} of the in-range fills (what TH2::GetMean /
+// GetStdDev read), out = {r, x, y}.
+static double sum_in_radius(const double* bins, int nx, double xmin, double wx, int ny, double ymin, double wy, double x, double y, double r) {
+  double r2 = r * r, total = 0.;
+  for (int ix = 1; ix <= nx; ++ix) {
+    double cx = xmin + (ix - 1) * wx + 0.5 * wx;  // TAxis::GetBinCenter
+    for (int iy = 1; iy <= ny; ++iy) {
+      double cy = ymin + (iy - 1) * wy + 0.5 * wy;
+      double c = bins[(ix - 1) + (size_t)nx * (iy - 1)];
+      if (c <= 0) continue;
+      double d2 = (cx - x) * (cx - x) + (cy - y) * (cy - y);
+      if (d2 <= r2) total += c;
+    }
+  }
+  return total;
+}
+int orc_containment_radius(const double* bins, int nx, double xmin, double xmax, int ny, double ymin, double ymax, const double* stats, double fraction,
+                           double* out) {
+  double wx = (xmax - xmin) / nx, wy = (ymax - ymin) / ny;
+  auto S = [&](double x, double y, double r) { return sum_in_radius(bins, nx, xmin, wx, ny, ymin, wy, x, y, r); };
+  double sw = stats[0];
+  double x = sw != 0 ? stats[1] / sw : 0, y = sw != 0 ? stats[2] / sw : 0;
+  double sdx = sw != 0 ? sqrt(fabs(stats[3] / sw - x * x)) : 0, sdy = sw != 0 ? sqrt(fabs(stats[4] / sw - y * y)) : 0;
+  double r = sqrt(sdx * sdx + sdy * sdy) * 1.5;
+  double dr = 0.1 * r;
+  double integral = 0;
+  for (size_t b = 0; b < (size_t)nx * ny; b++) integral += bins[b];
+  double sum_goal = integral * fraction;
+  int no_shift = 0, no_stable = 0;
+  for (int i = 0; i < 100 && no_shift < 30; i++) {
+    bool stable_r = false, stable_x = true, stable_y = true;
+    double sum0 = S(x, y, r);
+    double next_r = r;
+    if (sum0 < sum_goal) {
+      double sum1 = S(x, y, r + dr);
+      if (sum1 == sum0) { dr *= 2.; continue; }
+      next_r = r + dr * (sum_goal - sum0) / (sum1 - sum0);
+    } else if (sum0 != sum_goal) {
+      double sum1 = S(x, y, r - dr);
+      if (sum1 == sum0) { dr *= 2.; continue; }
+      next_r = r - dr * (sum0 - sum_goal) / (sum0 - sum1);
+    }
+    if (next_r < 0.) next_r = 0.5 * r;
+    if (next_r < 0.5 * r) next_r = 0.5 * r;
+    if (next_r > 2. * r) next_r = 2. * r;
+    stable_r = fabs(next_r - r) < 0.0001 * r;
+    r = next_r;
+    {
+      double sum1 = S(x, y, r);
+      dr *= sum0 != sum_goal ? fabs((sum1 - sum_goal) / (sum0 - sum_goal)) : 0.5;
+      if (dr > 0.5 * r) dr = 0.5 * r;
+      if (dr < 0.0005 * r) dr = 0.0005 * r;
+      no_shift++;
+      for (double dx = 0.25 * r; dx > 0.1 * dr; dx *= 0.25) {
+        double sum_x1 = S(x + dx, y, r), sum_x2 = S(x - dx, y, r);
+        while (sum_x1 > sum1) { no_shift = 0; x += dx; sum_x2 = sum1; sum1 = sum_x1; sum_x1 = S(x + dx, y, r); stable_x = false; }
+        while (sum_x2 > sum1) { no_shift = 0; x -= dx; sum_x1 = sum1; sum1 = sum_x2; sum_x2 = S(x - dx, y, r); stable_x = false; }
+      }
+    }
+    for (double dy = 0.1 * r; dy > 0.1 * dr; dy *= 0.25) {
+      double sum1 = S(x, y, r), sum_y1 = S(x, y + dy, r), sum_y2 = S(x, y - dy, r);
+      while (sum_y1 > sum1) { no_shift = 0; y += dy; sum_y2 = sum1; sum1 = sum_y1; sum_y1 = S(x, y + dy, r); stable_y = false; }
+      while (sum_y2 > sum1) { no_shift = 0; y -= dy; sum_y1 = sum1; sum1 = sum_y2; sum_y2 = S(x, y - dy, r); stable_y = false; }
+    }
+    if (stable_r && stable_x && stable_y) no_stable++;
+    else no_stable = 0;
+    if (no_stable >= 4) break;
+  }
+  out[0] = r; out[1] = x; out[2] = y;
+  return RBG_OK;
+}
+
 // shape-level entry points (local frame) for shape parity tests
 int orc_shape_contains(const rbg_scene_desc* desc, int shape, const double* p) {
   Scene S(desc);

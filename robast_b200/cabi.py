@@ -54,13 +54,16 @@ rbg_profile_enable = _proto("rbg_profile_enable", C.c_int, [C.c_int])
 rbg_profile_read = _proto("rbg_profile_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)])
 rbg_shoot = _proto("rbg_shoot", C.c_int, [C.POINTER(rbg_shoot_desc), C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_int, C.c_void_p])
 rbg_hist2d = _proto("rbg_hist2d", C.c_int, [C.c_int64, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, C.c_int, C.c_void_p])
+rbg_hist2d_stats = _proto("rbg_hist2d_stats", C.c_int, [C.c_int64, _dp, _dp, _dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_void_p])
+rbg_containment_radius = _proto("rbg_containment_radius", C.c_int, [C.c_int32, _dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, C.c_double, _dp, C.c_int, C.c_void_p])
+rbg_containment_radius_host = _proto("rbg_containment_radius_host", C.c_int, [_dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, C.c_double, _dp, C.c_int])
 rbg_moments = _proto("rbg_moments", C.c_int, [C.c_int64, _dp, _dp, _dp, _dp, C.c_int32, _dp, _dp, C.c_int, C.c_void_p])
 rbg_tmm = _proto("rbg_tmm", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, C.c_void_p])
 rbg_tmm_host = _proto("rbg_tmm_host", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp])
 
 ABI_SYMBOLS = ["rbg_abi_version", "rbg_last_error", "rbg_device_count", "rbg_scene_create", "rbg_scene_destroy",
                "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_scene_kernel_variant", "rbg_trace", "rbg_trace_history", "rbg_launch_count", "rbg_profile_enable",
-               "rbg_profile_read", "rbg_shoot", "rbg_hist2d", "rbg_moments", "rbg_tmm", "rbg_tmm_host"]
+               "rbg_profile_read", "rbg_shoot", "rbg_hist2d", "rbg_hist2d_stats", "rbg_containment_radius", "rbg_containment_radius_host", "rbg_moments", "rbg_tmm", "rbg_tmm_host"]
 
 
 class RbgError(RuntimeError):

@@ -116,6 +116,11 @@ PYBIND11_MODULE(_robast, m) {
       .def(py::init<const char*, double, double, int, double, double, double>())
       .def("SetControlPoints", (void(AGeoBezierPcon::*)(double, double)) & AGeoBezierPcon::SetControlPoints)
       .def("SetControlPoints", (void(AGeoBezierPcon::*)(double, double, double, double)) & AGeoBezierPcon::SetControlPoints);
+  m.def("ContainmentRadius", [](TH2* h, double fraction) {
+    double r, x, y;
+    AGeoUtil::ContainmentRadius(h, fraction, r, x, y);
+    return py::make_tuple(r, x, y);
+  });
   m.def("MakePointToPointTube", [](const char* name, TVector3 v1, TVector3 v2, double radius) {
     TGeoTube* t;
     TGeoCombiTrans* c;

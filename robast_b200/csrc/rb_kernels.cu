@@ -276,8 +276,9 @@ __global__ void k_shoot(rbg_shoot_desc s, long long first, long long n, double* 
 // ---- reducers
 #define HIST_SMEM_BINS 8192
 __global__ void k_hist2d(long long n, const double* __restrict__ x, const double* __restrict__ y, const int32_t* __restrict__ status, int sel, int nx,
-                         double xmin, double xmax, int ny, double ymin, double ymax, unsigned long long* hist, int use_smem) {
+                         double xmin, double xmax, int ny, double ymin, double ymax, unsigned long long* hist, int use_smem, double* stats, double x0, double y0) {
   __shared__ unsigned int sh[HIST_SMEM_BINS];
+  double st[5] = {0, 0, 0, 0, 0};  // TH2 statistics of the in-range fills: sum w, x, y, x^2, y^2
   int nb = nx * ny;
   if (use_smem) {
     for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
@@ -286,13 +287,21 @@ __global__ void k_hist2d(long long n, const double* __restrict__ x, const double
   double sx = nx / (xmax - xmin), sy = ny / (ymax - ymin);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (status[i] != sel) continue;
-    double vx = x[i], vy = y[i];
+    double vx = x[i] - x0, vy = y[i] - y0;
     if (vx < xmin || !(vx < xmax) || vy < ymin || !(vy < ymax)) continue;
     int bx = (int)((vx - xmin) * sx), by = (int)((vy - ymin) * sy);
     bx = bx >= nx ? nx - 1 : bx;
     by = by >= ny ? ny - 1 : by;
     if (use_smem) atomicAdd(&sh[bx + nx * by], 1u);
     else atomicAdd(&hist[bx + nx * by], 1ull);
+    st[0] += 1; st[1] += vx; st[2] += vy; st[3] += vx * vx; st[4] += vy * vy;
+  }
+  if (stats) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      for (int o = 16; o > 0; o >>= 1) st[k] += __shfl_down_sync(0xffffffffu, st[k], o);
+      if ((threadIdx.x & 31) == 0 && st[k] != 0) atomicAdd(&stats[k], st[k]);
+    }
   }
   if (use_smem) {
     __syncthreads();
@@ -325,6 +334,12 @@ __global__ void k_moments(long long n, const double* __restrict__ x, const doubl
       if (c[k]) atomicAdd(&counts[k], (unsigned long long)c[k]);
   }
 }
+
+// ---- AGeoUtil::ContainmentRadius: kernel in rb_reducers.cu (compiled with -fmad=false)
+int rb_launch_containment_u64(int nhist, const unsigned long long* hist, int nx, double xmin, double xmax, int ny, double ymin, double ymax, const double* stats,
+                              double fraction, double* out, cudaStream_t st);
+int rb_launch_containment_f64(int nhist, const double* hist, int nx, double xmin, double xmax, int ny, double ymin, double ymax, const double* stats,
+                              double fraction, double* out, cudaStream_t st);
 
 __global__ void k_tmm(DScene sc, int ml, long long n, const double* __restrict__ theta, const double* __restrict__ lambda, double* R, double* T) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -767,13 +782,17 @@ int rbg_shoot(const rbg_shoot_desc* d, int64_t first, int64_t n, double* x, doub
 
 int rbg_hist2d(int64_t n, const double* x, const double* y, const int32_t* status, int32_t sel, int32_t nx, double xmin, double xmax, int32_t ny,
                double ymin, double ymax, unsigned long long* hist, int device, void* stream) {
+  return rbg_hist2d_stats(n, x, y, status, sel, 0., 0., nx, xmin, xmax, ny, ymin, ymax, hist, nullptr, device, stream);
+}
+int rbg_hist2d_stats(int64_t n, const double* x, const double* y, const int32_t* status, int32_t sel, double x0, double y0, int32_t nx, double xmin,
+                     double xmax, int32_t ny, double ymin, double ymax, unsigned long long* hist, double* stats, int device, void* stream) {
   return guard([&] {
     if (nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin)) throw Invalid("bad histogram axes");
     if (n <= 0) return;
     CK(cudaSetDevice(device));
     int use_smem = (long long)nx * ny <= HIST_SMEM_BINS;
     int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-    k_hist2d<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, x, y, status, sel, nx, xmin, xmax, ny, ymin, ymax, hist, use_smem);
+    k_hist2d<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, x, y, status, sel, nx, xmin, xmax, ny, ymin, ymax, hist, use_smem, stats, x0, y0);
     g_launches++;
     CK(cudaGetLastError());
   });
@@ -788,6 +807,39 @@ int rbg_moments(int64_t n, const double* x, const double* y, const double* t, co
     k_moments<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, x, y, t, status, sel, moments, (unsigned long long*)counts);
     g_launches++;
     CK(cudaGetLastError());
+  });
+}
+
+int rbg_containment_radius(int32_t nhist, const unsigned long long* hist, int32_t nx, double xmin, double xmax, int32_t ny, double ymin, double ymax,
+                           const double* stats, double fraction, double* out, int device, void* stream) {
+  return guard([&] {
+    if (nhist < 0 || nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin) || !hist || !stats || !out) throw Invalid("bad containment-radius arguments");
+    if (nhist == 0) return;
+    CK(cudaSetDevice(device));
+    CK((cudaError_t)rb_launch_containment_u64(nhist, hist, nx, xmin, xmax, ny, ymin, ymax, stats, fraction, out, (cudaStream_t)stream));
+    g_launches++;
+  });
+}
+int rbg_containment_radius_host(const double* bins, int32_t nx, double xmin, double xmax, int32_t ny, double ymin, double ymax, const double* stats,
+                                double fraction, double* out, int device) {
+  return guard([&] {
+    if (nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin) || !bins || !stats || !out) throw Invalid("bad containment-radius arguments");
+    if (rbg_device_count() <= 0) throw std::runtime_error("cuda: no CUDA device available — the reducers have no CPU fallback");
+    CK(cudaSetDevice(device));
+    double* d = nullptr;
+    size_t nb = (size_t)nx * ny;
+    CK(cudaMalloc((void**)&d, (nb + 8) * 8));
+    try {
+      CK(cudaMemcpy(d, bins, nb * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d + nb, stats, 5 * 8, cudaMemcpyHostToDevice));
+      CK((cudaError_t)rb_launch_containment_f64(1, d, nx, xmin, xmax, ny, ymin, ymax, d + nb, fraction, d + nb + 5, nullptr));
+      g_launches++;
+      CK(cudaMemcpy(out, d + nb + 5, 3 * 8, cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cudaFree(d);
+      throw;
+    }
+    cudaFree(d);
   });
 }
 

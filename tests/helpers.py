@@ -37,6 +37,8 @@ def load_oracle():
     lib.orc_th2_interp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
     lib.orc_graph2d_interp.restype = C.c_double
     lib.orc_graph2d_interp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.orc_containment_radius.restype = C.c_int
+    lib.orc_containment_radius.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_void_p]
     lib.orc_uniform.restype = C.c_double
     lib.orc_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     lib.orc_shoot.restype = C.c_int
@@ -160,6 +162,23 @@ def trace_history_gpu(export, rays, o, depth, device=0):
     finally:
         R.rbg_scene_destroy(hnd)
     return h
+
+
+def psf_histogram(x, y, nx, xmin, xmax, ny, ymin, ymax):
+    """TH2::Fill of the points: bins[i + nx*j] (double) and the in-range statistics {sum w, x, y, x^2, y^2}"""
+    m = (x >= xmin) & (x < xmax) & (y >= ymin) & (y < ymax)
+    xs, ys = x[m], y[m]
+    bx = np.minimum((nx * (xs - xmin) / (xmax - xmin)).astype(np.int64), nx - 1)
+    by = np.minimum((ny * (ys - ymin) / (ymax - ymin)).astype(np.int64), ny - 1)
+    bins = np.bincount(bx + nx * by, minlength=nx * ny).astype(np.float64)
+    stats = np.array([m.sum(), xs.sum(), ys.sum(), (xs ** 2).sum(), (ys ** 2).sum()], dtype=np.float64)
+    return bins, stats
+
+
+def oracle_containment(oracle, bins, stats, nx, xmin, xmax, ny, ymin, ymax, fraction):
+    out = np.zeros(3)
+    assert oracle.orc_containment_radius(bins.ctypes.data, nx, xmin, xmax, ny, ymin, ymax, stats.ctypes.data, fraction, out.ctypes.data) == 0
+    return out
 
 
 def make_rays(oracle, params, first, n):

@@ -399,3 +399,50 @@ def test_history_through_mirror_classes(R):
     rays = R.ARayShooter.Square(400e-7, 1400., 20, None, R.TGeoTranslation("t", 0, 0, 3200.), R.TVector3(0, 0, -1))
     mgr.TraceNonSequential(rays)
     assert rays.GetFocused().At(0).GetNrecorded() == 0
+
+
+def test_containment_radius_on_device(R, oracle):
+    """rbg_hist2d_stats + rbg_containment_radius (AGeoUtil::ContainmentRadius, D80) against the oracle's restatement:
+    same histogram -> same search path -> same radius and centre"""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(2)
+    n = 300000
+    cases = []
+    for k, (sx, sy, cx, cy) in enumerate(((0.5, 0.5, 0.3, -0.2), (1.2, 0.3, -1.0, 0.8), (0.05, 0.07, 2.0, 2.0))):
+        x, y = cx + sx * rng.standard_normal(n), cy + sy * rng.standard_normal(n)
+        if k == 1:  # coma-like tail
+            x = x + 0.8 * rng.random(n) ** 3
+        cases.append((x, y))
+    nx, ny, lo, hi = 200, 180, -4., 5.
+    hist = torch.zeros((len(cases), nx * ny), dtype=torch.int64, device=dev)
+    stats = torch.zeros((len(cases), 5), dtype=torch.float64, device=dev)
+    st = torch.full((n,), 3, dtype=torch.int32, device=dev)
+    for k, (x, y) in enumerate(cases):
+        xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+        R.check(R.rbg_hist2d_stats(n, xd.data_ptr(), yd.data_ptr(), st.data_ptr(), 3, 0.25 * k, -0.5 * k, nx, lo, hi, ny, lo, hi, hist[k].data_ptr(), stats[k].data_ptr(), 0, None))
+    torch.cuda.synchronize()
+    for frac in (0.8, 0.68):
+        out = torch.zeros((len(cases), 3), dtype=torch.float64, device=dev)
+        R.check(R.rbg_containment_radius(len(cases), hist.data_ptr(), nx, lo, hi, ny, lo, hi, stats.data_ptr(), frac, out.data_ptr(), 0, None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for k, (x, y) in enumerate(cases):
+            bins, s5 = H.psf_histogram(x - 0.25 * k, y + 0.5 * k, nx, lo, hi, ny, lo, hi)
+            assert (hist[k].cpu().numpy() == bins.astype(np.int64)).all()
+            assert np.allclose(stats[k].cpu().numpy(), s5, rtol=1e-12)
+            # the search is driven by the device-accumulated statistics: give the oracle the same numbers
+            want = H.oracle_containment(oracle, bins, stats[k].cpu().numpy(), nx, lo, hi, ny, lo, hi, frac)
+            assert np.allclose(got[k], want, rtol=1e-12, atol=1e-14), (k, frac, got[k], want)
+            # host-histogram entry point (what AGeoUtil::ContainmentRadius(TH2*) binds)
+            o2 = np.zeros(3)
+            sk = stats[k].cpu().numpy().copy()
+            R.check(R.rbg_containment_radius_host(bins.ctypes.data, nx, lo, hi, ny, lo, hi, sk.ctypes.data, frac, o2.ctypes.data, 0))
+            assert np.allclose(o2, want, rtol=1e-12, atol=1e-14)
+    # mirror class
+    h2 = R.TH2D("h", "h", nx, lo, hi, ny, lo, hi)
+    x, y = cases[0]
+    for i in range(0, 20000):
+        h2.Fill(float(x[i]), float(y[i]))
+    r, cx, cy = R.ContainmentRadius(h2, 0.8)
+    assert abs(r / (0.5 * math.sqrt(-2 * math.log(0.2))) - 1) < 0.05 and abs(cx - 0.3) < 0.05 and abs(cy + 0.2) < 0.05

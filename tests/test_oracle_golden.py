@@ -342,3 +342,20 @@ def test_tgraph2d_delaunay_properties(R, oracle):
         v = g.Interpolate(a, b)
         assert abs(oracle.orc_graph2d_interp(ex.desc_ptr(), 0, a, b) - v) < 1e-12
         assert v == 0.0 or abs(v - f(a, b)) < 1e-12
+
+
+def test_containment_radius_of_gaussian_psf(oracle):  # src/AGeoUtil.cxx:198-308; closed form for a 2-D Gaussian
+    rng = np.random.default_rng(1)
+    n, sig = 400000, 0.7
+    x, y = 1.5 + sig * rng.standard_normal(n), -0.4 + sig * rng.standard_normal(n)
+    bins, stats = H.psf_histogram(x, y, 300, -3., 6., 300, -5., 4.)
+    for frac in (0.8, 0.5):
+        r, cx, cy = H.oracle_containment(oracle, bins, stats, 300, -3., 6., 300, -5., 4., frac)
+        want = sig * math.sqrt(-2 * math.log(1 - frac))
+        assert abs(r / want - 1) < 0.02 and abs(cx - 1.5) < 0.03 and abs(cy + 0.4) < 0.03
+    # the containing circle really holds the requested fraction of the histogram (bin centres)
+    r, cx, cy = H.oracle_containment(oracle, bins, stats, 300, -3., 6., 300, -5., 4., 0.8)
+    cxs = -3. + (np.arange(300) + 0.5) * 9. / 300
+    cys = -5. + (np.arange(300) + 0.5) * 9. / 300
+    inside = ((cxs[None, :] - cx) ** 2 + (cys[:, None] - cy) ** 2 <= r * r)
+    assert abs(bins.reshape(300, 300)[inside].sum() / bins.sum() - 0.8) < 2e-3
