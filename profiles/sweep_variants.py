@@ -1,6 +1,7 @@
 # throughput of one config under several compiled kernel instantiations (RB_VARIANT), device-resident rays
-# usage: sweep_variants.py <cfg> <theta> <n> name1,name2,...   (needs a library built with `make EXP=1` for x* names)
-import sys, os, ctypes as C, time
+# usage: sweep_variants.py <cfg> <theta> <n> name1,name2,... [json kwargs of the config builder] [beam side]
+# (x* names need a library built with `make EXP=1`)
+import sys, os, json, ctypes as C, time
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import torch, numpy as np
 import robast_b200 as R
@@ -9,9 +10,10 @@ import helpers as H
 cfg, theta, n = int(sys.argv[1]), float(sys.argv[2]), int(float(sys.argv[3]))
 names = sys.argv[4].split(',')
 dev = torch.device('cuda:0')
-mgr, keep = configs.BUILDERS[cfg]()
+kw = json.loads(sys.argv[5]) if len(sys.argv) > 5 else {}
+mgr, keep = configs.BUILDERS[cfg](**kw)
 ex = mgr.ExportScene()
-nside = int(round(n ** 0.5)) if cfg <= 3 else None
+nside = int(round(n ** 0.5)) if cfg <= 3 else (float(sys.argv[6]) if len(sys.argv) > 6 else None)
 d = H.shoot_desc(configs.beam(cfg, theta, n_side=nside))
 inp = torch.empty((8, n), dtype=torch.float64, device=dev); o = torch.empty((7, n), dtype=torch.float64, device=dev); io = torch.empty((3, n), dtype=torch.int32, device=dev)
 R.check(R.rbg_shoot(C.byref(d), 0, n, *[inp[i].data_ptr() for i in range(8)], 0, None))

@@ -12,6 +12,8 @@
 //  k_tmm            AMultilayer::CoherentTMMMixed per (theta, lambda) pair.
 #include <cuda_runtime.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -192,6 +194,63 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restric
     if (alive & (1u << k)) live_out[pos++] = idx[k];
 }
 
+// ---- coherence sort key: 30-bit Morton code of the point where the ray enters the bounding box of the top volume's
+// daughters (fp32 is plenty for a sort key).  Rays that miss the box sort last.  Also counts adjacent input rays whose
+// keys share the 12 leading bits: an already ordered beam (grid shooters) keeps its order and skips the sort.
+__device__ inline uint32_t morton_spread10(uint32_t v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void k_sortkey(long long n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                          const double* __restrict__ dx, const double* __restrict__ dy, const double* __restrict__ dz, float3 lo, float3 hi,
+                          uint32_t* __restrict__ keys, int32_t* __restrict__ iota, unsigned long long* coherent_pairs, int block_stride) {
+  // block_stride > 1: sampling pass (every block_stride-th run of 256 rays, nothing written but the counter)
+  long long i = (long long)blockIdx.x * block_stride * blockDim.x + threadIdx.x;
+  uint32_t key = 0x3fffffffu;
+  if (i < n) {
+    float px = (float)x[i], py = (float)y[i], pz = (float)z[i], vx = (float)dx[i], vy = (float)dy[i], vz = (float)dz[i];
+    float t0 = 0.f, t1 = 3.0e38f;
+    bool hit = true;
+    const float p[3] = {px, py, pz}, v[3] = {vx, vy, vz}, l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (v[a] != 0.f) {
+        float inv = 1.f / v[a], ta = (l[a] - p[a]) * inv, tb = (h[a] - p[a]) * inv;
+        t0 = fmaxf(t0, fminf(ta, tb));
+        t1 = fminf(t1, fmaxf(ta, tb));
+      } else hit = hit && p[a] >= l[a] && p[a] <= h[a];
+    }
+    if (hit && t0 <= t1) {
+      uint32_t q[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        float u = (p[a] + t0 * v[a] - l[a]) / fmaxf(h[a] - l[a], 1e-30f);
+        q[a] = (uint32_t)fminf(fmaxf(u * 1024.f, 0.f), 1023.f);
+      }
+      key = morton_spread10(q[0]) | (morton_spread10(q[1]) << 1) | (morton_spread10(q[2]) << 2);
+    }
+    if (keys) {
+      keys[i] = key;
+      iota[i] = (int32_t)i;
+    }
+  }
+  // neighbours in input order: lane k compares with lane k-1 (block edges are ignored)
+  uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+  bool coh = i < n && (threadIdx.x & 31) != 0 && (key >> 18) == (prev >> 18);
+  unsigned m = __ballot_sync(0xffffffffu, coh);
+  if ((threadIdx.x & 31) == 0 && m && coherent_pairs) atomicAdd(coherent_pairs, (unsigned long long)__popc(m));
+}
+
+// copies a device counter into pinned (UVA-mapped) host memory with a plain store: no copy-engine queueing
+__global__ void k_publish(const unsigned long long* d, unsigned long long* h) {
+  *h = *d;
+  __threadfence_system();
+}
+
 // ---- ARayShooter on device
 __global__ void k_shoot(rbg_shoot_desc s, long long first, long long n, double* x, double* y, double* z, double* t, double* dx, double* dy, double* dz,
                         double* lambda) {
@@ -337,9 +396,9 @@ __global__ void k_moments(long long n, const double* __restrict__ x, const doubl
 
 // ---- AGeoUtil::ContainmentRadius: kernel in rb_reducers.cu (compiled with -fmad=false)
 int rb_launch_containment_u64(int nhist, const unsigned long long* hist, int nx, double xmin, double xmax, int ny, double ymin, double ymax, const double* stats,
-                              double fraction, double* out, cudaStream_t st);
+                              double fraction, double* out, double* prefix, cudaStream_t st);
 int rb_launch_containment_f64(int nhist, const double* hist, int nx, double xmin, double xmax, int ny, double ymin, double ymax, const double* stats,
-                              double fraction, double* out, cudaStream_t st);
+                              double fraction, double* out, double* prefix, cudaStream_t st);
 
 __global__ void k_tmm(DScene sc, int ml, long long n, const double* __restrict__ theta, const double* __restrict__ lambda, double* R, double* T) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,6 +426,10 @@ struct rbg_scene {
   cudaStream_t streams[RB_HOST_STREAMS] = {};
   int32_t* d_count = nullptr;
   int32_t* h_count = nullptr;  // pinned
+  unsigned long long* h_pairs = nullptr;  // pinned, one per host stream: coherence counter of k_sortkey
+  float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};  // bounding box of the top volume's daughters
+  bool has_root = false;
+  int top_daughters = 0;
 };
 
 template <class T> static const T* upload(rbg_scene* s, const std::vector<T>& v) {
@@ -393,6 +456,7 @@ static void scene_free(rbg_scene* s) {
   }
   if (s->d_count) cudaFree(s->d_count);
   if (s->h_count) cudaFreeHost(s->h_count);
+  if (s->h_pairs) cudaFreeHost(s->h_pairs);
   delete s;
 }
 
@@ -441,9 +505,10 @@ static void ensure_scratch(rbg_scene* s, size_t bytes) {
   s->scratch_bytes = bytes;
 }
 
+static size_t sort_temp_bytes(long long n);
 // device-resident trace of n rays (n < 2^31) on stream st
 static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long long n, unsigned long long id_offset, cudaStream_t st, void* scratch,
-                         int32_t* d_count, int32_t* h_count) {
+                         int32_t* d_count, int32_t* h_count, unsigned long long* h_pairs) {
   if (n <= 0) return;
   if (n > 0x7fffff00LL) throw Invalid("at most 2^31-256 rays per call on the device path; shard the batch");
   DTraceParams tp;
@@ -476,6 +541,41 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   const int32_t* live = nullptr;
   long long nlive = n;
   int init = 1;
+  // Coherence sort (first bounce): a beam whose neighbouring rays are far apart (random shooters) makes every warp walk
+  // 32 different pieces of geometry — warp execution efficiency of 8/32 on the Winston-cone array (profiles/).  The rays
+  // stay where they are; only the order in which the index list visits them changes (outputs keep the input order).
+  static const int sort_mode = getenv("RB_SORT") ? atoi(getenv("RB_SORT")) : -1;  // -1 auto, 0 never, 1 always
+  // auto: only scenes with many daughters under the top volume can scatter a warp over different geometry, and only
+  // beams whose input order is not already spatially coherent need the sort (a sampled pass decides)
+  if (s->has_root && sort_mode != 0 && (sort_mode == 1 || s->top_daughters >= 32)) {
+    float3 lo = make_float3(s->root_lo[0], s->root_lo[1], s->root_lo[2]), hi = make_float3(s->root_hi[0], s->root_hi[1], s->root_hi[2]);
+    bool do_sort = sort_mode == 1;
+    if (!do_sort) {
+      unsigned long long* d_pairs = (unsigned long long*)take(256);
+      CK(cudaMemsetAsync(d_pairs, 0, 8, st));
+      long long blocks = (n + 255) / 256;
+      int stride = (int)std::max<long long>(1, blocks / 512);
+      long long sblocks = blocks / stride;  // full runs only
+      k_sortkey<<<(unsigned)sblocks, 256, 0, st>>>(n, R.x, R.y, R.z, R.dx, R.dy, R.dz, lo, hi, nullptr, nullptr, d_pairs, stride);
+      k_publish<<<1, 1, 0, st>>>(d_pairs, h_pairs);
+      g_launches += 2;
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));
+      do_sort = (double)*h_pairs < 0.5 * (double)sblocks * 256. * 31. / 32.;
+    }
+    if (do_sort) {
+      uint32_t* keys = (uint32_t*)take(n * 4);
+      uint32_t* keys_out = (uint32_t*)take(n * 4);
+      size_t tb = sort_temp_bytes(n);
+      void* temp = take(tb);
+      k_sortkey<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, R.x, R.y, R.z, R.dx, R.dy, R.dz, lo, hi, keys, liveB, nullptr, 1);
+      g_launches++;
+      CK(cudaGetLastError());
+      CK(cub::DeviceRadixSort::SortPairs(temp, tb, (const uint32_t*)keys, keys_out, (const int32_t*)liveB, liveA, (int)n, 0, 30, st));
+      g_launches += 4;
+      live = liveA;
+    }
+  }
   const long long tail = std::max<long long>(4096, n / 512);  // survivors below this finish in one per-ray-loop launch
   for (int iter = 0; nlive > 0; iter++) {
     if (iter > 100000) throw std::runtime_error("wavefront did not terminate");
@@ -505,9 +605,15 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     live = out;
   }
 }
+static size_t sort_temp_bytes(long long n) {
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 30);
+  return tb;
+}
 static size_t wavefront_scratch_bytes(long long n) {
   size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
-  return 4 * ((size_t)n * 4 + 256) + ntile * 8 + 256 + 512;
+  // cur, ndraw, liveA, liveB (+ sort keys in/out) + tile state + counter + radix-sort temporary
+  return 6 * ((size_t)n * 4 + 256) + ntile * 8 + 256 + 512 + sort_temp_bytes(n) + 768;
 }
 
 // ================================================================================================ C ABI
@@ -600,6 +706,13 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     s->d.top_shape = D->top_volume >= 0 ? D->volumes[D->top_volume].shape : -1;
     CK(cudaMalloc((void**)&s->d_count, RB_HOST_STREAMS * sizeof(int32_t)));
     CK(cudaMallocHost((void**)&s->h_count, RB_HOST_STREAMS * sizeof(int32_t)));
+    CK(cudaMallocHost((void**)&s->h_pairs, RB_HOST_STREAMS * sizeof(unsigned long long)));
+    if (!B.nodes.empty() && B.nodes[0].bvh_count > 0) {
+      const DBvh& rb = B.bvh[B.nodes[0].bvh_first];
+      for (int k = 0; k < 3; k++) { s->root_lo[k] = rb.lo[k]; s->root_hi[k] = rb.hi[k]; }
+      s->has_root = true;
+      for (const DNode& nd : B.nodes) s->top_daughters += nd.mother == 0 ? 1 : 0;
+    }
     // the CSG call chain is not inlined: give it stack
     size_t want = 8192, have = 0;
     CK(cudaDeviceGetLimit(&have, cudaLimitStackSize));
@@ -649,7 +762,7 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         R.hist.max_points = hpts;
       }
       if (o->steps_per_launch >= 0 && hpts == 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
-      trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count);
+      trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count, s->h_pairs);
       return;
     }
     // host buffers: chunked H2D -> trace -> D2H.  Up to RB_HOST_STREAMS chunks are in flight, each on its own stream
@@ -727,7 +840,7 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
           R.hist.stride = chunk;
           R.hist.max_points = hpts;
         }
-        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + scratch_off, s->d_count + k, s->h_count + k);
+        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + scratch_off, s->d_count + k, s->h_count + k, s->h_pairs + k);
         if (hpts > 0) {
           double* hd[4] = {hist->hx, hist->hy, hist->hz, hist->ht};
           double* dd[4] = {R.hist.x, R.hist.y, R.hist.z, R.hist.t};
@@ -816,7 +929,11 @@ int rbg_containment_radius(int32_t nhist, const unsigned long long* hist, int32_
     if (nhist < 0 || nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin) || !hist || !stats || !out) throw Invalid("bad containment-radius arguments");
     if (nhist == 0) return;
     CK(cudaSetDevice(device));
-    CK((cudaError_t)rb_launch_containment_u64(nhist, hist, nx, xmin, xmax, ny, ymin, ymax, stats, fraction, out, (cudaStream_t)stream));
+    double* prefix = nullptr;  // stream-ordered scratch for the per-row running sums
+    CK(cudaMallocAsync((void**)&prefix, (size_t)nhist * (nx + 1) * ny * sizeof(double), (cudaStream_t)stream));
+    int rc = rb_launch_containment_u64(nhist, hist, nx, xmin, xmax, ny, ymin, ymax, stats, fraction, out, prefix, (cudaStream_t)stream);
+    cudaFreeAsync(prefix, (cudaStream_t)stream);
+    CK((cudaError_t)rc);
     g_launches++;
   });
 }
@@ -828,11 +945,11 @@ int rbg_containment_radius_host(const double* bins, int32_t nx, double xmin, dou
     CK(cudaSetDevice(device));
     double* d = nullptr;
     size_t nb = (size_t)nx * ny;
-    CK(cudaMalloc((void**)&d, (nb + 8) * 8));
+    CK(cudaMalloc((void**)&d, (nb + 8 + (size_t)(nx + 1) * ny) * 8));
     try {
       CK(cudaMemcpy(d, bins, nb * 8, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(d + nb, stats, 5 * 8, cudaMemcpyHostToDevice));
-      CK((cudaError_t)rb_launch_containment_f64(1, d, nx, xmin, xmax, ny, ymin, ymax, d + nb, fraction, d + nb + 5, nullptr));
+      CK((cudaError_t)rb_launch_containment_f64(1, d, nx, xmin, xmax, ny, ymin, ymax, d + nb, fraction, d + nb + 5, d + nb + 8, nullptr));
       g_launches++;
       CK(cudaMemcpy(out, d + nb + 5, 3 * 8, cudaMemcpyDeviceToHost));
     } catch (...) {

@@ -17,12 +17,22 @@ struct DRays {
 
 #define TRACE_THREADS 128
 
+// Ray state streams through once per launch: mark it evict-first (ld/st .cs) so that it does not push the kernels'
+// local-memory working set (spill slots and the call stack, ~100 MB over all resident threads) out of the 126 MB L2.
+#if defined(__CUDA_ARCH__) && !defined(RB_NO_STREAM_HINTS)
+template <class T> __device__ inline T rb_ldcs(const T* p) { return __ldcs(p); }
+template <class T> __device__ inline void rb_stcs(T* p, T v) { __stcs(p, v); }
+#else
+template <class T> __device__ inline T rb_ldcs(const T* p) { return *p; }
+template <class T> __device__ inline void rb_stcs(T* p, T v) { *p = v; }
+#endif
+
 template <class K> __device__ inline void load_ray(const DScene& sc, const DTraceParams& tp, const DRays& R, long long idx, int init, RayReg& r, Philox& g) {
-  r.lambda = R.lambda[idx];
+  r.lambda = rb_ldcs(R.lambda + idx);
   if (init) {
-    r.p = v3(R.x[idx], R.y[idx], R.z[idx]);
-    r.t = R.t[idx];
-    V3 d = v3(R.dx[idx], R.dy[idx], R.dz[idx]);
+    r.p = v3(rb_ldcs(R.x + idx), rb_ldcs(R.y + idx), rb_ldcs(R.z + idx));
+    r.t = rb_ldcs(R.t + idx);
+    V3 d = v3(rb_ldcs(R.dx + idx), rb_ldcs(R.dy + idx), rb_ldcs(R.dz + idx));
     double mag = sqrt(dot(d, d));
     r.d = mag > 0 ? (1. / mag) * d : d;  // ARay::SetDirection normalises (src/ARay.cxx:210-223)
     r.status = RBG_RUN;
@@ -32,16 +42,16 @@ template <class K> __device__ inline void load_ray(const DScene& sc, const DTrac
     r.on_boundary = 0;
     r.cur = locate_start<K>(sc, r.p);
   } else {
-    r.p = v3(R.ox[idx], R.oy[idx], R.oz[idx]);
-    r.t = R.ot[idx];
-    r.d = v3(R.odx[idx], R.ody[idx], R.odz[idx]);
+    r.p = v3(rb_ldcs(R.ox + idx), rb_ldcs(R.oy + idx), rb_ldcs(R.oz + idx));
+    r.t = rb_ldcs(R.ot + idx);
+    r.d = v3(rb_ldcs(R.odx + idx), rb_ldcs(R.ody + idx), rb_ldcs(R.odz + idx));
     r.status = R.status[idx];
-    r.npoints = R.npoints[idx];
-    r.last_node = R.last_node[idx];
-    uint32_t nd = R.ndraw[idx];
+    r.npoints = rb_ldcs(R.npoints + idx);
+    r.last_node = rb_ldcs(R.last_node + idx);
+    uint32_t nd = rb_ldcs(R.ndraw + idx);
     r.ndraw = nd & 0x7fffffffu;
     r.on_boundary = nd >> 31;
-    r.cur = R.cur[idx];
+    r.cur = rb_ldcs(R.cur + idx);
   }
   unsigned long long id = tp.ray_id_offset + (unsigned long long)idx;
   g.k0 = (uint32_t)tp.seed;
@@ -51,14 +61,14 @@ template <class K> __device__ inline void load_ray(const DScene& sc, const DTrac
   g.ndraw = r.ndraw;
 }
 __device__ inline void store_ray(const DRays& R, long long idx, const RayReg& r, const Philox& g, int keep_state) {
-  R.ox[idx] = r.p.x; R.oy[idx] = r.p.y; R.oz[idx] = r.p.z; R.ot[idx] = r.t;
-  R.odx[idx] = r.d.x; R.ody[idx] = r.d.y; R.odz[idx] = r.d.z;
-  R.status[idx] = r.status;
-  R.last_node[idx] = r.last_node;
-  R.npoints[idx] = r.npoints;
+  rb_stcs(R.ox + idx, r.p.x); rb_stcs(R.oy + idx, r.p.y); rb_stcs(R.oz + idx, r.p.z); rb_stcs(R.ot + idx, r.t);
+  rb_stcs(R.odx + idx, r.d.x); rb_stcs(R.ody + idx, r.d.y); rb_stcs(R.odz + idx, r.d.z);
+  R.status[idx] = r.status;  // read again by k_compact right after this launch: leave it cached
+  rb_stcs(R.last_node + idx, (int32_t)r.last_node);
+  rb_stcs(R.npoints + idx, (int32_t)r.npoints);
   if (keep_state) {
-    R.cur[idx] = r.cur;
-    R.ndraw[idx] = (g.ndraw & 0x7fffffffu) | ((uint32_t)r.on_boundary << 31);
+    rb_stcs(R.cur + idx, (int32_t)r.cur);
+    rb_stcs(R.ndraw + idx, (uint32_t)((g.ndraw & 0x7fffffffu) | ((uint32_t)r.on_boundary << 31)));
   }
 }
 
