@@ -1132,14 +1132,19 @@ template <unsigned SM> RB_HD inline V3 prim_normal(const DScene& sc, const DShap
   return v3(0, 0, 1);
 }
 
+// RB_PRIM_CALL: a translation unit may define it empty (before including this header) to inline the primitive
+// dispatch into its callers — worthwhile only for instantiations with very few shape types.
+#ifndef RB_PRIM_CALL
+#define RB_PRIM_CALL RB_NOINLINE
+#endif
 template <unsigned SM> struct Csg<0, SM> {
-  static RB_HD RB_NOINLINE bool contains(const DScene& sc, int sh, V3 p) { return prim_contains<SM>(sc, sc.shapes[sh], p); }
-  static RB_HD RB_NOINLINE double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) { sel = 0; return prim_dist_in<SM>(sc, sc.shapes[sh], p, d); }
-  static RB_HD RB_NOINLINE double dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
+  static RB_HD RB_PRIM_CALL bool contains(const DScene& sc, int sh, V3 p) { return prim_contains<SM>(sc, sc.shapes[sh], p); }
+  static RB_HD RB_PRIM_CALL double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) { sel = 0; return prim_dist_in<SM>(sc, sc.shapes[sh], p, d); }
+  static RB_HD RB_PRIM_CALL double dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
     sel = 0;
     return prim_dist_out<SM>(sc, sc.shapes[sh], p, d, step);
   }
-  static RB_HD RB_NOINLINE V3 normal(const DScene& sc, int sh, V3 p, V3 d, int) { return prim_normal<SM>(sc, sc.shapes[sh], p, d); }
+  static RB_HD RB_PRIM_CALL V3 normal(const DScene& sc, int sh, V3 p, V3 d, int) { return prim_normal<SM>(sc, sc.shapes[sh], p, d); }
 };
 
 RB_HD inline V3 op_point(const DScene& sc, int m, V3 p) { return m < 0 ? p : to_local(sc.mats[m], p); }

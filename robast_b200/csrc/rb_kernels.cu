@@ -463,6 +463,7 @@ static void scene_free(rbg_scene* s) {
 // ------------------------------------------------------------------------------------------------ host: trace driver
 #ifdef RB_EXPERIMENTS
 extern const rb_variant* const rb_x_variants[];
+extern const rb_variant* const rb_xi_variants[];
 #endif
 static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys) {
   const char* force = getenv("RB_FORCE_GENERIC");
@@ -473,6 +474,8 @@ static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys)
       if (!strcmp(v->name, want) && v->depth >= depth && !(shapes & ~v->shapes) && !(phys & ~v->phys)) return v;
 #ifdef RB_EXPERIMENTS
     for (const rb_variant* const* pv = rb_x_variants; *pv; pv++)
+      if (!strcmp((*pv)->name, want) && (*pv)->depth >= depth && !(shapes & ~(*pv)->shapes) && !(phys & ~(*pv)->phys)) return *pv;
+    for (const rb_variant* const* pv = rb_xi_variants; *pv; pv++)
       if (!strcmp((*pv)->name, want) && (*pv)->depth >= depth && !(shapes & ~(*pv)->shapes) && !(phys & ~(*pv)->phys)) return *pv;
 #endif
   }
