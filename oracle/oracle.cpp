@@ -800,6 +800,13 @@ void poly_normal(const Poly& q, const double* p, const double* d, double* n) {
       if (dist < best) { best = dist; n[0] = ux / nn; n[1] = uy / nn; n[2] = -s / nn; }
     }
   }
+  if (fabs(q.dphi - 360.) > 1e-9)  // azimuthal segment: the two phi planes (TGeoShape::IsCloseToPhi / NormalPhi)
+    for (int k = 0; k < 2; k++) {
+      double ph = (q.phi1 + k * q.dphi) * kPi / 180., co = cos(ph), si = sin(ph);
+      if (p[0] * co + p[1] * si < 0) continue;
+      double dist = fabs(p[1] * co - p[0] * si);
+      if (dist < best) { best = dist; n[0] = -si; n[1] = co; n[2] = 0; }
+    }
   if (dot3(n, d) < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
 }
 

@@ -118,37 +118,35 @@ struct SceneBuilder {
           setbox(rm, rm, -P[2], P[2]);
           break;
         }
-        case RBG_SHAPE_PGON: {
-          int ne = (int)P[2], nz = (int)P[3];
-          if (fabs(P[1] - 360.) > 1e-9) throw NotSupported("TGeoPgon with dphi != 360 is not supported on the device path");
-          if (ne < 3 || nz < 2) throw Invalid("TGeoPgon needs nedges >= 3 and nz >= 2");
+        case RBG_SHAPE_PGON:
+        case RBG_SHAPE_PCON: {
+          // device layout (both): phi1,dphi,nedges (0 = polycone),nz, nz x (z,rmin,rmax), nedges x (cos,sin) of the edge-centre
+          // azimuths, then: general flag (hollow or azimuthal segment), cos/sin(phi1), cos/sin(phi1 + dphi)
+          const bool pgon = s.type == RBG_SHAPE_PGON;
+          int ne = pgon ? (int)P[2] : 0, nz = (int)P[pgon ? 3 : 2];
+          const double* sec = P + (pgon ? 4 : 3);
+          if ((pgon && ne < 3) || nz < 2) throw Invalid("TGeoPgon/TGeoPcon needs nedges >= 3 and nz >= 2");
+          if (!(P[1] > 0) || P[1] > 360. + 1e-9) throw Invalid("TGeoPgon/TGeoPcon needs 0 < dphi <= 360");
+          const bool seg = fabs(P[1] - 360.) > 1e-9;
+          bool hollow = false;
           double rmx = 0;
           for (int k = 0; k < nz; k++) {
-            if (P[4 + 3 * k + 1] > 0) throw NotSupported("TGeoPgon with rmin > 0 is not supported on the device path");
-            rmx = std::max(rmx, P[4 + 3 * k + 2]);
+            if (sec[3 * k + 1] > 0) hollow = true;
+            rmx = std::max(rmx, sec[3 * k + 2]);
+            if (k > 0 && sec[3 * k] < sec[3 * (k - 1)]) throw Invalid("TGeoPgon/TGeoPcon sections must be ordered in z");
           }
-          dpar.insert(dpar.end(), P, P + 4 + 3 * nz);
+          dpar.push_back(P[0]); dpar.push_back(P[1]); dpar.push_back((double)ne); dpar.push_back((double)nz);
+          dpar.insert(dpar.end(), sec, sec + 3 * nz);
           for (int e = 0; e < ne; e++) {
             double ph = (P[0] + (e + 0.5) * P[1] / ne) * deg;
             dpar.push_back(cos(ph));
             dpar.push_back(sin(ph));
           }
-          double R = rmx / cos(M_PI / ne);
-          setbox(R, R, P[4], P[4 + 3 * (nz - 1)]);
-          break;
-        }
-        case RBG_SHAPE_PCON: {  // device layout = the polygon's with nedges = 0: phi1,dphi,0,nz, nz x (z,rmin,rmax)
-          int nz = (int)P[2];
-          if (fabs(P[1] - 360.) > 1e-9) throw NotSupported("TGeoPcon with dphi != 360 is not supported on the device path");
-          if (nz < 2) throw Invalid("TGeoPcon needs nz >= 2");
-          double rmx = 0;
-          for (int k = 0; k < nz; k++) {
-            if (P[3 + 3 * k + 1] > 0) throw NotSupported("TGeoPcon with rmin > 0 is not supported on the device path");
-            rmx = std::max(rmx, P[3 + 3 * k + 2]);
-          }
-          dpar.push_back(P[0]); dpar.push_back(P[1]); dpar.push_back(0.); dpar.push_back((double)nz);
-          dpar.insert(dpar.end(), P + 3, P + 3 + 3 * nz);
-          setbox(rmx, rmx, P[3], P[3 + 3 * (nz - 1)]);
+          dpar.push_back(hollow || seg ? 1. : 0.);
+          dpar.push_back(cos(P[0] * deg)); dpar.push_back(sin(P[0] * deg));
+          dpar.push_back(cos((P[0] + P[1]) * deg)); dpar.push_back(sin((P[0] + P[1]) * deg));
+          double Rb = pgon ? rmx / cos(0.5 * P[1] / ne * deg) : rmx;  // circumscribed radius of the polygon's corners
+          setbox(Rb, Rb, sec[0], sec[3 * (nz - 1)]);
           break;
         }
         case RBG_SHAPE_ASPHERE: {

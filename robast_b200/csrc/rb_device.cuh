@@ -766,6 +766,155 @@ template <bool CONE> RB_HD inline V3 poly_normal(const double* P, V3 p, V3 d) {
   return n;
 }
 
+// ---- general TGeoPgon / TGeoPcon: hollow sections (rmin > 0) and/or an azimuthal range (dphi < 360 deg).
+// After the edge table the parameter block carries: general flag, cos/sin(phi1), cos/sin(phi1 + dphi).
+// Not convex any more, so the solid is handled like TGeoSphere: every crossing parameter of every bounding surface
+// (z planes, outer and inner lateral faces of each z slab, the two phi planes) is a candidate; the candidates are
+// visited in ascending order (selection of the smallest one above the last: no candidate array) and the interval
+// between two consecutive candidates is classified by Contains() at its midpoint.
+RB_HD inline const double* polyg_tail(const double* P) { return P + 4 + 3 * (int)P[3] + 2 * (int)P[2]; }
+RB_HD inline bool poly_is_general(const double* P) { return polyg_tail(P)[0] != 0.; }
+template <bool CONE> RB_HD inline bool polyg_contains(const double* P, V3 p) {
+  int ne = (int)P[2], nz = (int)P[3];
+  const double* sec = P + 4;
+  const double* cs = P + 4 + 3 * nz;
+  if (p.z < sec[0] || p.z > sec[3 * (nz - 1)]) return false;
+  double r;
+  const bool seg = fabs(P[1] - 360.) > 1e-9;
+  if (!CONE) {
+    double divphi = P[1] / ne, phi = rb_atan2(p.y, p.x) * 180. / RB_PI;
+    while (phi < P[0]) phi += 360.0;
+    double ddp = phi - P[0];
+    if (ddp > P[1]) return false;
+    int ipsec = (int)(ddp / divphi);
+    if (ipsec > ne - 1) ipsec = ne - 1;
+    r = p.x * cs[2 * ipsec] + p.y * cs[2 * ipsec + 1];
+  } else {
+    r = sqrt(p.x * p.x + p.y * p.y);
+    if (seg) {
+      double phi = rb_atan2(p.y, p.x) * 180. / RB_PI;
+      while (phi < P[0]) phi += 360.0;
+      if (phi - P[0] > P[1]) return false;
+    }
+  }
+  int iz = 0;
+  for (int i = 0; i < nz; i++)
+    if (sec[3 * i] <= p.z) iz = i;
+  if (iz == nz - 1) return !(r < sec[3 * iz + 1] || r > sec[3 * iz + 2]);
+  double dz = sec[3 * (iz + 1)] - sec[3 * iz];
+  if (dz < 1E-8) {
+    double rmin = rb_min(sec[3 * iz + 1], sec[3 * (iz + 1) + 1]), rmax = rb_max(sec[3 * iz + 2], sec[3 * (iz + 1) + 2]);
+    return !(r < rmin || r > rmax);
+  }
+  double dzrat = (p.z - sec[3 * iz]) / dz;
+  double rmin = sec[3 * iz + 1] + dzrat * (sec[3 * (iz + 1) + 1] - sec[3 * iz + 1]);
+  if (r < rmin) return false;
+  double rmax = sec[3 * iz + 2] + dzrat * (sec[3 * (iz + 1) + 2] - sec[3 * iz + 2]);
+  return !(r > rmax);
+}
+// smallest valid candidate strictly above `last` (RB_BIG if none)
+template <bool CONE> RB_HD inline double polyg_next(const double* P, V3 p, V3 d, double last) {
+  int ne = (int)P[2], nz = (int)P[3];
+  const double* sec = P + 4;
+  const double* cs = P + 4 + 3 * nz;
+  const double* tail = polyg_tail(P);
+  double best = RB_BIG;
+  auto offer = [&](double t) {
+    if (t > 1e-11 && t <= 1e29 && t > last && t < best) best = t;
+  };
+  if (d.z != 0)
+    for (int i = 0; i < nz; i++) offer((sec[3 * i] - p.z) / d.z);
+  const double dxy = d.x * d.x + d.y * d.y, pdxy = p.x * d.x + p.y * d.y, pxy = p.x * p.x + p.y * p.y;
+  for (int k = 0; k + 1 < nz; k++) {
+    double z0 = sec[3 * k], z1 = sec[3 * (k + 1)], dz = z1 - z0;
+    if (dz < 1E-8) continue;
+    for (int w = 0; w < 2; w++) {
+      double r0 = sec[3 * k + 1 + w], r1 = sec[3 * (k + 1) + 1 + w];
+      if (!w && r0 <= 0 && r1 <= 0) continue;
+      double s = (r1 - r0) / dz;
+      auto offer_in_slab = [&](double t) {  // keep only crossings inside this z slab
+        double zz = p.z + t * d.z;
+        if (zz >= z0 - 1e-9 && zz <= z1 + 1e-9) offer(t);
+      };
+      if (!CONE) {
+        for (int e = 0; e < ne; e++) {
+          double ux = cs[2 * e], uy = cs[2 * e + 1], den = d.x * ux + d.y * uy - s * d.z;
+          if (den != 0) offer_in_slab((r0 + (p.z - z0) * s - (p.x * ux + p.y * uy)) / den);
+        }
+      } else {
+        double a0 = r0 + (p.z - z0) * s, b0 = s * d.z, t0, t1;
+        cand_quadratic(dxy - b0 * b0, 2 * (pdxy - a0 * b0), pxy - a0 * a0, t0, t1);
+        offer_in_slab(t0);
+        offer_in_slab(t1);
+      }
+    }
+  }
+  if (fabs(P[1] - 360.) > 1e-9)
+    for (int k = 0; k < 2; k++) {
+      double co = tail[1 + 2 * k], si = tail[2 + 2 * k], den = d.y * co - d.x * si;
+      if (den != 0) offer(-(p.y * co - p.x * si) / den);
+    }
+  return best;
+}
+template <bool CONE> RB_HD inline double polyg_dist(const double* P, V3 p, V3 d, bool from_inside) {
+  double prev = 0, last = 0;
+  for (int it = 0; it < 4096; it++) {
+    double t = polyg_next<CONE>(P, p, d, last);
+    if (t > 1e29) break;
+    last = t;
+    if (t - prev < 1e-12) { prev = t; continue; }
+    bool in = polyg_contains<CONE>(P, along(p, d, 0.5 * (prev + t)));
+    if (from_inside ? !in : in) return prev;
+    prev = t;
+  }
+  return from_inside ? prev : RB_BIG;
+}
+template <bool CONE> RB_HD inline V3 polyg_normal(const double* P, V3 p, V3 d) {
+  int ne = (int)P[2], nz = (int)P[3];
+  const double* sec = P + 4;
+  const double* cs = P + 4 + 3 * nz;
+  const double* tail = polyg_tail(P);
+  double best = RB_BIG, ux = 0, uy = 0, r;
+  V3 n = v3(0, 0, 1);
+  if (!CONE) {
+    double divphi = P[1] / ne, phi = rb_atan2(p.y, p.x) * 180. / RB_PI;
+    while (phi < P[0]) phi += 360.0;
+    int ipsec = (int)((phi - P[0]) / divphi);
+    ipsec = ipsec < 0 ? 0 : (ipsec > ne - 1 ? ne - 1 : ipsec);
+    ux = cs[2 * ipsec]; uy = cs[2 * ipsec + 1];
+    r = p.x * ux + p.y * uy;
+  } else {
+    r = sqrt(p.x * p.x + p.y * p.y);
+    ux = r > 0 ? p.x / r : 1; uy = r > 0 ? p.y / r : 0;
+  }
+  for (int i = 0; i < nz; i++) {
+    bool cap = i == 0 || i == nz - 1;
+    bool step = (i + 1 < nz && sec[3 * (i + 1)] - sec[3 * i] < 1e-8) || (i > 0 && sec[3 * i] - sec[3 * (i - 1)] < 1e-8);
+    if (!cap && !step) continue;
+    double s = fabs(p.z - sec[3 * i]);
+    if (s < best) { best = s; n = v3(0, 0, 1); }
+  }
+  for (int k = 0; k + 1 < nz; k++) {
+    double z0 = sec[3 * k], z1 = sec[3 * (k + 1)], dz = z1 - z0;
+    if (dz < 1e-8 || p.z < z0 - 1e-6 || p.z > z1 + 1e-6) continue;
+    for (int w = 0; w < 2; w++) {
+      double r0 = sec[3 * k + 1 + w], r1 = sec[3 * (k + 1) + 1 + w];
+      if (!w && r0 <= 0 && r1 <= 0) continue;
+      double s = (r1 - r0) / dz, rr = r0 + (p.z - z0) * s, nn = sqrt(1 + s * s), dist = fabs(r - rr) / nn;
+      if (dist < best) { best = dist; n = v3(ux / nn, uy / nn, -s / nn); }
+    }
+  }
+  if (fabs(P[1] - 360.) > 1e-9)
+    for (int k = 0; k < 2; k++) {  // the two phi planes (only the half plane on the solid's side)
+      double co = tail[1 + 2 * k], si = tail[2 + 2 * k];
+      if (p.x * co + p.y * si < 0) continue;
+      double dist = fabs(p.y * co - p.x * si);
+      if (dist < best) { best = dist; n = v3(-si, co, 0); }
+    }
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
 // ---- AGeoAsphericDisk  P: z1,z2,c1,c2,k1,k2,rmin,rmax,n1,n2,oz,dz,K1[],K2[]
 RB_HD inline bool asph_F(const double* P, int s, double r, double& out) {
   double c = P[1 + s], kap = P[3 + s], z0 = P[s - 1];
@@ -1078,8 +1227,8 @@ template <unsigned SM> RB_HD inline bool prim_contains(const DScene& sc, const D
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_contains(P, p); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_contains(P, p); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_contains(P, p); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_contains<false>(P, p); else break;
-    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_contains<true>(P, p); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_is_general(P) ? polyg_contains<false>(P, p) : poly_contains<false>(P, p); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_is_general(P) ? polyg_contains<true>(P, p) : poly_contains<true>(P, p); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_contains(P, p); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_contains(P, false, p); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_contains(P, true, p); else break;
@@ -1093,8 +1242,8 @@ template <unsigned SM> RB_HD inline double prim_dist_in(const DScene& sc, const 
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_dist_in(P[0], P[1], P[2], p, d); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_dist(P, p, d, true); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_dist_in(P, p, d); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_dist_in<false>(P, p, d); else break;
-    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_dist_in<true>(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_is_general(P) ? polyg_dist<false>(P, p, d, true) : poly_dist_in<false>(P, p, d); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_is_general(P) ? polyg_dist<true>(P, p, d, true) : poly_dist_in<true>(P, p, d); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist4(P, p, d); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_in(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_in(P, true, p, d); else break;
@@ -1108,8 +1257,8 @@ template <unsigned SM> RB_HD inline double prim_dist_out(const DScene& sc, const
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_dist_out(P[0], P[1], P[2], p, d); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_dist(P, p, d, false); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_dist_out(P, p, d); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_dist_out<false>(P, p, d); else break;
-    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_dist_out<true>(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_is_general(P) ? polyg_dist<false>(P, p, d, false) : poly_dist_out<false>(P, p, d); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_is_general(P) ? polyg_dist<true>(P, p, d, false) : poly_dist_out<true>(P, p, d); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist_out(P, p, d, step); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_out(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_out(P, true, p, d); else break;
@@ -1123,8 +1272,8 @@ template <unsigned SM> RB_HD inline V3 prim_normal(const DScene& sc, const DShap
     case RBG_SHAPE_TUBE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_TUBE)) != 0) return tube_normal(P, p, d); else break;
     case RBG_SHAPE_SPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_SPHERE)) != 0) return sphere_normal(P, p, d); else break;
     case RBG_SHAPE_PARABOLOID: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PARABOLOID)) != 0) return para_normal(P, p, d); else break;
-    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_normal<false>(P, p, d); else break;
-    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_normal<true>(P, p, d); else break;
+    case RBG_SHAPE_PGON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PGON)) != 0) return poly_is_general(P) ? polyg_normal<false>(P, p, d) : poly_normal<false>(P, p, d); else break;
+    case RBG_SHAPE_PCON: if constexpr ((SM & RB_SBIT(RBG_SHAPE_PCON)) != 0) return poly_is_general(P) ? polyg_normal<true>(P, p, d) : poly_normal<true>(P, p, d); else break;
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_normal(P, p, d); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_normal(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_normal(P, true, p, d); else break;

@@ -76,3 +76,27 @@ def focal_box_with_qe(qe_lambda=None, qe_angle=None):  # unittest_robast.py:470-
     manager.GetTopVolume().AddNode(focal, 1)
     manager.CloseGeometry()
     return manager, focal
+
+
+def hollow_poly(kind, phi1=0., dphi=360., material="mirror"):
+    """one general TGeoPcon ('pcon') or TGeoPgon ('pgon') in the world: hollow sections (rmin > 0, like the Haube of
+    tutorials/AshraOptics.C:381-384), a radius step, and optionally an azimuthal range"""
+    manager = make_the_world()
+    if kind == "pcon":
+        shape = ROOT.TGeoPcon("poly", phi1, dphi, 5)
+    else:
+        shape = ROOT.TGeoPgon("poly", phi1, dphi, 5, 5)
+    for i, (z, rmin, rmax) in enumerate(((-12., 3., 6.), (-4., 5., 9.), (-4., 5., 11.), (3., 2., 11.), (10., 0., 4.))):
+        shape.DefineSection(i, z, rmin, rmax)
+    keep = [shape]
+    if material == "mirror":
+        comp = ROOT.AMirror("polymirror", shape)
+    else:  # glass: refraction, Fresnel reflection and total internal reflection at every face
+        comp = ROOT.ALens("polylens", shape)
+        idx = ROOT.ARefractiveIndex(1.5)
+        comp.SetRefractiveIndex(idx)
+        keep.append(idx)
+    manager.GetTopVolume().AddNode(comp, 1, ROOT.TGeoCombiTrans(1., -2., 3., ROOT.TGeoRotation("polyrot", 20., 35., 10.)))
+    manager.CloseGeometry()
+    manager.SetLimit(30)
+    return manager, keep + [comp]

@@ -121,3 +121,27 @@ def test_polyline_history_matches_oracle(oracle, emul, cfg, theta, n, kw):
     assert np.allclose(hb.pts[:3, 0, :], rb.inp[:3]) and (hb.node[0] == -1).all()
     assert np.allclose(hb.pts[:3, k, idx][:, full], rb.out[:3][:, full], atol=0) and (hb.node[k, idx][full & (rb.npoints > 1)] == rb.last_node[full & (rb.npoints > 1)]).all()
     assert rb.npoints.max() >= 3
+
+
+def point_source_rays(oracle, kind, origin, n, seed, theta=0.):
+    params = dict(kind=kind, nx=1, ny=1, dx=theta, dy=0., lambda_min=400e-7, lambda_max=400e-7, rot=[1, 0, 0, 0, 1, 0, 0, 0, 1], tr=list(origin), dir=[0, 0, 1], seed=seed)
+    return H.make_rays(oracle, params, 0, n)
+
+
+@pytest.mark.parametrize("kind,phi1,dphi", [("pcon", 0., 360.), ("pcon", 30., 250.), ("pgon", 0., 360.), ("pgon", -40., 200.)])
+def test_general_pcon_pgon_match_oracle(oracle, emul, kind, phi1, dphi):
+    """hollow / azimuthally segmented TGeoPcon and TGeoPgon (device: ordered-candidate walk; oracle: sorted candidates +
+    Contains): isotropic point sources outside the solid, in its bore and inside its material; mirror walls and glass"""
+    bounces = 0
+    for material, sources in (("mirror", (((40., 10., -5.), 1), ((1., -2., 3.), 2))), ("glass", (((40., 10., -5.), 3), ((1.5, 5.5, 4.), 4)))):
+        mgr, _keep = scenes.hollow_poly(kind, phi1, dphi, material)
+        ex = mgr.ExportScene()
+        for origin, seed in sources:
+            n = 3000
+            o = H.opts(seed=5, limit=30)
+            ref = H.trace_with(oracle.orc_trace, ex, point_source_rays(oracle, 5, origin, n, seed), o, nthreads=4)
+            got = H.trace_with(emul.emul_trace, ex, point_source_rays(oracle, 5, origin, n, seed), o)
+            rep = H.compare(ref, got)
+            assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (material, origin, rep)
+            bounces = max(bounces, int(got.npoints.max()))
+    assert bounces > 4  # walls are hit repeatedly (bore reflections, total internal reflection in the glass)

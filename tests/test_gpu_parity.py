@@ -446,3 +446,20 @@ def test_containment_radius_on_device(R, oracle):
         h2.Fill(float(x[i]), float(y[i]))
     r, cx, cy = R.ContainmentRadius(h2, 0.8)
     assert abs(r / (0.5 * math.sqrt(-2 * math.log(0.2))) - 1) < 0.05 and abs(cx - 0.3) < 0.05 and abs(cy + 0.2) < 0.05
+
+
+@pytest.mark.parametrize("kind,phi1,dphi", [("pcon", 0., 360.), ("pcon", 30., 250.), ("pgon", 0., 360.), ("pgon", -40., 200.)])
+def test_general_pcon_pgon_parity(R, oracle, kind, phi1, dphi):
+    """hollow (rmin > 0) and azimuthally segmented TGeoPcon / TGeoPgon (tutorials/AshraOptics.C:381-384 uses such a polycone)"""
+    for material, sources in (("mirror", (((40., 10., -5.), 1), ((1., -2., 3.), 2))), ("glass", (((40., 10., -5.), 3), ((1.5, 5.5, 4.), 4)))):
+        mgr, _keep = scenes.hollow_poly(kind, phi1, dphi, material)
+        ex = mgr.ExportScene()
+        for origin, seed in sources:
+            n = 20000
+            params = dict(kind=5, nx=1, ny=1, dx=0., dy=0., lambda_min=400e-7, lambda_max=400e-7, rot=[1, 0, 0, 0, 1, 0, 0, 0, 1], tr=list(origin), dir=[0, 0, 1], seed=seed)
+            for steps in (0, 1):
+                o = H.opts(seed=5, limit=30, steps_per_launch=steps)
+                ref = H.trace_with(oracle.orc_trace, ex, H.make_rays(oracle, params, 0, n), o, nthreads=os.cpu_count() or 4)
+                got = H.trace_gpu(ex, H.make_rays(oracle, params, 0, n), o)
+                rep = H.compare(ref, got)
+                assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (material, origin, steps, rep)
