@@ -8,6 +8,7 @@
 #ifndef ROBAST_ROBAST_H
 #define ROBAST_ROBAST_H
 
+#include <complex>
 #include <fstream>
 #include <functional>
 #include <sstream>
@@ -493,22 +494,51 @@ class AMultilayer : public TObject {
  private:
   std::vector<std::shared_ptr<ARefractiveIndex>> fRefractiveIndexList;  // [0]=top ... [n-1]=bottom
   std::vector<Double_t> fThicknessList;
+  std::vector<Bool_t> fCoherentList;  // per layer; the two semi-infinite ends are incoherent (src/AMultilayer.cxx:104-114)
   std::shared_ptr<TH2D> fPreCalculatedReflectanceMixed, fPreCalculatedTransmittanceMixed;
   void DeviceTMM(Int_t n, const Double_t* th, const Double_t* lam, Double_t* R, Double_t* T) const;  // defined below
+  // mode 0 = coherent (optionally reversed), 1 = incoherent; pol 0 = s, 1 = p, 2 = mixed
+  void DeviceTMMGeneral(Int_t mode, Int_t pol, Bool_t reverse, Int_t n, const std::complex<Double_t>* th, const Double_t* lam, Double_t* R, Double_t* T) const;
 
  public:
   AMultilayer(std::shared_ptr<ARefractiveIndex> top, std::shared_ptr<ARefractiveIndex> bottom) {
     const Double_t inf = std::numeric_limits<Double_t>::infinity();
     fRefractiveIndexList = {top, bottom};
     fThicknessList = {inf, inf};
+    fCoherentList = {kFALSE, kFALSE};
   }
-  void AddLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t = kTRUE) {
+  void AddLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t coherent = kTRUE) {
     fRefractiveIndexList.insert(fRefractiveIndexList.begin() + 1, idx);
     fThicknessList.insert(fThicknessList.begin() + 1, thickness);
+    fCoherentList.insert(fCoherentList.begin() + 1, coherent);
   }
-  void InsertLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t = kTRUE) {
+  void InsertLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t coherent = kTRUE) {
     fRefractiveIndexList.insert(fRefractiveIndexList.end() - 1, idx);
     fThicknessList.insert(fThicknessList.end() - 1, thickness);
+    fCoherentList.insert(fCoherentList.end() - 1, coherent);
+  }
+  const std::vector<Bool_t>& GetCoherentList() const { return fCoherentList; }
+  // reference src/AMultilayer.cxx:240-481 (one polarisation, complex angle, optionally the reversed stack) — on the GPU
+  void CoherentTMM(EPolarization pol, std::complex<Double_t> th_0, Double_t lam_vac, Double_t& reflectance, Double_t& transmittance, Bool_t reverse = kFALSE) const {
+    DeviceTMMGeneral(0, pol == kS ? 0 : 1, reverse, 1, &th_0, &lam_vac, &reflectance, &transmittance);
+  }
+  void CoherentTMMP(std::complex<Double_t> th_0, Double_t lam_vac, Double_t& r, Double_t& t) const { CoherentTMM(kP, th_0, lam_vac, r, t); }
+  void CoherentTMMS(std::complex<Double_t> th_0, Double_t lam_vac, Double_t& r, Double_t& t) const { CoherentTMM(kS, th_0, lam_vac, r, t); }
+  void CoherentTMMMixed(std::complex<Double_t> th_0, Double_t lam_vac, Double_t& reflectance, Double_t& transmittance) const {
+    DeviceTMMGeneral(0, 2, kFALSE, 1, &th_0, &lam_vac, &reflectance, &transmittance);
+  }
+  // reference src/AMultilayer.cxx:484-731 (tmm.inc_tmm): layers inserted with coherent = kFALSE exchange power only
+  void IncoherentTMM(EPolarization pol, std::complex<Double_t> th_0, Double_t lam_vac, Double_t& reflectance, Double_t& transmittance) const {
+    DeviceTMMGeneral(1, pol == kS ? 0 : 1, kFALSE, 1, &th_0, &lam_vac, &reflectance, &transmittance);
+  }
+  void IncoherentTMMP(std::complex<Double_t> th_0, Double_t lam_vac, Double_t& r, Double_t& t) const { IncoherentTMM(kP, th_0, lam_vac, r, t); }
+  void IncoherentTMMS(std::complex<Double_t> th_0, Double_t lam_vac, Double_t& r, Double_t& t) const { IncoherentTMM(kS, th_0, lam_vac, r, t); }
+  void IncoherentTMMMixed(std::complex<Double_t> th_0, Double_t lam_vac, Double_t& reflectance, Double_t& transmittance) const {
+    DeviceTMMGeneral(1, 2, kFALSE, 1, &th_0, &lam_vac, &reflectance, &transmittance);
+  }
+  // Snell's law with complex indices (include/AMultilayer.h Snell): angle in medium 2
+  static std::complex<Double_t> Snell(std::complex<Double_t> n_1, std::complex<Double_t> n_2, std::complex<Double_t> th_1) {
+    return std::asin(n_1 * std::sin(th_1) / n_2);
   }
   void ChangeThickness(std::size_t i, Double_t thickness) {
     if (i < 1 || i > fThicknessList.size() - 2) Error("ChangeThickness", "Cannot change the thickness of the %luth layer", (unsigned long)i);
@@ -555,6 +585,28 @@ class AMultilayer : public TObject {
     fPreCalculatedReflectanceMixed.reset();
     fPreCalculatedTransmittanceMixed.reset();
     DeviceTMM((Int_t)th.size(), th.data(), lam.data(), r.data(), t.data());
+    size_t k = 0;
+    for (Int_t j = 1; j <= th_nbins; ++j)
+      for (Int_t i = 1; i <= lam_nbins; ++i, ++k) {
+        R->SetBinContent(i, j, r[k]);
+        T->SetBinContent(i, j, t[k]);
+      }
+    fPreCalculatedReflectanceMixed = R;
+    fPreCalculatedTransmittanceMixed = T;
+  }
+  // reference include/AMultilayer.h:263-282: the same table filled by IncoherentTMMMixed
+  void PreCalculateIncoherentTMM(Int_t lam_nbins, Double_t lam_min, Double_t lam_max, Int_t th_nbins, Double_t th_min, Double_t th_max) {
+    auto R = std::make_shared<TH2D>("", "", lam_nbins, lam_min, lam_max, th_nbins, th_min, th_max);
+    auto T = std::make_shared<TH2D>("", "", lam_nbins, lam_min, lam_max, th_nbins, th_min, th_max);
+    std::vector<std::complex<Double_t>> th;
+    std::vector<Double_t> lam;
+    for (Int_t j = 1; j <= th_nbins; ++j)
+      for (Int_t i = 1; i <= lam_nbins; ++i) {
+        th.push_back(R->GetYaxis()->GetBinCenter(j));
+        lam.push_back(R->GetXaxis()->GetBinCenter(i));
+      }
+    std::vector<Double_t> r(th.size()), t(th.size());
+    DeviceTMMGeneral(1, 2, kFALSE, (Int_t)th.size(), th.data(), lam.data(), r.data(), t.data());
     size_t k = 0;
     for (Int_t j = 1; j <= th_nbins; ++j)
       for (Int_t i = 1; i <= lam_nbins; ++i, ++k) {
@@ -1276,7 +1328,7 @@ struct ASceneExport {
     for (int i = 0; i < r.n; i++) {
       rbg_layer l;
       l.index = AddIndex(m->GetIndexList()[i].get());
-      l.pad = 0;
+      l.incoherent = (i == 0 || i == r.n - 1 || !m->GetCoherentList()[i]) ? 1 : 0;
       l.thickness = m->GetThicknessList()[i];
       tmp.push_back(l);
     }
@@ -1379,6 +1431,20 @@ inline void AMultilayer::DeviceTMM(Int_t n, const Double_t* th, const Double_t* 
   rbg_scene* sc = nullptr;
   if (rbg_scene_create(&ex.desc, 0, &sc) != RBG_OK) throw std::runtime_error(std::string("AMultilayer: ") + rbg_last_error());
   int rc = rbg_tmm_host(sc, id, n, th, lam, R, T);
+  rbg_scene_destroy(sc);
+  if (rc != RBG_OK) throw std::runtime_error(std::string("AMultilayer: ") + rbg_last_error());
+}
+
+inline void AMultilayer::DeviceTMMGeneral(Int_t mode, Int_t pol, Bool_t reverse, Int_t n, const std::complex<Double_t>* th, const Double_t* lam, Double_t* R,
+                                          Double_t* T) const {
+  ASceneExport ex;
+  int id = ex.AddMultilayer(this);
+  ex.Finish(-1);
+  std::vector<Double_t> re(n), im(n);
+  for (Int_t i = 0; i < n; i++) { re[i] = th[i].real(); im[i] = th[i].imag(); }
+  rbg_scene* sc = nullptr;
+  if (rbg_scene_create(&ex.desc, 0, &sc) != RBG_OK) throw std::runtime_error(std::string("AMultilayer: ") + rbg_last_error());
+  int rc = rbg_tmm_general_host(sc, id, mode, pol, reverse ? 1 : 0, n, re.data(), im.data(), lam, R, T);
   rbg_scene_destroy(sc);
   if (rc != RBG_OK) throw std::runtime_error(std::string("AMultilayer: ") + rbg_last_error());
 }

@@ -133,7 +133,8 @@ typedef struct {        /* AMultilayer: layers[first .. first+n) top(0) ... bott
   int32_t table_r, table_t; /* PreCalculateCoherentTMM tables (th2 ids) or -1 */
 } rbg_multilayer;
 
-typedef struct { int32_t index; int32_t pad; double thickness; } rbg_layer; /* thickness cm; +inf ends */
+/* thickness cm, +inf for the two ends; incoherent != 0 marks a layer as incoherent for IncoherentTMM (the ends always are) */
+typedef struct { int32_t index; int32_t incoherent; double thickness; } rbg_layer;
 
 typedef struct {        /* TGraph2D baked to a Delaunay triangle list (x,y,z per vertex) */
   int32_t first_tri, ntri; /* slice of tri[] (3 vertex ids each, into g2x/g2y/g2z) */
@@ -296,6 +297,13 @@ int rbg_moments(int64_t n, const double* x, const double* y, const double* t, co
  * (include/AMultilayer.h:114-132,243-262).  Pointers are device pointers. */
 int rbg_tmm(rbg_scene* scene, int multilayer, int64_t n, const double* theta, const double* lambda,
             double* refl, double* trans, void* stream);
+/* AMultilayer::CoherentTMM (one polarisation, complex incidence angle, optionally the reversed stack;
+ * src/AMultilayer.cxx:240-481) and AMultilayer::IncoherentTMM (partly coherent stacks, :484-731) for host arrays
+ * of n (theta_re, theta_im, lambda) triples.  mode: 0 coherent, 1 incoherent.  pol: 0 = s, 1 = p, 2 = mean of both.
+ * `reverse` applies to mode 0 only.  Copies inside, synchronous. */
+int rbg_tmm_general_host(rbg_scene* scene, int multilayer, int mode, int pol, int reverse, int64_t n,
+                         const double* theta_re, const double* theta_im, const double* lambda,
+                         double* refl, double* trans);
 /* same with host arrays (copies inside, synchronous) — what AMultilayer::CoherentTMMMixed binds */
 int rbg_tmm_host(rbg_scene* scene, int multilayer, int64_t n, const double* theta, const double* lambda,
                  double* refl, double* trans);

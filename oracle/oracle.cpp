@@ -244,17 +244,11 @@ bool is_forward_angle(cplx n, cplx theta) {
   if (std::abs(ncostheta.imag()) > 100 * EPS) return ncostheta.imag() > 0;
   return ncostheta.real() > 0;
 }
-void coherent_tmm(const rbg_scene_desc* d, int ml, int pol /*0=S,1=P*/, double th0r, double lam, double& R, double& T) {
-  const rbg_multilayer& M = d->multilayers[ml];
-  int N = M.n;
-  std::vector<cplx> n_list(N), th_list(N), kz(N), cos_th(N), delta(N), t_list(N), r_list(N);
-  std::vector<double> thick(N);
-  for (int i = 0; i < N; i++) {
-    const rbg_layer& L = d->layers[M.first + i];
-    n_list[i] = cplx(index_n(d, L.index, lam), index_k(d, L.index, lam));
-    thick[i] = L.thickness;
-  }
-  cplx th_0(th0r, 0.);
+// CoherentTMM on explicit lists (the reference reverses copies of its lists for `reverse`, :268-277, and builds a
+// temporary AMultilayer per coherent stack inside IncoherentTMM, :612-624)
+void coherent_tmm_lists(const std::vector<cplx>& n_list, const std::vector<double>& thick, int pol /*0=S,1=P*/, cplx th_0, double lam, double& R, double& T) {
+  int N = (int)n_list.size();
+  std::vector<cplx> th_list(N), kz(N), cos_th(N), delta(N), t_list(N), r_list(N);
   cplx n0_sinth0 = n_list[0] * std::sin(th_0);
   for (int i = 0; i < N; i++) th_list[i] = std::asin(n0_sinth0 / n_list[i]);
   if (!is_forward_angle(n_list[0], th_list[0])) th_list[0] = kPi - th_list[0];
@@ -301,6 +295,123 @@ void coherent_tmm(const rbg_scene_desc* d, int ml, int pol /*0=S,1=P*/, double t
   cplx n_i = n_list[0], n_f = n_list[N - 1], th_i = th_0, th_f = th_list[N - 1];
   if (pol == 0) T = std::abs(t * t) * (((n_f * std::cos(th_f)).real()) / (n_i * std::cos(th_i)).real());
   else T = std::abs(t * t) * (((n_f * std::conj(std::cos(th_f))).real()) / (n_i * std::conj(std::cos(th_i))).real());
+}
+void multilayer_lists(const rbg_scene_desc* d, int ml, double lam, std::vector<cplx>& n_list, std::vector<double>& thick, std::vector<bool>& coherent) {
+  const rbg_multilayer& M = d->multilayers[ml];
+  n_list.resize(M.n); thick.resize(M.n); coherent.resize(M.n);
+  for (int i = 0; i < M.n; i++) {
+    const rbg_layer& L = d->layers[M.first + i];
+    n_list[i] = cplx(index_n(d, L.index, lam), index_k(d, L.index, lam));
+    thick[i] = L.thickness;
+    coherent[i] = !(i == 0 || i == M.n - 1 || L.incoherent);
+  }
+}
+void coherent_tmm_cplx(const rbg_scene_desc* d, int ml, int pol, cplx th_0, double lam, double& R, double& T, bool reverse) {
+  std::vector<cplx> n_list;
+  std::vector<double> thick;
+  std::vector<bool> coh;
+  multilayer_lists(d, ml, lam, n_list, thick, coh);
+  if (reverse) {
+    std::reverse(n_list.begin(), n_list.end());
+    std::reverse(thick.begin(), thick.end());
+  }
+  coherent_tmm_lists(n_list, thick, pol, th_0, lam, R, T);
+}
+void coherent_tmm(const rbg_scene_desc* d, int ml, int pol /*0=S,1=P*/, double th0r, double lam, double& R, double& T) {
+  coherent_tmm_cplx(d, ml, pol, cplx(th0r, 0.), lam, R, T, false);
+}
+// tmm.interface_R / interface_T (src/AMultilayer.cxx:26-56 interface_r/t, then |r|^2 and the power factor of T)
+void interface_RT(int pol, cplx n_i, cplx n_f, cplx th_i, cplx th_f, double& R, double& T) {
+  cplx r, t;
+  if (pol == 0) {
+    r = (n_i * std::cos(th_i) - n_f * std::cos(th_f)) / (n_i * std::cos(th_i) + n_f * std::cos(th_f));
+    t = 2. * n_i * std::cos(th_i) / (n_i * std::cos(th_i) + n_f * std::cos(th_f));
+    T = std::abs(t * t) * (((n_f * std::cos(th_f)).real()) / (n_i * std::cos(th_i)).real());
+  } else {
+    r = (n_f * std::cos(th_i) - n_i * std::cos(th_f)) / (n_f * std::cos(th_i) + n_i * std::cos(th_f));
+    t = 2. * n_i * std::cos(th_i) / (n_f * std::cos(th_i) + n_i * std::cos(th_f));
+    T = std::abs(t * t) * (((n_f * std::conj(std::cos(th_f))).real()) / (n_i * std::conj(std::cos(th_i))).real());
+  }
+  R = std::abs(r) * std::abs(r);
+}
+// AMultilayer::IncoherentTMM, src/AMultilayer.cxx:484-731 (tmm.inc_group_layers + tmm.inc_tmm)
+void incoherent_tmm(const rbg_scene_desc* d, int ml, int pol, cplx th_0, double lam, double& R, double& T) {
+  std::vector<cplx> n_list;
+  std::vector<double> thick;
+  std::vector<bool> coh;
+  multilayer_lists(d, ml, lam, n_list, thick, coh);
+  const int N = (int)n_list.size();
+  // inc_group_layers: stacks of consecutive coherent layers, each bracketed by the incoherent layers next to it
+  std::vector<std::vector<int>> all_from_stack;
+  std::vector<int> all_from_inc, stack_from_inc;
+  bool in_stack = false;
+  for (int i = 0; i < N; i++) {
+    if (coh[i]) {
+      if (!in_stack) { in_stack = true; all_from_stack.push_back({i - 1, i}); }
+      else all_from_stack.back().push_back(i);
+    } else {
+      all_from_inc.push_back(i);
+      if (!in_stack) stack_from_inc.push_back(-1);
+      else {
+        in_stack = false;
+        stack_from_inc.push_back((int)all_from_stack.size() - 1);
+        all_from_stack.back().push_back(i);
+      }
+    }
+  }
+  // ListSnell
+  std::vector<cplx> th_list(N);
+  for (int i = 0; i < N; i++) th_list[i] = std::asin(n_list[0] * std::sin(th_0) / n_list[i]);
+  if (!is_forward_angle(n_list[0], th_list[0])) th_list[0] = kPi - th_list[0];
+  if (!is_forward_angle(n_list[N - 1], th_list[N - 1])) th_list[N - 1] = kPi - th_list[N - 1];
+  // coherent stacks, forwards and backwards
+  std::vector<std::pair<double, double>> fwd, bwd;
+  for (auto& st : all_from_stack) {
+    std::vector<cplx> sn;
+    std::vector<double> sd;
+    for (size_t k = 0; k < st.size(); k++) {
+      sn.push_back(n_list[st[k]]);
+      sd.push_back(k == 0 || k + 1 == st.size() ? kInf : thick[st[k]]);
+    }
+    double r, t;
+    coherent_tmm_lists(sn, sd, pol, th_list[st.front()], lam, r, t);
+    fwd.push_back({r, t});
+    std::reverse(sn.begin(), sn.end());
+    std::reverse(sd.begin(), sd.end());
+    coherent_tmm_lists(sn, sd, pol, th_list[st.back()], lam, r, t);
+    bwd.push_back({r, t});
+  }
+  const int NI = (int)all_from_inc.size();
+  std::vector<double> P(NI, 0.);
+  for (int k = 1; k < NI - 1; k++) {
+    int i = all_from_inc[k];
+    P[k] = exp(-4 * kPi * thick[i] * (n_list[i] * std::cos(th_list[i])).imag() / lam);
+    if (P[k] < 1e-30) P[k] = 1e-30;
+  }
+  std::vector<std::vector<double>> Tl(NI, std::vector<double>(NI, 0.)), Rl(NI, std::vector<double>(NI, 0.));
+  for (int k = 0; k < NI - 1; k++) {
+    int a = all_from_inc[k], next_stack = stack_from_inc[k + 1];
+    if (next_stack < 0) {
+      interface_RT(pol, n_list[a], n_list[a + 1], th_list[a], th_list[a + 1], Rl[k][k + 1], Tl[k][k + 1]);
+      interface_RT(pol, n_list[a + 1], n_list[a], th_list[a + 1], th_list[a], Rl[k + 1][k], Tl[k + 1][k]);
+    } else {
+      Rl[k][k + 1] = fwd[next_stack].first; Tl[k][k + 1] = fwd[next_stack].second;
+      Rl[k + 1][k] = bwd[next_stack].first; Tl[k + 1][k] = bwd[next_stack].second;
+    }
+  }
+  double L[2][2] = {{1 / Tl[0][1], -Rl[1][0] / Tl[0][1]}, {Rl[0][1] / Tl[0][1], (Tl[1][0] * Tl[0][1] - Rl[1][0] * Rl[0][1]) / Tl[0][1]}};
+  for (int k = 1; k < NI - 1; k++) {
+    double L1[2][2] = {{1 / P[k], 0}, {0, P[k]}};
+    double L2[2][2] = {{1, -Rl[k + 1][k]}, {Rl[k][k + 1], Tl[k + 1][k] * Tl[k][k + 1] - Rl[k + 1][k] * Rl[k][k + 1]}};
+    double Lk[2][2], Ln[2][2];
+    for (int r = 0; r < 2; r++)
+      for (int c = 0; c < 2; c++) Lk[r][c] = (L1[r][0] * L2[0][c] + L1[r][1] * L2[1][c]) * (1 / Tl[k][k + 1]);
+    for (int r = 0; r < 2; r++)
+      for (int c = 0; c < 2; c++) Ln[r][c] = L[r][0] * Lk[0][c] + L[r][1] * Lk[1][c];
+    memcpy(L, Ln, sizeof(L));
+  }
+  T = 1 / L[0][0];
+  R = L[1][0] / L[0][0];
 }
 // include/AMultilayer.h:114-132
 void coherent_tmm_mixed(const rbg_scene_desc* d, int ml, double th, double lam, double& R, double& T) {
@@ -1922,6 +2033,14 @@ int orc_trace_history(const rbg_scene_desc* desc, const rbg_trace_opts* opts, co
   }
 }
 
+// AMultilayer::CoherentTMM (mode 0; complex angle, optional reversed stack) and IncoherentTMM (mode 1); pol 0 = S, 1 = P
+int orc_tmm_general(const rbg_scene_desc* desc, int ml, int mode, int pol, int reverse, double th_re, double th_im, double lambda, double* R, double* T) {
+  try {
+    if (mode == 0) coherent_tmm_cplx(desc, ml, pol, cplx(th_re, th_im), lambda, *R, *T, reverse != 0);
+    else incoherent_tmm(desc, ml, pol, cplx(th_re, th_im), lambda, *R, *T);
+    return RBG_OK;
+  } catch (...) { return RBG_EINTERNAL; }
+}
 // pol: 0 = S, 1 = P, 2 = mixed (uses precalculated tables when present)
 int orc_tmm(const rbg_scene_desc* desc, int ml, int pol, double theta, double lambda, double* R, double* T) {
   try {

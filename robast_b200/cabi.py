@@ -59,11 +59,12 @@ rbg_containment_radius = _proto("rbg_containment_radius", C.c_int, [C.c_int32, _
 rbg_containment_radius_host = _proto("rbg_containment_radius_host", C.c_int, [_dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, C.c_double, _dp, C.c_int])
 rbg_moments = _proto("rbg_moments", C.c_int, [C.c_int64, _dp, _dp, _dp, _dp, C.c_int32, _dp, _dp, C.c_int, C.c_void_p])
 rbg_tmm = _proto("rbg_tmm", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, C.c_void_p])
+rbg_tmm_general_host = _proto("rbg_tmm_general_host", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _dp])
 rbg_tmm_host = _proto("rbg_tmm_host", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp])
 
 ABI_SYMBOLS = ["rbg_abi_version", "rbg_last_error", "rbg_device_count", "rbg_scene_create", "rbg_scene_destroy",
                "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_scene_kernel_variant", "rbg_trace", "rbg_trace_history", "rbg_launch_count", "rbg_profile_enable",
-               "rbg_profile_read", "rbg_shoot", "rbg_hist2d", "rbg_hist2d_stats", "rbg_containment_radius", "rbg_containment_radius_host", "rbg_moments", "rbg_tmm", "rbg_tmm_host"]
+               "rbg_profile_read", "rbg_shoot", "rbg_hist2d", "rbg_hist2d_stats", "rbg_containment_radius", "rbg_containment_radius_host", "rbg_moments", "rbg_tmm", "rbg_tmm_host", "rbg_tmm_general_host"]
 
 
 class RbgError(RuntimeError):

@@ -5,6 +5,7 @@
 #include <pybind11/functional.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
+#include <pybind11/complex.h>
 #include <pybind11/stl.h>
 
 #include "../../include/robast/Robast.h"
@@ -174,7 +175,25 @@ PYBIND11_MODULE(_robast, m) {
       .def("InsertLayer", &AMultilayer::InsertLayer, py::arg("idx"), py::arg("thickness"), py::arg("coherent") = true)
       .def("ChangeThickness", &AMultilayer::ChangeThickness).def("GetThickness", &AMultilayer::GetThickness)
       .def("CoherentTMMMixed", [](const AMultilayer& a, double th, double lam) { double r, t; a.CoherentTMMMixed(th, lam, r, t); return py::make_tuple(r, t); })
-      .def("PreCalculateCoherentTMM", &AMultilayer::PreCalculateCoherentTMM);
+      .def("PreCalculateCoherentTMM", &AMultilayer::PreCalculateCoherentTMM)
+      .def("PreCalculateIncoherentTMM", &AMultilayer::PreCalculateIncoherentTMM)
+      .def("CoherentTMM", [](const AMultilayer& a, int pol, std::complex<double> th, double lam, bool reverse) {
+        double r, t;
+        a.CoherentTMM(pol == 0 ? AMultilayer::kS : AMultilayer::kP, th, lam, r, t, reverse);
+        return py::make_tuple(r, t);
+      }, py::arg("pol"), py::arg("th_0"), py::arg("lam_vac"), py::arg("reverse") = false)
+      .def("IncoherentTMM", [](const AMultilayer& a, int pol, std::complex<double> th, double lam) {
+        double r, t;
+        a.IncoherentTMM(pol == 0 ? AMultilayer::kS : AMultilayer::kP, th, lam, r, t);
+        return py::make_tuple(r, t);
+      })
+      .def("IncoherentTMMMixed", [](const AMultilayer& a, std::complex<double> th, double lam) {
+        double r, t;
+        a.IncoherentTMMMixed(th, lam, r, t);
+        return py::make_tuple(r, t);
+      })
+      .def_property_readonly_static("kS", [](py::object) { return 0; })
+      .def_property_readonly_static("kP", [](py::object) { return 1; });
 
   // ---- volumes
   py::class_<TGeoNode, TNamed, Raw<TGeoNode>>(m, "TGeoNode");

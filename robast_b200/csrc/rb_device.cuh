@@ -253,21 +253,22 @@ RB_HD inline bool tmm_is_forward(Cx n, Cx theta) {
   if (fabs(nc.im) > 100 * 2.220446049250313e-16) return nc.im > 0;
   return nc.re > 0;
 }
-// one polarisation (pol 0 = s, 1 = p)
-RB_HD inline void tmm_coherent(const DScene& sc, int ml, int pol, double th0, double lam, double& R, double& T) {
-  const rbg_multilayer M = sc.multilayers[ml];
-  int N = M.n;
+// AMultilayer::CoherentTMM (src/AMultilayer.cxx:240-481) for one polarisation (pol 0 = s, 1 = p) over the stack made of
+// layers a..b (inclusive) of sc.layers[first ...], entered through layer a, or through layer b when `reverse`; th0 is the
+// (possibly complex) angle in the entrance medium.
+RB_HD inline void tmm_coherent_sub(const DScene& sc, int first, int a, int b, bool reverse, int pol, Cx th0, double lam, double& R, double& T) {
+  int N = b - a + 1;
   Cx n0 = cx(1, 0), nprev = cx(1, 0), thprev = cx(0, 0), n_last = cx(1, 0), th_last = cx(0, 0);
   Cx n0s = cx(0, 0);
   Cx m00 = cx(1, 0), m01 = cx(0, 0), m10 = cx(0, 0), m11 = cx(1, 0);
   Cx r0 = cx(0, 0), t0 = cx(1, 0);
   for (int i = 0; i < N; i++) {
-    const rbg_layer L = sc.layers[M.first + i];
+    const rbg_layer L = sc.layers[first + (reverse ? b - i : a + i)];
     Cx ni = cx(index_n(sc, L.index, lam), index_k(sc, L.index, lam));
     Cx thi;
     if (i == 0) {
       n0 = ni;
-      n0s = ni * csin_(cx(th0, 0));
+      n0s = ni * csin_(th0);
       thi = casin_(n0s / ni);
       if (!tmm_is_forward(ni, thi)) thi = cx(RB_PI - thi.re, -thi.im);
     } else {
@@ -290,7 +291,7 @@ RB_HD inline void tmm_coherent(const DScene& sc, int ml, int pol, double th0, do
         // layer i-1 is an inner layer: M_{i-1} = (1/t) diag(e^{-iδ}, e^{iδ}) [[1,r],[r,1]]
         Cx kz = ((2 * RB_PI) * (nprev * ci));
         kz = cx(kz.re / lam, kz.im / lam);
-        double d = sc.layers[M.first + i - 1].thickness;
+        double d = sc.layers[first + (reverse ? b - (i - 1) : a + i - 1)].thickness;
         Cx delta = cx(kz.re * d, kz.im * d);
         if (delta.im > 35) delta.im = 35;
         Cx em = cexp_(cx(delta.im, -delta.re)), ep = cexp_(cx(-delta.im, delta.re));  // exp(-iδ), exp(iδ)
@@ -310,10 +311,78 @@ RB_HD inline void tmm_coherent(const DScene& sc, int ml, int pol, double th0, do
   Cx q00 = b00 * m00 + b01 * m10, q10 = b01 * m00 + b00 * m10;
   Cx r = q10 / q00, t = cx(1, 0) / q00;
   R = cabs2(r);
-  Cx cf = ccos_(th_last), ci = ccos_(cx(th0, 0));
+  Cx cf = ccos_(th_last), ci = ccos_(th0);
   double tt = cabs2(t);  // |t*t| = |t|^2
   if (pol == 0) T = tt * ((n_last * cf).re / (n0 * ci).re);
   else T = tt * ((n_last * cconj(cf)).re / (n0 * cconj(ci)).re);
+}
+RB_HD inline void tmm_coherent(const DScene& sc, int ml, int pol, double th0, double lam, double& R, double& T) {
+  const rbg_multilayer M = sc.multilayers[ml];
+  tmm_coherent_sub(sc, M.first, 0, M.n - 1, false, pol, cx(th0, 0), lam, R, T);
+}
+// power reflectance / transmittance of a single interface (tmm.interface_R / interface_T)
+RB_HD inline void tmm_interface_RT(int pol, Cx ni, Cx nf, Cx thi, Cx thf, double& R, double& T) {
+  Cx ci = ccos_(thi), cf = ccos_(thf), r, t;
+  if (pol == 0) {
+    r = (ni * ci - nf * cf) / (ni * ci + nf * cf);
+    t = (2. * (ni * ci)) / (ni * ci + nf * cf);
+    T = cabs2(t) * ((nf * cf).re / (ni * ci).re);
+  } else {
+    r = (nf * ci - ni * cf) / (nf * ci + ni * cf);
+    t = (2. * (ni * ci)) / (nf * ci + ni * cf);
+    T = cabs2(t) * ((nf * cconj(cf)).re / (ni * cconj(ci)).re);
+  }
+  R = cabs2(r);
+}
+// AMultilayer::IncoherentTMM (src/AMultilayer.cxx:484-731, tmm.inc_tmm): layers flagged incoherent (and the two
+// semi-infinite ends) exchange power, runs of coherent layers between them are condensed by the coherent TMM in both
+// directions; the 2x2 power transfer matrices are multiplied on the fly from the top incoherent layer down.
+RB_HD inline void tmm_incoherent(const DScene& sc, int ml, int pol, Cx th0, double lam, double& R, double& T) {
+  const rbg_multilayer M = sc.multilayers[ml];
+  const int N = M.n;
+  const rbg_layer L0 = sc.layers[M.first];
+  const Cx n0 = cx(index_n(sc, L0.index, lam), index_k(sc, L0.index, lam));
+  const Cx n0s = n0 * csin_(th0);
+  auto n_of = [&](int i) {
+    const rbg_layer L = sc.layers[M.first + i];
+    return cx(index_n(sc, L.index, lam), index_k(sc, L.index, lam));
+  };
+  auto th_of = [&](int i) {  // ListSnell: forward-angle correction for the first and the last layer only
+    Cx ni = n_of(i), th = casin_(n0s / ni);
+    if ((i == 0 || i == N - 1) && !tmm_is_forward(ni, th)) th = cx(RB_PI - th.re, -th.im);
+    return th;
+  };
+  double l00 = 1, l01 = 0, l10 = 0, l11 = 1;  // Ltilde
+  int prev = 0;                                // previous incoherent layer (index into the full list)
+  bool first_pair = true;
+  for (int i = 1; i < N; i++) {
+    const bool inc = i == N - 1 || sc.layers[M.first + i].incoherent != 0;
+    if (!inc) continue;
+    double Rf, Tf, Rb, Tb;  // prev -> i and i -> prev
+    if (i == prev + 1) {
+      tmm_interface_RT(pol, n_of(prev), n_of(i), th_of(prev), th_of(i), Rf, Tf);
+      tmm_interface_RT(pol, n_of(i), n_of(prev), th_of(i), th_of(prev), Rb, Tb);
+    } else {
+      tmm_coherent_sub(sc, M.first, prev, i, false, pol, th_of(prev), lam, Rf, Tf);
+      tmm_coherent_sub(sc, M.first, prev, i, true, pol, th_of(i), lam, Rb, Tb);
+    }
+    double a00 = 1, a01 = -Rb, a10 = Rf, a11 = Tb * Tf - Rb * Rf;
+    if (first_pair) {
+      l00 = a00 / Tf; l01 = a01 / Tf; l10 = a10 / Tf; l11 = a11 / Tf;
+      first_pair = false;
+    } else {
+      // L = diag(1/P, P) * [[1,-Rb],[Rf, Tb Tf - Rb Rf]] / Tf, P = single-pass transmission of incoherent layer `prev`
+      Cx np = n_of(prev);
+      double P = exp(-4 * RB_PI * sc.layers[M.first + prev].thickness * (np * ccos_(th_of(prev))).im / lam);
+      if (P < 1e-30) P = 1e-30;
+      double b00 = a00 / P / Tf, b01 = a01 / P / Tf, b10 = a10 * P / Tf, b11 = a11 * P / Tf;
+      double q00 = l00 * b00 + l01 * b10, q01 = l00 * b01 + l01 * b11, q10 = l10 * b00 + l11 * b10, q11 = l10 * b01 + l11 * b11;
+      l00 = q00; l01 = q01; l10 = q10; l11 = q11;
+    }
+    prev = i;
+  }
+  T = 1 / l00;
+  R = l10 / l00;
 }
 RB_HD inline void tmm_mixed(const DScene& sc, int ml, double th, double lam, double& R, double& T) {
   const rbg_multilayer M = sc.multilayers[ml];

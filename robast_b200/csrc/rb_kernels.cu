@@ -409,6 +409,26 @@ __global__ void k_tmm(DScene sc, int ml, long long n, const double* __restrict__
   T[i] = t;
 }
 
+// AMultilayer::CoherentTMM / IncoherentTMM for arrays of (complex theta, lambda); pol 2 = mean of s and p
+__global__ void k_tmm_general(DScene sc, int ml, int mode, int pol, int reverse, long long n, const double* __restrict__ th_re, const double* __restrict__ th_im,
+                              const double* __restrict__ lambda, double* R, double* T) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const rbg_multilayer M = sc.multilayers[ml];
+  Cx th = cx(th_re[i], th_im[i]);
+  double r = 0, t = 0;
+  for (int p = (pol == 2 ? 0 : pol); p <= (pol == 2 ? 1 : pol); p++) {
+    double rp, tp;
+    if (mode == 0) tmm_coherent_sub(sc, M.first, 0, M.n - 1, reverse != 0, p, th, lambda[i], rp, tp);
+    else tmm_incoherent(sc, ml, p, th, lambda[i], rp, tp);
+    r += rp;
+    t += tp;
+  }
+  if (pol == 2) { r *= 0.5; t *= 0.5; }
+  R[i] = r;
+  T[i] = t;
+}
+
 // ------------------------------------------------------------------------------------------------ host: scene
 #define RB_HOST_STREAMS 8  // chunks in flight on the host-buffer path of rbg_trace (one worker thread + stream + stage each)
 struct rbg_scene {
@@ -972,6 +992,33 @@ int rbg_tmm(rbg_scene* s, int ml, int64_t n, const double* theta, const double* 
     k_tmm<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(s->d, ml, n, theta, lambda, refl, trans);
     g_launches++;
     CK(cudaGetLastError());
+  });
+}
+
+int rbg_tmm_general_host(rbg_scene* s, int ml, int mode, int pol, int reverse, int64_t n, const double* theta_re, const double* theta_im, const double* lambda,
+                         double* refl, double* trans) {
+  return guard([&] {
+    if (!s) throw Invalid("null scene");
+    if (ml < 0 || mode < 0 || mode > 1 || pol < 0 || pol > 2 || !theta_re || !theta_im || !lambda || !refl || !trans) throw Invalid("bad TMM arguments");
+    if (n <= 0) return;
+    CK(cudaSetDevice(s->device));
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)n * 8 * 5));
+    try {
+      CK(cudaMemcpy(d, theta_re, (size_t)n * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d + n, theta_im, (size_t)n * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d + 2 * n, lambda, (size_t)n * 8, cudaMemcpyHostToDevice));
+      long long blocks = (n + 127) / 128;
+      k_tmm_general<<<(unsigned)blocks, 128>>>(s->d, ml, mode, pol, reverse, n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
+      g_launches++;
+      CK(cudaGetLastError());
+      CK(cudaMemcpy(refl, d + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(trans, d + 4 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cudaFree(d);
+      throw;
+    }
+    cudaFree(d);
   });
 }
 

@@ -89,3 +89,14 @@ extern "C" __attribute__((visibility("default"))) int emul_tmm(const rbg_scene_d
   else tmm_coherent(sc, ml, pol, th, lam, *R, *T);
   return 0;
 }
+extern "C" __attribute__((visibility("default"))) int emul_tmm_general(const rbg_scene_desc* D, int ml, int mode, int pol, int reverse, double th_re, double th_im,
+                                                                      double lam, double* R, double* T) {
+  DScene sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.graphs = D->graphs; sc.gx = D->gx; sc.gy = D->gy; sc.th2 = D->th2; sc.th2v = D->th2v; sc.indices = D->indices;
+  sc.multilayers = D->multilayers; sc.layers = D->layers;
+  const rbg_multilayer M = sc.multilayers[ml];
+  if (mode == 0) tmm_coherent_sub(sc, M.first, 0, M.n - 1, reverse != 0, pol, cx(th_re, th_im), lam, *R, *T);
+  else tmm_incoherent(sc, ml, pol, cx(th_re, th_im), lam, *R, *T);
+  return 0;
+}

@@ -27,6 +27,8 @@ def load_oracle():
     lib.orc_trace.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.c_int]
     lib.orc_trace_history.restype = C.c_int
     lib.orc_trace_history.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.POINTER(R.rbg_history), C.c_int]
+    lib.orc_tmm_general.restype = C.c_int
+    lib.orc_tmm_general.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.orc_tmm.restype = C.c_int
     lib.orc_tmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in ("orc_index_n", "orc_index_k", "orc_index_abslen", "orc_graph_eval"):

@@ -145,3 +145,30 @@ def test_general_pcon_pgon_match_oracle(oracle, emul, kind, phi1, dphi):
             assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (material, origin, rep)
             bounces = max(bounces, int(got.npoints.max()))
     assert bounces > 4  # walls are hit repeatedly (bore reflections, total internal reflection in the glass)
+
+
+def test_general_tmm_device_code_matches_oracle_and_golden(R, oracle, emul):
+    """tmm_coherent_sub (complex angle, reversed) and tmm_incoherent of rb_device.cuh against the oracle and tmm.py's values"""
+    import test_oracle_golden as G
+    emul.emul_tmm_general.restype = C.c_int
+    emul.emul_tmm_general.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    multi, keep, th_0 = G.incoherent_stack(R)
+    ex, mid = R.export_multilayer(multi)
+    want = {0: (0.3776110935131179, 1.2856977234844612e-05), 1: (0.03199545463016445, 2.0900281396463212e-05)}
+    for pol in (0, 1):
+        r, t = C.c_double(), C.c_double()
+        assert emul.emul_tmm_general(ex.desc_ptr(), mid, 1, pol, 0, th_0.real, th_0.imag, 400., C.byref(r), C.byref(t)) == 0
+        assert abs(r.value - want[pol][0]) < 1e-12 and abs(t.value / want[pol][1] - 1) < 1e-10
+    rng = np.random.default_rng(4)
+    for k in range(200):
+        th = complex(rng.random() * 1.5, 0.0)
+        lam = 300. + 500. * rng.random()
+        for mode, rev in ((0, 0), (0, 1), (1, 0)):
+            for pol in (0, 1):
+                a, b, c, d_ = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+                # an absorbing entrance medium needs the matching complex angle: take it from Snell's law out of vacuum
+                thc = np.lib.scimath.arcsin(math.sin(th.real) / (1 + 0.1j)) if rev == 0 else np.lib.scimath.arcsin(math.sin(th.real) / (4 + 0.2j))
+                thc = complex(thc)
+                assert emul.emul_tmm_general(ex.desc_ptr(), mid, mode, pol, rev, thc.real, thc.imag, lam, C.byref(a), C.byref(b)) == 0
+                assert oracle.orc_tmm_general(ex.desc_ptr(), mid, mode, pol, rev, thc.real, thc.imag, lam, C.byref(c), C.byref(d_)) == 0
+                assert abs(a.value - c.value) < 1e-11 * max(1, abs(c.value)) and abs(b.value - d_.value) < 1e-11 * max(1e-3, abs(d_.value)), (k, mode, rev, pol)

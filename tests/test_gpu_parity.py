@@ -465,3 +465,48 @@ def test_general_pcon_pgon_parity(R, oracle, kind, phi1, dphi):
                 got = H.trace_gpu(ex, H.make_rays(oracle, params, 0, n), o)
                 rep = H.compare(ref, got)
                 assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (material, origin, steps, rep)
+
+
+def test_reference_tmm_unit_tests_on_gpu(R, oracle):
+    """tutorials/unittest_robast.py testTMM (:627-666, incl. the reversed stack) and testIncoherentTMM (:711-781) through the
+    mirror class AMultilayer, whose TMM methods run on the GPU (rbg_tmm_general_host)"""
+    import test_oracle_golden as G
+    multi, keep = G.basic_stack(R)
+    rs, rp = 0.37273208839139516, 0.37016110373044969
+    ts, tp = 0.22604491247079261, 0.22824374314132009
+    r, t = multi.CoherentTMM(R.AMultilayer.kS, 0.1, 100.)
+    assert abs(r - rs) < 1e-12 and abs(t - ts) < 1e-12
+    r, t = multi.CoherentTMM(R.AMultilayer.kP, 0.1, 100.)
+    assert abs(r - rp) < 1e-12 and abs(t - tp) < 1e-12
+    r, t = multi.CoherentTMMMixed(0.1, 100.)
+    assert abs(r - (rs + rp) / 2) < 1e-12 and abs(t - (ts + tp) / 2) < 1e-12
+    rev, keep2 = G.basic_stack(R, reverse=True)
+    r, t = rev.CoherentTMM(R.AMultilayer.kS, 0.1, 100., True)
+    assert abs(r - rs) < 1e-12 and abs(t - ts) < 1e-12
+    r, t = rev.CoherentTMM(R.AMultilayer.kP, 0.1, 100., True)
+    assert abs(r - rp) < 1e-12 and abs(t - tp) < 1e-12
+    inc, keep3, th_0 = G.incoherent_stack(R)
+    r, t = inc.IncoherentTMM(R.AMultilayer.kS, complex(th_0), 400.)
+    assert abs(r - 0.3776110935131179) < 1e-12 and abs(t / 1.2856977234844612e-05 - 1) < 1e-10
+    r, t = inc.IncoherentTMM(R.AMultilayer.kP, complex(th_0), 400.)
+    assert abs(r - 0.03199545463016445) < 1e-12 and abs(t / 2.0900281396463212e-05 - 1) < 1e-10
+    rm, tm = inc.IncoherentTMMMixed(complex(th_0), 400.)
+    assert abs(rm - (0.3776110935131179 + 0.03199545463016445) / 2) < 1e-12
+    # device vs oracle over a sweep of wavelengths / angles (C ABI, arrays)
+    ex, mid = R.export_multilayer(inc)
+    h = C.c_void_p()
+    R.check(R.rbg_scene_create(ex.desc_ptr(), 0, C.byref(h)))
+    rng = np.random.default_rng(8)
+    n = 500
+    ang = np.array([complex(np.lib.scimath.arcsin(math.sin(a) / (1 + 0.1j))) for a in rng.random(n) * 1.5])
+    lam = 300. + 500. * rng.random(n)
+    re, im = np.ascontiguousarray(ang.real), np.ascontiguousarray(ang.imag)
+    for mode in (0, 1):
+        for pol in (0, 1):
+            Rr, Tt = np.zeros(n), np.zeros(n)
+            R.check(R.rbg_tmm_general_host(h, mid, mode, pol, 0, n, re.ctypes.data, im.ctypes.data, lam.ctypes.data, Rr.ctypes.data, Tt.ctypes.data))
+            for i in range(0, n, 9):
+                a, b = C.c_double(), C.c_double()
+                oracle.orc_tmm_general(ex.desc_ptr(), mid, mode, pol, 0, re[i], im[i], lam[i], C.byref(a), C.byref(b))
+                assert abs(a.value - Rr[i]) < 1e-11 * max(1, abs(a.value)) and abs(b.value - Tt[i]) < 1e-11 * max(1e-3, abs(b.value))
+    R.rbg_scene_destroy(h)

@@ -359,3 +359,52 @@ def test_containment_radius_of_gaussian_psf(oracle):  # src/AGeoUtil.cxx:198-308
     cys = -5. + (np.arange(300) + 0.5) * 9. / 300
     inside = ((cxs[None, :] - cx) ** 2 + (cys[:, None] - cy) ** 2 <= r * r)
     assert abs(bins.reshape(300, 300)[inside].sum() / bins.sum() - 0.8) < 2e-3
+
+
+def tmm_general(oracle, ml, mode, pol, th, lam, reverse=0):
+    import robast_b200 as R
+    ex, mid = R.export_multilayer(ml)
+    r, t = C.c_double(), C.c_double()
+    assert oracle.orc_tmm_general(ex.desc_ptr(), mid, mode, pol, reverse, complex(th).real, complex(th).imag, lam, C.byref(r), C.byref(t)) == 0
+    return r.value, t.value
+
+
+def incoherent_stack(R):  # unittest_robast.py:711-759
+    n0, n1, n2, n3 = R.ARefractiveIndex(1., 0.1), R.ARefractiveIndex(2., 0.2), R.ARefractiveIndex(3., 0.004), R.ARefractiveIndex(4., 0.2)
+    d1, d2 = 100, 1000
+    multi = R.AMultilayer(n0, n3)
+    multi.InsertLayer(n1, d1)
+    multi.InsertLayer(n2, d2, False)
+    multi.InsertLayer(n1, d1)
+    multi.InsertLayer(n2, d1)
+    multi.InsertLayer(n3, d1)
+    multi.InsertLayer(n1, d2, False)
+    multi.InsertLayer(n3, d1)
+    multi.InsertLayer(n1, d1)
+    th_0 = np.lib.scimath.arcsin(1. / (1 + 0.1j) * math.sin(math.pi / 3.))
+    return multi, [n0, n1, n2, n3], th_0
+
+
+def test_kat_tmm_reversed_stack(R, oracle):  # unittest_robast.py:657-666: the reversed stack evaluated with reverse = True
+    rev, keep = basic_stack(R, reverse=True)
+    rs, rp = 0.37273208839139516, 0.37016110373044969
+    ts, tp = 0.22604491247079261, 0.22824374314132009
+    for pol, (r0, t0) in ((0, (rs, ts)), (1, (rp, tp))):
+        r, t = tmm_general(oracle, rev, 0, pol, 0.1, 100., reverse=1)
+        assert abs(r - r0) < 1e-12 and abs(t - t0) < 1e-12
+
+
+def test_kat_incoherent_tmm(R, oracle):  # unittest_robast.py:711-781, values from tmm.inc_tmm
+    multi, keep, th_0 = incoherent_stack(R)
+    rs, ts = 0.3776110935131179, 1.2856977234844612e-05
+    rp, tp = 0.03199545463016445, 2.0900281396463212e-05
+    r, t = tmm_general(oracle, multi, 1, 0, th_0, 400.)
+    assert abs(r - rs) < 1e-12 and abs(t / ts - 1) < 1e-10
+    r, t = tmm_general(oracle, multi, 1, 1, th_0, 400.)
+    assert abs(r - rp) < 1e-12 and abs(t / tp - 1) < 1e-10
+    # an all-coherent stack: the incoherent TMM degenerates to the coherent one
+    co, keep2 = basic_stack(R)
+    for pol in (0, 1):
+        a = tmm_general(oracle, co, 1, pol, 0.1, 100.)
+        b = tmm_general(oracle, co, 0, pol, 0.1, 100.)
+        assert abs(a[0] - b[0]) < 1e-13 and abs(a[1] - b[1]) < 1e-13
