@@ -161,6 +161,48 @@ class AFilmetrixDotCom : public ARefractiveIndex {
   }
 };
 
+// reference src/ARefractiveIndexDotInfo.cxx:24-105 — tables from refractiveindex.info: a "wl,n" (or tab-separated) block in um,
+// optionally followed by a "wl,k" block; LF or CRLF line ends
+class ARefractiveIndexDotInfo : public ARefractiveIndex {
+ public:
+  ARefractiveIndexDotInfo(const char* fname) {
+    std::ifstream fin(fname);
+    if (!fin.is_open()) {
+      Error("ARefractiveIndexDotInfo", "Cannot open %s", fname);
+      return;
+    }
+    std::string line;
+    std::getline(fin, line);
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    char sep;
+    if (line == "wl,n") sep = ',';
+    else if (line == "wl\tn") sep = '\t';
+    else {
+      Error("ARefractiveIndexDotInfo", "Invalid data format");
+      return;
+    }
+    fRefractiveIndex = std::make_shared<TGraph>();
+    std::shared_ptr<TGraph> cur = fRefractiveIndex;
+    while (std::getline(fin, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      size_t pos = line.find(sep);
+      if (pos == std::string::npos) break;
+      std::string a = line.substr(0, pos), b = line.substr(pos + 1);
+      char *e1, *e2;
+      double wl = strtod(a.c_str(), &e1), v = strtod(b.c_str(), &e2);
+      if (*e1 != '\0' || *e2 != '\0' || a.empty() || b.empty()) {  // a header line: only "wl<sep>k" continues the file
+        if (cur == fRefractiveIndex && a == "wl" && b == "k") {
+          fExtinctionCoefficient = std::make_shared<TGraph>();
+          cur = fExtinctionCoefficient;
+          continue;
+        }
+        break;
+      }
+      cur->SetPoint(cur->GetN(), wl * 1e-4, v);  // um -> cm
+    }
+  }
+};
+
 // reference src/AGlassCatalog.cxx:27-121 — Zemax AGF parser (formula 2 = Sellmeier only, as there)
 class AGlassCatalog : public TObject {
   std::map<std::string, std::shared_ptr<ARefractiveIndex>> fIndexMap;

@@ -167,6 +167,7 @@ PYBIND11_MODULE(_robast, m) {
       .def(py::init<std::shared_ptr<ARefractiveIndex>, std::shared_ptr<ARefractiveIndex>, double, double>())
       .def("SetFraction", &AMixedRefractiveIndex::SetFraction);
   py::class_<AFilmetrixDotCom, ARefractiveIndex, std::shared_ptr<AFilmetrixDotCom>>(m, "AFilmetrixDotCom").def(py::init<const char*>());
+  py::class_<ARefractiveIndexDotInfo, ARefractiveIndex, std::shared_ptr<ARefractiveIndexDotInfo>>(m, "ARefractiveIndexDotInfo").def(py::init<const char*>());
   py::class_<AGlassCatalog>(m, "AGlassCatalog").def(py::init<const std::string&>()).def("GetRefractiveIndex", &AGlassCatalog::GetRefractiveIndex);
 
   py::class_<AMultilayer, std::shared_ptr<AMultilayer>> ml(m, "AMultilayer");

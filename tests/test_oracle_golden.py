@@ -408,3 +408,22 @@ def test_kat_incoherent_tmm(R, oracle):  # unittest_robast.py:711-781, values fr
         a = tmm_general(oracle, co, 1, pol, 0.1, 100.)
         b = tmm_general(oracle, co, 0, pol, 0.1, 100.)
         assert abs(a[0] - b[0]) < 1e-13 and abs(a[1] - b[1]) < 1e-13
+
+
+def test_refractiveindex_dot_info_parser(R, oracle, tmp_path):  # src/ARefractiveIndexDotInfo.cxx:24-105
+    for sep, eol in ((",", "\n"), (",", "\r\n"), ("\t", "\n"), ("\t", "\r\n")):
+        f = tmp_path / "nk.csv"
+        rows_n = [(0.30, 1.50), (0.40, 1.47), (0.50, 1.46), (0.70, 1.455)]
+        rows_k = [(0.30, 1e-6), (0.70, 3e-6)]
+        txt = "wl" + sep + "n" + eol + "".join("%g%s%g%s" % (w, sep, v, eol) for w, v in rows_n)
+        txt += "wl" + sep + "k" + eol + "".join("%g%s%g%s" % (w, sep, v, eol) for w, v in rows_k)
+        f.write_bytes(txt.encode())
+        idx = R.ARefractiveIndexDotInfo(str(f))
+        assert abs(idx.GetRefractiveIndex(450 * nm) - 1.465) < 1e-12
+        assert abs(idx.GetExtinctionCoefficient(500 * nm) - 2e-6) < 1e-18
+        ex, iid = R.export_index(idx)
+        assert abs(oracle.orc_index_n(ex.desc_ptr(), iid, 450 * nm) - 1.465) < 1e-12
+        assert abs(oracle.orc_index_k(ex.desc_ptr(), iid, 500 * nm) - 2e-6) < 1e-18
+    (tmp_path / "n.csv").write_text("wl,n\n0.4,1.5\n0.6,1.4\n")
+    only_n = R.ARefractiveIndexDotInfo(str(tmp_path / "n.csv"))
+    assert abs(only_n.GetRefractiveIndex(500 * nm) - 1.45) < 1e-12 and only_n.GetExtinctionCoefficient(500 * nm) == 0
