@@ -10,6 +10,7 @@
 
 #include <complex>
 #include <fstream>
+#include <iostream>
 #include <functional>
 #include <sstream>
 
@@ -828,6 +829,28 @@ class ARay : public TObject {
     x = p[0]; y = p[1]; z = p[2]; t = p[3];
     return i;
   }
+  // TVirtualGeoTrack-style lookup by time of flight (tutorials/AbsLengthTest.C:54 calls GetPoint(0, p0)): the point of the
+  // polyline at time `tof`, linearly interpolated between the recorded vertices; clamps to the first / last point
+  Int_t GetPoint(Double_t tof, Double_t* point, Int_t istart = 0) const {
+    Int_t n = GetNrecorded();
+    const Double_t* first = n > 0 ? &fHist[0] : fFirst;
+    const Double_t* last = n > 0 && n == fNpoints ? &fHist[4 * (n - 1)] : fLast;
+    if (!(tof > first[3]) || fNpoints < 2) { memcpy(point, first, 4 * sizeof(Double_t)); return 0; }
+    if (!(tof < last[3])) { memcpy(point, last, 4 * sizeof(Double_t)); return fNpoints - 1; }
+    for (Int_t i = std::max(istart, 0); i + 1 < n; i++) {
+      const Double_t *a = &fHist[4 * i], *b = &fHist[4 * (i + 1)];
+      if (tof >= a[3] && tof <= b[3] && b[3] > a[3]) {
+        Double_t u = (tof - a[3]) / (b[3] - a[3]);
+        for (int k = 0; k < 3; k++) point[k] = a[k] + u * (b[k] - a[k]);
+        point[3] = tof;
+        return i;
+      }
+    }
+    Double_t u = (tof - first[3]) / (last[3] - first[3]);
+    for (int k = 0; k < 3; k++) point[k] = first[k] + u * (last[k] - first[k]);
+    point[3] = tof;
+    return 0;
+  }
   Int_t GetNrecorded() const { return (Int_t)(fHist.size() / 4); }
   Int_t GetNnodesRecorded() const { return (Int_t)fNodeObjs.size(); }  // node-history slots, a trailing null (world exit) included
   Int_t GetNpoints() const { return fNpoints; }
@@ -904,13 +927,29 @@ class TCanvas : public TNamed {
   TCanvas* cd(Int_t = 0) { return this; }
   void SetGridx() {}
   void SetGridy() {}
+  void SetLogx() {}
+  void SetLogy() {}
   void SetLogz() {}
   void Update() {}
+  TH1* DrawFrame(Double_t, Double_t, Double_t, Double_t, const char* = "") {  // display stub: an empty frame histogram
+    static TH1D frame("frame", "", 1, 0, 1);
+    return &frame;
+  }
 };
+struct TStyle {
+  void SetOptStat(Int_t = 1) {}
+  void SetOptFit(Int_t = 1) {}
+  void SetPalette(Int_t = 0) {}
+};
+inline TStyle*& gStyleRef() { static TStyle* p = new TStyle; return p; }
+#define gStyle (gStyleRef())
 class TLegend : public TObject {
  public:
   TLegend(Double_t, Double_t, Double_t, Double_t) {}
   void SetFillStyle(Int_t) {}
+  void SetTextFont(Int_t) {}
+  void SetTextSize(Double_t) {}
+  void SetBorderSize(Int_t) {}
   void AddEntry(TObject*, const char*, const char* = "") {}
 };
 inline TCanvas*& gPadRef() { static TCanvas* p = new TCanvas; return p; }

@@ -8,11 +8,14 @@
 #define ROBAST_ROOTCOMPAT_H
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <ctime>
 #include <complex>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -785,6 +788,31 @@ struct TThread {
   static void Initialize() {}
 };
 
+// wall-clock / CPU timer (tutorials/multithread.C:32-35)
+class TStopwatch {
+  std::chrono::steady_clock::time_point fT0 = std::chrono::steady_clock::now();
+  std::clock_t fC0 = std::clock();
+  Double_t fReal = 0, fCpu = 0;
+  Bool_t fRunning = kFALSE;
+
+ public:
+  void Start(Bool_t reset = kTRUE) {
+    if (reset) fReal = fCpu = 0;
+    fT0 = std::chrono::steady_clock::now();
+    fC0 = std::clock();
+    fRunning = kTRUE;
+  }
+  void Stop() {
+    if (!fRunning) return;
+    fReal += std::chrono::duration<Double_t>(std::chrono::steady_clock::now() - fT0).count();
+    fCpu += Double_t(std::clock() - fC0) / CLOCKS_PER_SEC;
+    fRunning = kFALSE;
+  }
+  Double_t RealTime() { Stop(); return fReal; }
+  Double_t CpuTime() { Stop(); return fCpu; }
+  void Print(const char* = "") { Stop(); printf("Real time %.6f s, CP time %.3f s\n", fReal, fCpu); }
+};
+
 // ---------------------------------------------------------------------------- TGraph / TGraph2D
 struct TAxisStub {  // display-only axis handle
   void SetTitle(const char*) {}
@@ -831,7 +859,10 @@ class TGraph : public TNamed {
   }
   void SetLineStyle(Int_t) {}
   void SetMarkerStyle(Int_t) {}
+  void SetMarkerColor(Int_t) {}
+  void SetMarkerSize(Double_t) {}
   void SetLineColor(Int_t) {}
+  void SetLineWidth(Int_t) {}
   TAxisStub* GetXaxis() { return &fAxis; }
   TAxisStub* GetYaxis() { return &fAxis; }
   void SetTitle(const char* t) override { TNamed::SetTitle(t); }
@@ -960,6 +991,8 @@ class TAxis {
   void SetTitle(const char*) {}
   void SetLimits(Double_t, Double_t) {}
   void SetRangeUser(Double_t, Double_t) {}
+  void SetNdivisions(Int_t, Bool_t = kTRUE) {}
+  void SetTitleOffset(Double_t = 1.) {}
 };
 
 class TH1 : public TNamed {
@@ -971,6 +1004,8 @@ class TH1 : public TNamed {
   TH1(const char* n, const char* t) : TNamed(n, t) {}
   Double_t GetEntries() const { return fEntries; }
   void SetLineColor(Int_t) {}
+  void SetMaximum(Double_t = -1111) {}
+  void SetMinimum(Double_t = -1111) {}
 };
 
 class TH1D : public TH1 {
@@ -1054,6 +1089,12 @@ class TH2 : public TH1 {
     for (Int_t j = 1; j <= fYaxis.fN; j++)
       for (Int_t i = 1; i <= fXaxis.fN; i++) s += fC[GetBin(i, j)];
     return s;
+  }
+  // drawing is out of scope; with ROBAST_DRAW_SUMMARY set, Draw() prints what the plot would have shown
+  void Draw(Option_t* = "") override {
+    if (getenv("ROBAST_DRAW_SUMMARY"))
+      printf("TH2 name=\"%s\" title=\"%s\" entries=%.0f inrange=%.0f meanx=%.9g meany=%.9g rmsx=%.9g rmsy=%.9g\n", GetName(), GetTitle(), fEntries, fSw,
+             GetMean(1), GetMean(2), GetStdDev(1), GetStdDev(2));
   }
   // TH2::Interpolate: bilinear between the four surrounding bin centres
   Double_t Interpolate(Double_t x, Double_t y) const {

@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(co
   // a ray shot from outside the top volume first has to enter it (no daughters to examine, no interaction
   // besides AddPoint): take that step here instead of spending a whole bounce launch on it
   if (init && r.cur < 0 && r.status == RBG_RUN) trace_step<K>(sc, tp, r, g);
-  __syncthreads();
   const bool run = r.status == RBG_RUN;
   const bool push = (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0;
   RayReg nav = r;
@@ -128,9 +127,8 @@ __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(co
   st.o.nvis = -1;
   if (run) nb_begin<K>(sc, nav, push, st);
   bool overflow = false;
-  while (true) {
-    const bool want = run && st.mode == 1 && st.bvh_next >= 0;
-    if (!__syncthreads_or(want)) break;
+  bool want = run && st.mode == 1 && st.bvh_next >= 0;
+  do {  // one pass unless some ray touches more than RB_MAXVIS daughter boxes
     int first = 0;
     if (want) {
       if (st.o.nvis >= RB_MAXVIS) { st.o.nvis = 0; overflow = true; }
@@ -140,7 +138,8 @@ __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(co
     __syncthreads();  // all warps enter the shape code together; inside the phase they run unsynchronised
     if (want)
       for (int k = first; k < st.o.nvis; k++) nb_eval<K>(sc, nav, st, k);
-  }
+    want = run && st.mode == 1 && st.bvh_next >= 0;
+  } while (__syncthreads_or(want));
   if (overflow) st.o.nvis = -1;
   if (run) nb_finish<K>(sc, nav, st);
   __syncthreads();

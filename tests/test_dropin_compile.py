@@ -7,7 +7,10 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/tutorials"
-MACROS = ["SimpleParabolicTelescope", "DaviesCotton", "SchwarzschildCouder", "HexWinstonCone", "SchmidtCassegrain"]
+MACROS = ["SimpleParabolicTelescope", "DaviesCotton", "SchwarzschildCouder", "HexWinstonCone", "SchmidtCassegrain",
+          "HESS1", "MST", "HexOkumuraCone", "AbsLengthTest", "EdmundOptics", "multilayer", "multithread"]
+# not covered: AshraOptics.C (TGeoArb8 / TGeoXtru), CORSIKA.C (ACorsikaIACTFile), Optimize.C / optimize_multilayer.C (MINUIT),
+# SellmeierFit.C (TFile / TF1 fitting)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not available (GPU box)")
