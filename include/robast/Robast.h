@@ -963,27 +963,18 @@ class ARayArray : public TObject {
     std::vector<Double_t> x0, y0, z0, t0, x, y, z, t, dx, dy, dz, lambda;
     std::vector<int32_t> status, npoints, last_node;
     std::vector<ARay*> obj;  // lazily created ARay views (owned)
-    // optional polyline record, ray-major: ray i owns hpts[4*hist_depth*i ...] (x,y,z,t per point), hnode[hist_depth*i ...]
-    // and hcount[i] valid points (0 = none)
-    int32_t hist_depth = 0;
+    // optional polyline record, packed: ray i owns points hoff[i] .. hoff[i+1] of hpts (x,y,z,t per point) and hnode
+    // (hoff is empty while no trace has recorded anything)
+    std::vector<int64_t> hoff;
     std::vector<Double_t> hpts;
-    std::vector<int32_t> hnode, hcount;
+    std::vector<int32_t> hnode;
     size_t size() const { return x.size(); }
-    void EnsureHistory(int32_t depth) {  // (re)shape the record to `depth` points per ray, keeping what fits
-      if (depth == hist_depth && hcount.size() == size()) return;
-      std::vector<Double_t> np((size_t)4 * depth * size(), 0.);
-      std::vector<int32_t> nn((size_t)depth * size(), -1), nc(size(), 0);
-      for (size_t i = 0; i < hcount.size() && i < size(); i++) {
-        int32_t c = std::min(hcount[i], depth);
-        nc[i] = c;
-        for (int32_t k = 0; k < c; k++) {
-          for (int a = 0; a < 4; a++) np[4 * ((size_t)depth * i + k) + a] = hpts[4 * ((size_t)hist_depth * i + k) + a];
-          nn[(size_t)depth * i + k] = hnode[(size_t)hist_depth * i + k];
-        }
-      }
-      hpts.swap(np); hnode.swap(nn); hcount.swap(nc);
-      hist_depth = depth;
+    bool HasHistory() const { return !hoff.empty(); }
+    void EnsureHistoryOffsets() {  // rays appended since the last trace own empty records
+      if (hoff.empty()) hoff.push_back(0);
+      while (hoff.size() < size() + 1) hoff.push_back(hoff.back());
     }
+    int32_t HistCount(size_t i) const { return hoff.size() > i + 1 ? (int32_t)(hoff[i + 1] - hoff[i]) : 0; }
   };
 
  private:
@@ -1001,8 +992,7 @@ class ARayArray : public TObject {
       const char* nn = nullptr;
       if (fNodeNames && fT.last_node[i] >= 0 && fT.last_node[i] < (int32_t)fNodeNames->size()) nn = (*fNodeNames)[fT.last_node[i]].c_str();
       fT.obj[i]->SetTraced(last, dir, fT.status[i], fT.npoints[i], nn);
-      if (fT.hist_depth > 0 && i < fT.hcount.size() && fT.hcount[i] > 0)
-        fT.obj[i]->SetHistory(&fT.hpts[4 * (size_t)fT.hist_depth * i], fT.hcount[i], &fT.hnode[(size_t)fT.hist_depth * i], fNodeNames.get());
+      if (fT.HistCount(i) > 0) fT.obj[i]->SetHistory(&fT.hpts[4 * (size_t)fT.hoff[i]], fT.HistCount(i), &fT.hnode[(size_t)fT.hoff[i]], fNodeNames.get());
       fBucket[fT.status[i]].Add(fT.obj[i]);
     }
     fViewsValid = kTRUE;
@@ -1036,11 +1026,7 @@ class ARayArray : public TObject {
     fT.dx.push_back(dx); fT.dy.push_back(dy); fT.dz.push_back(dz); fT.lambda.push_back(lambda);
     fT.status.push_back(RBG_RUN); fT.npoints.push_back(1); fT.last_node.push_back(-1);
     fT.obj.push_back(nullptr);
-    if (fT.hist_depth > 0) {
-      fT.hpts.resize(4 * (size_t)fT.hist_depth * fT.size(), 0.);
-      fT.hnode.resize((size_t)fT.hist_depth * fT.size(), -1);
-      fT.hcount.resize(fT.size(), 0);
-    }
+    if (fT.HasHistory()) fT.EnsureHistoryOffsets();
     fViewsValid = kFALSE;
   }
   void Reserve(size_t n) {
@@ -1053,15 +1039,15 @@ class ARayArray : public TObject {
     if (!array) return;
     Table& o = array->fT;
     static const int order[6] = {RBG_ABSORB, RBG_EXIT, RBG_FOCUSED, RBG_RUN, RBG_STOP, RBG_SUSPEND};
-    const int32_t depth = std::max(fT.hist_depth, o.hist_depth);
-    if (depth > 0) { fT.EnsureHistory(depth); o.EnsureHistory(depth); }
+    const bool hist = fT.HasHistory() || o.HasHistory();
+    if (hist) { fT.EnsureHistoryOffsets(); o.EnsureHistoryOffsets(); }
     for (int s : order)
       for (size_t i = 0; i < o.size(); i++) {
         if (o.status[i] != s) continue;
-        if (depth > 0) {
-          fT.hpts.insert(fT.hpts.end(), o.hpts.begin() + 4 * (size_t)depth * i, o.hpts.begin() + 4 * (size_t)depth * (i + 1));
-          fT.hnode.insert(fT.hnode.end(), o.hnode.begin() + (size_t)depth * i, o.hnode.begin() + (size_t)depth * (i + 1));
-          fT.hcount.push_back(o.hcount[i]);
+        if (hist) {
+          fT.hpts.insert(fT.hpts.end(), o.hpts.begin() + 4 * o.hoff[i], o.hpts.begin() + 4 * o.hoff[i + 1]);
+          fT.hnode.insert(fT.hnode.end(), o.hnode.begin() + o.hoff[i], o.hnode.begin() + o.hoff[i + 1]);
+          fT.hoff.push_back(fT.hoff.back() + (o.hoff[i + 1] - o.hoff[i]));
         }
         fT.x0.push_back(o.x0[i]); fT.y0.push_back(o.y0[i]); fT.z0.push_back(o.z0[i]); fT.t0.push_back(o.t0[i]);
         fT.x.push_back(o.x[i]); fT.y.push_back(o.y[i]); fT.z.push_back(o.z[i]); fT.t.push_back(o.t[i]);
@@ -1543,6 +1529,8 @@ class AOpticsManager : public TGeoManager {
   ULong64_t fRayCounter = 0;  // global ray index so that successive calls use fresh random streams
   Int_t fDevice = 0;
   Int_t fHistoryDepth = -1;  // < 0: automatic (see SetHistoryDepth)
+  std::vector<Double_t> fHistBuf;     // receive buffers of rbg_trace_history, reused across calls
+  std::vector<int32_t> fHistNodeBuf;
   rbg_scene* fScene = nullptr;
   std::string fSceneKey;
   std::shared_ptr<std::vector<std::string>> fNodeNames;
@@ -1669,35 +1657,47 @@ class AOpticsManager : public TGeoManager {
         for (int i = 0; i < rbg_scene_num_nodes(fScene); i++) fNodeNames->push_back(rbg_scene_node_name(fScene, i));
       }
       int32_t depth = fHistoryDepth >= 0 ? fHistoryDepth : (n < 262144 ? std::min<Int_t>(fLimit, 16) : 0);
-      std::vector<Double_t> hbuf;
-      std::vector<int32_t> hnbuf;
+      // receive buffers in the layout of rbg_history (point k of ray j at k*n + j); kept across calls, never cleared: only
+      // the entries k < npoints of each ray are read
       rbg_history hist;
       memset(&hist, 0, sizeof(hist));
       if (depth > 0) {
-        hbuf.resize((size_t)4 * depth * n);
-        hnbuf.assign((size_t)depth * n, -1);
+        if (fHistBuf.size() < (size_t)4 * depth * n) fHistBuf.resize((size_t)4 * depth * n);
+        if (fHistNodeBuf.size() < (size_t)depth * n) fHistNodeBuf.resize((size_t)depth * n);
         hist.max_points = depth;
-        hist.hx = hbuf.data(); hist.hy = hbuf.data() + (size_t)depth * n; hist.hz = hbuf.data() + (size_t)2 * depth * n;
-        hist.ht = hbuf.data() + (size_t)3 * depth * n;
-        hist.hnode = hnbuf.data();
+        hist.hx = fHistBuf.data(); hist.hy = fHistBuf.data() + (size_t)depth * n; hist.hz = fHistBuf.data() + (size_t)2 * depth * n;
+        hist.ht = fHistBuf.data() + (size_t)3 * depth * n;
+        hist.hnode = fHistNodeBuf.data();
       }
       rc = rbg_trace_history(fScene, &opts, &r, depth > 0 ? &hist : nullptr, nullptr);
       if (rc != RBG_OK) throw std::runtime_error(std::string("AOpticsManager::TraceNonSequential: ") + rbg_last_error());
-      if (depth > 0) {  // point-major device layout -> ray-major table rows
-        T.EnsureHistory(std::max(depth, T.hist_depth));
-        const int32_t D = T.hist_depth;
-        for (size_t j = 0; j < n; j++) {
-          size_t i = run[j];
-          int32_t c = std::min<int32_t>(icol[2][j], depth);
-          T.hcount[i] = c;
-          for (int32_t k = 0; k < c; k++) {
-            size_t src = (size_t)k * n + j, dst = (size_t)D * i + k;
-            T.hpts[4 * dst] = hist.hx[src]; T.hpts[4 * dst + 1] = hist.hy[src]; T.hpts[4 * dst + 2] = hist.hz[src]; T.hpts[4 * dst + 3] = hist.ht[src];
-            T.hnode[dst] = hist.hnode[src];
+      if (depth > 0 || T.HasHistory()) {  // rebuild the packed per-ray records: traced rays get their new polyline
+        T.EnsureHistoryOffsets();
+        std::vector<int64_t> traced(T.size(), -1);
+        for (size_t j = 0; j < n; j++) traced[run[j]] = (int64_t)j;
+        std::vector<int64_t> noff(T.size() + 1, 0);
+        for (size_t i = 0; i < T.size(); i++) {
+          int64_t c = traced[i] >= 0 ? (depth > 0 ? std::min<int32_t>(icol[2][traced[i]], depth) : 0) : T.hoff[i + 1] - T.hoff[i];
+          noff[i + 1] = noff[i] + c;
+        }
+        std::vector<Double_t> np((size_t)4 * noff.back());
+        std::vector<int32_t> nn((size_t)noff.back());
+        for (size_t i = 0; i < T.size(); i++) {
+          int64_t c = noff[i + 1] - noff[i], dst = noff[i];
+          if (traced[i] >= 0) {
+            size_t j = (size_t)traced[i];
+            for (int64_t k = 0; k < c; k++) {
+              size_t src = (size_t)k * n + j;
+              np[4 * (dst + k)] = hist.hx[src]; np[4 * (dst + k) + 1] = hist.hy[src]; np[4 * (dst + k) + 2] = hist.hz[src]; np[4 * (dst + k) + 3] = hist.ht[src];
+              nn[dst + k] = hist.hnode[src];
+            }
+          } else if (c > 0) {
+            memcpy(&np[4 * dst], &T.hpts[4 * T.hoff[i]], (size_t)c * 4 * sizeof(Double_t));
+            memcpy(&nn[dst], &T.hnode[T.hoff[i]], (size_t)c * sizeof(int32_t));
           }
         }
-      } else if (T.hist_depth > 0)
-        for (size_t j = 0; j < n; j++) T.hcount[run[j]] = 0;
+        T.hoff.swap(noff); T.hpts.swap(np); T.hnode.swap(nn);
+      }
     }
     if (!contiguous)
       for (size_t j = 0; j < n; j++) {
@@ -1722,7 +1722,7 @@ class AOpticsManager : public TGeoManager {
     const char* nn = (fNodeNames && T.last_node[0] >= 0) ? (*fNodeNames)[T.last_node[0]].c_str() : nullptr;
     const bool fresh = ray.GetNpoints() == 1;
     ray.SetTraced(last, dir, T.status[0], ray.GetNpoints() + T.npoints[0] - 1, nn);
-    if (fresh && T.hist_depth > 0 && T.hcount[0] > 0) ray.SetHistory(&T.hpts[0], T.hcount[0], &T.hnode[0], fNodeNames.get());
+    if (fresh && T.HistCount(0) > 0) ray.SetHistory(&T.hpts[0], T.HistCount(0), &T.hnode[0], fNodeNames.get());
   }
   void TraceNonSequential(ARay* ray) { TraceNonSequential(*ray); }
   void TraceNonSequential(TObjArray* array) {

@@ -748,6 +748,7 @@ template <bool CONE> RB_HD inline bool poly_slab(const double* P, int k, V3 p, V
     tin = rb_min(ta, tb);
     tout = rb_max(ta, tb);
   } else if (p.z < z0 || p.z > z1) return false;
+  if (tout <= 1e-11) return false;  // the whole slab lies behind the ray: no caller uses such an interval
   double s = (r1 - r0) / dz, base = r0 + (p.z - z0) * s;
   if constexpr (CONE) {
     // inside the frustum: f(t) = |xy(t)|^2 - (base + s dz t)^2 <= 0 on the nappe with non-negative radius, which is
@@ -792,17 +793,32 @@ template <bool CONE> RB_HD inline double poly_dist_out(const double* P, V3 p, V3
   }
   return best;
 }
+// From inside: leave slab after slab until the exit point is not inside a neighbouring slab any more.  The slabs are stacked
+// in z, so the slab that continues the path is the next non-degenerate one in the direction of d.z: the march is linear in
+// the number of slabs crossed (a Bezier profile has 100 sections).
 template <bool CONE> RB_HD inline double poly_dist_in(const double* P, V3 p, V3 d) {
   int nz = (int)P[3];
+  const double* sec = P + 4;
   double cur = 0;
-  for (int iter = 0; iter < nz; iter++) {
-    bool advanced = false;
-    for (int k = 0; k + 1 < nz; k++) {
-      double tin, tout;
-      if (!poly_slab<CONE>(P, k, p, d, tin, tout)) continue;
-      if (tin <= cur + 1e-9 && tout > cur + 1e-9) { cur = tout; advanced = true; }
-    }
-    if (!advanced) break;
+  // slabs whose z range holds the start point (two when it sits on a section plane)
+  int k = -1;
+  for (int j = 0; j + 1 < nz; j++) {
+    if (p.z < sec[3 * j] - 1e-9 || p.z > sec[3 * (j + 1)] + 1e-9) continue;
+    double tin, tout;
+    if (!poly_slab<CONE>(P, j, p, d, tin, tout)) continue;
+    if (tin <= cur + 1e-9 && tout > cur + 1e-9) { cur = tout; k = j; }
+  }
+  if (k < 0) return cur;
+  const int dir = d.z > 0 ? 1 : (d.z < 0 ? -1 : 0);
+  while (dir != 0) {
+    int j = k + dir;
+    while (j >= 0 && j + 1 < nz && sec[3 * (j + 1)] - sec[3 * j] < 1E-8) j += dir;  // radius steps have no volume
+    if (j < 0 || j + 1 >= nz) break;
+    double tin, tout;
+    if (!poly_slab<CONE>(P, j, p, d, tin, tout)) break;
+    if (!(tin <= cur + 1e-9 && tout > cur + 1e-9)) break;
+    cur = tout;
+    k = j;
   }
   return cur;
 }

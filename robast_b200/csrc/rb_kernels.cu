@@ -245,8 +245,21 @@ __global__ void k_sortkey(long long n, const double* __restrict__ x, const doubl
   if ((threadIdx.x & 31) == 0 && m && coherent_pairs) atomicAdd(coherent_pairs, (unsigned long long)__popc(m));
 }
 
+// largest npoints of a batch, written to pinned host memory (how many rows of a polyline record hold data)
+__global__ void k_max_npoints(const int32_t* __restrict__ np, long long n, int32_t* out) {
+  int m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = max(m, np[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 // copies a device counter into pinned (UVA-mapped) host memory with a plain store: no copy-engine queueing
 __global__ void k_publish(const unsigned long long* d, unsigned long long* h) {
+  *h = *d;
+  __threadfence_system();
+}
+
+__global__ void k_publish32(const int32_t* d, int32_t* h) {
   *h = *d;
   __threadfence_system();
 }
@@ -450,6 +463,8 @@ struct rbg_scene {
   float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};  // bounding box of the top volume's daughters
   bool has_root = false;
   int top_daughters = 0;
+  void* pin = nullptr;  // pinned host staging of the small-batch path
+  size_t pin_bytes = 0;
 };
 
 template <class T> static const T* upload(rbg_scene* s, const std::vector<T>& v) {
@@ -477,6 +492,7 @@ static void scene_free(rbg_scene* s) {
   if (s->d_count) cudaFree(s->d_count);
   if (s->h_count) cudaFreeHost(s->h_count);
   if (s->h_pairs) cudaFreeHost(s->h_pairs);
+  if (s->pin) cudaFreeHost(s->pin);
   delete s;
 }
 
@@ -786,6 +802,80 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
       }
       if (o->steps_per_launch >= 0 && hpts == 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
       trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count, s->h_pairs);
+      return;
+    }
+    // small batches (the tutorial / MINUIT-loop regime, thousands of calls of 1e3..1e5 rays): latency matters, not bandwidth.
+    // Inputs are packed into one pinned staging block (1 H2D), results come back as one block (1 D2H), and of a polyline
+    // record only the rows that hold data are fetched.  18 small pageable copies would cost more than the trace itself.
+    if (rays->n < 262144) {
+      const long long n = rays->n;
+      if (!s->streams[0]) CK(cudaStreamCreateWithFlags(&s->streams[0], cudaStreamNonBlocking));
+      cudaStream_t st = s->streams[0];
+      const size_t in_b = (size_t)n * 64, out_b = (size_t)n * 68, hist_b = (size_t)n * hpts * 36;
+      const size_t scr = o->steps_per_launch > 0 ? wavefront_scratch_bytes(n) : 0;
+      const size_t dev_b = in_b + out_b + 512 + scr + hist_b + 1024;
+      if (s->stage_bytes[0] < dev_b) {
+        if (s->stage[0]) CK(cudaFree(s->stage[0]));
+        s->stage[0] = nullptr;
+        s->stage_bytes[0] = 0;
+        CK(cudaMalloc(&s->stage[0], dev_b));
+        s->stage_bytes[0] = dev_b;
+      }
+      const size_t pin_b = in_b + out_b + hist_b + 256;
+      if (s->pin_bytes < pin_b) {
+        if (s->pin) CK(cudaFreeHost(s->pin));
+        s->pin = nullptr;
+        s->pin_bytes = 0;
+        CK(cudaMallocHost(&s->pin, pin_b + pin_b / 2));
+        s->pin_bytes = pin_b + pin_b / 2;
+      }
+      char* base = (char*)s->stage[0];
+      char* pin = (char*)s->pin;
+      const double* hin[8] = {rays->x, rays->y, rays->z, rays->t, rays->dx, rays->dy, rays->dz, rays->lambda};
+      double* hout[7] = {rays->ox, rays->oy, rays->oz, rays->ot, rays->odx, rays->ody, rays->odz};
+      int32_t* hiout[3] = {rays->status, rays->last_node, rays->npoints};
+      for (int a = 0; a < 8; a++) memcpy(pin + (size_t)a * n * 8, hin[a], (size_t)n * 8);
+      CK(cudaMemcpyAsync(base, pin, in_b, cudaMemcpyHostToDevice, st));
+      DRays R;
+      double* din = (double*)base;
+      double* dout = (double*)(base + in_b);
+      int32_t* diout = (int32_t*)(base + in_b + (size_t)n * 56);
+      R.x = din; R.y = din + n; R.z = din + 2 * n; R.t = din + 3 * n; R.dx = din + 4 * n; R.dy = din + 5 * n; R.dz = din + 6 * n; R.lambda = din + 7 * n;
+      R.ox = dout; R.oy = dout + n; R.oz = dout + 2 * n; R.ot = dout + 3 * n; R.odx = dout + 4 * n; R.ody = dout + 5 * n; R.odz = dout + 6 * n;
+      R.status = diout; R.last_node = diout + n; R.npoints = diout + 2 * n;
+      R.cur = nullptr; R.ndraw = nullptr;
+      memset(&R.hist, 0, sizeof(R.hist));
+      char* scratch = base + ((in_b + out_b + 511) & ~size_t(255));
+      char* hb = scratch + ((scr + 255) & ~size_t(255));
+      if (hpts > 0) {
+        size_t plane = (size_t)n * hpts * 8;
+        R.hist.x = (double*)hb; R.hist.y = (double*)(hb + plane); R.hist.z = (double*)(hb + 2 * plane); R.hist.t = (double*)(hb + 3 * plane);
+        R.hist.node = (int32_t*)(hb + 4 * plane);
+        R.hist.stride = n;
+        R.hist.max_points = hpts;
+      }
+      trace_device(s, o, R, n, o->ray_id_offset, st, scratch, s->d_count, s->h_count, s->h_pairs);
+      if (hpts > 0) {
+        CK(cudaMemsetAsync(s->d_count + 1, 0, 4, st));
+        k_max_npoints<<<(unsigned)std::min<long long>((n + 255) / 256, 296), 256, 0, st>>>(R.npoints, n, s->d_count + 1);
+        k_publish32<<<1, 1, 0, st>>>(s->d_count + 1, s->h_count + 1);
+        g_launches += 2;
+      }
+      CK(cudaMemcpyAsync(pin + in_b, dout, out_b, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (int a = 0; a < 7; a++) memcpy(hout[a], pin + in_b + (size_t)a * n * 8, (size_t)n * 8);
+      for (int a = 0; a < 3; a++) memcpy(hiout[a], pin + in_b + (size_t)n * 56 + (size_t)a * n * 4, (size_t)n * 4);
+      if (hpts > 0) {
+        const int rows = std::min<int>(std::max<int>(s->h_count[1], 1), hpts);  // rows k < max npoints hold data
+        char* ph = pin + in_b + out_b;
+        size_t plane = (size_t)n * hpts * 8, used = (size_t)n * rows * 8;
+        for (int a = 0; a < 4; a++) CK(cudaMemcpyAsync(ph + a * used, hb + a * plane, used, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ph + 4 * used, hb + 4 * plane, used / 2, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        double* hd[4] = {hist->hx, hist->hy, hist->hz, hist->ht};
+        for (int a = 0; a < 4; a++) memcpy(hd[a], ph + a * used, used);
+        memcpy(hist->hnode, ph + 4 * used, used / 2);
+      }
       return;
     }
     // host buffers: chunked H2D -> trace -> D2H.  Up to RB_HOST_STREAMS chunks are in flight, each on its own stream
