@@ -32,7 +32,9 @@
 #define RB_PH_QE 16u         /* AFocalSurface QE graphs */
 #define RB_PH_MIRROR_TABLE 32u /* AMirror reflectance != constant */
 #define RB_PH_ALL 0xffu
-template <int D, unsigned S, unsigned P, int MINB = 1, int STEP_THREADS = 512, int STEP_MINB = 2> struct TraceCfg {
+// TAG: distinguishes experiment instantiations whose other parameters coincide (same type = same kernel symbol across
+// translation units, whatever macros the unit was compiled with)
+template <int D, unsigned S, unsigned P, int MINB = 1, int STEP_THREADS = 512, int STEP_MINB = 2, int TAG = 0> struct TraceCfg {
   static constexpr int depth = D;
   static constexpr unsigned shapes = S;
   static constexpr unsigned phys = P;
@@ -1620,7 +1622,9 @@ template <class K> RB_HD inline int search_node(const DScene& sc, int node, V3 q
   }
 }
 
+#ifndef RB_MAXVIS
 #define RB_MAXVIS 12
+#endif
 struct StepOut {
   double step;
   int next;        // node now containing the point (-1 outside)

@@ -498,8 +498,9 @@ static void scene_free(rbg_scene* s) {
 
 // ------------------------------------------------------------------------------------------------ host: trace driver
 #ifdef RB_EXPERIMENTS
-extern const rb_variant* const rb_x_variants[];
-extern const rb_variant* const rb_xi_variants[];
+// experiment translation units (make EXP=1) register their instantiations from static initialisers
+static std::vector<const rb_variant*>& x_variants() { static std::vector<const rb_variant*> v; return v; }
+int rb_register_x_variant(const rb_variant* v) { x_variants().push_back(v); return 0; }
 #endif
 static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys) {
   const char* force = getenv("RB_FORCE_GENERIC");
@@ -509,10 +510,8 @@ static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys)
     for (const rb_variant* v : rb_variants)
       if (!strcmp(v->name, want) && v->depth >= depth && !(shapes & ~v->shapes) && !(phys & ~v->phys)) return v;
 #ifdef RB_EXPERIMENTS
-    for (const rb_variant* const* pv = rb_x_variants; *pv; pv++)
-      if (!strcmp((*pv)->name, want) && (*pv)->depth >= depth && !(shapes & ~(*pv)->shapes) && !(phys & ~(*pv)->phys)) return *pv;
-    for (const rb_variant* const* pv = rb_xi_variants; *pv; pv++)
-      if (!strcmp((*pv)->name, want) && (*pv)->depth >= depth && !(shapes & ~(*pv)->shapes) && !(phys & ~(*pv)->phys)) return *pv;
+    for (const rb_variant* v : x_variants())
+      if (!strcmp(v->name, want) && v->depth >= depth && !(shapes & ~v->shapes) && !(phys & ~v->phys)) return v;
 #endif
   }
   for (const rb_variant* v : rb_variants) {

@@ -16,6 +16,11 @@ struct DRays {
 };
 
 #define TRACE_THREADS 128
+// k_step phase barriers: 1 = before the candidate shapes, 2 = barrier + vote around the candidate loop (re-synchronises the
+// batches of rays with more than RB_MAXVIS candidates), 4 = before the interaction
+#ifndef RB_STEP_BARRIERS
+#define RB_STEP_BARRIERS 7
+#endif
 
 // Ray state streams through once per launch: mark it evict-first (ld/st .cs) so that it does not push the kernels'
 // local-memory working set (spill slots and the call stack, ~100 MB over all resident threads) out of the 126 MB L2.
@@ -104,6 +109,49 @@ __global__ void __launch_bounds__(TRACE_THREADS, K::min_blocks) k_trace(const __
 // separated by barriers so that all warps of a block run the same code region at the same time: the per-SM
 // instruction cache is then shared instead of thrashed (profiles/r1d: icc hit rate 58 %, L1.5 saturated by
 // instruction requests without this).  Idle lanes of the last block shadow the last ray and store nothing.
+// Split ray load for k_step: the navigation phases need only the point, the direction, the node and the on-boundary bit;
+// time, wavelength, counters and the segment start are read when the interaction is evaluated, so that they are not
+// live (= spilled around every non-inlined shape call) during navigation.
+template <class K> __device__ inline void load_nav(const DScene& sc, const DRays& R, long long idx, int from_out, RayReg& r) {
+  if (!from_out) {
+    r.p = v3(rb_ldcs(R.x + idx), rb_ldcs(R.y + idx), rb_ldcs(R.z + idx));
+    V3 d = v3(rb_ldcs(R.dx + idx), rb_ldcs(R.dy + idx), rb_ldcs(R.dz + idx));
+    double mag = sqrt(dot(d, d));
+    r.d = mag > 0 ? (1. / mag) * d : d;  // ARay::SetDirection normalises (src/ARay.cxx:210-223)
+    r.status = RBG_RUN;
+    r.on_boundary = 0;
+    r.cur = locate_start<K>(sc, r.p);
+  } else {
+    r.p = v3(rb_ldcs(R.ox + idx), rb_ldcs(R.oy + idx), rb_ldcs(R.oz + idx));
+    r.d = v3(rb_ldcs(R.odx + idx), rb_ldcs(R.ody + idx), rb_ldcs(R.odz + idx));
+    r.status = R.status[idx];
+    r.on_boundary = R.ndraw[idx] >> 31;
+    r.cur = rb_ldcs(R.cur + idx);
+  }
+}
+__device__ inline void load_rest(const DTraceParams& tp, const DRays& R, long long idx, int from_out, RayReg& r, Philox& g) {
+  r.lambda = rb_ldcs(R.lambda + idx);
+  if (!from_out) {
+    r.p = v3(rb_ldcs(R.x + idx), rb_ldcs(R.y + idx), rb_ldcs(R.z + idx));
+    r.t = rb_ldcs(R.t + idx);
+    r.npoints = 1;
+    r.last_node = -1;
+    r.ndraw = 0;
+  } else {
+    r.p = v3(rb_ldcs(R.ox + idx), rb_ldcs(R.oy + idx), rb_ldcs(R.oz + idx));
+    r.t = rb_ldcs(R.ot + idx);
+    r.npoints = rb_ldcs(R.npoints + idx);
+    r.last_node = rb_ldcs(R.last_node + idx);
+    r.ndraw = rb_ldcs(R.ndraw + idx) & 0x7fffffffu;
+  }
+  unsigned long long id = tp.ray_id_offset + (unsigned long long)idx;
+  g.k0 = (uint32_t)tp.seed;
+  g.k1 = (uint32_t)(tp.seed >> 32);
+  g.id0 = (uint32_t)id;
+  g.id1 = (uint32_t)(id >> 32);
+  g.ndraw = r.ndraw;
+}
+
 template <class K>
 __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
                                                                               const __grid_constant__ DRays R, const int32_t* __restrict__ live,
@@ -112,22 +160,35 @@ __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(co
   const bool active = i < n;
   if (!active) i = n - 1;
   long long idx = live ? (long long)live[i] : i;
-  RayReg r;
-  Philox g;
-  load_ray<K>(sc, tp, R, idx, init, r, g);
+  int from_out = !init;
+  RayReg nav;
+  load_nav<K>(sc, R, idx, from_out, nav);
   // a ray shot from outside the top volume first has to enter it (no daughters to examine, no interaction
   // besides AddPoint): take that step here instead of spending a whole bounce launch on it
-  if (init && r.cur < 0 && r.status == RBG_RUN) trace_step<K>(sc, tp, r, g);
-  const bool run = r.status == RBG_RUN;
+  if (active && init && nav.cur < 0) {
+    RayReg r = nav;
+    Philox g;
+    load_rest(tp, R, idx, 0, r, g);
+    r.p = nav.p;
+    trace_step<K>(sc, tp, r, g);
+    store_ray(R, idx, r, g, 1);
+    nav.p = r.p; nav.d = r.d; nav.cur = r.cur; nav.status = r.status; nav.on_boundary = r.on_boundary;
+    from_out = 1;
+  }
+  const bool run = active && nav.status == RBG_RUN;
   const bool push = (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0;
-  RayReg nav = r;
+  const int cur0 = nav.cur;
   NavStep st;
   st.mode = 0;
   st.bvh_next = -1;
   st.o.nvis = -1;
   if (run) nb_begin<K>(sc, nav, push, st);
+#if (RB_STEP_BARRIERS & 16)
+  __syncthreads();
+#endif
   bool overflow = false;
   bool want = run && st.mode == 1 && st.bvh_next >= 0;
+#if (RB_STEP_BARRIERS & 2)
   do {  // one pass unless some ray touches more than RB_MAXVIS daughter boxes
     int first = 0;
     if (want) {
@@ -136,15 +197,52 @@ __global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(co
       nb_collect<K>(sc, nav, st);
     }
     __syncthreads();  // all warps enter the shape code together; inside the phase they run unsynchronised
+#if (RB_STEP_BARRIERS & 8)
+    for (int k = first; __syncthreads_or(want && k < st.o.nvis); k++)
+      if (want && k < st.o.nvis) nb_eval<K>(sc, nav, st, k);
+#else
     if (want)
       for (int k = first; k < st.o.nvis; k++) nb_eval<K>(sc, nav, st, k);
+#endif
     want = run && st.mode == 1 && st.bvh_next >= 0;
   } while (__syncthreads_or(want));
+#else
+  if (want) nb_collect<K>(sc, nav, st);
+#if (RB_STEP_BARRIERS & 1)
+  __syncthreads();  // all warps enter the shape code together; inside the phase they run unsynchronised
+#endif
+  if (want) {
+    int first = 0;
+    while (true) {
+      for (int k = first; k < st.o.nvis; k++) nb_eval<K>(sc, nav, st, k);
+      if (st.bvh_next < 0) break;  // rare: more than RB_MAXVIS daughter boxes touched, continue the walk in batches
+      st.o.nvis = 0;
+      overflow = true;
+      nb_collect<K>(sc, nav, st);
+    }
+  }
+#endif
   if (overflow) st.o.nvis = -1;
   if (run) nb_finish<K>(sc, nav, st);
+#if (RB_STEP_BARRIERS & 4)
   __syncthreads();
-  if (run) trace_shade<K>(sc, tp, r, nav, st.o, g);
-  if (active) store_ray(R, idx, r, g, 1);
+#endif
+  if (run) {
+    RayReg r;
+    Philox g;
+    load_rest(tp, R, idx, from_out, r, g);
+    r.d = nav.d;
+    r.cur = cur0;
+    r.status = RBG_RUN;
+    r.on_boundary = 0;
+    trace_shade<K>(sc, tp, r, nav, st.o, g);
+    store_ray(R, idx, r, g, 1);
+  } else if (active && !from_out) {  // a first launch always leaves a complete record (not reached: every ray starts running)
+    RayReg r = nav;
+    Philox g;
+    load_rest(tp, R, idx, 0, r, g);
+    store_ray(R, idx, r, g, 1);
+  }
 }
 
 // Launch entry points per compiled variant (each variant in its own translation unit so they build in parallel).
@@ -157,8 +255,11 @@ struct rb_variant {
   rb_launch_fn launch;       // k_trace: per-ray loop
   rb_launch_fn launch_step;  // k_step : one lock-step boundary step (wavefront)
 };
+#ifndef RB_X_TAG
+#define RB_X_TAG 0
+#endif
 #define RB_DEFINE_TRACE_VARIANT(NAME, D, S, P, MB, STH, SMB)                                                                          \
-  typedef TraceCfg<D, S, P, MB, STH, SMB> rb_cfg_##NAME;                                                                              \
+  typedef TraceCfg<D, S, P, MB, STH, SMB, RB_X_TAG> rb_cfg_##NAME;                                                                              \
   int rb_launch_trace_##NAME(const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init,   \
                              int keep, cudaStream_t st) {                                                                            \
     long long blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;                                                                      \
@@ -172,4 +273,9 @@ struct rb_variant {
     return (int)cudaGetLastError();                                                                                                  \
   }                                                                                                                                  \
   extern const rb_variant rb_variant_##NAME = {#NAME, D, S, P, rb_launch_trace_##NAME, rb_launch_step_##NAME};
+// experiment instantiations (make EXP=1) add themselves to the RB_VARIANT=<name> lookup
+int rb_register_x_variant(const rb_variant* v);
+#define RB_DEFINE_X_VARIANT(NAME, D, S, P, MB, STH, SMB) \
+  RB_DEFINE_TRACE_VARIANT(NAME, D, S, P, MB, STH, SMB)   \
+  static int rb_reg_##NAME = rb_register_x_variant(&rb_variant_##NAME);
 #endif
