@@ -510,6 +510,55 @@ inline void MakePointToPointBBox(const char* name, const TVector3& v1, const TVe
   (*combi)->SetName(Form("%scombi", name));
   (*combi)->RegisterYourself();
 }
+// reference src/AGeoUtil.cxx:47-82: an Arb8 prism from the four corners of its top face (clockwise seen from the top) and the
+// corner of the bottom face below the first one
+inline TGeoRotation AxisRotation(Double_t theta, Double_t phi) {  // TGeoRotation("",0,0,phi+90) * TGeoRotation("",0,theta,0), angles in rad
+  TGeoRotation rot("", 0, 0, phi * TMath::RadToDeg() + 90), tilt("", 0, theta * TMath::RadToDeg(), 0);
+  rot.MultiplyBy(&tilt, kTRUE);
+  return rot;
+}
+inline void MakeArb8FromPoints(const char* name, const TVector3& v1, const TVector3& v2, const TVector3& v3, const TVector3& v4, const TVector3& v5,
+                               TGeoArb8** arb8, TGeoCombiTrans** combi) {
+  TVector3 normal = v1 - v5;
+  Double_t dZ = normal.Mag() / 2., theta = normal.Theta(), phi = normal.Phi();
+  TVector3 v[4] = {TVector3(0, 0, 0), v2 - v1, v3 - v1, v4 - v1};
+  Double_t vertices[16] = {0};
+  for (Int_t i = 1; i <= 3; ++i) {
+    v[i].RotateZ(-phi - TMath::Pi() / 2.);
+    v[i].RotateX(-theta);
+    vertices[2 * i] = vertices[2 * i + 8] = v[i].X();
+    vertices[2 * i + 1] = vertices[2 * i + 9] = v[i].Y();
+  }
+  *arb8 = new TGeoArb8(name, dZ, vertices);
+  TGeoTranslation tr(v5.X() + normal.X() / 2., v5.Y() + normal.Y() / 2., v5.Z() + normal.Z() / 2.);
+  *combi = new TGeoCombiTrans(tr, AxisRotation(theta, phi));
+  (*combi)->SetName(Form("%scombi", name));
+  (*combi)->RegisterYourself();
+}
+// reference src/AGeoUtil.cxx:84-125: an Xtru prism from the corners of its top face and the bottom corner below the first one
+inline void MakeXtruFromPoints(const char* name, const std::vector<TVector3>& vecs, TGeoXtru** xtru, TGeoCombiTrans** combi) {
+  std::size_t nvert = vecs.size() - 1;
+  TVector3 normal = vecs[0] - vecs[nvert];
+  Double_t dZ = normal.Mag() / 2., theta = normal.Theta(), phi = normal.Phi();
+  std::vector<Double_t> x(nvert), y(nvert);
+  for (std::size_t i = 0; i < nvert; ++i) {
+    TVector3 v = vecs[i] - vecs[0];
+    v.RotateZ(-phi - TMath::Pi() / 2.);
+    v.RotateX(-theta);
+    x[i] = v.X();
+    y[i] = v.Y();
+  }
+  *xtru = new TGeoXtru(2);
+  (*xtru)->SetName(name);
+  (*xtru)->DefinePolygon((Int_t)nvert, x.data(), y.data());
+  (*xtru)->DefineSection(0, -dZ);
+  (*xtru)->DefineSection(1, +dZ);
+  TVector3 shift = vecs[0] - normal * .5;
+  TGeoTranslation tr(shift.X(), shift.Y(), shift.Z());
+  *combi = new TGeoCombiTrans(tr, AxisRotation(theta, phi));
+  (*combi)->SetName(Form("%scombi", name));
+  (*combi)->RegisterYourself();
+}
 // reference src/AGeoUtil.cxx:198-308: radius and centre of the circle containing `fraction` of the histogram (D80 for
 // fraction = 0.8).  Runs on the GPU (rbg_containment_radius_host: one block, the reference's search step for step).
 inline void ContainmentRadius(TH2* h2, Double_t fraction, Double_t& r, Double_t& x, Double_t& y, Int_t device = 0) {
@@ -920,9 +969,39 @@ class TPolyLine3D : public TObject {
   void SetLineWidth(Int_t) {}
 };
 inline TPolyLine3D* ARay::MakePolyLine3D() const { return new TPolyLine3D; }
+// display stub of the OpenGL viewer (tutorials/AshraOptics.C:194-196)
+class TGLViewer : public TObject {
+ public:
+  enum ECameraType { kCameraPerspXOZ, kCameraPerspYOZ, kCameraPerspXOY, kCameraOrthoXOY, kCameraOrthoXOZ, kCameraOrthoZOY };
+  void SetPerspectiveCamera(ECameraType, Double_t, Double_t, Double_t*, Double_t, Double_t) {}
+  void SetPerspectiveCamera(ECameraType, Double_t, Double_t, int, Double_t, Double_t) {}
+};
+// TNtuple of doubles kept in memory (tutorials/AshraOptics.C:143,179): rows of the variables named in the constructor
+class TNtuple : public TNamed {
+  Int_t fNvar = 0;
+  std::vector<Float_t> fRows;
+
+ public:
+  TNtuple(const char* name, const char* title, const char* varlist) : TNamed(name, title) {
+    fNvar = 1;
+    for (const char* c = varlist; c && *c; c++) fNvar += *c == ':';
+  }
+  Int_t Fill(Float_t x0, Float_t x1 = 0, Float_t x2 = 0, Float_t x3 = 0, Float_t x4 = 0, Float_t x5 = 0) {
+    const Float_t v[6] = {x0, x1, x2, x3, x4, x5};
+    for (Int_t i = 0; i < fNvar && i < 6; i++) fRows.push_back(v[i]);
+    return fNvar * (Int_t)sizeof(Float_t);
+  }
+  Long64_t GetEntries() const { return fNvar ? (Long64_t)fRows.size() / fNvar : 0; }
+  Int_t GetNvar() const { return fNvar; }
+  const Float_t* GetRow(Long64_t i) const { return fRows.data() + i * fNvar; }
+};
 class TCanvas : public TNamed {
  public:
   TCanvas(const char* n = "", const char* t = "", Int_t = 0, Int_t = 0) : TNamed(n, t) {}
+  TGLViewer* GetViewer3D(const char* = "") {
+    static TGLViewer viewer;
+    return &viewer;
+  }
   void Divide(Int_t, Int_t, Double_t = 0, Double_t = 0) {}
   TCanvas* cd(Int_t = 0) { return this; }
   void SetGridx() {}
@@ -1305,6 +1384,21 @@ struct ASceneExport {
         auto* t = static_cast<const AGeoWinstonConePoly*>(s);
         r.type = RBG_SHAPE_WINSTONPOLY;
         P({t->GetR1(), t->GetR2(), (double)t->GetPolyN()});
+        break;
+      }
+      case TGeoShape::kArb8: {
+        auto* t = static_cast<const TGeoArb8*>(s);
+        r.type = RBG_SHAPE_ARB8;
+        P({t->GetDz()});
+        for (int i = 0; i < 16; i++) dpar.push_back(t->GetVertices()[i]);
+        break;
+      }
+      case TGeoShape::kXtru: {
+        auto* t = static_cast<const TGeoXtru*>(s);
+        r.type = RBG_SHAPE_XTRU;
+        P({(double)t->GetNvert(), (double)t->GetNz()});
+        for (Int_t i = 0; i < t->GetNvert(); i++) P({t->GetX(i), t->GetY(i)});
+        for (Int_t i = 0; i < t->GetNz(); i++) P({t->GetZ(i), t->GetXOffset(i), t->GetYOffset(i), t->GetScale(i)});
         break;
       }
       case TGeoShape::kComposite: {

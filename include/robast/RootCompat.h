@@ -338,7 +338,11 @@ class TGeoMatrix : public TNamed {
   TGeoMatrix(const char* name) : TNamed(name) {}
   const Double_t* GetRotationMatrix() const { return fRot; }
   const Double_t* GetTranslation() const { return fTr; }
-  void RegisterYourself() { RobastRegistry::Get().matrices[fName] = this; }
+  // ROOT keeps every registered matrix in gGeoManager's list, where composite-shape expressions find them by name
+  virtual void RegisterYourself() {
+    if (!fName.empty()) RobastRegistry::Get().matrices[fName] = this;
+  }
+  virtual ~TGeoMatrix() {}
   Bool_t IsIdentity() const {
     static const Double_t id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     return !memcmp(fRot, id, sizeof(id)) && fTr[0] == 0 && fTr[1] == 0 && fTr[2] == 0;
@@ -438,14 +442,23 @@ class TGeoCombiTrans : public TGeoMatrix {
     memcpy(fTr, tr.GetTranslation(), sizeof(fTr));
     memcpy(fRot, rot.GetRotationMatrix(), sizeof(fRot));
   }
-  TGeoCombiTrans(Double_t dx, Double_t dy, Double_t dz, TGeoRotation* rot) {
+  TGeoCombiTrans(Double_t dx, Double_t dy, Double_t dz, TGeoRotation* rot) : fRotation(rot) {
     fTr[0] = dx; fTr[1] = dy; fTr[2] = dz;
     if (rot) memcpy(fRot, rot->GetRotationMatrix(), sizeof(fRot));
   }
-  TGeoCombiTrans(const char* name, Double_t dx, Double_t dy, Double_t dz, TGeoRotation* rot) : TGeoMatrix(name) {
+  TGeoCombiTrans(const char* name, Double_t dx, Double_t dy, Double_t dz, TGeoRotation* rot) : TGeoMatrix(name), fRotation(rot) {
     fTr[0] = dx; fTr[1] = dy; fTr[2] = dz;
     if (rot) memcpy(fRot, rot->GetRotationMatrix(), sizeof(fRot));
   }
+  // TGeoCombiTrans::RegisterYourself also registers the rotation it was built from (tutorials/AshraOptics.C:865-866 relies on
+  // it: "30_rot3" is only ever handed to a TGeoCombiTrans that AddNode registers, and is then named in a composite expression)
+  void RegisterYourself() override {
+    TGeoMatrix::RegisterYourself();
+    if (fRotation) fRotation->RegisterYourself();
+  }
+
+ private:
+  TGeoRotation* fRotation = nullptr;
 };
 
 class TGeoHMatrix : public TGeoMatrix {
@@ -470,7 +483,7 @@ inline TGeoHMatrix operator*(const TGeoMatrix& a, const TGeoMatrix& b) {
 // ---------------------------------------------------------------------------- shapes (description only)
 class TGeoShape : public TNamed {
  public:
-  enum EKind { kBBox, kTube, kSphere, kParaboloid, kPgon, kPcon, kAsphere, kWinston2D, kWinstonPoly, kComposite };
+  enum EKind { kBBox, kTube, kSphere, kParaboloid, kPgon, kPcon, kAsphere, kWinston2D, kWinstonPoly, kComposite, kArb8, kXtru };
   TGeoShape() {}
   TGeoShape(const char* name) : TNamed(name) {
     if (name && *name) RobastRegistry::Get().shapes[fName] = this;
@@ -610,6 +623,78 @@ class TGeoPgon : public TGeoPcon {
   Int_t GetNedges() const { return fNedges; }
 };
 
+// TGeoArb8: 8 vertices on two z planes (0-3 at -dz, 4-7 at +dz), possibly twisted (tutorials/AshraOptics.C:264-284)
+class TGeoArb8 : public TGeoBBox {
+ protected:
+  Double_t fDz = 0, fXY[8][2] = {};
+  void Box() {
+    Double_t xm = 0, ym = 0;
+    for (int i = 0; i < 8; i++) { xm = std::max(xm, std::fabs(fXY[i][0])); ym = std::max(ym, std::fabs(fXY[i][1])); }
+    fDX = xm; fDY = ym; fDZ = fDz;  // loose (centred); the scene builder computes the exact box
+  }
+
+ public:
+  TGeoArb8() {}
+  TGeoArb8(Double_t dz, Double_t* vertices = nullptr) : fDz(dz) { Init(vertices); }
+  TGeoArb8(const char* name, Double_t dz, Double_t* vertices = nullptr) : fDz(dz) { SetName(name); Init(vertices); }
+  void Init(const Double_t* vertices) {
+    if (vertices)
+      for (int i = 0; i < 8; i++) { fXY[i][0] = vertices[2 * i]; fXY[i][1] = vertices[2 * i + 1]; }
+    Box();
+  }
+  void SetVertex(Int_t vnum, Double_t x, Double_t y) {
+    if (vnum < 0 || vnum > 7) return;
+    fXY[vnum][0] = x; fXY[vnum][1] = y;
+    Box();
+  }
+  void SetDz(Double_t dz) { fDz = dz; Box(); }
+  EKind Kind() const override { return kArb8; }
+  Double_t GetDz() const { return fDz; }
+  Double_t* GetVertices() { return &fXY[0][0]; }
+  const Double_t* GetVertices() const { return &fXY[0][0]; }
+};
+
+// TGeoXtru: polygon extruded along z with a placement (x0,y0) and scale per section (tutorials/AshraOptics.C:791-1021)
+class TGeoXtru : public TGeoBBox {
+ protected:
+  Int_t fNz = 0;
+  std::vector<Double_t> fX, fY, fZ, fX0, fY0, fScale;
+  void Box() {
+    Double_t xm = 0, ym = 0;
+    for (Int_t k = 0; k < fNz; k++)
+      for (size_t i = 0; i < fX.size(); i++) {
+        xm = std::max(xm, std::fabs(fX0[k] + fScale[k] * fX[i]));
+        ym = std::max(ym, std::fabs(fY0[k] + fScale[k] * fY[i]));
+      }
+    fDX = xm; fDY = ym;
+    if (fNz > 0) { fDZ = 0.5 * (fZ[fNz - 1] - fZ[0]); fOrigin[2] = 0.5 * (fZ[fNz - 1] + fZ[0]); }
+  }
+
+ public:
+  TGeoXtru(Int_t nz) : fNz(nz), fZ(nz, 0.), fX0(nz, 0.), fY0(nz, 0.), fScale(nz, 1.) {}
+  Bool_t DefinePolygon(Int_t nvert, const Double_t* xv, const Double_t* yv) {
+    if (nvert < 3) return kFALSE;
+    fX.assign(xv, xv + nvert);
+    fY.assign(yv, yv + nvert);
+    Box();
+    return kTRUE;
+  }
+  virtual void DefineSection(Int_t snum, Double_t z, Double_t x0 = 0., Double_t y0 = 0., Double_t scale = 1.) {
+    if (snum < 0 || snum >= fNz) return;
+    fZ[snum] = z; fX0[snum] = x0; fY0[snum] = y0; fScale[snum] = scale;
+    Box();
+  }
+  EKind Kind() const override { return kXtru; }
+  Int_t GetNz() const { return fNz; }
+  Int_t GetNvert() const { return (Int_t)fX.size(); }
+  Double_t GetX(Int_t i) const { return fX[i]; }
+  Double_t GetY(Int_t i) const { return fY[i]; }
+  Double_t GetZ(Int_t i) const { return fZ[i]; }
+  Double_t GetXOffset(Int_t i) const { return fX0[i]; }
+  Double_t GetYOffset(Int_t i) const { return fY0[i]; }
+  Double_t GetScale(Int_t i) const { return fScale[i]; }
+};
+
 // Boolean expression tree of a TGeoCompositeShape
 struct TGeoBoolNode {
   enum EOp { kUnion, kIntersection, kSubtraction };
@@ -698,7 +783,9 @@ class TGeoCompositeShape : public TGeoBBox {
     TGeoMatrix* m = nullptr;
     TGeoShape* s = Parse(Strip(expression), &m, name);
     auto* c = dynamic_cast<TGeoCompositeShape*>(s);
-    if (!c || c->fNode == nullptr || m) throw std::runtime_error(std::string("TGeoCompositeShape ") + name + ": expression has no boolean operator");
+    if (!c || c->fNode == nullptr) throw std::runtime_error(std::string("TGeoCompositeShape ") + name + ": expression has no boolean operator");
+    // "(A*B):m" at the top level (tutorials/AshraOptics.C:303-304): ROOT's TGeoCompositeShape::MakeNode warns and drops the matrix
+    if (m) fprintf(stderr, "Warning in <TGeoCompositeShape::MakeNode>: %s: no geometrical transformation allowed at this level\n", name);
     fNode = c->fNode;
     SetName(name);
   }
@@ -734,9 +821,11 @@ class TGeoVolume : public TNamed {
   TGeoVolume(const char* name, const TGeoShape* shape, const TGeoMedium* = nullptr) : TNamed(name), fShape(const_cast<TGeoShape*>(shape)) {}
   TGeoShape* GetShape() const { return fShape; }
   virtual void AddNode(TGeoVolume* vol, Int_t copy_no, TGeoMatrix* mat = nullptr, Option_t* = "") {
+    if (mat) mat->RegisterYourself();  // TGeoVolume::AddNode registers the placement matrix
     fNodes.push_back(new TGeoNode(vol, copy_no, mat, kFALSE));
   }
   virtual void AddNodeOverlap(TGeoVolume* vol, Int_t copy_no, TGeoMatrix* mat = nullptr, Option_t* = "") {
+    if (mat) mat->RegisterYourself();
     fNodes.push_back(new TGeoNode(vol, copy_no, mat, kTRUE));
   }
   Int_t GetNdaughters() const { return (Int_t)fNodes.size(); }

@@ -54,7 +54,11 @@ enum {
   RBG_SHAPE_WINSTONPOLY = 8, /* AGeoWinstonConePoly dpar: r1,r2,npoly */
   RBG_SHAPE_UNION = 9,       /* TGeoCompositeShape / TGeoUnion        left,right,lmat,rmat */
   RBG_SHAPE_INTERSECTION = 10,
-  RBG_SHAPE_SUBTRACTION = 11
+  RBG_SHAPE_SUBTRACTION = 11,
+  RBG_SHAPE_ARB8 = 12,       /* TGeoArb8      dpar: dz, 8 x (x,y): vertices 0-3 at -dz, 4-7 at +dz (tutorials/AshraOptics.C:264,
+                                src/AGeoUtil.cxx:47-82); may be twisted, vertices may coincide */
+  RBG_SHAPE_XTRU = 13        /* TGeoXtru      dpar: nvert,nz, nvert x (x,y), nz x (z,x0,y0,scale) (tutorials/AshraOptics.C:791,
+                                src/AGeoUtil.cxx:84-125) */
 };
 
 /* refractive-index kinds, reference include/ARefractiveIndex.h:36-65 and the formula classes */

@@ -1249,6 +1249,265 @@ void winston_normal(const Winston& w, const double* p, const double* d, double* 
   if (dot3(n, d) < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
 }
 
+// ---- TGeoArb8 (ROOT, external; call sites tutorials/AshraOptics.C:264-284,403-441, src/AGeoUtil.cxx:47-82).
+// Parity unpinned (no reference test traces through an Arb8).  Restated face by face: the section of the solid at height z is the
+// quadrilateral of the vertices interpolated between the two z faces (TGeoArb8::Contains / InsidePolygon, vertices clockwise);
+// a lateral face is the ruled surface swept by one edge of that quadrilateral.  A ray meets the surface of edge i where the point
+// lies on the carrier line of the edge at the point's own height — a quadratic in the ray parameter whose coefficients are
+// obtained here by sampling that condition at three parameters — and the hit counts when it lies between the edge's end points.
+struct Arb8 {
+  double dz, v[8][2];
+  explicit Arb8(const double* P) : dz(P[0]) {
+    for (int i = 0; i < 8; i++) { v[i][0] = P[1 + 2 * i]; v[i][1] = P[2 + 2 * i]; }
+    double s1 = 0, s2 = 0;  // TGeoArb8::ComputeTwist re-orders counter-clockwise input
+    for (int i = 0; i < 4; i++) {
+      int j = (i + 1) % 4;
+      s1 += v[i][0] * v[j][1] - v[j][0] * v[i][1];
+      s2 += v[i + 4][0] * v[j + 4][1] - v[j + 4][0] * v[i + 4][1];
+    }
+    if (s1 > 1e-10 || s2 > 1e-10) {
+      std::swap(v[1][0], v[3][0]); std::swap(v[1][1], v[3][1]);
+      std::swap(v[5][0], v[7][0]); std::swap(v[5][1], v[7][1]);
+    }
+  }
+  void section(double z, double q[4][2]) const {
+    double cf = 0.5 * (dz - z) / dz;  // ROOT: poly = top + cf (bottom - top)
+    for (int i = 0; i < 4; i++)
+      for (int k = 0; k < 2; k++) q[i][k] = v[i + 4][k] + cf * (v[i][k] - v[i + 4][k]);
+  }
+  double side(int i, const double* x) const {  // > 0 on the inner side of edge i at the height of x
+    double q[4][2];
+    section(x[2], q);
+    int j = (i + 1) % 4;
+    return (x[0] - q[i][0]) * (q[j][1] - q[i][1]) - (x[1] - q[i][1]) * (q[j][0] - q[i][0]);
+  }
+};
+bool arb8_contains(const Arb8& a, const double* p) {
+  if (fabs(p[2]) > a.dz) return false;
+  for (int i = 0; i < 4; i++)
+    if (a.side(i, p) < 0) return false;
+  return true;
+}
+// boundary crossings of the ray that lie on the solid's surface, ascending
+void arb8_hits(const Arb8& a, const double* p, const double* d, std::vector<double>& hits) {
+  hits.clear();
+  auto at = [&](double t, double* x) { for (int k = 0; k < 3; k++) x[k] = p[k] + t * d[k]; };
+  for (int sgn = -1; sgn <= 1; sgn += 2) {  // z faces
+    if (d[2] == 0) continue;
+    double t = (sgn * a.dz - p[2]) / d[2], x[3];
+    if (!(t > 1e-11 && t < 1e29)) continue;
+    at(t, x);
+    x[2] = sgn * a.dz;
+    bool in = true;
+    for (int i = 0; i < 4; i++)
+      if (a.side(i, x) < -1e-9) in = false;
+    if (in) hits.push_back(t);
+  }
+  for (int i = 0; i < 4; i++) {
+    double x0[3], x1[3], x2[3];
+    at(0, x0); at(1, x1); at(2, x2);
+    double f0 = a.side(i, x0), f1 = a.side(i, x1), f2 = a.side(i, x2);
+    double c0 = f0, c2 = 0.5 * (f2 - 2 * f1 + f0), c1 = f1 - f0 - c2, r[2];
+    int nr = 0;
+    double scale = fabs(c0) + fabs(c1) + fabs(c2);
+    if (scale == 0) continue;  // degenerate edge (coinciding vertices): no face
+    if (fabs(c2) < 1e-13 * scale) {
+      if (c1 != 0) r[nr++] = -c0 / c1;
+    } else {
+      double disc = c1 * c1 - 4 * c2 * c0;
+      if (disc < 0) continue;
+      double sq_ = sqrt(disc), q = -0.5 * (c1 + (c1 >= 0 ? sq_ : -sq_));
+      r[nr++] = q / c2;
+      if (q != 0) r[nr++] = c0 / q;
+    }
+    for (int k = 0; k < nr; k++) {
+      double t = r[k], x[3], q[4][2];
+      if (!(t > 1e-11 && t < 1e29)) continue;
+      at(t, x);
+      if (fabs(x[2]) > a.dz + 1e-9) continue;
+      a.section(x[2] > a.dz ? a.dz : (x[2] < -a.dz ? -a.dz : x[2]), q);
+      int j = (i + 1) % 4;
+      double ex = q[j][0] - q[i][0], ey = q[j][1] - q[i][1], len2 = ex * ex + ey * ey;
+      if (len2 < 1e-20) continue;
+      double fr = ((x[0] - q[i][0]) * ex + (x[1] - q[i][1]) * ey) / len2;
+      if (fr < -1e-9 || fr > 1 + 1e-9) continue;
+      hits.push_back(t);
+    }
+  }
+  std::sort(hits.begin(), hits.end());
+}
+double arb8_dist_in(const Arb8& a, const double* p, const double* d) {
+  std::vector<double> h;
+  arb8_hits(a, p, d, h);
+  for (size_t k = 0; k < h.size(); k++) {  // leave through the first surface point behind which the ray is outside
+    double t = 0.5 * (h[k] + (k + 1 < h.size() ? h[k + 1] : h[k] + 1.)), x[3] = {p[0] + t * d[0], p[1] + t * d[1], p[2] + t * d[2]};
+    if (k + 1 < h.size() && h[k + 1] - h[k] < 1e-12) continue;
+    if (!arb8_contains(a, x)) return h[k];
+  }
+  return h.empty() ? 0. : h.back();
+}
+double arb8_dist_out(const Arb8& a, const double* p, const double* d) {
+  std::vector<double> h;
+  arb8_hits(a, p, d, h);
+  if (!h.empty()) {  // already inside before the first surface point
+    double t = 0.5 * h[0], x[3] = {p[0] + t * d[0], p[1] + t * d[1], p[2] + t * d[2]};
+    if (h[0] >= 1e-12 && arb8_contains(a, x)) return 0.;
+  }
+  for (size_t k = 0; k < h.size(); k++) {
+    if (k + 1 < h.size() && h[k + 1] - h[k] < 1e-12) continue;
+    double t = 0.5 * (h[k] + (k + 1 < h.size() ? h[k + 1] : h[k] + 1.)), x[3] = {p[0] + t * d[0], p[1] + t * d[1], p[2] + t * d[2]};
+    if (arb8_contains(a, x)) return h[k];
+  }
+  return kBig;
+}
+// TGeoArb8::ComputeNormal: z face within 10 tolerances; else the face of the closest edge of the section, normal = edge x ruling
+void arb8_normal(const Arb8& a, const double* p, const double* d, double* n) {
+  if (a.dz - fabs(p[2]) < 10 * kTol) { n[0] = n[1] = 0; n[2] = d[2] >= 0 ? 1 : -1; return; }
+  double z = p[2] > a.dz ? a.dz : (p[2] < -a.dz ? -a.dz : p[2]), q[4][2];
+  a.section(z, q);
+  double best = kBig, frac = 0;
+  int iseg = 0;
+  for (int i = 0; i < 4; i++) {
+    int j = (i + 1) % 4;
+    double ex = q[j][0] - q[i][0], ey = q[j][1] - q[i][1], len2 = ex * ex + ey * ey, ux = p[0] - q[i][0], uy = p[1] - q[i][1], f = 0, d2;
+    bool degenerate = len2 < 1e-20;
+    if (degenerate) d2 = ux * ux + uy * uy;
+    else {
+      f = (ux * ex + uy * ey) / len2;
+      f = std::min(1., std::max(0., f));
+      d2 = sq(ux - f * ex) + sq(uy - f * ey);
+    }
+    if (d2 < best - (degenerate ? 0. : 1e-24)) { best = d2; iseg = i; frac = f; }
+  }
+  int j = (iseg + 1) % 4;
+  double ex = q[j][0] - q[iseg][0], ey = q[j][1] - q[iseg][1];
+  if (ex * ex + ey * ey < 1e-20) {  // apex: take the edge direction from the opposite z face
+    double q2[4][2];
+    a.section(z < 0 ? a.dz : -a.dz, q2);
+    ex = q2[j][0] - q2[iseg][0]; ey = q2[j][1] - q2[iseg][1];
+  }
+  double rx = (1 - frac) * (a.v[iseg + 4][0] - a.v[iseg][0]) + frac * (a.v[j + 4][0] - a.v[j][0]);
+  double ry = (1 - frac) * (a.v[iseg + 4][1] - a.v[iseg][1]) + frac * (a.v[j + 4][1] - a.v[j][1]);
+  double rz = 2 * a.dz;
+  n[0] = ey * rz; n[1] = -ex * rz; n[2] = ex * ry - ey * rx;
+  double mag = sqrt(dot3(n, n));
+  if (!(mag > 0)) { n[0] = n[1] = 0; n[2] = d[2] >= 0 ? 1 : -1; return; }
+  for (int k = 0; k < 3; k++) n[k] /= mag;
+  if (dot3(n, d) < 0) for (int k = 0; k < 3; k++) n[k] = -n[k];
+}
+
+// ---- TGeoXtru (ROOT, external; call sites tutorials/AshraOptics.C:791-1021, src/AGeoUtil.cxx:84-125).  Parity unpinned.
+// The outline (any simple polygon) is placed per section at (x0,y0) with a scale, interpolated linearly between sections
+// (TGeoXtru::SetCurrentZ); a lateral face is the planar trapezoid between the copies of one edge on two consecutive sections.
+struct Xtru {
+  int nv, nz;
+  const double *V, *sec;
+  explicit Xtru(const double* P) : nv((int)P[0]), nz((int)P[1]), V(P + 2), sec(P + 2 + 2 * (int)P[0]) {}
+  double z(int k) const { return sec[4 * k]; }
+  void frame(int k, double f, double& x0, double& y0, double& sc) const {  // between sections k and k+1
+    x0 = sec[4 * k + 1] + f * (sec[4 * k + 5] - sec[4 * k + 1]);
+    y0 = sec[4 * k + 2] + f * (sec[4 * k + 6] - sec[4 * k + 2]);
+    sc = sec[4 * k + 3] + f * (sec[4 * k + 7] - sec[4 * k + 3]);
+  }
+  bool in_outline(double x, double y) const {  // winding number
+    int wn = 0;
+    for (int k = 0; k < nv; k++) {
+      int j = (k + 1) % nv;
+      double x1 = V[2 * k], y1 = V[2 * k + 1], x2 = V[2 * j], y2 = V[2 * j + 1];
+      double left = (x2 - x1) * (y - y1) - (x - x1) * (y2 - y1);
+      if (y1 <= y) { if (y2 > y && left > 0) wn++; }
+      else if (y2 <= y && left < 0) wn--;
+    }
+    return wn != 0;
+  }
+};
+bool xtru_contains(const Xtru& X, const double* p) {
+  if (p[2] < X.z(0) || p[2] > X.z(X.nz - 1)) return false;
+  int k = 0;
+  for (int i = 0; i + 1 < X.nz; i++)
+    if (X.z(i) <= p[2]) k = i;
+  double dzs = X.z(k + 1) - X.z(k), f = dzs > 1e-8 ? (p[2] - X.z(k)) / dzs : 0., x0, y0, sc;
+  X.frame(k, f, x0, y0, sc);
+  if (!(sc > 0)) return false;
+  return X.in_outline((p[0] - x0) / sc, (p[1] - y0) / sc);
+}
+void xtru_hits(const Xtru& X, const double* p, const double* d, std::vector<double>& hits) {
+  hits.clear();
+  if (d[2] != 0)
+    for (int i = 0; i < X.nz; i++) {  // section planes (end faces, outline jumps; a plane inside the solid is classified away later)
+      double t = (X.z(i) - p[2]) / d[2];
+      if (t > 1e-11 && t < 1e29) hits.push_back(t);
+    }
+  for (int s = 0; s + 1 < X.nz; s++) {
+    double z0 = X.z(s), z1 = X.z(s + 1);
+    if (z1 - z0 < 1e-8) continue;
+    double xa, ya, sa, xb, yb, sb;
+    X.frame(s, 0., xa, ya, sa);
+    X.frame(s, 1., xb, yb, sb);
+    for (int k = 0; k < X.nv; k++) {
+      int j = (k + 1) % X.nv;
+      // plane through A0, B0 (lower copies of the edge's end points) and A1 (upper copy of the first)
+      double A0[3] = {xa + sa * X.V[2 * k], ya + sa * X.V[2 * k + 1], z0}, B0[3] = {xa + sa * X.V[2 * j], ya + sa * X.V[2 * j + 1], z0};
+      double A1[3] = {xb + sb * X.V[2 * k], yb + sb * X.V[2 * k + 1], z1};
+      double e1[3] = {B0[0] - A0[0], B0[1] - A0[1], 0.}, e2[3] = {A1[0] - A0[0], A1[1] - A0[1], z1 - z0};
+      double nn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+      double den = dot3(nn, d);
+      if (den == 0) continue;
+      double w[3] = {A0[0] - p[0], A0[1] - p[1], A0[2] - p[2]}, t = dot3(nn, w) / den;
+      if (!(t > 1e-11 && t < 1e29)) continue;
+      double zz = p[2] + t * d[2];
+      if (zz < z0 - 1e-9 || zz > z1 + 1e-9) continue;
+      hits.push_back(t);
+    }
+  }
+  std::sort(hits.begin(), hits.end());
+}
+double xtru_dist(const Xtru& X, const double* p, const double* d, bool from_inside) {
+  std::vector<double> h;
+  xtru_hits(X, p, d, h);
+  double prev = 0;
+  for (size_t k = 0; k < h.size(); k++) {
+    if (h[k] - prev < 1e-12) { prev = h[k]; continue; }
+    double t = 0.5 * (prev + h[k]), x[3] = {p[0] + t * d[0], p[1] + t * d[1], p[2] + t * d[2]};
+    bool in = xtru_contains(X, x);
+    if (from_inside ? !in : in) return prev;
+    prev = h[k];
+  }
+  return from_inside ? prev : kBig;
+}
+void xtru_normal(const Xtru& X, const double* p, const double* d, double* n) {
+  double best = kBig;
+  n[0] = n[1] = 0; n[2] = 1;
+  for (int i = 0; i < X.nz; i++) {
+    bool cap = i == 0 || i == X.nz - 1;
+    bool jump = (i + 1 < X.nz && X.z(i + 1) - X.z(i) < 1e-8) || (i > 0 && X.z(i) - X.z(i - 1) < 1e-8);
+    if (!cap && !jump) continue;
+    double s = fabs(p[2] - X.z(i));
+    if (s < best) { best = s; n[0] = n[1] = 0; n[2] = 1; }
+  }
+  for (int s = 0; s + 1 < X.nz; s++) {
+    double z0 = X.z(s), z1 = X.z(s + 1), dzs = z1 - z0;
+    if (dzs < 1e-8 || p[2] < z0 - 1e-6 || p[2] > z1 + 1e-6) continue;
+    double x0, y0, sc, xa, ya, sa, xb, yb, sb;
+    X.frame(s, (p[2] - z0) / dzs, x0, y0, sc);
+    X.frame(s, 0., xa, ya, sa);
+    X.frame(s, 1., xb, yb, sb);
+    for (int k = 0; k < X.nv; k++) {
+      int j = (k + 1) % X.nv;
+      double ax = x0 + sc * X.V[2 * k], ay = y0 + sc * X.V[2 * k + 1], ex = sc * (X.V[2 * j] - X.V[2 * k]), ey = sc * (X.V[2 * j + 1] - X.V[2 * k + 1]);
+      double len2 = ex * ex + ey * ey;
+      if (len2 < 1e-20) continue;
+      double ux = p[0] - ax, uy = p[1] - ay, fr = std::min(1., std::max(0., (ux * ex + uy * ey) / len2));
+      double foot = sqrt(sq(ux - fr * ex) + sq(uy - fr * ey));
+      // direction in which vertex k travels per unit z
+      double rx = ((xb + sb * X.V[2 * k]) - (xa + sa * X.V[2 * k])) / dzs, ry = ((yb + sb * X.V[2 * k + 1]) - (ya + sa * X.V[2 * k + 1])) / dzs;
+      double fn[3] = {ey, -ex, ex * ry - ey * rx}, mag = sqrt(dot3(fn, fn)), dist = foot * sqrt(len2) / mag;
+      if (dist < best) { best = dist; for (int q = 0; q < 3; q++) n[q] = fn[q] / mag; }
+    }
+  }
+  if (dot3(n, d) < 0) for (int k = 0; k < 3; k++) n[k] = -n[k];
+}
+
 // ---- dispatch + TGeoBoolNode algorithms (TGeoUnion / TGeoIntersection / TGeoSubtraction, ROOT 6)
 bool contains(const Scene& S, int sh, const double* p);
 double dist_in(const Scene& S, int sh, const double* p, const double* d, int* sel);
@@ -1267,6 +1526,8 @@ bool contains(const Scene& S, int sh, const double* p) {
     case RBG_SHAPE_ASPHERE: return asph_contains(Asph(P), p);
     case RBG_SHAPE_WINSTON2D: return winston_contains(Winston(P, false), p);
     case RBG_SHAPE_WINSTONPOLY: return winston_contains(Winston(P, true), p);
+    case RBG_SHAPE_ARB8: return arb8_contains(Arb8(P), p);
+    case RBG_SHAPE_XTRU: return xtru_contains(Xtru(P), p);
     default: break;
   }
   double l[3], r[3];
@@ -1291,6 +1552,8 @@ double dist_in(const Scene& S, int sh, const double* p, const double* d, int* se
     case RBG_SHAPE_ASPHERE: return asph_dist4(Asph(P), p, d);
     case RBG_SHAPE_WINSTON2D: return winston_dist_in(Winston(P, false), p, d);
     case RBG_SHAPE_WINSTONPOLY: return winston_dist_in(Winston(P, true), p, d);
+    case RBG_SHAPE_ARB8: return arb8_dist_in(Arb8(P), p, d);
+    case RBG_SHAPE_XTRU: return xtru_dist(Xtru(P), p, d, true);
     default: break;
   }
   Mat ML = S.mat(s.lmat), MR = S.mat(s.rmat);
@@ -1377,6 +1640,8 @@ double dist_out(const Scene& S, int sh, const double* p, const double* d, double
     case RBG_SHAPE_ASPHERE: return asph_dist_out(Asph(P), p, d, step);
     case RBG_SHAPE_WINSTON2D: return winston_dist_out(Winston(P, false), p, d);
     case RBG_SHAPE_WINSTONPOLY: return winston_dist_out(Winston(P, true), p, d);
+    case RBG_SHAPE_ARB8: return arb8_dist_out(Arb8(P), p, d);
+    case RBG_SHAPE_XTRU: return xtru_dist(Xtru(P), p, d, false);
     default: break;
   }
   Mat ML = S.mat(s.lmat), MR = S.mat(s.rmat);
@@ -1484,6 +1749,8 @@ void normal(const Scene& S, int sh, const double* p, const double* d, int sel, d
     case RBG_SHAPE_ASPHERE: asph_normal(Asph(P), p, d, n); return;
     case RBG_SHAPE_WINSTON2D: winston_normal(Winston(P, false), p, d, n); return;
     case RBG_SHAPE_WINSTONPOLY: winston_normal(Winston(P, true), p, d, n); return;
+    case RBG_SHAPE_ARB8: arb8_normal(Arb8(P), p, d, n); return;
+    case RBG_SHAPE_XTRU: xtru_normal(Xtru(P), p, d, n); return;
     default: break;
   }
   int side = sel & 3;

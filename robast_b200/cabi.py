@@ -4,6 +4,9 @@ import ctypes as C
 from . import lib
 
 RBG_RUN, RBG_STOP, RBG_EXIT, RBG_FOCUSED, RBG_SUSPEND, RBG_ABSORB = range(6)
+# shape types of the flat scene ABI (include/robast_b200.h)
+RBG_SHAPE_BBOX, RBG_SHAPE_TUBE, RBG_SHAPE_SPHERE, RBG_SHAPE_PARABOLOID, RBG_SHAPE_PGON, RBG_SHAPE_PCON, RBG_SHAPE_ASPHERE = range(7)
+RBG_SHAPE_WINSTON2D, RBG_SHAPE_WINSTONPOLY, RBG_SHAPE_UNION, RBG_SHAPE_INTERSECTION, RBG_SHAPE_SUBTRACTION, RBG_SHAPE_ARB8, RBG_SHAPE_XTRU = range(7, 14)
 RBG_QUIRK_STEPBACK, RBG_QUIRK_BOUNDARY_PUSH = 1, 2
 RBG_QUIRKS_DEFAULT = 3
 

@@ -92,6 +92,20 @@ PYBIND11_MODULE(_robast, m) {
   py::class_<TGeoParaboloid, TGeoBBox, Raw<TGeoParaboloid>>(m, "TGeoParaboloid").def(py::init<const char*, double, double, double>());
   py::class_<TGeoPcon, TGeoBBox, Raw<TGeoPcon>>(m, "TGeoPcon").def(py::init<const char*, double, double, int>()).def("DefineSection", &TGeoPcon::DefineSection);
   py::class_<TGeoPgon, TGeoPcon, Raw<TGeoPgon>>(m, "TGeoPgon").def(py::init<const char*, double, double, int, int>());
+  py::class_<TGeoArb8, TGeoBBox, Raw<TGeoArb8>>(m, "TGeoArb8")
+      .def(py::init([](const char* name, double dz, std::vector<double> v) {
+             if (!v.empty() && v.size() != 16) throw std::runtime_error("TGeoArb8: 16 vertex coordinates expected");
+             return new TGeoArb8(name, dz, v.empty() ? nullptr : v.data());
+           }), py::arg("name"), py::arg("dz"), py::arg("vertices") = std::vector<double>())
+      .def("SetVertex", &TGeoArb8::SetVertex);
+  py::class_<TGeoXtru, TGeoBBox, Raw<TGeoXtru>>(m, "TGeoXtru")
+      .def(py::init<int>())
+      .def("SetName", [](TGeoXtru& x, const char* n) { x.SetName(n); })
+      .def("DefinePolygon", [](TGeoXtru& x, std::vector<double> xv, std::vector<double> yv) {
+        if (xv.size() != yv.size()) throw std::runtime_error("TGeoXtru::DefinePolygon: x and y differ in length");
+        return (bool)x.DefinePolygon((int)xv.size(), xv.data(), yv.data());
+      })
+      .def("DefineSection", &TGeoXtru::DefineSection, py::arg("snum"), py::arg("z"), py::arg("x0") = 0., py::arg("y0") = 0., py::arg("scale") = 1.);
   py::class_<TGeoCompositeShape, TGeoBBox, Raw<TGeoCompositeShape>>(m, "TGeoCompositeShape").def(py::init<const char*, const char*>());
   py::class_<AGeoAsphericDisk, TGeoBBox, Raw<AGeoAsphericDisk>>(m, "AGeoAsphericDisk")
       .def(py::init<const char*, double, double, double, double, double, double>(), py::arg("name"), py::arg("z1"), py::arg("curve1"), py::arg("z2"),

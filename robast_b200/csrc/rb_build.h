@@ -173,6 +173,53 @@ struct SceneBuilder {
           }
           break;
         }
+        case RBG_SHAPE_ARB8: {
+          // dz, 8 x (x,y).  TGeoArb8::ComputeTwist: both faces must turn the same way; counter-clockwise input is re-ordered
+          // (vertices 1 <-> 3 and 5 <-> 7) so that the device sees ROOT's clockwise convention.
+          if (s.npar < 17 || !(P[0] > 0)) throw Invalid("TGeoArb8 needs dz > 0 and 8 vertices");
+          double v[16];
+          memcpy(v, P + 1, sizeof(v));
+          double sum1 = 0, sum2 = 0;
+          for (int k = 0; k < 4; k++) {
+            int j = (k + 1) % 4;
+            sum1 += v[2 * k] * v[2 * j + 1] - v[2 * j] * v[2 * k + 1];
+            sum2 += v[2 * k + 8] * v[2 * j + 9] - v[2 * j + 8] * v[2 * k + 9];
+          }
+          if (sum1 * sum2 < -1e-10) throw Invalid("TGeoArb8: lower and upper faces turn in opposite directions");
+          if (sum1 > 1e-10 || sum2 > 1e-10) {
+            std::swap(v[2], v[6]); std::swap(v[3], v[7]);
+            std::swap(v[10], v[14]); std::swap(v[11], v[15]);
+          }
+          dpar.push_back(P[0]);
+          dpar.insert(dpar.end(), v, v + 16);
+          double xlo = v[0], xhi = v[0], ylo = v[1], yhi = v[1];
+          for (int k = 1; k < 8; k++) {
+            xlo = std::min(xlo, v[2 * k]); xhi = std::max(xhi, v[2 * k]);
+            ylo = std::min(ylo, v[2 * k + 1]); yhi = std::max(yhi, v[2 * k + 1]);
+          }
+          b = Box{{xlo, ylo, -P[0]}, {xhi, yhi, P[0]}};
+          break;
+        }
+        case RBG_SHAPE_XTRU: {
+          // nvert, nz, nvert x (x,y), nz x (z,x0,y0,scale)
+          int nv = s.npar >= 2 ? (int)P[0] : 0, nz = s.npar >= 2 ? (int)P[1] : 0;
+          if (nv < 3 || nz < 2 || s.npar < 2 + 2 * nv + 4 * nz) throw Invalid("TGeoXtru needs >= 3 vertices and >= 2 sections");
+          const double* V = P + 2;
+          const double* sec = P + 2 + 2 * nv;
+          double lo[3] = {1e300, 1e300, sec[0]}, hi[3] = {-1e300, -1e300, sec[4 * (nz - 1)]};
+          for (int k = 0; k < nz; k++) {
+            if (k > 0 && sec[4 * k] < sec[4 * (k - 1)]) throw Invalid("TGeoXtru sections must be ordered in z");
+            if (!(sec[4 * k + 3] > 0)) throw Invalid("TGeoXtru section scale must be positive");
+            for (int q = 0; q < nv; q++) {
+              double x = sec[4 * k + 1] + sec[4 * k + 3] * V[2 * q], y = sec[4 * k + 2] + sec[4 * k + 3] * V[2 * q + 1];
+              lo[0] = std::min(lo[0], x); hi[0] = std::max(hi[0], x);
+              lo[1] = std::min(lo[1], y); hi[1] = std::max(hi[1], y);
+            }
+          }
+          dpar.insert(dpar.end(), P, P + 2 + 2 * nv + 4 * nz);
+          b = Box{{lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}};
+          break;
+        }
         case RBG_SHAPE_UNION:
         case RBG_SHAPE_INTERSECTION:
         case RBG_SHAPE_SUBTRACTION: {

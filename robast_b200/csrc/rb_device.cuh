@@ -1298,8 +1298,218 @@ RB_HD inline V3 win_normal(const double* P, bool poly, V3 p, V3 d) {
   return n;
 }
 
+// ---- TGeoArb8  P: dz, 8 x (x,y): vertices 0-3 at z = -dz, 4-7 at z = +dz, clockwise seen from +z (TGeoArb8 convention;
+// tutorials/AshraOptics.C:264-284,403-441, src/AGeoUtil.cxx:47-82).  Vertices may coincide (triangular / pyramidal solids) and
+// a lateral face may be twisted (its lower and upper edges not parallel: a ruled bilinear patch).  At height z the section is
+// the quadrilateral of the interpolated vertices; inside means cross((B-A),(P-A)) >= 0 for its four edges (ROOT's
+// TGeoArb8::Contains / InsidePolygon).  Along a ray each of these cross products is a quadratic in the ray parameter, so every
+// boundary crossing is a root of one of four quadratics or of the two z planes: the solid is evaluated like TGeoSphere
+// (register-resident candidate roots, intervals classified by Contains at their midpoints).
+RB_HD inline void arb8_edge(const double* P, int i, double s, double& ax, double& ay, double& bx, double& by) {
+  const double* v = P + 1;
+  int j = (i + 1) & 3;
+  ax = v[2 * i] + s * (v[2 * i + 8] - v[2 * i]);
+  ay = v[2 * i + 1] + s * (v[2 * i + 9] - v[2 * i + 1]);
+  bx = v[2 * j] + s * (v[2 * j + 8] - v[2 * j]);
+  by = v[2 * j + 1] + s * (v[2 * j + 9] - v[2 * j + 1]);
+}
+RB_HD inline bool arb8_contains(const double* P, V3 p) {
+  double dz = P[0];
+  if (fabs(p.z) > dz) return false;
+  double s = 0.5 * (p.z + dz) / dz;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double ax, ay, bx, by;
+    arb8_edge(P, i, s, ax, ay, bx, by);
+    if ((p.x - ax) * (by - ay) - (p.y - ay) * (bx - ax) < 0) return false;
+  }
+  return true;
+}
+RB_HD inline double arb8_dist(const double* P, V3 p, V3 d, bool from_inside) {
+  double c[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) c[k] = RB_BIG;
+  const double dz = P[0];
+  const double* v = P + 1;
+  if (d.z != 0) {
+    c[8] = cand_ok((dz - p.z) / d.z);
+    c[9] = cand_ok((-dz - p.z) / d.z);
+  }
+  const double s0 = 0.5 * (p.z + dz) / dz, s1 = 0.5 * d.z / dz;  // height fraction along the ray: s0 + s1 t
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int j = (i + 1) & 3;
+    double eax = v[2 * i + 8] - v[2 * i], eay = v[2 * i + 9] - v[2 * i + 1], ebx = v[2 * j + 8] - v[2 * j], eby = v[2 * j + 9] - v[2 * j + 1];
+    double a0x = v[2 * i] + s0 * eax, a0y = v[2 * i + 1] + s0 * eay, b0x = v[2 * j] + s0 * ebx, b0y = v[2 * j + 1] + s0 * eby;
+    // U = P - A = u0 + u1 t, W = B - A = w0 + w1 t
+    double u0x = p.x - a0x, u0y = p.y - a0y, u1x = d.x - s1 * eax, u1y = d.y - s1 * eay;
+    double w0x = b0x - a0x, w0y = b0y - a0y, w1x = s1 * (ebx - eax), w1y = s1 * (eby - eay);
+    cand_quadratic(u1x * w1y - u1y * w1x, u0x * w1y + u1x * w0y - u0y * w1x - u1y * w0x, u0x * w0y - u0y * w0x, c[2 * i], c[2 * i + 1]);
+  }
+  double prev = 0, last = 0;
+  for (int it = 0; it < 10; it++) {
+    double t = RB_BIG;
+#pragma unroll
+    for (int k = 0; k < 10; k++) t = (c[k] > last && c[k] < t) ? c[k] : t;
+    if (t > 1e29) break;
+    last = t;
+    if (t - prev < 1e-12) { prev = t; continue; }
+    bool in = arb8_contains(P, along(p, d, 0.5 * (prev + t)));
+    if (from_inside ? !in : in) return prev;
+    prev = t;
+  }
+  return from_inside ? prev : RB_BIG;
+}
+// TGeoArb8::ComputeNormal: a z face within 10 tolerances, else the lateral face of the closest edge of the section at the
+// point's height; its normal is (edge direction) x (ruling direction at the foot point), exact on a twisted face too.
+RB_HD inline V3 arb8_normal(const double* P, V3 p, V3 d) {
+  const double dz = P[0];
+  const double* v = P + 1;
+  if (dz - fabs(p.z) < 10. * RB_TOL) return v3(0, 0, d.z >= 0 ? 1. : -1.);
+  double s = 0.5 * (p.z + dz) / dz;
+  s = s < 0 ? 0 : (s > 1 ? 1 : s);
+  double best = RB_BIG, frac = 0;
+  int iseg = 0;
+  for (int i = 0; i < 4; i++) {
+    double ax, ay, bx, by;
+    arb8_edge(P, i, s, ax, ay, bx, by);
+    double ex = bx - ax, ey = by - ay, len2 = ex * ex + ey * ey, ux = p.x - ax, uy = p.y - ay, f = 0, dist2;
+    if (len2 < 1e-20) dist2 = ux * ux + uy * uy;
+    else {
+      f = (ux * ex + uy * ey) / len2;
+      f = f < 0 ? 0 : (f > 1 ? 1 : f);
+      double qx = ux - f * ex, qy = uy - f * ey;
+      dist2 = qx * qx + qy * qy;
+      // a degenerate neighbour edge (coinciding vertices) ties with this one at the shared corner: prefer the real edge
+    }
+    if (dist2 < best - (len2 < 1e-20 ? 0. : 1e-24)) { best = dist2; iseg = i; frac = f; }
+  }
+  int j = (iseg + 1) & 3;
+  double ax, ay, bx, by;
+  arb8_edge(P, iseg, s, ax, ay, bx, by);
+  double ex = bx - ax, ey = by - ay;
+  double rx = (1 - frac) * (v[2 * iseg + 8] - v[2 * iseg]) + frac * (v[2 * j + 8] - v[2 * j]);
+  double ry = (1 - frac) * (v[2 * iseg + 9] - v[2 * iseg + 1]) + frac * (v[2 * j + 9] - v[2 * j + 1]);
+  double rz = 2 * dz;
+  if (ex * ex + ey * ey < 1e-20) {  // the section collapses to a point here (apex): use the edge of the opposite z face
+    arb8_edge(P, iseg, s < 0.5 ? 1. : 0., ax, ay, bx, by);
+    ex = bx - ax; ey = by - ay;
+  }
+  V3 n = v3(ey * rz, -ex * rz, ex * ry - ey * rx);  // (e,0) x r
+  double mag = sqrt(dot(n, n));
+  if (!(mag > 0)) return v3(0, 0, d.z >= 0 ? 1. : -1.);
+  n = (1. / mag) * n;
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
+// ---- TGeoXtru  P: nvert, nz, nvert x (x,y), nz x (z,x0,y0,scale)   (tutorials/AshraOptics.C:791-1021, src/AGeoUtil.cxx:84-125)
+// A (possibly concave) polygon extruded along z; each section places the polygon at (x0,y0) with a scale, linearly interpolated
+// between sections (TGeoXtru::SetCurrentZ).  A scaled and shifted copy of an edge stays parallel to it, so every lateral face
+// is a planar trapezoid: one linear crossing per (slab, edge).  Evaluated like the general TGeoPgon: the next crossing above the
+// last one is recomputed on demand (no candidate array), intervals are classified by Contains at their midpoints.
+RB_HD inline bool xtru_contains(const double* P, V3 p) {
+  int nv = (int)P[0], nz = (int)P[1];
+  const double* V = P + 2;
+  const double* sec = P + 2 + 2 * nv;
+  if (p.z < sec[0] || p.z > sec[4 * (nz - 1)]) return false;
+  int iz = 0;
+  for (int i = 0; i + 1 < nz; i++)
+    if (sec[4 * i] <= p.z) iz = i;
+  double z0 = sec[4 * iz], dzs = sec[4 * (iz + 1)] - z0, f = dzs > 1e-8 ? (p.z - z0) / dzs : 0.;
+  double x0 = sec[4 * iz + 1] + f * (sec[4 * (iz + 1) + 1] - sec[4 * iz + 1]), y0 = sec[4 * iz + 2] + f * (sec[4 * (iz + 1) + 2] - sec[4 * iz + 2]);
+  double sc = sec[4 * iz + 3] + f * (sec[4 * (iz + 1) + 3] - sec[4 * iz + 3]);
+  if (!(sc > 0)) return false;
+  double x = (p.x - x0) / sc, y = (p.y - y0) / sc;
+  bool in = false;  // crossing number
+  for (int k = 0, j = nv - 1; k < nv; j = k++) {
+    double xk = V[2 * k], yk = V[2 * k + 1], xj = V[2 * j], yj = V[2 * j + 1];
+    if ((yk > y) != (yj > y) && x < (xj - xk) * (y - yk) / (yj - yk) + xk) in = !in;
+  }
+  return in;
+}
+RB_HD inline double xtru_next(const double* P, V3 p, V3 d, double last) {
+  int nv = (int)P[0], nz = (int)P[1];
+  const double* V = P + 2;
+  const double* sec = P + 2 + 2 * nv;
+  double best = RB_BIG;
+  auto offer = [&](double t) {
+    if (t > 1e-11 && t <= 1e29 && t > last && t < best) best = t;
+  };
+  if (d.z != 0)
+    for (int i = 0; i < nz; i++) offer((sec[4 * i] - p.z) / d.z);
+  for (int s = 0; s + 1 < nz; s++) {
+    double z0 = sec[4 * s], z1 = sec[4 * (s + 1)], dzs = z1 - z0;
+    if (dzs < 1e-8) continue;
+    double f0 = (p.z - z0) / dzs, f1 = d.z / dzs;
+    double dox = sec[4 * (s + 1) + 1] - sec[4 * s + 1], doy = sec[4 * (s + 1) + 2] - sec[4 * s + 2], dsc = sec[4 * (s + 1) + 3] - sec[4 * s + 3];
+    double sc0 = sec[4 * s + 3] + f0 * dsc, sc1 = f1 * dsc;
+    double bx = p.x - sec[4 * s + 1] - f0 * dox, by = p.y - sec[4 * s + 2] - f0 * doy, mx = d.x - f1 * dox, my = d.y - f1 * doy;
+    for (int k = 0, j = nv - 1; k < nv; j = k++) {  // edge j -> k
+      double ex = V[2 * k] - V[2 * j], ey = V[2 * k + 1] - V[2 * j + 1];
+      double q0x = bx - sc0 * V[2 * j], q0y = by - sc0 * V[2 * j + 1], q1x = mx - sc1 * V[2 * j], q1y = my - sc1 * V[2 * j + 1];
+      double den = q1x * ey - q1y * ex;
+      if (den == 0) continue;
+      double t = -(q0x * ey - q0y * ex) / den, zz = p.z + t * d.z;
+      if (zz >= z0 - 1e-9 && zz <= z1 + 1e-9) offer(t);
+    }
+  }
+  return best;
+}
+RB_HD inline double xtru_dist(const double* P, V3 p, V3 d, bool from_inside) {
+  double prev = 0, last = 0;
+  for (int it = 0; it < 4096; it++) {
+    double t = xtru_next(P, p, d, last);
+    if (t > 1e29) break;
+    last = t;
+    if (t - prev < 1e-12) { prev = t; continue; }
+    bool in = xtru_contains(P, along(p, d, 0.5 * (prev + t)));
+    if (from_inside ? !in : in) return prev;
+    prev = t;
+  }
+  return from_inside ? prev : RB_BIG;
+}
+// nearest of: the two end planes, section planes where the outline jumps, the lateral trapezoids of the point's slab
+RB_HD inline V3 xtru_normal(const double* P, V3 p, V3 d) {
+  int nv = (int)P[0], nz = (int)P[1];
+  const double* V = P + 2;
+  const double* sec = P + 2 + 2 * nv;
+  double best = RB_BIG;
+  V3 n = v3(0, 0, 1);
+  for (int i = 0; i < nz; i++) {
+    bool cap = i == 0 || i == nz - 1;
+    bool step = (i + 1 < nz && sec[4 * (i + 1)] - sec[4 * i] < 1e-8) || (i > 0 && sec[4 * i] - sec[4 * (i - 1)] < 1e-8);
+    if (!cap && !step) continue;
+    double s = fabs(p.z - sec[4 * i]);
+    if (s < best) { best = s; n = v3(0, 0, 1); }
+  }
+  for (int s = 0; s + 1 < nz; s++) {
+    double z0 = sec[4 * s], z1 = sec[4 * (s + 1)], dzs = z1 - z0;
+    if (dzs < 1e-8 || p.z < z0 - 1e-6 || p.z > z1 + 1e-6) continue;
+    double f = (p.z - z0) / dzs;
+    double dox = (sec[4 * (s + 1) + 1] - sec[4 * s + 1]) / dzs, doy = (sec[4 * (s + 1) + 2] - sec[4 * s + 2]) / dzs, dsc = (sec[4 * (s + 1) + 3] - sec[4 * s + 3]) / dzs;
+    double x0 = sec[4 * s + 1] + f * dzs * dox, y0 = sec[4 * s + 2] + f * dzs * doy, sc = sec[4 * s + 3] + f * dzs * dsc;
+    for (int k = 0, j = nv - 1; k < nv; j = k++) {
+      double ax = x0 + sc * V[2 * j], ay = y0 + sc * V[2 * j + 1], ex = sc * (V[2 * k] - V[2 * j]), ey = sc * (V[2 * k + 1] - V[2 * j + 1]);
+      double len2 = ex * ex + ey * ey;
+      if (len2 < 1e-20) continue;
+      double ux = p.x - ax, uy = p.y - ay, fr = (ux * ex + uy * ey) / len2;
+      fr = fr < 0 ? 0 : (fr > 1 ? 1 : fr);
+      double qx = ux - fr * ex, qy = uy - fr * ey;
+      // the face contains the edge direction (ex,ey,0) and the path of vertex j along z: (dox + dsc Vx, doy + dsc Vy, 1)
+      double rx = dox + dsc * V[2 * j], ry = doy + dsc * V[2 * j + 1];
+      V3 fn = v3(ey, -ex, ex * ry - ey * rx);
+      double mag = sqrt(dot(fn, fn)), dist = sqrt(qx * qx + qy * qy) * sqrt(len2) / mag;  // in-plane foot distance -> distance to the face
+      if (dist < best) { best = dist; n = (1. / mag) * fn; }
+    }
+  }
+  if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
+  return n;
+}
+
 // ================================================================== shape dispatch, boolean composites
 // DEPTH = remaining boolean nesting levels compiled in (scene build picks the instantiation).
+RB_HD inline bool rb_is_bool(int type) { return type >= RBG_SHAPE_UNION && type <= RBG_SHAPE_SUBTRACTION; }
 template <int DEPTH, unsigned SM> struct Csg {
   static RB_HD RB_NOINLINE bool contains(const DScene& sc, int sh, V3 p);
   static RB_HD RB_NOINLINE double dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel);
@@ -1319,6 +1529,8 @@ template <unsigned SM> RB_HD inline bool prim_contains(const DScene& sc, const D
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_contains(P, p); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_contains(P, false, p); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_contains(P, true, p); else break;
+    case RBG_SHAPE_ARB8: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ARB8)) != 0) return arb8_contains(P, p); else break;
+    case RBG_SHAPE_XTRU: if constexpr ((SM & RB_SBIT(RBG_SHAPE_XTRU)) != 0) return xtru_contains(P, p); else break;
   }
   return false;
 }
@@ -1334,6 +1546,8 @@ template <unsigned SM> RB_HD inline double prim_dist_in(const DScene& sc, const 
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist4(P, p, d); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_in(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_in(P, true, p, d); else break;
+    case RBG_SHAPE_ARB8: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ARB8)) != 0) return arb8_dist(P, p, d, true); else break;
+    case RBG_SHAPE_XTRU: if constexpr ((SM & RB_SBIT(RBG_SHAPE_XTRU)) != 0) return xtru_dist(P, p, d, true); else break;
   }
   return RB_BIG;
 }
@@ -1349,6 +1563,8 @@ template <unsigned SM> RB_HD inline double prim_dist_out(const DScene& sc, const
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_dist_out(P, p, d, step); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_dist_out(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_dist_out(P, true, p, d); else break;
+    case RBG_SHAPE_ARB8: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ARB8)) != 0) return arb8_dist(P, p, d, false); else break;
+    case RBG_SHAPE_XTRU: if constexpr ((SM & RB_SBIT(RBG_SHAPE_XTRU)) != 0) return xtru_dist(P, p, d, false); else break;
   }
   return RB_BIG;
 }
@@ -1364,6 +1580,8 @@ template <unsigned SM> RB_HD inline V3 prim_normal(const DScene& sc, const DShap
     case RBG_SHAPE_ASPHERE: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ASPHERE)) != 0) return asph_normal(P, p, d); else break;
     case RBG_SHAPE_WINSTON2D: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTON2D)) != 0) return win_normal(P, false, p, d); else break;
     case RBG_SHAPE_WINSTONPOLY: if constexpr ((SM & RB_SBIT(RBG_SHAPE_WINSTONPOLY)) != 0) return win_normal(P, true, p, d); else break;
+    case RBG_SHAPE_ARB8: if constexpr ((SM & RB_SBIT(RBG_SHAPE_ARB8)) != 0) return arb8_normal(P, p, d); else break;
+    case RBG_SHAPE_XTRU: if constexpr ((SM & RB_SBIT(RBG_SHAPE_XTRU)) != 0) return xtru_normal(P, p, d); else break;
   }
   return v3(0, 0, 1);
 }
@@ -1388,7 +1606,7 @@ RB_HD inline V3 op_vec(const DScene& sc, int m, V3 d) { return m < 0 ? d : to_lo
 
 template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE bool Csg<DEPTH, SM>::contains(const DScene& sc, int sh, V3 p) {
   const DShape s = sc.shapes[sh];
-  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::contains(sc, sh, p);  // one shared copy of the primitive code
+  if (!rb_is_bool(s.type)) return Csg<0, SM>::contains(sc, sh, p);  // one shared copy of the primitive code
   typedef Csg<DEPTH - 1, SM> Sub;
   bool l = Sub::contains(sc, s.left, op_point(sc, s.lmat, p));
   if ((SM & RB_SBIT(RBG_SHAPE_UNION)) != 0 && s.type == RBG_SHAPE_UNION) return l || Sub::contains(sc, s.right, op_point(sc, s.rmat, p));
@@ -1400,7 +1618,7 @@ template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE bool Csg<DEPTH, SM>::contain
 template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE double Csg<DEPTH, SM>::dist_in(const DScene& sc, int sh, V3 p, V3 d, int& sel) {
   const DShape s = sc.shapes[sh];
   sel = 0;
-  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::dist_in(sc, sh, p, d, sel);
+  if (!rb_is_bool(s.type)) return Csg<0, SM>::dist_in(sc, sh, p, d, sel);
   typedef Csg<DEPTH - 1, SM> Sub;
   V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p), ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
   int s1 = 0, s2 = 0;
@@ -1463,7 +1681,7 @@ template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE double Csg<DEPTH, SM>::dist_
 template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE double Csg<DEPTH, SM>::dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
   const DShape s = sc.shapes[sh];
   sel = 0;
-  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::dist_out(sc, sh, p, d, step, sel);
+  if (!rb_is_bool(s.type)) return Csg<0, SM>::dist_out(sc, sh, p, d, step, sel);
   typedef Csg<DEPTH - 1, SM> Sub;
   V3 ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
   V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p);
@@ -1486,7 +1704,7 @@ template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE double Csg<DEPTH, SM>::dist_
       if (inl && inr) return snext;
     }
     // either operand missing means no hit: try the cheaper primitive first (same result, fewer instructions)
-    const bool right_first = sc.shapes[s.right].type < sc.shapes[s.left].type && sc.shapes[s.left].type < RBG_SHAPE_UNION ? false : sc.shapes[s.right].type != RBG_SHAPE_SPHERE;
+    const bool right_first = sc.shapes[s.right].type < sc.shapes[s.left].type && !rb_is_bool(sc.shapes[s.left].type) ? false : sc.shapes[s.right].type != RBG_SHAPE_SPHERE;
     for (int guard = 0; guard < 64; guard++) {
       d1 = d2 = 0;
       if (right_first && !inr) {
@@ -1557,7 +1775,7 @@ template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE double Csg<DEPTH, SM>::dist_
 
 template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE V3 Csg<DEPTH, SM>::normal(const DScene& sc, int sh, V3 p, V3 d, int sel) {
   const DShape s = sc.shapes[sh];
-  if (s.type < RBG_SHAPE_UNION) return Csg<0, SM>::normal(sc, sh, p, d, 0);
+  if (!rb_is_bool(s.type)) return Csg<0, SM>::normal(sc, sh, p, d, 0);
   typedef Csg<DEPTH - 1, SM> Sub;
   int side = sel & 3;
   if (side == 0) {

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/tutorials"
 OUT = os.path.join(ROOT, "tests", "_build", "tutorials")
 MACROS = {"SimpleParabolicTelescope": "SimpleParabolicTelescope()", "DaviesCotton": "DaviesCotton()", "HESS1": "HESS1()", "MST": "MST()",
-          "SchwarzschildCouder": "SchwarzschildCouder()"}
+          "SchwarzschildCouder": "SchwarzschildCouder()", "AshraOptics": "AshraOptics()"}
 
 
 def build(verbose=False):

@@ -100,3 +100,71 @@ def hollow_poly(kind, phi1=0., dphi=360., material="mirror"):
     manager.CloseGeometry()
     manager.SetLimit(30)
     return manager, keep + [comp]
+
+
+# outline of the extruded aluminium profile of tutorials/AshraOptics.C:782-789 (12 vertices, concave), in cm
+_ASHRA_X = [-5.0, -0.4, -0.4, -5.0, -5.0, 5.0, 5.0, 0.4, 0.4, 5.0, 5.0, -5.0]
+_ASHRA_Y = [5.0, 4.2, -4.2, -4.2, -5.0, -5.0, -4.2, -4.2, 4.2, 4.2, 5.0, 5.0]
+
+
+def arb8_xtru_shape(kind):
+    """TGeoArb8 / TGeoXtru solids of the kinds tutorials/AshraOptics.C builds (all lengths in cm, enlarged to tens of cm)"""
+    if kind == "arb8_prism":  # trapezoidal prism, equal faces (AGeoUtil::MakeArb8FromPoints output, src/AGeoUtil.cxx:47-82)
+        v = [-6., -4., -5., 5., 7., 4., 6., -5.]
+        return ROOT.TGeoArb8("arb", 8., v + v)
+    if kind == "arb8_twisted":  # AshraOptics.C:403-411 (pip_arb1): two coinciding vertices, non-parallel lower and upper edges
+        s = ROOT.TGeoArb8("arb", 10.)
+        for i, (x, y) in enumerate(((20., 8.0936), (20., -14.), (20., -14.), (4.66, -14.), (20., -6.7987), (20., -14.), (20., -14.), (15., -14.))):
+            s.SetVertex(i, x, y)
+        return s
+    if kind == "arb8_pyramid":  # AshraOptics.C:264-276 (mir_cut2): the lower face shrunk to (almost) a point
+        import math
+        s = ROOT.TGeoArb8("arb", 12.)
+        for j, r in enumerate((1e-7, 15.)):
+            for i, a in enumerate((60., -8.6, 188.6, 120.)):
+                s.SetVertex(i + 4 * j, r * math.cos(math.radians(a)), r * math.sin(math.radians(a)))
+        return s
+    if kind == "arb8_ccw":  # counter-clockwise input: ROOT re-orders it (TGeoArb8::ComputeTwist)
+        v = [-6., -4., 6., -5., 7., 4., -5., 5.]
+        return ROOT.TGeoArb8("arb", 8., v + [1.2 * c for c in v])
+    if kind == "xtru_profile":  # AshraOptics.C:791-795 (30_xtru1)
+        s = ROOT.TGeoXtru(2)
+        s.SetName("xtru")
+        s.DefinePolygon(_ASHRA_X, _ASHRA_Y)
+        s.DefineSection(0, -9.)
+        s.DefineSection(1, 9.)
+        return s
+    if kind == "xtru_scaled":  # three sections with offsets and scales, and an outline jump (two sections at one z)
+        s = ROOT.TGeoXtru(4)
+        s.SetName("xtru")
+        s.DefinePolygon(_ASHRA_X, _ASHRA_Y)
+        s.DefineSection(0, -9., 0., 0., 1.)
+        s.DefineSection(1, -1., 1., -0.5, 0.7)
+        s.DefineSection(2, -1., 1., -0.5, 1.2)
+        s.DefineSection(3, 8., -1., 0.5, 0.9)
+        return s
+    raise ValueError(kind)
+
+
+def arb8_xtru(kind, material="mirror", composite=False):
+    """one TGeoArb8 / TGeoXtru (optionally cut by a sphere, like the mirror segments of AshraOptics.C:286-300) in the world"""
+    manager = make_the_world()
+    shape = arb8_xtru_shape(kind)
+    keep = [shape]
+    if composite:
+        sph = ROOT.TGeoSphere("cutsph", 0., 13.)
+        tr = ROOT.TGeoTranslation("cuttr", *((14., -8., 1.) if kind == "arb8_twisted" else (2., 1., -3.)))
+        tr.RegisterYourself()
+        shape = ROOT.TGeoCompositeShape("cutcomp", "cutsph:cuttr*%s" % shape.GetName())
+        keep += [sph, tr, shape]
+    if material == "mirror":
+        comp = ROOT.AMirror("solidmirror", shape)
+    else:
+        comp = ROOT.ALens("solidlens", shape)
+        idx = ROOT.ARefractiveIndex(1.5)
+        comp.SetRefractiveIndex(idx)
+        keep.append(idx)
+    manager.GetTopVolume().AddNode(comp, 1, ROOT.TGeoCombiTrans(1., -2., 3., ROOT.TGeoRotation("solidrot", 20., 35., 10.)))
+    manager.CloseGeometry()
+    manager.SetLimit(30)
+    return manager, keep + [comp]

@@ -172,3 +172,29 @@ def test_general_tmm_device_code_matches_oracle_and_golden(R, oracle, emul):
                 assert emul.emul_tmm_general(ex.desc_ptr(), mid, mode, pol, rev, thc.real, thc.imag, lam, C.byref(a), C.byref(b)) == 0
                 assert oracle.orc_tmm_general(ex.desc_ptr(), mid, mode, pol, rev, thc.real, thc.imag, lam, C.byref(c), C.byref(d_)) == 0
                 assert abs(a.value - c.value) < 1e-11 * max(1, abs(c.value)) and abs(b.value - d_.value) < 1e-11 * max(1e-3, abs(d_.value)), (k, mode, rev, pol)
+
+
+ARB8_XTRU_KINDS = ["arb8_prism", "arb8_twisted", "arb8_pyramid", "arb8_ccw", "xtru_profile", "xtru_scaled"]
+
+
+@pytest.mark.parametrize("kind", ARB8_XTRU_KINDS)
+@pytest.mark.parametrize("composite", [False, True])
+def test_arb8_xtru_match_oracle(oracle, emul, kind, composite):
+    """TGeoArb8 (prism, twisted face, pyramid, counter-clockwise input) and TGeoXtru (concave outline, scaled sections with an
+    outline jump) — tutorials/AshraOptics.C:264-284,403-441,791-1021 — alone and cut by a sphere: device code (candidate roots
+    + Contains at midpoints) against the oracle's face-by-face restatement; isotropic point sources outside and inside"""
+    bounces = 0
+    inside = (1.5, -1.5, 3.2) if kind != "arb8_twisted" else (14.2, -9.0, 8.6)
+    for material, sources in (("mirror", (((26., 8., -3.), 1), ((-17., -12., 18.), 2))), ("glass", (((26., 8., -3.), 3), (inside, 4)))):
+        mgr, _keep = scenes.arb8_xtru(kind, material, composite)
+        ex = mgr.ExportScene()
+        for origin, seed in sources:
+            n = 3000
+            o = H.opts(seed=5, limit=12)
+            ref = H.trace_with(oracle.orc_trace, ex, point_source_rays(oracle, 5, origin, n, seed), o, nthreads=4)
+            got = H.trace_with(emul.emul_trace, ex, point_source_rays(oracle, 5, origin, n, seed), o)
+            rep = H.compare(ref, got)
+            assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (material, origin, rep)
+            bounces = max(bounces, int(got.npoints.max()))
+            assert (got.npoints > 2).mean() > 0.005  # the solid is hit
+    assert bounces > 3

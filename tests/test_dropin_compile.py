@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/tutorials"
 MACROS = ["SimpleParabolicTelescope", "DaviesCotton", "SchwarzschildCouder", "HexWinstonCone", "SchmidtCassegrain",
-          "HESS1", "MST", "HexOkumuraCone", "AbsLengthTest", "EdmundOptics", "multilayer", "multithread"]
-# not covered: AshraOptics.C (TGeoArb8 / TGeoXtru), CORSIKA.C (ACorsikaIACTFile), Optimize.C / optimize_multilayer.C (MINUIT),
+          "HESS1", "MST", "HexOkumuraCone", "AbsLengthTest", "EdmundOptics", "multilayer", "multithread", "AshraOptics"]
+# not covered: CORSIKA.C (ACorsikaIACTFile), Optimize.C / optimize_multilayer.C (MINUIT),
 # SellmeierFit.C (TFile / TF1 fitting)
 
 

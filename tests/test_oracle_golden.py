@@ -427,3 +427,140 @@ def test_refractiveindex_dot_info_parser(R, oracle, tmp_path):  # src/ARefractiv
     (tmp_path / "n.csv").write_text("wl,n\n0.4,1.5\n0.6,1.4\n")
     only_n = R.ARefractiveIndexDotInfo(str(tmp_path / "n.csv"))
     assert abs(only_n.GetRefractiveIndex(500 * nm) - 1.45) < 1e-12 and only_n.GetExtinctionCoefficient(500 * nm) == 0
+
+
+# ---------------------------------------------------------------------------------------------- TGeoArb8 / TGeoXtru (oracle pins)
+def _shape_of_type(ex, want):
+    """id of the first shape of type `want` in an exported scene (rbg_scene_desc: nshapes at int32[2], shapes* at byte 88)"""
+    import ctypes as C
+    base = ex.desc_ptr()
+    nshapes = C.cast(base, C.POINTER(C.c_int32))[2]
+    shapes = C.cast(C.cast(base + 88, C.POINTER(C.c_void_p))[0], C.POINTER(C.c_int32))
+    for i in range(nshapes):
+        if shapes[7 * i] == want:
+            return i
+    raise KeyError(want)
+
+
+def _solo(R, shape):
+    import scenes
+    mgr = scenes.make_the_world()
+    comp = R.AMirror("m", shape)
+    mgr.GetTopVolume().AddNode(comp, 1)
+    mgr.CloseGeometry()
+    return mgr, mgr.ExportScene(), comp
+
+
+def _probe(oracle, ex, sid, pts, dirs):
+    import ctypes as C
+    out = []
+    for p, d in zip(pts, dirs):
+        pa, da, na = (C.c_double * 3)(*p), (C.c_double * 3)(*d), (C.c_double * 3)()
+        inside = oracle.orc_shape_contains(ex.desc_ptr(), sid, pa)
+        dist = oracle.orc_shape_dist(ex.desc_ptr(), sid, pa, da, 1 if inside else 0)
+        n = (0., 0., 0.)
+        if dist < 1e29:
+            q = (C.c_double * 3)(*[p[k] + dist * d[k] for k in range(3)])
+            oracle.orc_shape_normal(ex.desc_ptr(), sid, q, da, na)
+            n = tuple(na)
+        out.append((inside, dist, n))
+    return out
+
+
+def _random_probes(seed, n, box):
+    rng = np.random.default_rng(seed)
+    pts = (rng.random((n, 3)) * 2 - 1) * box
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    return pts.tolist(), dirs.tolist()
+
+
+def _same(a, b, tol=1e-9):
+    hit = compared = 0
+    for (ia, da, na), (ib, db, nb) in zip(a, b):
+        assert ia == ib
+        if da > 1e29 or db > 1e29:
+            assert da > 1e29 and db > 1e29
+            continue
+        compared += 1
+        assert abs(da - db) < tol * max(1., abs(da)), (da, db)
+        # normals agree except on edges, where the nearest face is ambiguous
+        if abs(sum(x * y for x, y in zip(na, nb)) - 1) < 1e-9:
+            hit += 1
+    assert compared > 60 and hit > 0.97 * compared
+
+
+def test_arb8_and_xtru_boxes_equal_tgeobbox(R, oracle):
+    """closed form: a TGeoArb8 with equal rectangular faces and a TGeoXtru with a rectangular outline are the TGeoBBox of the same
+    half lengths — Contains, DistFromInside/Outside and normals of the oracle's three restatements agree"""
+    hx, hy, hz = 4., 2.5, 6.
+    rect = [-hx, -hy, -hx, hy, hx, hy, hx, -hy]  # clockwise seen from +z
+    _m1, ex_box, _k1 = _solo(R, R.TGeoBBox("b", hx, hy, hz))
+    _m2, ex_arb, _k2 = _solo(R, R.TGeoArb8("a", hz, rect + rect))
+    xt = R.TGeoXtru(2)
+    xt.SetName("x")
+    xt.DefinePolygon(rect[0::2], rect[1::2])
+    xt.DefineSection(0, -hz)
+    xt.DefineSection(1, hz)
+    _m3, ex_xtru, _k3 = _solo(R, xt)
+    pts, dirs = _random_probes(11, 600, np.array([9., 7., 11.]))
+    # shape 0 is the world box in every export; the solid under test is the other TGeoBBox / the Arb8 / the Xtru
+    ref = _probe(oracle, ex_box, 1, pts, dirs)
+    assert sum(1 for r in ref if r[0]) > 30 and sum(1 for r in ref if not r[0] and r[1] < 1e29) > 30
+    _same(ref, _probe(oracle, ex_arb, _shape_of_type(ex_arb, R.RBG_SHAPE_ARB8), pts, dirs))
+    _same(ref, _probe(oracle, ex_xtru, _shape_of_type(ex_xtru, R.RBG_SHAPE_XTRU), pts, dirs))
+
+
+def test_scaled_xtru_equals_arb8_frustum(R, oracle):
+    """a TGeoXtru whose upper section is scaled and shifted is the TGeoArb8 with the corresponding upper vertices (planar faces)"""
+    lo = [-4., -3., -5., 3., 4., 2., 3., -3.]
+    sc, ox, oy, hz = 0.55, 0.8, -0.4, 5.
+    up = [v * sc + (ox if i % 2 == 0 else oy) for i, v in enumerate(lo)]
+    _m1, ex_arb, _k1 = _solo(R, R.TGeoArb8("a", hz, lo + up))
+    xt = R.TGeoXtru(2)
+    xt.SetName("x")
+    xt.DefinePolygon(lo[0::2], lo[1::2])
+    xt.DefineSection(0, -hz, 0., 0., 1.)
+    xt.DefineSection(1, hz, ox, oy, sc)
+    _m2, ex_xtru, _k2 = _solo(R, xt)
+    pts, dirs = _random_probes(12, 600, np.array([8., 7., 9.]))
+    ref = _probe(oracle, ex_arb, _shape_of_type(ex_arb, R.RBG_SHAPE_ARB8), pts, dirs)
+    assert sum(1 for r in ref if r[0]) > 30
+    _same(ref, _probe(oracle, ex_xtru, _shape_of_type(ex_xtru, R.RBG_SHAPE_XTRU), pts, dirs))
+
+
+def test_twisted_arb8_hits_lie_on_the_ruled_surface(R, oracle):
+    """twisted TGeoArb8 (upper face rotated against the lower one): every reported boundary point separates inside from outside,
+    lateral hits satisfy the bilinear-patch equation of their face, and the normal is perpendicular to edge and ruling there"""
+    import ctypes as C
+    lo = [(-4., -4.), (-4., 4.), (4., 4.), (4., -4.)]
+    a = math.radians(25.)
+    up = [(x * math.cos(a) - y * math.sin(a), x * math.sin(a) + y * math.cos(a)) for x, y in lo]
+    hz = 6.
+    _m, ex, _k = _solo(R, R.TGeoArb8("tw", hz, [c for v in lo + up for c in v]))
+    sid = _shape_of_type(ex, R.RBG_SHAPE_ARB8)
+    pts, dirs = _random_probes(13, 800, np.array([9., 9., 10.]))
+    res = _probe(oracle, ex, sid, pts, dirs)
+    lateral = 0
+    for p, d, (inside, dist, n) in zip(pts, dirs, res):
+        if dist > 1e29:
+            continue
+        for sgn, want in ((-1, inside), (1, not inside)):
+            q = (C.c_double * 3)(*[p[k] + (dist + sgn * 1e-7) * d[k] for k in range(3)])
+            if dist + sgn * 1e-7 > 0:
+                assert bool(oracle.orc_shape_contains(ex.desc_ptr(), sid, q)) == bool(want), (p, d, dist, sgn)
+        q = [p[k] + dist * d[k] for k in range(3)]
+        if abs(abs(q[2]) - hz) < 1e-9:
+            assert abs(abs(n[2]) - 1) < 1e-12
+            continue
+        s = 0.5 * (q[2] + hz) / hz
+        quad = [(l[0] + s * (u[0] - l[0]), l[1] + s * (u[1] - l[1])) for l, u in zip(lo, up)]
+        # on the carrier line of one edge of the section at this height
+        cross = [(q[0] - quad[i][0]) * (quad[(i + 1) % 4][1] - quad[i][1]) - (q[1] - quad[i][1]) * (quad[(i + 1) % 4][0] - quad[i][0]) for i in range(4)]
+        i = int(np.argmin(np.abs(cross)))
+        assert abs(cross[i]) < 1e-8
+        e = (quad[(i + 1) % 4][0] - quad[i][0], quad[(i + 1) % 4][1] - quad[i][1], 0.)
+        assert abs(sum(x * y for x, y in zip(n, e))) < 1e-9 * math.hypot(*e[:2])
+        assert sum(x * y for x, y in zip(n, d)) >= 0
+        lateral += 1
+    assert lateral > 100
