@@ -1806,38 +1806,71 @@ struct Nav {
     m2l(glob[lv], pt, l);
     return contains(*S, shape_at(lv), l);
   }
+  bool many(int lv) const { return lv > 0 && S->d->nodes[node[lv]].overlap != 0; }
+  // daughters of the current volume (not `skip`, index >= from) whose shape holds pt, in AddNode order
+  int next_daughter_holding(const double* pt, int skip, int from) const {
+    const rbg_volume& v = S->d->volumes[vol[level]];
+    for (int k = from; k < v.nnodes; k++) {
+      int ni = v.first_node + k;
+      if (ni == skip) continue;
+      const rbg_node& nd = S->d->nodes[ni];
+      Mat g = mul(glob[level], S->mat(nd.matrix));
+      double l[3];
+      m2l(g, pt, l);
+      if (contains(*S, S->d->volumes[nd.volume].shape, l)) return k;
+    }
+    return -1;
+  }
+  // Downward half of TGeoNavigator::SearchNode.  Returns true when the branch entered an ordinary ("ONLY") node.
+  // A daughter placed with AddNodeOverlap ("MANY") that holds the point forms a cluster with the later daughters holding it
+  // (TGeoNavigator::GetTouchedCluster); TGeoNavigator::FindInCluster then takes the first member whose branch reaches an ONLY
+  // node or that is the node FindNextBoundary announced (fNextNode, `prefer`), else the member whose branch ends deepest (the
+  // first one on ties).
+  bool descend(const double* pt, int skip, int prefer) {
+    bool only = false;
+    while (true) {
+      const rbg_volume& v = S->d->volumes[vol[level]];
+      int k = next_daughter_holding(pt, skip, 0);
+      if (k < 0) return only;
+      if (!S->d->nodes[v.first_node + k].overlap) {
+        cd_down(v.first_node + k);
+        only = true;
+        skip = -1;
+        continue;
+      }
+      const Nav top = *this;
+      Nav best = *this;
+      int best_level = -1;
+      for (int m = k; m >= 0; m = top.next_daughter_holding(pt, skip, m + 1)) {
+        Nav trial = top;
+        trial.cd_down(v.first_node + m);
+        bool o = !S->d->nodes[v.first_node + m].overlap;
+        if (trial.descend(pt, -1, prefer)) o = true;
+        if (o || v.first_node + m == prefer) { *this = trial; return true; }
+        if (trial.level > best_level) { best = trial; best_level = trial.level; }
+      }
+      *this = best;
+      return only;
+    }
+  }
   // TGeoNavigator::SearchNode(downwards, skipnode) — skip is a desc.nodes index or -1
   // returns false when the point is outside the top volume (level = -1)
-  bool search_node(bool downwards, int skip, const double* pt) {
+  bool search_node(bool downwards, int skip, const double* pt, int prefer = -1) {
     if (!downwards) {
       while (true) {
         bool inside_current = (level > 0 && node[level] == skip) ? true : inside_level(level, pt);
+        if (inside_current && many(level)) {  // GotoSafeLevel: up to the first ordinary node above the overlapping ones
+          while (many(level)) level--;
+          continue;
+        }
         if (inside_current) break;
         skip = node[level];
         if (level == 0) { level = -1; return false; }
         level--;
       }
     }
-    // descend
-    while (true) {
-      const rbg_volume& v = S->d->volumes[vol[level]];
-      bool found = false;
-      for (int k = 0; k < v.nnodes; k++) {
-        int ni = v.first_node + k;
-        if (ni == skip) continue;
-        const rbg_node& nd = S->d->nodes[ni];
-        Mat g = mul(glob[level], S->mat(nd.matrix));
-        double l[3];
-        m2l(g, pt, l);
-        if (contains(*S, S->d->volumes[nd.volume].shape, l)) {
-          cd_down(ni);
-          found = true;
-          break;
-        }
-      }
-      skip = -1;
-      if (!found) return true;
-    }
+    descend(pt, skip, prefer);
+    return true;
   }
   // InitTrack -> FindNode
   void init_track(const double* p, const double* d) {
@@ -1859,12 +1892,12 @@ struct Nav {
     return id;
   }
   // CrossBoundaryAndLocate: relocate at P + extra*D, then undo the push
-  void cross_and_locate(bool downwards, int skip) {
+  void cross_and_locate(bool downwards, int skip, int prefer = -1) {
     const double* tr = glob[level < 0 ? 0 : level].t;
     double trmax = 1. + fabs(tr[0]) + fabs(tr[1]) + fabs(tr[2]);
     double extra = 100. * (trmax + step) * kTol;
     double q[3] = {P[0] + extra * D[0], P[1] + extra * D[1], P[2] + extra * D[2]};
-    search_node(downwards, skip, q);
+    search_node(downwards, skip, q, prefer);
   }
   // TGeoNavigator::FindNextBoundaryAndStep(Big).  Returns false if nothing is hit from outside.
   bool find_next_boundary_and_step(bool push_quirk) {
@@ -1922,10 +1955,58 @@ struct Nav {
       double s = dist_out(*S, S->d->volumes[nd.volume].shape, dp, dd, step, &sel);
       if (s < step - kTol) { step = s; idaughter = v.first_node + k; dsel = sel; entering = true; exiting = false; }
     }
+    // overlapping nodes on the branch (TGeoNavigator::FindNextBoundary, fNmany > 0): the mother of each such node and the node's
+    // sisters bound the step as well
+    int xkind = 0, xlevel = -1, xnode = -1, xsel = 0;
+    for (int lv = level; lv >= 1; lv--) {
+      if (!many(lv)) continue;
+      double mp[3], md[3];
+      m2l(glob[lv - 1], P, mp);
+      m2lv(glob[lv - 1], D, md);
+      int sel = 0;
+      double s = dist_in(*S, shape_at(lv - 1), mp, md, &sel);
+      if (s < step - kTol) { step = s; xkind = 1; xlevel = lv - 1; xsel = sel; entering = exiting = false; }
+      const rbg_volume& mv = S->d->volumes[vol[lv - 1]];
+      for (int k = 0; k < mv.nnodes; k++) {
+        int ni = mv.first_node + k;
+        if (ni == node[lv]) continue;
+        const rbg_node& nd = S->d->nodes[ni];
+        Mat lm = S->mat(nd.matrix);
+        double dp[3], dd[3];
+        m2l(lm, mp, dp);
+        m2lv(lm, md, dd);
+        int shp = S->d->volumes[nd.volume].shape;
+        sel = 0;
+        if (nd.overlap && contains(*S, shp, dp)) s = dist_in(*S, shp, dp, dd, &sel);
+        else s = dist_out(*S, shp, dp, dd, step, &sel);
+        if (s < step - kTol) { step = s; xkind = 2; xlevel = lv - 1; xnode = ni; xsel = sel; entering = exiting = false; }
+      }
+    }
     for (int i = 0; i < 3; i++) P[i] += step * D[i];
     step += extra;
     on_boundary = true;
+    if (xkind == 1) {  // left the mother of an overlapping node
+      n_shape = shape_at(xlevel); n_mat = glob[xlevel]; n_sel = xsel;
+      int skip = node[xlevel];
+      if (xlevel == 0) { level = -1; return true; }
+      level = xlevel - 1;
+      cross_and_locate(false, skip);
+      return true;
+    }
+    if (xkind == 2) {  // met a sister of an overlapping node: relocate from their mother
+      const rbg_node& nd = S->d->nodes[xnode];
+      n_shape = S->d->volumes[nd.volume].shape; n_mat = mul(glob[xlevel], S->mat(nd.matrix)); n_sel = xsel;
+      level = xlevel;
+      cross_and_locate(false, -1, xnode);
+      return true;
+    }
     if (entering) {
+      if (S->d->nodes[idaughter].overlap) {  // an ordinary sister holding the point has priority over an overlapping daughter
+        const rbg_node& nd = S->d->nodes[idaughter];
+        n_shape = S->d->volumes[nd.volume].shape; n_mat = mul(glob[level], S->mat(nd.matrix)); n_sel = dsel;
+        cross_and_locate(false, -1, idaughter);
+        return true;
+      }
       cd_down(idaughter);
       n_shape = shape_at(level); n_mat = glob[level]; n_sel = dsel;
       cross_and_locate(true, -1);

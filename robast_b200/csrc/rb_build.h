@@ -251,6 +251,7 @@ struct SceneBuilder {
     n.type = D->volumes[vol].type;
     n.mother = mother;
     n.overlap = overlap;
+    n.level = mother < 0 ? 0 : nodes[mother].level + 1;
     nodes.push_back(n);
     names.push_back(name);
     const rbg_volume& v = D->volumes[vol];
@@ -353,6 +354,8 @@ static void scene_features_needed(const rbg_scene_desc* D, unsigned& shapes, uns
   }
   for (int i = 0; i < D->nmirrors; i++)
     if (D->mirrors[i].graph1d >= 0 || D->mirrors[i].th2 >= 0 || D->mirrors[i].graph2d >= 0) phys |= 32u;
+  for (int i = 0; i < D->nnodes; i++)
+    if (D->nodes[i].overlap) phys |= 64u;  // RB_PH_OVERLAP
 }
 
 static int scene_depth_needed(const SceneBuilder& B) {

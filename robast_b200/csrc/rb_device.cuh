@@ -31,6 +31,7 @@
 #define RB_PH_LAMBERT 8u     /* Lambertian border */
 #define RB_PH_QE 16u         /* AFocalSurface QE graphs */
 #define RB_PH_MIRROR_TABLE 32u /* AMirror reflectance != constant */
+#define RB_PH_OVERLAP 64u     /* AddNodeOverlap ("MANY") nodes: overlap-cluster point location, sister candidates */
 #define RB_PH_ALL 0xffu
 // TAG: distinguishes experiment instantiations whose other parameters coincide (same type = same kernel symbol across
 // translation units, whatever macros the unit was compiled with)
@@ -1799,8 +1800,8 @@ struct RayReg {           // register-resident ray state
   int on_boundary;
 };
 
-// first (lowest id = daughter order) child of `node` whose shape contains q; -1 if none
-template <class K> RB_HD inline int child_containing(const DScene& sc, int node, V3 q, int skip) {
+// first (lowest id = daughter order) child of `node` with id > after whose shape contains q; -1 if none
+template <class K> RB_HD inline int child_containing(const DScene& sc, int node, V3 q, int skip, int after = -1) {
   const DNode& nd = sc.nodes[node];
   int best = -1;
   int i = nd.bvh_count > 0 ? nd.bvh_first : -1;
@@ -1811,7 +1812,7 @@ template <class K> RB_HD inline int child_containing(const DScene& sc, int node,
     if (!in) { i = b.skip; continue; }
     if (b.child >= 0) {
       int c = b.child;
-      if (c != skip && (best < 0 || c < best)) {
+      if (c != skip && c > after && (best < 0 || c < best)) {
         const DNode& cn = sc.nodes[c];
         if (Csg<K::depth, K::shapes>::contains(sc, cn.shape, to_local(cn.g, q))) best = c;
       }
@@ -1820,24 +1821,57 @@ template <class K> RB_HD inline int child_containing(const DScene& sc, int node,
   }
   return best;
 }
+// Descent of TGeoNavigator::SearchNode(downwards) from `node`.  Nodes placed with AddNodeOverlap ("MANY") may share space with
+// their sisters: when the first daughter holding q is such a node, every later daughter holding q joins its cluster
+// (GetTouchedCluster) and FindInCluster decides — a member whose branch reaches an ordinary ("ONLY") node wins at once, otherwise
+// the member whose branch ends deepest, the first one on ties; the node FindNextBoundary announced (`prefer`, fNextNode) wins like
+// an ONLY branch.  LV bounds the nesting of clusters inside cluster members.
+template <class K, int LV> struct Locate {
+  static RB_HD int down(const DScene& sc, int node, V3 q, int skip, bool& only, int prefer) {
+    while (true) {
+      int c = child_containing<K>(sc, node, q, skip);
+      if (c < 0) return node;
+      if constexpr ((K::phys & RB_PH_OVERLAP) != 0 && LV > 0) {
+        if (sc.nodes[c].overlap) {
+          int best = -1, best_level = -1;
+          for (int m = c; m >= 0; m = child_containing<K>(sc, node, q, skip, m)) {
+            bool o = !sc.nodes[m].overlap;
+            int r = Locate<K, LV - 1>::down(sc, m, q, -1, o, prefer);
+            if (o || m == prefer) { only = true; return r; }
+            if (sc.nodes[r].level > best_level) { best = r; best_level = sc.nodes[r].level; }
+          }
+          return best;
+        }
+      }
+      skip = -1;
+      only = true;
+      node = c;
+    }
+  }
+};
 // TGeoNavigator::SearchNode(downwards=false, skip) starting at `node`; returns the deepest node containing q or -1
-template <class K> RB_HD inline int search_node(const DScene& sc, int node, V3 q, int skip, bool check_current) {
+template <class K> RB_HD inline int search_node(const DScene& sc, int node, V3 q, int skip, bool check_current, int prefer = -1) {
   if (check_current) {
     while (true) {
       if (node < 0) return -1;
       const DNode& nd = sc.nodes[node];
       bool inside = node == skip ? true : Csg<K::depth, K::shapes>::contains(sc, nd.shape, to_local(nd.g, q));
+      if constexpr ((K::phys & RB_PH_OVERLAP) != 0) {
+        // GotoSafeLevel: the search restarts from the first ordinary node above a run of overlapping ones
+        if (inside && nd.overlap && nd.mother >= 0) {
+          int up = nd.mother;
+          while (sc.nodes[up].overlap && sc.nodes[up].mother >= 0) up = sc.nodes[up].mother;
+          node = up;
+          continue;
+        }
+      }
       if (inside) break;
       skip = node;
       node = nd.mother;
     }
   }
-  while (true) {
-    int c = child_containing<K>(sc, node, q, skip);
-    skip = -1;
-    if (c < 0) return node;
-    node = c;
-  }
+  bool only = false;
+  return Locate<K, 2>::down(sc, node, q, skip, only, prefer);
 }
 
 #ifndef RB_MAXVIS
@@ -1871,6 +1905,7 @@ struct NavStep {
   int sel_exit, enter, esel;
   int mode;      // 0 = finished in nb_begin, 1 = daughters to examine
   int bvh_next;  // >= 0: traversal stopped because o.vis was full; resume here after evaluating the batch
+  int xkind, xnode, xsel;  // overlap extension (nb_many): 0 none, 1 = left the mother `xnode` of an overlapping node, 2 = met its sister `xnode`
 };
 
 // phase A: boundary push, outside-world entry, DistFromInside of the current shape
@@ -1884,6 +1919,7 @@ template <class K> RB_HD inline void nb_begin(const DScene& sc, RayReg& r, bool 
   st.bvh_next = -1;
   st.enter = -1;
   st.esel = 0;
+  st.xkind = 0;
   double extra = (r.on_boundary && push_quirk) ? RB_TOL : 0.0;
   st.extra = extra;
   r.on_boundary = 0;
@@ -1960,17 +1996,69 @@ template <class K> RB_HD inline void nb_eval(const DScene& sc, const RayReg& r, 
   if (s < st.best - RB_TOL || (st.enter >= 0 && c < st.enter && s <= st.best + RB_TOL)) { st.best = s; st.enter = c; st.esel = sel; }
 }
 
+// TGeoNavigator::FindNextBoundary with overlapping nodes on the current branch (fNmany > 0): for every node A of the branch
+// that was placed with AddNodeOverlap, the boundary of A's mother and the sisters of A are candidates too — an ordinary sister
+// from outside, an overlapping sister from inside if it holds the point.  (ROOT restricts the sisters to A's overlap list; a
+// sister outside that list cannot be nearer than A's own boundary, so examining all of them gives the same step.)
+template <class K> RB_HD inline void nb_many(const DScene& sc, const RayReg& r, NavStep& st) {
+  typedef Csg<K::depth, K::shapes> G;
+  for (int a = r.cur; a >= 0 && sc.nodes[a].mother >= 0; a = sc.nodes[a].mother) {
+    if (!sc.nodes[a].overlap) continue;
+    const int y = sc.nodes[a].mother;
+    const DNode& yn = sc.nodes[y];
+    int sel = 0;
+    double s = G::dist_in(sc, yn.shape, to_local(yn.g, r.p), to_local_vec(yn.g, r.d), sel);
+    if (s < st.best - RB_TOL) { st.best = s; st.xkind = 1; st.xnode = y; st.xsel = sel; }
+    for (int i = yn.bvh_count > 0 ? yn.bvh_first : -1; i >= 0;) {
+      const DBvh& b = sc.bvh[i];
+      if (b.child < 0) { i = i + 1; continue; }  // every leaf is examined: this path is rare
+      const int c = b.child;
+      i = b.skip;
+      if (c == a) continue;
+      const DNode& cn = sc.nodes[c];
+      V3 lp = to_local(cn.g, r.p), ld = to_local_vec(cn.g, r.d);
+      sel = 0;
+      if (cn.overlap && G::contains(sc, cn.shape, lp)) s = G::dist_in(sc, cn.shape, lp, ld, sel);
+      else s = G::dist_out(sc, cn.shape, lp, ld, st.best + 2 * RB_TOL, sel);
+      if (s < st.best - RB_TOL) { st.best = s; st.xkind = 2; st.xnode = c; st.xsel = sel; }
+    }
+  }
+}
+
 // phase D: move to the boundary and locate the node behind it (CrossBoundaryAndLocate)
 template <class K> RB_HD inline void nb_finish(const DScene& sc, RayReg& r, NavStep& st) {
   if (st.mode != 1) return;
   StepOut& o = st.o;
   const DNode& cn = sc.nodes[r.cur];
+  if constexpr ((K::phys & RB_PH_OVERLAP) != 0) {
+    if (sc.has_many) {
+      nb_many<K>(sc, r, st);
+      o.nvis = -1;  // relocate_back must not take its sibling shortcut in a scene with overlapping nodes
+      if (st.xkind != 0) {
+        r.p = along(r.p, r.d, st.best);
+        o.step = st.best + st.extra;
+        r.on_boundary = 1;
+        o.crossed = st.xnode;
+        o.sel = st.xsel;
+        const int y = sc.nodes[st.xnode].mother;  // left node: relocate above it; met sister: relocate from the common mother
+        if (y < 0) { o.next = -1; return; }
+        o.next = search_node<K>(sc, y, along(r.p, r.d, locate_extra(sc, y, o.step)), st.xkind == 1 ? st.xnode : -1, true, st.xkind == 2 ? st.xnode : -1);
+        return;
+      }
+    }
+  }
   r.p = along(r.p, r.d, st.best);
   o.step = st.best + st.extra;
   r.on_boundary = 1;
   if (st.enter >= 0) {
     o.crossed = st.enter;
     o.sel = st.esel;
+    if constexpr ((K::phys & RB_PH_OVERLAP) != 0) {
+      if (sc.nodes[st.enter].overlap) {  // an overlapping daughter: an ordinary sister holding the point has priority
+        o.next = search_node<K>(sc, r.cur, along(r.p, r.d, locate_extra(sc, r.cur, o.step)), -1, true, st.enter);
+        return;
+      }
+    }
     o.next = search_node<K>(sc, st.enter, along(r.p, r.d, locate_extra(sc, st.enter, o.step)), -1, false);
     return;
   }

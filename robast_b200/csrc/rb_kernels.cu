@@ -520,7 +520,7 @@ static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys)
     int cost = __builtin_popcount(v->shapes) + __builtin_popcount(v->phys) + 4 * (v->depth - depth);
     if (cost < best_cost) { best_cost = cost; best = v; }
   }
-  if (!best) throw NotSupported("boolean composite nesting deeper than 3 is not supported");
+  if (!best) throw NotSupported("boolean composite nesting deeper than 6 is not supported");
   return best;
 }
 static void launch_trace(const rb_variant* v, const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init,
@@ -708,7 +708,7 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     B.build_shapes();
     if (D->top_volume >= 0) B.flatten(D->top_volume, mat_identity(), -1, 0, std::string(D->names + D->volumes[D->top_volume].name) + "_1");
     int depth = scene_depth_needed(B);
-    if (depth > 3) throw NotSupported("boolean composite nesting deeper than 3 is not supported");
+    if (depth > 6) throw NotSupported("boolean composite nesting deeper than 6 is not supported");
     CK(cudaSetDevice(device));
     s = new rbg_scene;
     s->device = device;
@@ -742,6 +742,7 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     s->d.g2z = upload(s, D->g2z, D->ng2pts);
     s->d.nnodes = (int)B.nodes.size();
     s->d.top_shape = D->top_volume >= 0 ? D->volumes[D->top_volume].shape : -1;
+    s->d.has_many = (need_phys & RB_PH_OVERLAP) != 0;
     CK(cudaMalloc((void**)&s->d_count, RB_HOST_STREAMS * sizeof(int32_t)));
     CK(cudaMallocHost((void**)&s->h_count, RB_HOST_STREAMS * sizeof(int32_t)));
     CK(cudaMallocHost((void**)&s->h_pairs, RB_HOST_STREAMS * sizeof(unsigned long long)));

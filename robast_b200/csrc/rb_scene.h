@@ -33,8 +33,8 @@ struct DNode {
   int32_t mother;    // physical id of the mother, -1 for top
   int32_t bvh_first; // slice of bvh[] over this node's daughters (bvh_count == 0: no daughters)
   int32_t bvh_count;
-  int32_t overlap;
-  int32_t pad;
+  int32_t overlap;   // placed with AddNodeOverlap ("MANY")
+  int32_t level;     // depth in the physical tree (top = 0)
 };
 
 struct DBvh {   // 32 B; boxes are fp32, rounded outwards and padded, traversal is fp32-conservative
@@ -75,6 +75,8 @@ struct DScene {
   const double* g2z;
   int32_t nnodes;
   int32_t top_shape;
+  int32_t has_many;  // some node is placed with AddNodeOverlap
+  int32_t pad_;
 };
 
 #define RB_MAX_TMM_LAYERS 16

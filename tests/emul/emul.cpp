@@ -64,6 +64,7 @@ extern "C" __attribute__((visibility("default"))) int emul_trace_history(const r
     sc.graph2d = D->graph2d; sc.tri = D->tri; sc.g2x = D->g2x; sc.g2y = D->g2y; sc.g2z = D->g2z;
     sc.nnodes = (int)B.nodes.size();
     sc.top_shape = D->volumes[D->top_volume].shape;
+    for (const DNode& nd : B.nodes) sc.has_many |= nd.overlap != 0;
     DTraceParams tp;
     tp.limit = o->limit > 0 ? o->limit : 100; tp.disable_fresnel = o->disable_fresnel; tp.quirks = o->quirks; tp.max_steps = 0;
     tp.seed = o->seed; tp.ray_id_offset = o->ray_id_offset;
@@ -72,6 +73,7 @@ extern "C" __attribute__((visibility("default"))) int emul_trace_history(const r
       case 1: run<TraceCfg<1, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
       case 2: run<TraceCfg<2, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
       case 3: run<TraceCfg<3, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
+      case 4: case 5: case 6: run<TraceCfg<6, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
       default: return RBG_ENOTSUP;
     }
     return RBG_OK;

@@ -168,3 +168,42 @@ def arb8_xtru(kind, material="mirror", composite=False):
     manager.CloseGeometry()
     manager.SetLimit(30)
     return manager, keep + [comp]
+
+
+def overlapping_frame(nested=False, holder=True, bars=True, stop_ring=True):
+    """nodes placed with AddNodeOverlap ("MANY"), as tutorials/AshraOptics.C:1117-1120 uses them: a big AOpticalComponent box `comp`
+    holding obscuring bars is laid over the whole optical system; a mirror, a glass plate and a focal plane are ordinary daughters
+    of the same mother and share space with it; a ring-shaped stop is a second overlapping node.  nested=True puts a second
+    overlapping holder with its own bar inside `comp`'s mother so that two overlapping nodes hold the same points."""
+    manager = make_the_world()
+    opt = ROOT.AOpticalComponent("opt", ROOT.TGeoBBox("optbox", 3 * m, 3 * m, 3 * m))
+    keep = [opt]
+    glass = ROOT.ALens("plate", ROOT.TGeoTube("platetube", 0., 40., 1.5))
+    idx = ROOT.ARefractiveIndex(1.5)
+    glass.SetRefractiveIndex(idx)
+    opt.AddNode(glass, 1, ROOT.TGeoTranslation(0., 0., -20.))
+    mirror = ROOT.AMirror("dish", ROOT.TGeoSphere("dishsph", 200., 201., 166., 180.))  # concave towards +z, focus near z = 0
+    opt.AddNode(mirror, 1, ROOT.TGeoTranslation(0., 0., 100.))
+    focal = ROOT.AFocalSurface("focal", ROOT.TGeoTube("focaltube", 0., 6., 0.05))
+    opt.AddNode(focal, 1, ROOT.TGeoTranslation(0., 0., 1.))
+    comp = ROOT.AOpticalComponent("comp", ROOT.TGeoBBox("compbox", 1.9 * m, 1.9 * m, 1.9 * m))
+    for i, (x, y, z) in enumerate(((25., 0., -40.), (-25., 5., 30.), (0., -30., 60.)) if bars else ()):
+        bar = ROOT.AObscuration("bar%d" % i, ROOT.TGeoBBox("barbox%d" % i, 2., 60., 2.))
+        comp.AddNode(bar, 1, ROOT.TGeoCombiTrans(x, y, z, ROOT.TGeoRotation("barrot%d" % i, 30. * i, 0., 0.)))
+        keep.append(bar)
+    if holder:
+        opt.AddNodeOverlap(comp, 1, ROOT.TGeoCombiTrans(5., -3., 8., ROOT.TGeoRotation("comprot", 10., 5., 0.)))
+    stop = ROOT.AObscuration("stop", ROOT.TGeoTube("stoptube", 45., 150., 0.5))
+    if stop_ring:
+        opt.AddNodeOverlap(stop, 1, ROOT.TGeoTranslation(0., 0., -30.))
+    keep += [glass, idx, mirror, focal, comp, stop]
+    if nested:
+        comp2 = ROOT.AOpticalComponent("comp2", ROOT.TGeoBBox("comp2box", 80., 80., 40.))
+        bar = ROOT.AObscuration("bar9", ROOT.TGeoBBox("barbox9", 50., 1.5, 1.5))
+        comp2.AddNode(bar, 1, ROOT.TGeoTranslation(0., 12., 5.))
+        opt.AddNodeOverlap(comp2, 1, ROOT.TGeoTranslation(0., 0., 40.))
+        keep += [comp2, bar]
+    manager.GetTopVolume().AddNode(opt, 1, ROOT.TGeoRotation("optrot", 0., 0., 0.))
+    manager.CloseGeometry()
+    manager.SetLimit(20)
+    return manager, keep

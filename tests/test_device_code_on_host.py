@@ -198,3 +198,32 @@ def test_arb8_xtru_match_oracle(oracle, emul, kind, composite):
             bounces = max(bounces, int(got.npoints.max()))
             assert (got.npoints > 2).mean() > 0.005  # the solid is hit
     assert bounces > 3
+
+
+def overlap_beam(n_side, tilt_deg):
+    """parallel beam onto the scenes.overlapping_frame system, starting inside the overlapping holder"""
+    th = math.radians(tilt_deg)
+    xs = np.linspace(-60., 60., n_side)
+    X, Y = np.meshgrid(xs, xs)
+    inp = np.zeros((n_side * n_side, 8))
+    inp[:, 0], inp[:, 1], inp[:, 2] = X.ravel(), Y.ravel(), 150.
+    inp[:, 4], inp[:, 5], inp[:, 6], inp[:, 7] = math.sin(th), 0., -math.cos(th), 400e-7
+    return inp
+
+
+@pytest.mark.parametrize("nested", [False, True])
+@pytest.mark.parametrize("tilt", [0.0, 3.0])
+def test_overlapping_nodes_match_oracle(oracle, emul, nested, tilt):
+    """AddNodeOverlap ("MANY") nodes (tutorials/AshraOptics.C:91,1117-1120): rays start inside an overlapping holder laid over the
+    whole system and still meet the ordinary sisters (glass plate, mirror, focal plane) and the holder's own bars — flattened
+    device navigation against the oracle's path-stack navigator"""
+    mgr, _keep = scenes.overlapping_frame(nested)
+    ex = mgr.ExportScene()
+    o = H.opts(seed=3, limit=20, disable_fresnel=1)
+    ref = H.trace_with(oracle.orc_trace, ex, H.Rays(overlap_beam(60, tilt)), o, nthreads=4)
+    got = H.trace_with(emul.emul_trace, ex, H.Rays(overlap_beam(60, tilt)), o)
+    rep = H.compare(ref, got)
+    assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, rep
+    st = np.bincount(got.status, minlength=6)
+    assert st[3] > 200 and st[1] > 200, st  # focused via plate + mirror; stopped on the holder's bars or the overlapping stop ring
+    assert got.npoints[got.status == 3].max() >= 6  # start, plate in/out, mirror, plate in/out, focal plane

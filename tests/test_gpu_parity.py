@@ -534,3 +534,22 @@ def test_arb8_xtru_parity(R, oracle, kind, composite):
                 rep = H.compare(ref, got)
                 assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (material, origin, steps, rep)
                 assert (got.npoints > 2).mean() > 0.005
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nested", [False, True])
+@pytest.mark.parametrize("tilt", [0.0, 3.0])
+def test_overlapping_nodes_parity(R, oracle, nested, tilt):
+    """AddNodeOverlap ("MANY") nodes (tutorials/AshraOptics.C:91,1117-1120): overlap-cluster point location (ONLY priority, deepest
+    branch, fNextNode) and the sister / mother candidates of FindNextBoundary, both launch modes"""
+    import test_device_code_on_host as T
+    mgr, _keep = scenes.overlapping_frame(nested)
+    ex = mgr.ExportScene()
+    for steps in (0, 1):
+        o = H.opts(seed=3, limit=20, disable_fresnel=1, steps_per_launch=steps)
+        ref = H.trace_with(oracle.orc_trace, ex, H.Rays(T.overlap_beam(150, tilt)), o, nthreads=os.cpu_count() or 4)
+        got = H.trace_gpu(ex, H.Rays(T.overlap_beam(150, tilt)), o)
+        rep = H.compare(ref, got)
+        assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (steps, rep)
+        st = np.bincount(got.status, minlength=6)
+        assert st[3] > 1000 and st[1] > 1000

@@ -59,3 +59,18 @@ def test_hess1_and_mst_macros():
 def test_schwarzschild_couder_macro():
     rows, out = run_macro("SchwarzschildCouder")
     assert len(rows) >= 8 and all(r["entries"] > 5000 for r in rows[:8])
+
+
+def test_ashra_optics_macro():
+    """tutorials/AshraOptics.C: Baker-Nunn optics with TGeoArb8 / TGeoXtru frame parts, composites nested six deep and two nodes
+    placed with AddNodeOverlap over the whole system; 22 field angles x 30 wavelengths x 400 rays"""
+    rows, out = run_macro("AshraOptics")
+    spots = {r["name"]: r for r in rows if str(r["name"]).startswith("hist")}
+    assert len(spots) >= 22
+    on = spots["hist0_1"]
+    # 400-ray grids over a 1.2 m square, 1 m aperture, frame obscurations: ~100 of 400 reach the focal sphere per wavelength;
+    # the spot (mm on the focal sphere) stays within a small fraction of a millimetre out to 20 degrees (wide-field Baker-Nunn)
+    assert on["entries"] > 30 * 60
+    assert on["rmsx"] < 0.5 and on["rmsy"] < 0.5
+    off = spots["hist20_1"]
+    assert off["entries"] > 30 * 30 and off["rmsx"] < 1.0 and off["rmsy"] < 1.0

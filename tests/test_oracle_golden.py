@@ -564,3 +564,25 @@ def test_twisted_arb8_hits_lie_on_the_ruled_surface(R, oracle):
         assert sum(x * y for x, y in zip(n, d)) >= 0
         lateral += 1
     assert lateral > 100
+
+
+def test_empty_overlapping_holder_is_transparent(R, oracle):
+    """semantic pin of the AddNodeOverlap ("MANY") restatement: a holder without daughters laid over the whole system (the role of
+    `comp` in tutorials/AshraOptics.C:883-884,1117-1120) must not change where any ray ends — the ordinary nodes sharing its space
+    are found from inside it (ONLY priority, sister candidates) exactly as without it"""
+    import helpers as H
+    import scenes
+    import test_device_code_on_host as T
+    res = []
+    for holder in (False, True):
+        mgr, _keep = scenes.overlapping_frame(nested=False, holder=holder, bars=False, stop_ring=True)
+        rays = H.Rays(T.overlap_beam(50, 2.0))
+        H.trace_with(oracle.orc_trace, mgr.ExportScene(), rays, H.opts(seed=3, limit=20, disable_fresnel=1), nthreads=4)
+        res.append(rays)
+    plain, held = res
+    assert (plain.status == held.status).all()
+    st = np.bincount(plain.status, minlength=6)
+    assert st[3] > 200 and st[1] > 100
+    done = plain.status != 2  # exiting rays end on the world box in both cases too, but cross the holder's own boundary on the way
+    assert np.abs(plain.out[:3] - held.out[:3]).max() < 1e-9
+    assert (plain.npoints[done] == held.npoints[done]).all()
