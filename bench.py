@@ -38,18 +38,51 @@ ANGLES = [0.5 * i for i in range(9)]
 BYTES_IN, BYTES_OUT = 64, 68
 
 
-def sample_clocks(stop, out):
+def make_clock_reader():
+    """-> function returning one row [sm MHz, max sm MHz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap].  In-process NVML
+    (nvidia_ml_py), initialised HERE, before the timed region: nvmlInit and every `nvidia-smi` process take the driver's global
+    lock for ~0.1 s, which showed up as 80 vs 115 ms per step in a 0.4 s timed region.  nvidia-smi is the fallback."""
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(dev)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (0x8, 0x40, 0x20, 0x4)  # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+
+        def read():
+            r = int(get_reasons(h))
+            return [str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx)] + ["Active" if r & b else "Not Active" for b in bits]
+        read()
+        read.inline = True  # cheap enough to call from the timing thread between steps
+        return read
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    dev = os.environ.get("LOCAL_RANK", "0")
+
+    def read_smi():
+        txt = subprocess.run(["nvidia-smi", "-i", str(dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in txt.strip().split(",")]
+        return f if len(f) >= 6 else None
+    read_smi.inline = False
+    return read_smi
+
+
+def sample_clocks(stop, out, read):
+    """background sampler, used only with the nvidia-smi fallback.  NVML queries from a second thread contend for the driver lock
+    with the launching thread: measured on B200, steps of 78.5 ms became 110-770 ms now and then.  The NVML reader is therefore
+    called by the timing thread itself after each step is queued (the GPU is still working on it: the sample is under load)."""
+    if read.inline:
+        return
     while not stop.is_set():
         try:
-            txt = subprocess.run(["nvidia-smi", "-i", dev, "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-            f = [x.strip() for x in txt.strip().split(",")]
-            if len(f) >= 6:
-                out.append(f)
+            row = read()
+            if row:
+                out.append(row)
         except Exception:
             pass
-        stop.wait(0.2)
+        stop.wait(0.1)
 
 
 def clocks_summary(samples):
@@ -200,6 +233,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clock_reader = make_clock_reader()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -207,19 +241,28 @@ def main():
     bm, bn, cm_, cn = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
     R.rbg_profile_read(C.byref(bm), C.byref(bn), C.byref(cm_), C.byref(cn))  # reset
     stop, samples = threading.Event(), []
-    th_clock = threading.Thread(target=sample_clocks, args=(stop, samples), daemon=True)
+    th_clock = threading.Thread(target=sample_clocks, args=(stop, samples, clock_reader), daemon=True)
     th_clock.start()
     launches0 = R.rbg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    marks = []
     for _ in range(args.steps):
         step()
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
+        if clock_reader.inline:
+            try:
+                samples.append(clock_reader())
+            except Exception:
+                pass
     e1.record()
     barrier()
     stop.set()
     th_clock.join()
     ms = e0.elapsed_time(e1)
+    step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
     launches = R.rbg_launch_count() - launches0
     R.rbg_profile_read(C.byref(bm), C.byref(bn), C.byref(cm_), C.byref(cn))
     R.rbg_profile_enable(0)
@@ -332,7 +375,7 @@ def main():
             "config": {"workload": "DaviesCotton.C (BASELINE configs[1]): 88 hex facets + camera + masts, 9 field angles 0-4 deg, Square(400 nm, 14 m, n=3334) each",
                        "rays_per_step_per_gpu": n * nang, "rays_per_step": rays_per_step, "l2_policy": "inputs (711 MB per batch) larger than L2, no flush",
                        "steps_per_launch": args.steps_per_launch, "parallelism": "rays sharded over %d GPU(s), geometry replicated" % world},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks_summary(samples),
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks_summary(samples), "step_ms": step_ms,
             "check": {"focused_fraction": focused_frac, "status_counts": counts, "d80_cm_by_angle": [round(v, 4) for v in d80[:, 0].cpu().numpy().tolist()]},
         }))
     R.rbg_scene_destroy(scene)

@@ -1042,7 +1042,19 @@ int rbg_containment_radius(int32_t nhist, const unsigned long long* hist, int32_
     if (nhist < 0 || nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin) || !hist || !stats || !out) throw Invalid("bad containment-radius arguments");
     if (nhist == 0) return;
     CK(cudaSetDevice(device));
-    double* prefix = nullptr;  // stream-ordered scratch for the per-row running sums
+    // Stream-ordered scratch for the per-row running sums.  With the default release threshold (0) the pool hands its memory back
+    // to the driver at every synchronisation — rbg_trace synchronises after each bounce — and this call then pays a fresh
+    // device allocation (seen as 30-700 ms stalls of a 78 ms bench step whenever anything else held the driver lock): keep it.
+    static std::atomic<unsigned> pool_kept{0};
+    if (device >= 0 && device < 32 && !(pool_kept.fetch_or(1u << device) & (1u << device))) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    }
+    double* prefix = nullptr;
     CK(cudaMallocAsync((void**)&prefix, (size_t)nhist * (nx + 1) * ny * sizeof(double), (cudaStream_t)stream));
     int rc = rb_launch_containment_u64(nhist, hist, nx, xmin, xmax, ny, ymin, ymax, stats, fraction, out, prefix, (cudaStream_t)stream);
     cudaFreeAsync(prefix, (cudaStream_t)stream);
