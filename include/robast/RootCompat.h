@@ -921,6 +921,13 @@ class TGraph : public TNamed {
     fX[i] = x; fY[i] = y;
   }
   void AddPoint(Double_t x, Double_t y) { SetPoint(GetN(), x, y); }
+  // drawing is out of scope; with ROBAST_DRAW_SUMMARY set, Draw() prints the points the plot would have shown
+  void Draw(Option_t* = "") override {
+    if (!getenv("ROBAST_DRAW_SUMMARY")) return;
+    printf("TGraph name=\"%s\" n=%d points=", GetName(), GetN());
+    for (Int_t i = 0; i < GetN(); i++) printf("%s%.9g:%.9g", i ? "," : "", fX[i], fY[i]);
+    printf("\n");
+  }
   Int_t GetN() const { return (Int_t)fX.size(); }
   const Double_t* GetX() const { return fX.data(); }
   const Double_t* GetY() const { return fY.data(); }
@@ -1126,6 +1133,10 @@ class TH1D : public TH1 {
     return std::sqrt(std::fabs(fSwx2 / fSw - m * m));
   }
   Double_t GetRMS(Int_t a = 1) const { return GetStdDev(a); }
+  void Draw(Option_t* = "") override {
+    if (getenv("ROBAST_DRAW_SUMMARY"))
+      printf("TH1 name=\"%s\" title=\"%s\" entries=%.0f inrange=%.9g mean=%.9g rms=%.9g\n", GetName(), GetTitle(), fEntries, fSw, GetMean(), GetStdDev());
+  }
   Double_t Integral() const {
     Double_t s = 0;
     for (Int_t i = 1; i <= fXaxis.fN; i++) s += fC[i];
