@@ -269,6 +269,27 @@ typedef struct {
 int rbg_shoot(const rbg_shoot_desc* d, int64_t first, int64_t n, double* x, double* y, double* z,
               double* t, double* dx, double* dy, double* dz, double* lambda, int device, void* stream);
 
+/* CORSIKA IACT photon bunches -> rays on the device: ACorsikaIACTFile::GetRayArray (src/ACorsikaIACTFile.cxx:71-133) for the
+ * bunches of one telescope.  Bunch arrays are HOST pointers in CORSIKA units (x,y cm at the observation level relative to the
+ * telescope, time ns, direction cosines cx,cy,cz with cz < 0, lambda nm or 0 = undetermined, photons = bunch size); the rays are
+ * written to DEVICE arrays in the tracer's units (cm, s).  Bunch i yields the rays j = 0,1,.. while j < photons[i] (the reference's
+ * loop, i.e. ceil(photons) rays), all starting at (x - d cx, y - d cy, z) with d = (z - telescope_z) * (-1/cz) at time
+ * t*ns - d/(c/n).  A bunch with lambda == 0 draws 1/lambda uniformly between 1/lambda_min and 1/lambda_max (Philox stream of the
+ * global ray index, draw 0).  NB the reference passes fMaxPhotonBunches where fMaxWavelength is meant (:123-125); the caller
+ * decides what to pass as lambda_max_nm.  rbg_bunch_rays counts the rays; rbg_shoot_bunches fills rays [first, first+n). */
+typedef struct {
+  int64_t nbunches;
+  const float *x, *y, *time, *cx, *cy, *cz, *lambda, *photons;
+  double z;                 /* start height of the rays above the CORSIKA observation level (cm) */
+  double telescope_z;       /* ACorsikaIACTFile::GetTelescopeZ(telNo) (cm) */
+  double refractive_index;  /* of the air above the telescope */
+  double lambda_min_nm, lambda_max_nm;
+  uint64_t seed;
+} rbg_bunches;
+int rbg_bunch_rays(const rbg_bunches* b, int64_t* nrays);
+int rbg_shoot_bunches(const rbg_bunches* b, int64_t first, int64_t n, double* x, double* y, double* z, double* t, double* dx,
+                      double* dy, double* dz, double* lambda, int device, void* stream);
+
 /* On-device reducers replacing the user-side TH2D fill + GetMean/GetRMS loops
  * (tutorials/SimpleParabolicTelescope.C:114-172).  Only rays with status==sel are used.
  * hist: nx*ny uint64 bins (device), under/overflow dropped.  moments: 8 doubles (device):

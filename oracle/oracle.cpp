@@ -2493,6 +2493,37 @@ int orc_shape_normal(const rbg_scene_desc* desc, int shape, const double* p, con
   return 0;
 }
 
+// ACorsikaIACTFile::GetRayArray restated (src/ACorsikaIACTFile.cxx:71-133): bunch i yields rays while j < photons[i]; rays
+// [first, first+n) of the concatenation are written (tracer units: cm, s).  The random wavelength of an undetermined bunch uses
+// the Philox stream of the global ray index instead of the shared gRandom.
+int orc_shoot_bunches(const rbg_bunches* b, int64_t first, int64_t n, double* x, double* y, double* z, double* t, double* dx, double* dy, double* dz,
+                      double* lambda) {
+  const double cm = 1., ns = 1e-9, nm = 1e-7, m = 100.;
+  int64_t ray = 0, out = 0;
+  for (int64_t i = 0; i < b->nbunches && out < n; i++) {
+    double airmass = -1. / b->cz[i];
+    double tel_dist = (b->z - b->telescope_z * cm) * airmass;
+    double speed = 2.99792458e8 * m / b->refractive_index;
+    double px = b->x[i] * cm - tel_dist * b->cx[i], py = b->y[i] * cm - tel_dist * b->cy[i], pt = b->time[i] * ns - tel_dist / speed;
+    for (int j = 0; j < b->photons[i] && out < n; j++, ray++) {
+      if (ray < first) continue;
+      double lam = b->lambda[i];
+      if (lam == 0) {
+        Rng r;
+        r.key[0] = (uint32_t)b->seed; r.key[1] = (uint32_t)(b->seed >> 32);
+        r.id[0] = (uint32_t)ray; r.id[1] = (uint32_t)((uint64_t)ray >> 32);
+        r.ndraw = 0;
+        lam = 1. / (1. / b->lambda_min_nm - r.uniform() * (1. / b->lambda_min_nm - 1. / b->lambda_max_nm));
+      }
+      x[out] = px; y[out] = py; z[out] = b->z; t[out] = pt;
+      dx[out] = b->cx[i]; dy[out] = b->cy[i]; dz[out] = b->cz[i];
+      lambda[out] = lam * nm;
+      out++;
+    }
+  }
+  return out == n ? 0 : -1;
+}
+
 // Philox uniform stream check: k-th uniform of ray `id`
 double orc_uniform(uint64_t seed, uint64_t id, uint32_t k) {
   Rng r;

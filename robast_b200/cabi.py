@@ -56,6 +56,13 @@ rbg_launch_count = _proto("rbg_launch_count", C.c_int64, [])
 rbg_profile_enable = _proto("rbg_profile_enable", C.c_int, [C.c_int])
 rbg_profile_read = _proto("rbg_profile_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)])
 rbg_shoot = _proto("rbg_shoot", C.c_int, [C.POINTER(rbg_shoot_desc), C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_int, C.c_void_p])
+class rbg_bunches(C.Structure):
+    _fields_ = [("nbunches", C.c_int64)] + [(k, C.POINTER(C.c_float)) for k in ("x", "y", "time", "cx", "cy", "cz", "lambda_", "photons")] + \
+        [(k, C.c_double) for k in ("z", "telescope_z", "refractive_index", "lambda_min_nm", "lambda_max_nm")] + [("seed", C.c_uint64)]
+
+
+rbg_bunch_rays = _proto("rbg_bunch_rays", C.c_int, [C.POINTER(rbg_bunches), C.POINTER(C.c_int64)])
+rbg_shoot_bunches = _proto("rbg_shoot_bunches", C.c_int, [C.POINTER(rbg_bunches), C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_int, C.c_void_p])
 rbg_hist2d = _proto("rbg_hist2d", C.c_int, [C.c_int64, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, C.c_int, C.c_void_p])
 rbg_hist2d_stats = _proto("rbg_hist2d_stats", C.c_int, [C.c_int64, _dp, _dp, _dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_void_p])
 rbg_containment_radius = _proto("rbg_containment_radius", C.c_int, [C.c_int32, _dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, C.c_double, _dp, C.c_int, C.c_void_p])
@@ -67,7 +74,7 @@ rbg_tmm_host = _proto("rbg_tmm_host", C.c_int, [C.c_void_p, C.c_int, C.c_int64, 
 
 ABI_SYMBOLS = ["rbg_abi_version", "rbg_last_error", "rbg_device_count", "rbg_scene_create", "rbg_scene_destroy",
                "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_scene_kernel_variant", "rbg_trace", "rbg_trace_history", "rbg_launch_count", "rbg_profile_enable",
-               "rbg_profile_read", "rbg_shoot", "rbg_hist2d", "rbg_hist2d_stats", "rbg_containment_radius", "rbg_containment_radius_host", "rbg_moments", "rbg_tmm", "rbg_tmm_host", "rbg_tmm_general_host"]
+               "rbg_profile_read", "rbg_shoot", "rbg_bunch_rays", "rbg_shoot_bunches", "rbg_hist2d", "rbg_hist2d_stats", "rbg_containment_radius", "rbg_containment_radius_host", "rbg_moments", "rbg_tmm", "rbg_tmm_host", "rbg_tmm_general_host"]
 
 
 class RbgError(RuntimeError):

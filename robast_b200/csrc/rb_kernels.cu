@@ -1006,6 +1006,93 @@ int rbg_shoot(const rbg_shoot_desc* d, int64_t first, int64_t n, double* x, doub
   });
 }
 
+// ---- ACorsikaIACTFile::GetRayArray on device: one thread per ray, the bunch found by bisection of the ray-count prefix sums
+static long long bunch_count(float photons) {  // rays of `for (j = 0; j < photons; j++)`
+  if (!(photons > 0)) return 0;
+  long long c = (long long)ceilf(photons);
+  return c;
+}
+__global__ void k_shoot_bunches(long long nb, const long long* __restrict__ offs, const float* __restrict__ bx, const float* __restrict__ by,
+                                const float* __restrict__ bt, const float* __restrict__ bcx, const float* __restrict__ bcy, const float* __restrict__ bcz,
+                                const float* __restrict__ blam, double z, double telz, double refidx, double lmin, double lmax, unsigned long long seed,
+                                long long first, long long n, double* x, double* y, double* zz, double* t, double* dx, double* dy, double* dz, double* lambda) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  long long ray = first + j;
+  long long lo = 0, hi = nb;  // last bunch with offs[b] <= ray
+  while (hi - lo > 1) {
+    long long mid = (lo + hi) >> 1;
+    if (offs[mid] <= ray) lo = mid; else hi = mid;
+  }
+  const double cm = 1., ns = 1e-9, nm = 1e-7, m = 100.;
+  double cx = bcx[lo], cy = bcy[lo], cz = bcz[lo];
+  double airmass = -1. / cz, tel_dist = (z - telz * cm) * airmass, speed = 2.99792458e8 * m / refidx;
+  double lam = blam[lo];
+  if (lam == 0) {
+    Philox g;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.id0 = (uint32_t)ray; g.id1 = (uint32_t)((unsigned long long)ray >> 32);
+    g.ndraw = 0;
+    lam = 1. / (1. / lmin - rng_uniform(g) * (1. / lmin - 1. / lmax));
+  }
+  x[j] = bx[lo] * cm - tel_dist * cx;
+  y[j] = by[lo] * cm - tel_dist * cy;
+  zz[j] = z;
+  t[j] = bt[lo] * ns - tel_dist / speed;
+  dx[j] = cx; dy[j] = cy; dz[j] = cz;
+  lambda[j] = lam * nm;
+}
+static void check_bunches(const rbg_bunches* b) {
+  if (!b || b->nbunches < 0) throw Invalid("bad bunch table");
+  if (b->nbunches > 0 && (!b->x || !b->y || !b->time || !b->cx || !b->cy || !b->cz || !b->lambda || !b->photons)) throw Invalid("null bunch array");
+}
+int rbg_bunch_rays(const rbg_bunches* b, int64_t* nrays) {
+  return guard([&] {
+    check_bunches(b);
+    if (!nrays) throw Invalid("null argument");
+    long long tot = 0;
+    for (int64_t i = 0; i < b->nbunches; i++) tot += bunch_count(b->photons[i]);
+    *nrays = tot;
+  });
+}
+int rbg_shoot_bunches(const rbg_bunches* b, int64_t first, int64_t n, double* x, double* y, double* z, double* t, double* dx, double* dy, double* dz,
+                      double* lambda, int device, void* stream) {
+  return guard([&] {
+    check_bunches(b);
+    if (first < 0 || n < 0) throw Invalid("bad ray range");
+    if (n == 0) return;
+    if (rbg_device_count() <= 0) throw std::runtime_error("cuda: no CUDA device available — the shooters have no CPU fallback");
+    std::vector<long long> offs((size_t)b->nbunches + 1, 0);
+    for (int64_t i = 0; i < b->nbunches; i++) offs[i + 1] = offs[i] + bunch_count(b->photons[i]);
+    if (first + n > offs[b->nbunches]) throw Invalid("ray range beyond the bunches' photons");
+    // only the bunches that hold rays [first, first+n) travel to the device
+    int64_t b0 = std::upper_bound(offs.begin(), offs.end(), (long long)first) - offs.begin() - 1;
+    int64_t b1 = std::lower_bound(offs.begin(), offs.end(), (long long)(first + n)) - offs.begin();
+    int64_t nb = b1 - b0;
+    CK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    char* d = nullptr;
+    size_t fb = ((size_t)nb * 4 + 255) & ~size_t(255), ob = ((size_t)(nb + 1) * 8 + 255) & ~size_t(255);
+    CK(cudaMallocAsync((void**)&d, ob + 7 * fb, st));
+    try {
+      CK(cudaMemcpyAsync(d, offs.data() + b0, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
+      const float* src[7] = {b->x, b->y, b->time, b->cx, b->cy, b->cz, b->lambda};
+      for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(d + ob + a * fb, src[a] + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+      auto f = [&](int a) { return (const float*)(d + ob + a * fb); };
+      long long blocks = (n + 255) / 256;
+      k_shoot_bunches<<<(unsigned)blocks, 256, 0, st>>>(nb, (const long long*)d, f(0), f(1), f(2), f(3), f(4), f(5), f(6), b->z, b->telescope_z,
+                                                         b->refractive_index, b->lambda_min_nm, b->lambda_max_nm, b->seed, first, n, x, y, z, t, dx, dy, dz, lambda);
+      g_launches++;
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));  // offs (a host temporary) and the caller's bunch arrays may go away after the return
+    } catch (...) {
+      cudaFreeAsync(d, st);
+      throw;
+    }
+    cudaFreeAsync(d, st);
+  });
+}
+
 int rbg_hist2d(int64_t n, const double* x, const double* y, const int32_t* status, int32_t sel, int32_t nx, double xmin, double xmax, int32_t ny,
                double ymin, double ymax, unsigned long long* hist, int device, void* stream) {
   return rbg_hist2d_stats(n, x, y, status, sel, 0., 0., nx, xmin, xmax, ny, ymin, ymax, hist, nullptr, device, stream);

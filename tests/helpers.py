@@ -45,6 +45,8 @@ def load_oracle():
     lib.orc_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     lib.orc_shoot.restype = C.c_int
     lib.orc_shoot.argtypes = [C.POINTER(R.rbg_shoot_desc), C.c_int64, C.c_int64] + [C.c_void_p] * 8
+    lib.orc_shoot_bunches.restype = C.c_int
+    lib.orc_shoot_bunches.argtypes = [C.POINTER(R.rbg_bunches), C.c_int64, C.c_int64] + [C.c_void_p] * 8
     lib.orc_shape_contains.restype = C.c_int
     lib.orc_shape_contains.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.orc_shape_dist.restype = C.c_double
@@ -231,3 +233,32 @@ def compare(a, b, tol_pos=1e-7, tol_dir=1e-9, tol_time=1e-7 / 2.99792458e10):
     return dict(n=a.n, status_mismatch=int((~same_status).sum()), max_dpos=float(dpos[same_status].max() if same_status.any() else 0),
                 max_dang=float(dang[same_status].max() if same_status.any() else 0), max_dt=float(dt[same_status].max() if same_status.any() else 0),
                 npoints_mismatch=int((a.npoints != b.npoints).sum()), node_mismatch=int((a.last_node != b.last_node).sum()), bad=int((~ok).sum()))
+
+
+def make_bunches(n_bunch, seed, z=1000., telescope_z=250., refidx=1.00027, lam_min=300., lam_max=600.):
+    """synthetic CORSIKA photon bunches of one telescope (the columns ACorsikaIACTFile keeps, src/ACorsikaIACTFile.cxx:86-97):
+    positions over a 12 m dish, near-vertical directions, bunch sizes around 1 with fractional parts, a third of the bunches with
+    undetermined wavelength (lambda = 0).  Returns (rbg_bunches, dict of the float32 arrays kept alive)."""
+    import robast_b200 as R
+    rng = np.random.default_rng(seed)
+    a = {}
+    a["x"] = (rng.random(n_bunch) * 1200. - 600.).astype(np.float32)
+    a["y"] = (rng.random(n_bunch) * 1200. - 600.).astype(np.float32)
+    a["time"] = (rng.random(n_bunch) * 50.).astype(np.float32)
+    th, ph = np.radians(rng.random(n_bunch) * 3.), rng.random(n_bunch) * 2 * np.pi
+    a["cx"] = (np.sin(th) * np.cos(ph)).astype(np.float32)
+    a["cy"] = (np.sin(th) * np.sin(ph)).astype(np.float32)
+    a["cz"] = (-np.cos(th)).astype(np.float32)
+    lam = 300. + 300. * rng.random(n_bunch)
+    lam[rng.random(n_bunch) < 0.33] = 0.
+    a["lambda_"] = lam.astype(np.float32)
+    ph_ = rng.random(n_bunch) * 3.2
+    ph_[rng.random(n_bunch) < 0.1] = 0.
+    ph_[::7] = 2.0
+    a["photons"] = ph_.astype(np.float32)
+    b = R.rbg_bunches()
+    b.nbunches = n_bunch
+    for k, v in a.items():
+        setattr(b, k, v.ctypes.data_as(C.POINTER(C.c_float)))
+    b.z, b.telescope_z, b.refractive_index, b.lambda_min_nm, b.lambda_max_nm, b.seed = z, telescope_z, refidx, lam_min, lam_max, 20110306
+    return b, a

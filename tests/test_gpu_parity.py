@@ -553,3 +553,33 @@ def test_overlapping_nodes_parity(R, oracle, nested, tilt):
         assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (steps, rep)
         st = np.bincount(got.status, minlength=6)
         assert st[3] > 1000 and st[1] > 1000
+
+
+@pytest.mark.gpu
+def test_corsika_bunches_on_device_match_oracle(R, oracle):
+    """rbg_shoot_bunches (ACorsikaIACTFile::GetRayArray, src/ACorsikaIACTFile.cxx:71-133) against the oracle, whole table and a
+    shard of it, then traced through the Davies-Cotton telescope"""
+    import ctypes as C
+    import torch
+    b, a = H.make_bunches(200000, 11, z=3300., telescope_z=0.)
+    nr = C.c_int64()
+    R.check(R.rbg_bunch_rays(C.byref(b), C.byref(nr)))
+    n = nr.value
+    ref = np.zeros((8, n))
+    assert oracle.orc_shoot_bunches(C.byref(b), 0, n, *[ref[i].ctypes.data for i in range(8)]) == 0
+    dev = torch.empty((8, n), dtype=torch.float64, device="cuda:0")
+    R.check(R.rbg_shoot_bunches(C.byref(b), 0, n, *[dev[i].data_ptr() for i in range(8)], 0, None))
+    got = dev.cpu().numpy()
+    assert (got[2] == ref[2]).all() and (got[4:7] == ref[4:7]).all()
+    assert np.abs(got[0] - ref[0]).max() < 1e-9 and np.abs(got[1] - ref[1]).max() < 1e-9 and np.abs(got[3] - ref[3]).max() < 1e-18
+    assert np.abs(got[7] / ref[7] - 1).max() < 1e-14
+    first, m = n // 3, n // 4
+    R.check(R.rbg_shoot_bunches(C.byref(b), first, m, *[dev[i].data_ptr() for i in range(8)], 0, None))
+    assert (dev[:, :m].cpu().numpy() == got[:, first:first + m]).all()
+    # the rays feed the tracer like any other batch
+    from robast_b200 import configs
+    mgr, _keep = configs.davies_cotton()
+    rays = H.Rays(np.ascontiguousarray(got.T))
+    H.trace_gpu(mgr.ExportScene(), rays, H.opts(disable_fresnel=1))
+    st = np.bincount(rays.status, minlength=6)
+    assert st[3] > 0.2 * n and st[0] == 0

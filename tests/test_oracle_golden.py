@@ -586,3 +586,37 @@ def test_empty_overlapping_holder_is_transparent(R, oracle):
     done = plain.status != 2  # exiting rays end on the world box in both cases too, but cross the holder's own boundary on the way
     assert np.abs(plain.out[:3] - held.out[:3]).max() < 1e-9
     assert (plain.npoints[done] == held.npoints[done]).all()
+
+
+def test_corsika_bunch_expansion_closed_form(R, oracle):
+    """ACorsikaIACTFile::GetRayArray (src/ACorsikaIACTFile.cxx:71-133): ray count per bunch = iterations of `j < photons`, start
+    point projected back along the direction to height z, arrival time shifted by the path at c/n — against a numpy restatement;
+    the library's ray count (rbg_bunch_rays, host side) agrees"""
+    import ctypes as C
+    import helpers as H
+    b, a = H.make_bunches(2000, 7)
+    counts = np.where(a["photons"] > 0, np.ceil(a["photons"].astype(np.float64)), 0).astype(np.int64)
+    total = int(counts.sum())
+    nr = C.c_int64()
+    R.check(R.rbg_bunch_rays(C.byref(b), C.byref(nr)))
+    assert nr.value == total and total > 2000
+    out = np.zeros((8, total))
+    assert oracle.orc_shoot_bunches(C.byref(b), 0, total, *[out[i].ctypes.data for i in range(8)]) == 0
+    idx = np.repeat(np.arange(2000), counts)
+    f = {k: v.astype(np.float64)[idx] for k, v in a.items()}
+    dist = (b.z - b.telescope_z) * (-1. / f["cz"])
+    assert np.allclose(out[0], f["x"] - dist * f["cx"], rtol=0, atol=1e-9)
+    assert np.allclose(out[1], f["y"] - dist * f["cy"], rtol=0, atol=1e-9)
+    assert (out[2] == b.z).all()
+    assert np.allclose(out[3], f["time"] * 1e-9 - dist / (2.99792458e10 / b.refractive_index), rtol=0, atol=1e-18)
+    assert (out[4] == f["cx"]).all() and (out[5] == f["cy"]).all() and (out[6] == f["cz"]).all()
+    fixed = f["lambda_"] != 0
+    assert np.allclose(out[7][fixed], f["lambda_"][fixed] * 1e-7, rtol=1e-15)
+    lam = out[7][~fixed] / 1e-7
+    assert (~fixed).sum() > 500 and lam.min() >= 300. and lam.max() <= 600.
+    # uniform in 1/lambda: the median of 1/lambda sits halfway between the ends
+    assert abs(np.median(1. / lam) - 0.5 * (1 / 300. + 1 / 600.)) < 1.5e-4
+    # a sub-range reproduces the same rays (streams are keyed by the global ray index)
+    part = np.zeros((8, 500))
+    assert oracle.orc_shoot_bunches(C.byref(b), 1234, 500, *[part[i].ctypes.data for i in range(8)]) == 0
+    assert (part == out[:, 1234:1734]).all()
