@@ -239,14 +239,15 @@ RB_HD inline Cx csqrt_(Cx z) {  // principal branch
   if (z.re >= 0) return cx(s, o);
   return cx(fabs(o), z.im >= 0 ? s : -s);
 }
-RB_HD inline Cx cexp_(Cx z) {
+// the transcendental helpers are not inlined: each is hundreds of instructions and the TMM calls them from several places
+RB_HD inline RB_NOINLINE Cx cexp_(Cx z) {
   double e = exp(z.re);
   return cx(e * cos(z.im), e * sin(z.im));
 }
 RB_HD inline Cx clog_(Cx z) { return cx(log(hypot(z.re, z.im)), atan2(z.im, z.re)); }
-RB_HD inline Cx ccos_(Cx z) { return cx(cos(z.re) * cosh(z.im), -sin(z.re) * sinh(z.im)); }
+RB_HD inline RB_NOINLINE Cx ccos_(Cx z) { return cx(cos(z.re) * cosh(z.im), -sin(z.re) * sinh(z.im)); }
 RB_HD inline Cx csin_(Cx z) { return cx(sin(z.re) * cosh(z.im), cos(z.re) * sinh(z.im)); }
-RB_HD inline Cx casin_(Cx z) {  // asin z = -i log(i z + sqrt(1 - z^2))
+RB_HD inline RB_NOINLINE Cx casin_(Cx z) {  // asin z = -i log(i z + sqrt(1 - z^2))
   Cx w = csqrt_(cx(1, 0) - z * z);
   Cx l = clog_(cx(-z.im + w.re, z.re + w.im));
   return cx(l.im, -l.re);
@@ -259,12 +260,18 @@ RB_HD inline bool tmm_is_forward(Cx n, Cx theta) {
 // AMultilayer::CoherentTMM (src/AMultilayer.cxx:240-481) for one polarisation (pol 0 = s, 1 = p) over the stack made of
 // layers a..b (inclusive) of sc.layers[first ...], entered through layer a, or through layer b when `reverse`; th0 is the
 // (possibly complex) angle in the entrance medium.
-RB_HD inline void tmm_coherent_sub(const DScene& sc, int first, int a, int b, bool reverse, int pol, Cx th0, double lam, double& R, double& T) {
+// NP = 1: polarisation `pol0`; NP = 2: both (index 0 = s, 1 = p) in one pass — refractive indices, Snell angles, their cosines
+// and the layer phases do not depend on the polarisation, only the interface coefficients and the matrix products do, so the
+// unpolarised CoherentTMMMixed costs one set of transcendentals instead of two.  Per polarisation the arithmetic is the same
+// sequence of operations either way.
+template <int NP> RB_HD inline void tmm_coherent_multi(const DScene& sc, int first, int a, int b, bool reverse, int pol0, Cx th0, double lam, double* R, double* T) {
   int N = b - a + 1;
-  Cx n0 = cx(1, 0), nprev = cx(1, 0), thprev = cx(0, 0), n_last = cx(1, 0), th_last = cx(0, 0);
+  Cx n0 = cx(1, 0), nprev = cx(1, 0), n_last = cx(1, 0);
   Cx n0s = cx(0, 0);
-  Cx m00 = cx(1, 0), m01 = cx(0, 0), m10 = cx(0, 0), m11 = cx(1, 0);
-  Cx r0 = cx(0, 0), t0 = cx(1, 0);
+  Cx cprev = cx(1, 0), c_last = cx(1, 0);  // cos of the Snell angle in the previous / last layer
+  Cx m00[NP], m01[NP], m10[NP], m11[NP], r0[NP], t0[NP];
+#pragma unroll
+  for (int q = 0; q < NP; q++) { m00[q] = cx(1, 0); m01[q] = cx(0, 0); m10[q] = cx(0, 0); m11[q] = cx(1, 0); r0[q] = cx(0, 0); t0[q] = cx(1, 0); }
   for (int i = 0; i < N; i++) {
     const rbg_layer L = sc.layers[first + (reverse ? b - i : a + i)];
     Cx ni = cx(index_n(sc, L.index, lam), index_k(sc, L.index, lam));
@@ -274,50 +281,67 @@ RB_HD inline void tmm_coherent_sub(const DScene& sc, int first, int a, int b, bo
       n0s = ni * csin_(th0);
       thi = casin_(n0s / ni);
       if (!tmm_is_forward(ni, thi)) thi = cx(RB_PI - thi.re, -thi.im);
+      cprev = ccos_(thi);
     } else {
       thi = casin_(n0s / ni);
       if (i == N - 1 && !tmm_is_forward(ni, thi)) thi = cx(RB_PI - thi.re, -thi.im);
       // interface (i-1) -> i
-      Cx ci = ccos_(thprev), cf = ccos_(thi), r, t;
+      Cx ci = cprev, cf = ccos_(thi);
       Cx ii = nprev * ci;
-      if (pol == 0) {
-        Cx ff = ni * cf;
-        r = (ii - ff) / (ii + ff);
-        t = (2. * ii) / (ii + ff);
-      } else {
-        Cx fi = ni * ci, i_f = nprev * cf;
-        r = (fi - i_f) / (fi + i_f);
-        t = (2. * ii) / (fi + i_f);
-      }
-      if (i == 1) { r0 = r; t0 = t; }
-      else {
+      Cx em = cx(1, 0), ep = cx(1, 0);
+      if (i > 1) {
         // layer i-1 is an inner layer: M_{i-1} = (1/t) diag(e^{-iδ}, e^{iδ}) [[1,r],[r,1]]
         Cx kz = ((2 * RB_PI) * (nprev * ci));
         kz = cx(kz.re / lam, kz.im / lam);
         double d = sc.layers[first + (reverse ? b - (i - 1) : a + i - 1)].thickness;
         Cx delta = cx(kz.re * d, kz.im * d);
         if (delta.im > 35) delta.im = 35;
-        Cx em = cexp_(cx(delta.im, -delta.re)), ep = cexp_(cx(-delta.im, delta.re));  // exp(-iδ), exp(iδ)
-        Cx s = cx(1, 0) / t;
-        Cx d00 = s * em, d11 = s * ep;
-        Cx a00 = d00, a01 = d00 * r, a10 = d11 * r, a11 = d11;
-        Cx q00 = m00 * a00 + m01 * a10, q01 = m00 * a01 + m01 * a11, q10 = m10 * a00 + m11 * a10, q11 = m10 * a01 + m11 * a11;
-        m00 = q00; m01 = q01; m10 = q10; m11 = q11;
+        em = cexp_(cx(delta.im, -delta.re));  // exp(-iδ)
+        ep = cexp_(cx(-delta.im, delta.re));  // exp(iδ)
       }
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        const int pol = NP == 1 ? pol0 : q;
+        Cx r, t;
+        if (pol == 0) {
+          Cx ff = ni * cf;
+          r = (ii - ff) / (ii + ff);
+          t = (2. * ii) / (ii + ff);
+        } else {
+          Cx fi = ni * ci, i_f = nprev * cf;
+          r = (fi - i_f) / (fi + i_f);
+          t = (2. * ii) / (fi + i_f);
+        }
+        if (i == 1) { r0[q] = r; t0[q] = t; }
+        else {
+          Cx s = cx(1, 0) / t;
+          Cx d00 = s * em, d11 = s * ep;
+          Cx a00 = d00, a01 = d00 * r, a10 = d11 * r, a11 = d11;
+          Cx q00 = m00[q] * a00 + m01[q] * a10, q01 = m00[q] * a01 + m01[q] * a11, q10 = m10[q] * a00 + m11[q] * a10, q11 = m10[q] * a01 + m11[q] * a11;
+          m00[q] = q00; m01[q] = q01; m10[q] = q10; m11[q] = q11;
+        }
+      }
+      cprev = cf;
     }
     nprev = ni;
-    thprev = thi;
     n_last = ni;
-    th_last = thi;
+    c_last = cprev;
   }
-  Cx b00 = cx(1, 0) / t0, b01 = r0 / t0;
-  Cx q00 = b00 * m00 + b01 * m10, q10 = b01 * m00 + b00 * m10;
-  Cx r = q10 / q00, t = cx(1, 0) / q00;
-  R = cabs2(r);
-  Cx cf = ccos_(th_last), ci = ccos_(th0);
-  double tt = cabs2(t);  // |t*t| = |t|^2
-  if (pol == 0) T = tt * ((n_last * cf).re / (n0 * ci).re);
-  else T = tt * ((n_last * cconj(cf)).re / (n0 * cconj(ci)).re);
+  Cx cf = c_last, ci = ccos_(th0);
+#pragma unroll
+  for (int q = 0; q < NP; q++) {
+    const int pol = NP == 1 ? pol0 : q;
+    Cx b00 = cx(1, 0) / t0[q], b01 = r0[q] / t0[q];
+    Cx q00 = b00 * m00[q] + b01 * m10[q], q10 = b01 * m00[q] + b00 * m10[q];
+    Cx r = q10 / q00, t = cx(1, 0) / q00;
+    R[q] = cabs2(r);
+    double tt = cabs2(t);  // |t*t| = |t|^2
+    if (pol == 0) T[q] = tt * ((n_last * cf).re / (n0 * ci).re);
+    else T[q] = tt * ((n_last * cconj(cf)).re / (n0 * cconj(ci)).re);
+  }
+}
+RB_HD inline void tmm_coherent_sub(const DScene& sc, int first, int a, int b, bool reverse, int pol, Cx th0, double lam, double& R, double& T) {
+  tmm_coherent_multi<1>(sc, first, a, b, reverse, pol, th0, lam, &R, &T);
 }
 RB_HD inline void tmm_coherent(const DScene& sc, int ml, int pol, double th0, double lam, double& R, double& T) {
   const rbg_multilayer M = sc.multilayers[ml];
@@ -387,16 +411,16 @@ RB_HD inline void tmm_incoherent(const DScene& sc, int ml, int pol, Cx th0, doub
   T = 1 / l00;
   R = l10 / l00;
 }
-RB_HD inline void tmm_mixed(const DScene& sc, int ml, double th, double lam, double& R, double& T) {
+RB_HD inline RB_NOINLINE void tmm_mixed(const DScene& sc, int ml, double th, double lam, double& R, double& T) {  // one copy: two call sites
   const rbg_multilayer M = sc.multilayers[ml];
   if (M.table_r >= 0 && M.table_t >= 0) {
     R = th2_interp(sc, M.table_r, lam, th);
     T = th2_interp(sc, M.table_t, lam, th);
     return;
   }
-  double rp, tp, rs, ts;
-  tmm_coherent(sc, ml, 1, th, lam, rp, tp);
-  tmm_coherent(sc, ml, 0, th, lam, rs, ts);
+  double r2[2], t2[2];  // 0 = s, 1 = p
+  tmm_coherent_multi<2>(sc, M.first, 0, M.n - 1, false, 0, cx(th, 0), lam, r2, t2);
+  const double rp = r2[1], tp = t2[1], rs = r2[0], ts = t2[0];
   R = (rp + rs) / 2.;
   T = (tp + ts) / 2.;
 }
