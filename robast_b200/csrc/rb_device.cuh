@@ -752,9 +752,11 @@ template <bool CONE> RB_HD inline bool poly_contains(const double* P, V3 p) {
   if (p.z < sec[0] || p.z > sec[3 * (nz - 1)]) return false;
   int eb;
   double r = poly_radius<CONE>(P, p, eb);
-  int iz = 0;
-  for (int i = 1; i < nz; i++)
-    if (sec[3 * i] <= p.z) iz = i;
+  int iz = 0, hi = nz;  // last section with z <= p.z (sections ascend; bisection instead of a scan over up to 100 of them)
+  while (hi - iz > 1) {
+    int mid = (iz + hi) >> 1;
+    if (sec[3 * mid] <= p.z) iz = mid; else hi = mid;
+  }
   if (iz == nz - 1) return !(r > sec[3 * iz + 2]);
   double dz = sec[3 * (iz + 1)] - sec[3 * iz];
   if (dz < 1E-8) return !(r > rb_max(sec[3 * iz + 2], sec[3 * (iz + 1) + 2]));
@@ -809,16 +811,33 @@ template <bool CONE> RB_HD inline bool poly_slab(const double* P, int k, V3 p, V
 }
 template <bool CONE> RB_HD inline double poly_dist_out(const double* P, V3 p, V3 d) {
   int nz = (int)P[3];
-  double best = RB_BIG;
-  for (int k = 0; k + 1 < nz; k++) {
+  const double* sec = P + 4;
+  if (d.z == 0) {  // the ray stays in its z slab(s)
+    double best = RB_BIG;
+    for (int k = 0; k + 1 < nz; k++) {
+      double tin, tout;
+      if (!poly_slab<CONE>(P, k, p, d, tin, tout)) continue;
+      if (tout <= 1e-11) continue;
+      double t = tin > 0 ? tin : 0.0;
+      if (tout - t < 1e-12) continue;
+      if (t < best) best = t;
+    }
+    return best;
+  }
+  // The slabs are stacked in z and z is monotonic along the ray: visited in the order the ray meets them, the first slab with
+  // a valid interval holds the smallest entry parameter (a Bezier profile has 100 sections: no need to clip against all).
+  const bool up = d.z > 0;
+  for (int j = 0; j + 1 < nz; j++) {
+    const int k = up ? j : nz - 2 - j;
+    if (up ? sec[3 * (k + 1)] <= p.z : sec[3 * k] >= p.z) continue;  // wholly behind the start point
     double tin, tout;
     if (!poly_slab<CONE>(P, k, p, d, tin, tout)) continue;
     if (tout <= 1e-11) continue;
     double t = tin > 0 ? tin : 0.0;
     if (tout - t < 1e-12) continue;
-    if (t < best) best = t;
+    return t;
   }
-  return best;
+  return RB_BIG;
 }
 // From inside: leave slab after slab until the exit point is not inside a neighbouring slab any more.  The slabs are stacked
 // in z, so the slab that continues the path is the next non-degenerate one in the direction of d.z: the march is linear in
