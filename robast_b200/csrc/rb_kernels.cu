@@ -741,6 +741,10 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     s->d.g2y = upload(s, D->g2y, D->ng2pts);
     s->d.g2z = upload(s, D->g2z, D->ng2pts);
     s->d.nnodes = (int)B.nodes.size();
+    s->d.nbvh = (int)B.bvh.size();
+    s->d.nshapes = (int)B.shapes.size();
+    s->d.ndpar = (int)B.dpar.size();
+    s->d.nmats = (int)B.mats.size();
     s->d.top_shape = D->top_volume >= 0 ? D->volumes[D->top_volume].shape : -1;
     s->d.has_many = (need_phys & RB_PH_OVERLAP) != 0;
     CK(cudaMalloc((void**)&s->d_count, RB_HOST_STREAMS * sizeof(int32_t)));

@@ -76,6 +76,7 @@ struct DScene {
   int32_t nnodes;
   int32_t top_shape;
   int32_t has_many;  // some node is placed with AddNodeOverlap
+  int32_t nbvh, nshapes, ndpar, nmats;  // table lengths (shared-memory staging of the geometry tables)
   int32_t pad_;
 };
 

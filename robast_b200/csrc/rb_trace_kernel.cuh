@@ -109,6 +109,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, K::min_blocks) k_trace(const __
 // separated by barriers so that all warps of a block run the same code region at the same time: the per-SM
 // instruction cache is then shared instead of thrashed (profiles/r1d: icc hit rate 58 %, L1.5 saturated by
 // instruction requests without this).  Idle lanes of the last block shadow the last ray and store nothing.
+#ifndef RB_SMEM_SCENE
+#define RB_SMEM_SCENE 0
+#endif
+__host__ __device__ inline size_t rb_smem_round(size_t b) { return (b + 15) & ~size_t(15); }
+// block-cooperative copy of `bytes` (multiple of 16; the source tables are cudaMalloc'ed, i.e. 256-byte aligned and padded by the
+// allocator's granularity) into shared memory
+__device__ inline void rb_smem_copy(char* dst, const void* src, size_t bytes) {
+  const int4* s4 = (const int4*)src;
+  int4* d4 = (int4*)dst;
+  for (size_t k = threadIdx.x; k < bytes / 16; k += blockDim.x) d4[k] = s4[k];
+}
 // Split ray load for k_step: the navigation phases need only the point, the direction, the node and the on-boundary bit;
 // time, wavelength, counters and the segment start are read when the interaction is evaluated, so that they are not
 // live (= spilled around every non-inlined shape call) during navigation.
@@ -153,9 +164,37 @@ __device__ inline void load_rest(const DTraceParams& tp, const DRays& R, long lo
 }
 
 template <class K>
-__global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
+__global__ void __launch_bounds__(K::step_threads, K::step_min_blocks) k_step(const __grid_constant__ DScene sc_, const __grid_constant__ DTraceParams tp,
                                                                               const __grid_constant__ DRays R, const int32_t* __restrict__ live,
-                                                                              long long n, int init) {
+                                                                              long long n, int init, int smem_bytes) {
+#if RB_SMEM_SCENE
+  // Geometry tables (nodes, BVH, shapes, parameters, operand matrices: tens of kB) staged in shared memory when they fit the
+  // block's dynamic allocation: their loads then no longer compete for L1 with the kernel's local-memory traffic.
+  extern __shared__ double4 rb_smem[];
+  __shared__ DScene ssc;
+  {
+    char* base = (char*)rb_smem;
+    const size_t b0 = rb_smem_round((size_t)sc_.nnodes * sizeof(DNode)), b1 = rb_smem_round((size_t)sc_.nbvh * sizeof(DBvh)),
+                 b2 = rb_smem_round((size_t)sc_.nshapes * sizeof(DShape)), b3 = rb_smem_round((size_t)sc_.ndpar * 8),
+                 b4 = rb_smem_round((size_t)sc_.nmats * sizeof(DMat));
+    const bool fits = b0 + b1 + b2 + b3 + b4 <= (size_t)smem_bytes;
+    if (threadIdx.x == 0) {
+      ssc = sc_;
+      if (fits) {
+        ssc.nodes = (const DNode*)base; ssc.bvh = (const DBvh*)(base + b0); ssc.shapes = (const DShape*)(base + b0 + b1);
+        ssc.dpar = (const double*)(base + b0 + b1 + b2); ssc.mats = (const DMat*)(base + b0 + b1 + b2 + b3);
+      }
+    }
+    if (fits) {
+      rb_smem_copy(base, sc_.nodes, b0); rb_smem_copy(base + b0, sc_.bvh, b1); rb_smem_copy(base + b0 + b1, sc_.shapes, b2);
+      rb_smem_copy(base + b0 + b1 + b2, sc_.dpar, b3); rb_smem_copy(base + b0 + b1 + b2 + b3, sc_.mats, b4);
+    }
+    __syncthreads();
+  }
+  const DScene& sc = ssc;
+#else
+  const DScene& sc = sc_;
+#endif
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < n;
   if (!active) i = n - 1;
@@ -269,7 +308,14 @@ struct rb_variant {
   int rb_launch_step_##NAME(const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init,    \
                             int, cudaStream_t st) {                                                                                  \
     long long blocks = (n + STH - 1) / STH;                                                                                          \
-    k_step<rb_cfg_##NAME><<<(unsigned)blocks, STH, 0, st>>>(sc, tp, R, live, n, init);                                               \
+    int smem = 0;                                                                                                                    \
+    if (RB_SMEM_SCENE) {                                                                                                             \
+      size_t need = rb_smem_round((size_t)sc.nnodes * sizeof(DNode)) + rb_smem_round((size_t)sc.nbvh * sizeof(DBvh)) +               \
+                    rb_smem_round((size_t)sc.nshapes * sizeof(DShape)) + rb_smem_round((size_t)sc.ndpar * 8) +                      \
+                    rb_smem_round((size_t)sc.nmats * sizeof(DMat));                                                                 \
+      if (need <= 46 * 1024) smem = (int)need;                                                                                       \
+    }                                                                                                                                \
+    k_step<rb_cfg_##NAME><<<(unsigned)blocks, STH, smem, st>>>(sc, tp, R, live, n, init, smem);                                      \
     return (int)cudaGetLastError();                                                                                                  \
   }                                                                                                                                  \
   extern const rb_variant rb_variant_##NAME = {#NAME, D, S, P, rb_launch_trace_##NAME, rb_launch_step_##NAME};
