@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=int(os.environ.get("RB_STEPS_PER_LAUNCH", "0")))
     ap.add_argument("--n-side", type=int, default=N_SIDE, help="grid side per field angle (profiling runs only; the bench metric uses 3334)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=int(os.environ.get("RB_E2E_THREADS", "2")), help="TraceNonSequential calls in flight on the host-buffer path")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -278,28 +279,62 @@ def main():
     # ---- e2e: host (pinned) buffers through the same C-ABI call
     e2e = None
     if not args.no_e2e:
+        # The user-facing call with HOST buffers: AOpticsManager::TraceNonSequential's path, rbg_trace(on_device = 0), H2D and D2H
+        # inside.  The field angles are independent TraceNonSequential calls; --e2e-threads of them are in flight at a time, each
+        # from its own host thread on its own scene handle and output buffers (the C ABI is thread-safe across handles), so the
+        # pipeline fill and drain of one call overlap the steady state of another.
+        T = max(1, min(args.e2e_threads, nang))
         hin = torch.empty((nang, 8, n), dtype=torch.float64).pin_memory()
         hin.copy_(inp.cpu())
-        hout = torch.empty((7, n), dtype=torch.float64).pin_memory()
-        hiout = torch.empty((3, n), dtype=torch.int32).pin_memory()
+        hout = [torch.empty((7, n), dtype=torch.float64).pin_memory() for _ in range(T)]
+        hiout = [torch.empty((3, n), dtype=torch.int32).pin_memory() for _ in range(T)]
+        scenes_e2e = [scene]
+        for _ in range(1, T):
+            h = C.c_void_p()
+            R.check(R.rbg_scene_create(export.desc_ptr(), local, C.byref(h)))
+            scenes_e2e.append(h)
 
-        def host_struct(k):
+        def host_struct(k, t):
             r = R.rbg_rays()
             r.n, r.on_device = n, 0
             for i, key in enumerate(["x", "y", "z", "t", "dx", "dy", "dz", "lambda_"]):
                 setattr(r, key, hin[k, i].data_ptr())
             for i, key in enumerate(["ox", "oy", "oz", "ot", "odx", "ody", "odz"]):
-                setattr(r, key, hout[i].data_ptr())
+                setattr(r, key, hout[t][i].data_ptr())
             for i, key in enumerate(["status", "last_node", "npoints"]):
-                setattr(r, key, hiout[i].data_ptr())
+                setattr(r, key, hiout[t][i].data_ptr())
             return r
 
-        hs = [host_struct(k) for k in range(nang)]
+        hs = [host_struct(k, k % T) for k in range(nang)]
+        host_counts = torch.zeros(6, dtype=torch.int64)
+        errors = []
 
-        def e2e_step():
-            for k in range(nang):
-                opts.ray_id_offset = (rank * nang + k) * n
-                R.check(R.rbg_trace(scene, C.byref(opts), C.byref(hs[k]), None))
+        def e2e_worker(t, count):
+            try:
+                o = H.opts(disable_fresnel=1, steps_per_launch=args.steps_per_launch, seed=20180601)
+                for k in range(t, nang, T):
+                    o.ray_id_offset = (rank * nang + k) * n
+                    R.check(R.rbg_trace(scenes_e2e[t], C.byref(o), C.byref(hs[k]), None))
+                    if count:
+                        c = torch.bincount(hiout[t][0].to(torch.int64), minlength=6)
+                        with count_lock:
+                            host_counts.add_(c)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        count_lock = threading.Lock()
+
+        def e2e_step(count=False):
+            if T == 1:
+                e2e_worker(0, count)
+            else:
+                ths = [threading.Thread(target=e2e_worker, args=(t, count)) for t in range(T)]
+                for th in ths:
+                    th.start()
+                for th in ths:
+                    th.join()
+            if errors:
+                raise errors[0]
 
         e2e_step()
         barrier()
@@ -312,13 +347,11 @@ def main():
         if dist is not None:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         # untimed verification: the host-buffer path returns the same status counts as the device-resident path
-        host_counts = torch.zeros(6, dtype=torch.int64)
-        for k in range(nang):
-            opts.ray_id_offset = (rank * nang + k) * n
-            R.check(R.rbg_trace(scene, C.byref(opts), C.byref(hs[k]), None))
-            host_counts += torch.bincount(hiout[0].to(torch.int64), minlength=6)
+        e2e_step(count=True)
         e2e = {"value": rays_per_step * ksteps / float(dt.item()), "unit": "rays/s", "h2d_bytes_per_step": BYTES_IN * n * nang, "d2h_bytes_per_step": BYTES_OUT * n * nang,
-               "steps": ksteps, "status_counts_match_device_path": bool((host_counts == cnt.sum(0).cpu()).all().item()) if world == 1 else None}
+               "steps": ksteps, "calls_in_flight": T, "status_counts_match_device_path": bool((host_counts == cnt.sum(0).cpu()).all().item()) if world == 1 else None}
+        for h in scenes_e2e[1:]:
+            R.rbg_scene_destroy(h)
         del hin, hout, hiout
 
     # ---- CPU baseline (rank 0, N=1): the oracle on all host threads, bounded sample

@@ -136,6 +136,19 @@ PYBIND11_MODULE(_robast, m) {
     AGeoUtil::ContainmentRadius(h, fraction, r, x, y);
     return py::make_tuple(r, x, y);
   });
+  m.def("MakeArb8FromPoints", [](const char* name, TVector3 v1, TVector3 v2, TVector3 v3, TVector3 v4, TVector3 v5) {
+    TGeoArb8* a;
+    TGeoCombiTrans* c;
+    AGeoUtil::MakeArb8FromPoints(name, v1, v2, v3, v4, v5, &a, &c);
+    return py::make_tuple(py::cast(a, py::return_value_policy::reference), py::cast(c, py::return_value_policy::reference));
+  });
+  m.def("MakeXtruFromPoints", [](const char* name, std::vector<TVector3> vecs) {
+    if (vecs.size() < 4) throw std::runtime_error("MakeXtruFromPoints: at least three top corners and the bottom corner");
+    TGeoXtru* x;
+    TGeoCombiTrans* c;
+    AGeoUtil::MakeXtruFromPoints(name, vecs, &x, &c);
+    return py::make_tuple(py::cast(x, py::return_value_policy::reference), py::cast(c, py::return_value_policy::reference));
+  });
   m.def("MakePointToPointTube", [](const char* name, TVector3 v1, TVector3 v2, double radius) {
     TGeoTube* t;
     TGeoCombiTrans* c;

@@ -620,3 +620,56 @@ def test_corsika_bunch_expansion_closed_form(R, oracle):
     part = np.zeros((8, 500))
     assert oracle.orc_shoot_bunches(C.byref(b), 1234, 500, *[part[i].ctypes.data for i in range(8)]) == 0
     assert (part == out[:, 1234:1734]).all()
+
+
+def test_arb8_and_xtru_from_points_place_the_solid_on_its_corners(R, oracle):
+    """AGeoUtil::MakeArb8FromPoints / MakeXtruFromPoints (src/AGeoUtil.cxx:47-125): a prism given by the corners of its top face
+    (clockwise seen from the top) and the bottom corner under the first one; the returned solid, placed with the returned
+    TGeoCombiTrans, must hold points just inside every given corner and exclude points just outside"""
+    import ctypes as C
+    import scenes
+    rng = np.random.default_rng(21)
+    for kind in ("arb8", "xtru"):
+        for trial in range(6):
+            # an arbitrarily oriented prism: orthonormal frame (e1, e2, axis), top face in the plane spanned by e1, e2
+            q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            if np.linalg.det(q) < 0:
+                q[:, 2] = -q[:, 2]
+            e1, e2, axis = q[:, 0], q[:, 1], q[:, 2]
+            origin = rng.normal(size=3) * 30.
+            height = 5. + 10. * rng.random()
+            if kind == "arb8":
+                outline = [(0., 0.), (0., 6.), (8., 7.), (9., -1.)]  # clockwise seen from +axis
+            else:
+                outline = [(0., 0.), (0., 6.), (5., 9.), (8., 7.), (9., -1.)]  # five corners, clockwise (concave outlines: test_device_code_on_host)
+            top = [origin + u * e1 + v * e2 for u, v in outline]
+            bottom0 = top[0] - height * axis
+            vec = lambda a: R.TVector3(float(a[0]), float(a[1]), float(a[2]))  # noqa: E731
+            if kind == "arb8":
+                shape, combi = R.MakeArb8FromPoints("fp%s%d" % (kind, trial), vec(top[0]), vec(top[1]), vec(top[2]), vec(top[3]), vec(bottom0))
+            else:
+                shape, combi = R.MakeXtruFromPoints("fp%s%d" % (kind, trial), [vec(t) for t in top] + [vec(bottom0)])
+            mgr = scenes.make_the_world()
+            comp = R.AMirror("m%s%d" % (kind, trial), shape)
+            mgr.GetTopVolume().AddNode(comp, 1, combi)
+            mgr.CloseGeometry()
+            rays = []
+            centroid = np.mean(top, axis=0) - 0.5 * height * axis
+            corners = [t - s * height * axis for t in top for s in (0., 1.)]
+            for c in corners:  # shoot from far outside through a point 1 % inside / 1 % outside the corner (seen from the centroid)
+                for f, want in ((0.99, True), (1.01, False)):
+                    target = centroid + f * (c - centroid)
+                    rays.append((target, want))
+            inp = np.zeros((len(rays), 8))
+            for i, (target, _w) in enumerate(rays):
+                d = rng.normal(size=3)
+                d /= np.linalg.norm(d)
+                inp[i, :3] = target - 1e-3 * d  # start right next to the probe point: inside the solid the first step ends within ~20 cm
+                inp[i, 4:7] = d
+                inp[i, 7] = 400e-7
+            batch = H.Rays(inp)
+            H.trace_with(oracle.orc_trace, mgr.ExportScene(), batch, H.opts(limit=2), nthreads=1)
+            # a ray starting inside the mirror solid is stopped at once (typeCurrent == mirror), one starting outside flies on
+            inside_flags = np.array([w for _t, w in rays])
+            stopped = batch.status == 1
+            assert (stopped[inside_flags]).all() and not (stopped[~inside_flags] & (np.linalg.norm(batch.out[:3].T - inp[:, :3], axis=1)[~inside_flags] < 0.5)).any(), (kind, trial)
