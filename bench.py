@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=int(os.environ.get("RB_STEPS_PER_LAUNCH", "0")))
     ap.add_argument("--n-side", type=int, default=N_SIDE, help="grid side per field angle (profiling runs only; the bench metric uses 3334)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-threads", type=int, default=int(os.environ.get("RB_E2E_THREADS", "2")), help="TraceNonSequential calls in flight on the host-buffer path")
+    ap.add_argument("--e2e-threads", type=int, default=int(os.environ.get("RB_E2E_THREADS", "1")), help="TraceNonSequential calls in flight on the host-buffer path")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
