@@ -24,7 +24,7 @@ def struct(first, count):
     for i, key in enumerate(["ox", "oy", "oz", "ot", "odx", "ody", "odz"]): setattr(r, key, hout[i].data_ptr() + 8 * first)
     for i, key in enumerate(["status", "last_node", "npoints"]): setattr(r, key, hio[i].data_ptr() + 4 * first)
     return r
-op = H.opts(disable_fresnel=1, steps_per_launch=0, seed=5)
+op = H.opts(disable_fresnel=1, steps_per_launch=int(sys.argv[1]) if len(sys.argv) > 1 else 0, seed=5)
 def nine():
     for k in range(nang):
         op.ray_id_offset = k * n
