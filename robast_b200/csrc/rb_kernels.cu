@@ -588,6 +588,9 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   if (s->has_root && sort_mode != 0 && (sort_mode == 1 || s->top_daughters >= 32)) {
     float3 lo = make_float3(s->root_lo[0], s->root_lo[1], s->root_lo[2]), hi = make_float3(s->root_hi[0], s->root_hi[1], s->root_hi[2]);
     bool do_sort = sort_mode == 1;
+    static const int coarse_bits = getenv("RB_SORT_COARSE_BITS") ? std::min(30, atoi(getenv("RB_SORT_COARSE_BITS"))) : 21;
+    static const int full_bits = getenv("RB_SORT_FULL_BITS") ? std::min(30, std::max(1, atoi(getenv("RB_SORT_FULL_BITS")))) : 30;
+    int sort_bits = full_bits;
     if (!do_sort) {
       unsigned long long* d_pairs = (unsigned long long*)take(256);
       CK(cudaMemsetAsync(d_pairs, 0, 8, st));
@@ -600,6 +603,14 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));
       do_sort = (double)*h_pairs < 0.5 * (double)sblocks * 256. * 31. / 32.;
+      // A beam that is coherent along its input order (grid shooters: a block of 512 rays is a 2 m strip of one grid row
+      // and crosses several facets) still gains from square tiles: every warp of a block then walks the same facet and the
+      // phase barriers of k_step wait less.  A coarse key is enough for that (top bits only = fewer radix passes, input
+      // order kept inside a cell so the ray loads stay contiguous); large batches only, the sort is launch-bound on small ones.
+      if (!do_sort && coarse_bits > 0 && n >= (1ll << 20)) {
+        do_sort = true;
+        sort_bits = coarse_bits;
+      }
     }
     if (do_sort) {
       uint32_t* keys = (uint32_t*)take(n * 4);
@@ -609,8 +620,8 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
       k_sortkey<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, R.x, R.y, R.z, R.dx, R.dy, R.dz, lo, hi, keys, liveB, nullptr, 1);
       g_launches++;
       CK(cudaGetLastError());
-      CK(cub::DeviceRadixSort::SortPairs(temp, tb, (const uint32_t*)keys, keys_out, (const int32_t*)liveB, liveA, (int)n, 0, 30, st));
-      g_launches += 4;
+      CK(cub::DeviceRadixSort::SortPairs(temp, tb, (const uint32_t*)keys, keys_out, (const int32_t*)liveB, liveA, (int)n, 30 - sort_bits, 30, st));
+      g_launches += (sort_bits + 7) / 8;
       live = liveA;
     }
   }
