@@ -607,7 +607,8 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
       // and crosses several facets) still gains from square tiles: every warp of a block then walks the same facet and the
       // phase barriers of k_step wait less.  A coarse key is enough for that (top bits only = fewer radix passes, input
       // order kept inside a cell so the ray loads stay contiguous); large batches only, the sort is launch-bound on small ones.
-      if (!do_sort && coarse_bits > 0 && n >= (1ll << 20)) {
+      static const long long coarse_min = getenv("RB_SORT_COARSE_MIN") ? atoll(getenv("RB_SORT_COARSE_MIN")) : (1ll << 20);
+      if (!do_sort && coarse_bits > 0 && n >= coarse_min) {
         do_sort = true;
         sort_bits = coarse_bits;
       }
