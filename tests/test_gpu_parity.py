@@ -583,3 +583,46 @@ def test_corsika_bunches_on_device_match_oracle(R, oracle):
     H.trace_gpu(mgr.ExportScene(), rays, H.opts(disable_fresnel=1))
     st = np.bincount(rays.status, minlength=6)
     assert st[3] > 0.2 * n and st[0] == 0
+
+
+def test_grid_beam_tile_ordering_parity_davies_cotton(R, oracle):
+    """a device-resident grid beam of >= 2^20 rays on the 88-facet reflector takes the coarse coherence sort (blocks tiled
+    onto facets, rb_kernels.cu trace_device): every ray must still equal the oracle's, in input order"""
+    import torch
+    dev = torch.device("cuda:0")
+    mgr, _k = configs.BUILDERS[2]()
+    ex = mgr.ExportScene()
+    nside = 1100
+    n = nside * nside
+    assert n >= 1 << 20
+    params = configs.beam(2, 1.0, n_side=nside)
+    host = H.make_rays(oracle, params, 0, n)
+    o = H.opts(disable_fresnel=1, seed=11, steps_per_launch=0)
+    ref = H.trace_with(oracle.orc_trace, ex, H.make_rays(oracle, params, 0, n), o, nthreads=os.cpu_count() or 4)
+    h = C.c_void_p()
+    R.check(R.rbg_scene_create(ex.desc_ptr(), 0, C.byref(h)))
+    try:
+        inp = torch.from_numpy(host.inp).to(dev)
+        out = torch.zeros((7, n), dtype=torch.float64, device=dev)
+        iout = torch.zeros((3, n), dtype=torch.int32, device=dev)
+        r = R.rbg_rays()
+        r.n, r.on_device = n, 1
+        for i, k in enumerate(["x", "y", "z", "t", "dx", "dy", "dz", "lambda_"]):
+            setattr(r, k, inp[i].data_ptr())
+        for i, k in enumerate(["ox", "oy", "oz", "ot", "odx", "ody", "odz"]):
+            setattr(r, k, out[i].data_ptr())
+        for i, k in enumerate(["status", "last_node", "npoints"]):
+            setattr(r, k, iout[i].data_ptr())
+        l0 = R.rbg_launch_count()
+        R.check(R.rbg_trace(h, C.byref(o), C.byref(r), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        launches = R.rbg_launch_count() - l0
+        got = H.Rays(host.inp.T)
+        got.out[:] = out.cpu().numpy()
+        got.iout[:] = iout.cpu().numpy()
+        rep = H.compare(ref, got)
+        assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, rep
+        # sampled key pass + publish + key pass + 3 radix passes on top of the bounce / compaction launches
+        assert launches >= 9, launches
+    finally:
+        R.rbg_scene_destroy(h)
