@@ -110,9 +110,28 @@ inline Mat mul(const Mat& a, const Mat& b) {  // a*b: apply b first
   return o;
 }
 
+// Daughter look-up acceleration, the role TGeoVoxelFinder plays for TGeoNavigator (ROOT voxelises every volume with daughters at
+// CloseGeometry; the brute-force walk over all daughters is what TGeo does only for tiny volumes).  Per volume: the bounding box
+// of every daughter in the mother's frame and a binary tree over them.  It is a pure culling structure: a daughter is skipped
+// only if the ray cannot reach its (padded) box before the current step / the point lies outside the box, i.e. exactly when
+// its DistFromOutside / Contains could not have changed the outcome, and the survivors are evaluated in AddNode order with
+// the same running step as the full walk — the results are bit-identical with and without it (tests/test_oracle_golden.py).
+struct VoxNode {
+  double lo[3], hi[3];
+  int left, right;   // children, or -1
+  int first, count;  // leaf: slice of VolVox::order
+};
+struct VolVox {
+  std::vector<double> box;  // 6 per daughter: lo[3], hi[3] in the mother's frame (padded)
+  std::vector<int> order;   // daughter indices (0 .. nnodes-1) as the leaves hold them
+  std::vector<VoxNode> tree;
+};
+static int g_use_voxels = 1;
+
 struct Scene {
   const rbg_scene_desc* d;
   std::vector<int> subtree;  // physical nodes in the subtree of each volume (incl. itself)
+  std::vector<VolVox> vox;   // per volume; empty tree = walk all daughters
   Mat mat(int id) const {
     if (id < 0) return kIdentity;
     Mat m;
@@ -1772,6 +1791,186 @@ void normal(const Scene& S, int sh, const double* p, const double* d, int sel, d
 }
 
 // ================================================================== navigator (TGeoNavigator restated)
+// ================================================================== daughter boxes (see VolVox)
+// axis-aligned bounding box of a shape in its own frame
+static void shape_box(const Scene& S, int sh, double* lo, double* hi) {
+  const rbg_shape& s = S.d->shapes[sh];
+  const double* P = S.d->dpar + s.ipar;
+  auto sym = [&](double x, double y, double z) { lo[0] = -x; lo[1] = -y; lo[2] = -z; hi[0] = x; hi[1] = y; hi[2] = z; };
+  switch (s.type) {
+    case RBG_SHAPE_BBOX:
+      for (int i = 0; i < 3; i++) { lo[i] = P[3 + i] - P[i]; hi[i] = P[3 + i] + P[i]; }
+      return;
+    case RBG_SHAPE_TUBE: sym(P[1], P[1], P[2]); return;
+    case RBG_SHAPE_SPHERE: sym(P[1], P[1], P[1]); return;
+    case RBG_SHAPE_PARABOLOID: { double r = std::max(P[0], P[1]); sym(r, r, P[2]); return; }
+    case RBG_SHAPE_PGON:
+    case RBG_SHAPE_PCON: {
+      const bool pg = s.type == RBG_SHAPE_PGON;
+      int nz = (int)P[pg ? 3 : 2];
+      const double* sec = P + (pg ? 4 : 3);
+      double rmax = 0, z0 = kBig, z1 = -kBig;
+      for (int i = 0; i < nz; i++) { rmax = std::max(rmax, sec[3 * i + 2]); z0 = std::min(z0, sec[3 * i]); z1 = std::max(z1, sec[3 * i]); }
+      if (pg) rmax /= cos(0.5 * P[1] / P[2] * kPi / 180.);  // rmax of a polygon section is the apothem
+      sym(rmax, rmax, 0);
+      lo[2] = z0; hi[2] = z1;
+      return;
+    }
+    case RBG_SHAPE_ASPHERE: sym(P[7], P[7], 0); lo[2] = P[10] - P[11]; hi[2] = P[10] + P[11]; return;
+    case RBG_SHAPE_WINSTON2D:
+    case RBG_SHAPE_WINSTONPOLY: {
+      double th = asin(P[1] / P[0]), dz = (P[0] + P[1]) / (2 * tan(th));
+      if (s.type == RBG_SHAPE_WINSTON2D) sym(P[0], P[2], dz);
+      else { double r = P[0] / cos(kPi / P[2]); sym(r, r, dz); }
+      return;
+    }
+    case RBG_SHAPE_ARB8: {
+      double x = 0, y = 0;
+      for (int i = 0; i < 8; i++) { x = std::max(x, fabs(P[1 + 2 * i])); y = std::max(y, fabs(P[2 + 2 * i])); }
+      sym(x, y, P[0]);
+      return;
+    }
+    case RBG_SHAPE_XTRU: {
+      int nv = (int)P[0], nz = (int)P[1];
+      const double* V = P + 2;
+      const double* Z = P + 2 + 2 * nv;
+      for (int i = 0; i < 3; i++) { lo[i] = kBig; hi[i] = -kBig; }
+      for (int k = 0; k < nz; k++) {
+        lo[2] = std::min(lo[2], Z[4 * k]); hi[2] = std::max(hi[2], Z[4 * k]);
+        for (int i = 0; i < nv; i++) {
+          double x = Z[4 * k + 1] + Z[4 * k + 3] * V[2 * i], y = Z[4 * k + 2] + Z[4 * k + 3] * V[2 * i + 1];
+          lo[0] = std::min(lo[0], x); hi[0] = std::max(hi[0], x); lo[1] = std::min(lo[1], y); hi[1] = std::max(hi[1], y);
+        }
+      }
+      return;
+    }
+    default: break;
+  }
+  // booleans: the left operand bounds a subtraction; an intersection lies in both operands' boxes; a union needs both
+  auto operand = [&](int sub, int m, double* l, double* h) {
+    double a[3], b[3];
+    shape_box(S, sub, a, b);
+    Mat M = S.mat(m);
+    for (int i = 0; i < 3; i++) { l[i] = kBig; h[i] = -kBig; }
+    for (int c = 0; c < 8; c++) {
+      double q[3] = {c & 1 ? b[0] : a[0], c & 2 ? b[1] : a[1], c & 4 ? b[2] : a[2]}, w[3];
+      l2m(M, q, w);
+      for (int i = 0; i < 3; i++) { l[i] = std::min(l[i], w[i]); h[i] = std::max(h[i], w[i]); }
+    }
+  };
+  operand(s.left, s.lmat, lo, hi);
+  if (s.type == RBG_SHAPE_UNION) {
+    double l2[3], h2[3];
+    operand(s.right, s.rmat, l2, h2);
+    for (int i = 0; i < 3; i++) { lo[i] = std::min(lo[i], l2[i]); hi[i] = std::max(hi[i], h2[i]); }
+  } else if (s.type == RBG_SHAPE_INTERSECTION) {
+    double l2[3], h2[3];
+    operand(s.right, s.rmat, l2, h2);
+    for (int i = 0; i < 3; i++) { lo[i] = std::max(lo[i], l2[i]); hi[i] = std::min(hi[i], h2[i]); }
+  }
+}
+static int vox_split(VolVox& V, int first, int count) {
+  VoxNode nd;
+  for (int i = 0; i < 3; i++) { nd.lo[i] = kBig; nd.hi[i] = -kBig; }
+  for (int k = first; k < first + count; k++) {
+    const double* b = &V.box[6 * V.order[k]];
+    for (int i = 0; i < 3; i++) { nd.lo[i] = std::min(nd.lo[i], b[i]); nd.hi[i] = std::max(nd.hi[i], b[3 + i]); }
+  }
+  nd.left = nd.right = -1;
+  nd.first = first;
+  nd.count = count;
+  int id = (int)V.tree.size();
+  V.tree.push_back(nd);
+  if (count > 4) {
+    int ax = 0;
+    for (int i = 1; i < 3; i++)
+      if (nd.hi[i] - nd.lo[i] > nd.hi[ax] - nd.lo[ax]) ax = i;
+    std::sort(V.order.begin() + first, V.order.begin() + first + count,
+              [&](int a, int b) { return V.box[6 * a + ax] + V.box[6 * a + 3 + ax] < V.box[6 * b + ax] + V.box[6 * b + 3 + ax]; });
+    int l = vox_split(V, first, count / 2), r = vox_split(V, first + count / 2, count - count / 2);
+    V.tree[id].left = l;
+    V.tree[id].right = r;
+  }
+  return id;
+}
+static void build_voxels(Scene& S) {
+  S.vox.assign(S.d->nvolumes, VolVox());
+  for (int vi = 0; vi < S.d->nvolumes; vi++) {
+    const rbg_volume& v = S.d->volumes[vi];
+    if (v.nnodes < 4) continue;  // nothing to gain below a handful of daughters
+    VolVox& V = S.vox[vi];
+    V.box.resize(6 * (size_t)v.nnodes);
+    for (int k = 0; k < v.nnodes; k++) {
+      const rbg_node& nd = S.d->nodes[v.first_node + k];
+      double a[3], b[3];
+      shape_box(S, S.d->volumes[nd.volume].shape, a, b);
+      Mat M = S.mat(nd.matrix);
+      double* o = &V.box[6 * k];
+      for (int i = 0; i < 3; i++) { o[i] = kBig; o[3 + i] = -kBig; }
+      for (int c = 0; c < 8; c++) {
+        double q[3] = {c & 1 ? b[0] : a[0], c & 2 ? b[1] : a[1], c & 4 ? b[2] : a[2]}, w[3];
+        l2m(M, q, w);
+        for (int i = 0; i < 3; i++) { o[i] = std::min(o[i], w[i]); o[3 + i] = std::max(o[3 + i], w[i]); }
+      }
+      for (int i = 0; i < 3; i++) {  // padding: far above every tolerance the shape algorithms use (1e-8 nudges, 1e-6 steps)
+        double pad = 1e-4 + 1e-9 * (fabs(o[i]) + fabs(o[3 + i]));
+        o[i] -= pad;
+        o[3 + i] += pad;
+      }
+      V.order.push_back(k);
+    }
+    vox_split(V, 0, v.nnodes);
+  }
+}
+// daughters (ascending index) whose box the ray p + t d meets for some 0 <= t <= tmax
+static void vox_ray(const VolVox& V, const double* p, const double* d, double tmax, std::vector<int>& out) {
+  out.clear();
+  int stack[64], sp = 0;
+  stack[sp++] = 0;
+  auto hit = [&](const double* lo, const double* hi) {
+    double t0 = 0, t1 = tmax;
+    for (int i = 0; i < 3; i++) {
+      if (d[i] != 0) {
+        double a = (lo[i] - p[i]) / d[i], b = (hi[i] - p[i]) / d[i];
+        if (a > b) std::swap(a, b);
+        if (a > t0) t0 = a;
+        if (b < t1) t1 = b;
+      } else if (p[i] < lo[i] || p[i] > hi[i]) return false;
+    }
+    return t0 <= t1;
+  };
+  while (sp > 0) {
+    const VoxNode& n = V.tree[stack[--sp]];
+    if (!hit(n.lo, n.hi)) continue;
+    if (n.left < 0) {
+      for (int k = n.first; k < n.first + n.count; k++) {
+        const double* b = &V.box[6 * V.order[k]];
+        if (hit(b, b + 3)) out.push_back(V.order[k]);
+      }
+    } else { stack[sp++] = n.left; stack[sp++] = n.right; }
+  }
+  std::sort(out.begin(), out.end());
+}
+// daughters (ascending index) whose box holds the point
+static void vox_point(const VolVox& V, const double* p, std::vector<int>& out) {
+  out.clear();
+  int stack[64], sp = 0;
+  stack[sp++] = 0;
+  auto in = [&](const double* lo, const double* hi) { return p[0] >= lo[0] && p[0] <= hi[0] && p[1] >= lo[1] && p[1] <= hi[1] && p[2] >= lo[2] && p[2] <= hi[2]; };
+  while (sp > 0) {
+    const VoxNode& n = V.tree[stack[--sp]];
+    if (!in(n.lo, n.hi)) continue;
+    if (n.left < 0) {
+      for (int k = n.first; k < n.first + n.count; k++) {
+        const double* b = &V.box[6 * V.order[k]];
+        if (in(b, b + 3)) out.push_back(V.order[k]);
+      }
+    } else { stack[sp++] = n.left; stack[sp++] = n.right; }
+  }
+  std::sort(out.begin(), out.end());
+}
+
+// ================================================================== navigator
 const int kMaxLevel = 16;
 struct Nav {
   const Scene* S;
@@ -1810,6 +2009,23 @@ struct Nav {
   // daughters of the current volume (not `skip`, index >= from) whose shape holds pt, in AddNode order
   int next_daughter_holding(const double* pt, int skip, int from) const {
     const rbg_volume& v = S->d->volumes[vol[level]];
+    if (!S->vox.empty() && !S->vox[vol[level]].tree.empty()) {  // only daughters whose box holds the point (in the mother's frame)
+      double lp[3];
+      m2l(glob[level], pt, lp);
+      std::vector<int> cand;
+      vox_point(S->vox[vol[level]], lp, cand);
+      for (int k : cand) {
+        if (k < from) continue;
+        int ni = v.first_node + k;
+        if (ni == skip) continue;
+        const rbg_node& nd = S->d->nodes[ni];
+        Mat g = mul(glob[level], S->mat(nd.matrix));
+        double l[3];
+        m2l(g, pt, l);
+        if (contains(*S, S->d->volumes[nd.volume].shape, l)) return k;
+      }
+      return -1;
+    }
     for (int k = from; k < v.nnodes; k++) {
       int ni = v.first_node + k;
       if (ni == skip) continue;
@@ -1945,7 +2161,12 @@ struct Nav {
     // FindNextDaughterBoundary: nearest daughter entry (first wins within tolerance)
     const rbg_volume& v = S->d->volumes[vol[level]];
     int idaughter = -1, dsel = 0;
-    for (int k = 0; k < v.nnodes; k++) {
+    const bool voxels = !S->vox.empty() && !S->vox[vol[level]].tree.empty();
+    std::vector<int> cand;
+    if (voxels) vox_ray(S->vox[vol[level]], lp, ld, step > 1e29 ? kBig : step, cand);
+    const int ncand = voxels ? (int)cand.size() : v.nnodes;
+    for (int c = 0; c < ncand; c++) {
+      const int k = voxels ? cand[c] : c;
       const rbg_node& nd = S->d->nodes[v.first_node + k];
       Mat lm = S->mat(nd.matrix);
       double dp[3], dd[3];
@@ -2331,6 +2552,7 @@ int orc_trace_history(const rbg_scene_desc* desc, const rbg_trace_opts* opts, co
     check_desc(desc);
     if (rays->on_device) return RBG_EINVAL;
     Scene S(desc);
+    if (g_use_voxels) build_voxels(S);
     int64_t n = rays->n;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > n) nthreads = n > 0 ? (int)n : 1;
@@ -2379,6 +2601,13 @@ int orc_trace_history(const rbg_scene_desc* desc, const rbg_trace_opts* opts, co
     fprintf(stderr, "orc_trace: %s\n", ex.what());
     return RBG_EINTERNAL;
   }
+}
+
+// daughter-box trees on (default) / off (walk all daughters of a volume like a TGeoVolume without voxels); returns the old setting
+int orc_set_voxels(int on) {
+  int old = g_use_voxels;
+  g_use_voxels = on;
+  return old;
 }
 
 // AMultilayer::CoherentTMM (mode 0; complex angle, optional reversed stack) and IncoherentTMM (mode 1); pol 0 = S, 1 = P

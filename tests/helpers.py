@@ -47,6 +47,8 @@ def load_oracle():
     lib.orc_shoot.argtypes = [C.POINTER(R.rbg_shoot_desc), C.c_int64, C.c_int64] + [C.c_void_p] * 8
     lib.orc_shoot_bunches.restype = C.c_int
     lib.orc_shoot_bunches.argtypes = [C.POINTER(R.rbg_bunches), C.c_int64, C.c_int64] + [C.c_void_p] * 8
+    lib.orc_set_voxels.restype = C.c_int
+    lib.orc_set_voxels.argtypes = [C.c_int]
     lib.orc_shape_contains.restype = C.c_int
     lib.orc_shape_contains.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.orc_shape_dist.restype = C.c_double

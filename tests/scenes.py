@@ -207,3 +207,73 @@ def overlapping_frame(nested=False, holder=True, bars=True, stop_ring=True):
     manager.CloseGeometry()
     manager.SetLimit(20)
     return manager, keep
+
+
+# ----------------------------------------------------------------------------- round-2 parity branches
+def winston2d(mode, material="mirror"):
+    """AGeoWinstonCone2D traced for real (src/AGeoWinstonCone2D.cxx:120-428).
+    mode 'solid': one 2-D cone as a solid body (rotated, shifted) — DistFromOutside, ComputeNormal on all five kinds of face,
+                  and, as a glass body, DistFromInside + Contains;
+    mode 'hex3' : tutorials/HexWinstonCone.C:54-61 (mode 1) — pgon:rot30 - coneV*(coneV:rot60)*(coneV:rot120) with the PMT below."""
+    rin, rout = 20 * mm, 10 * mm
+    manager = ROOT.AOpticsManager("manager", "Winston2D")
+    world = ROOT.AOpticalComponent("world", ROOT.TGeoBBox("worldbox", 30 * cm, 30 * cm, 30 * cm))
+    manager.SetTopVolume(world)
+    cone = ROOT.AGeoWinstonCone2D("coneV", rin, rout, rin * 1.733)
+    dz = cone.GetDZ()
+    keep = [cone]
+    if mode == "solid":
+        if material == "mirror":
+            comp = ROOT.AMirror("coneSolid", cone)
+        else:
+            comp = ROOT.ALens("coneSolid", cone)
+            idx = ROOT.ARefractiveIndex(1.5)
+            comp.SetRefractiveIndex(idx)
+            keep.append(idx)
+        world.AddNode(comp, 1, ROOT.TGeoCombiTrans(0.3, -0.2, 0.5, ROOT.TGeoRotation("conerot", 25., 15., 40.)))
+        keep.append(comp)
+        manager.SetLimit(40)
+    else:
+        rots = []
+        for name, ang in (("rot30", 30), ("rot60", 60), ("rot120", 120)):
+            r = ROOT.TGeoRotation(name, ang, 0, 0)
+            r.RegisterYourself()
+            rots.append(r)
+        pgon = ROOT.TGeoPgon("pgon", 0, 360, 6, 4)
+        pgon.DefineSection(0, -dz * 0.999, 0, rout * 1.1)
+        pgon.DefineSection(1, -dz * 0.5, 0, rin * 0.9)
+        pgon.DefineSection(2, -dz * 0., 0, rin * 0.99)
+        pgon.DefineSection(3, dz * 0.999, 0, rin * 1.001)
+        c1 = ROOT.TGeoCompositeShape("coneComp1", "coneV*(coneV:rot60)*(coneV:rot120)")
+        c2 = ROOT.TGeoCompositeShape("coneComp2", "pgon:rot30 - coneComp1")
+        mirror = ROOT.AMirror("coneMirror", c2)
+        world.AddNode(mirror, 1)
+        pmt_shape = ROOT.TGeoPgon("pgonPMT", 0, 360, 6, 2)
+        pmt_shape.DefineSection(0, -dz - 0.01 * mm, 0, rout * 1.01)
+        pmt_shape.DefineSection(1, -dz, 0, rout * 1.01)
+        pmt = ROOT.AFocalSurface("pmt", pmt_shape)
+        world.AddNode(pmt, 1, rots[0])
+        keep += rots + [pgon, c1, c2, mirror, pmt_shape, pmt]
+    manager.CloseGeometry()
+    return manager, keep
+
+
+def th2_mirror():
+    """AMirror with a TH2 reflectance R(lambda, angle) (src/AMirror.cxx:39-60; priority TGraph2D > TH2 > TGraph > constant):
+    0 at (300 nm, 0), rising along both axes, so that the bilinear interpolation between bin centres and the edge half-bins
+    are all visited by a beam spread in wavelength and incidence angle."""
+    import math
+    h = ROOT.TH2D("refl", "refl", 8, 300 * nm, 500 * nm, 6, 0., math.pi / 2)
+    for i in range(1, 9):
+        for j in range(1, 7):
+            h.SetBinContent(i, j, min(1.0, 0.08 * i + 0.07 * j))
+    manager, mirror, keep = mirror_box_with_border(reflectance=h)
+    return manager, mirror, keep + [h]
+
+
+def dispersive_lens(index, half=0.5 * m):
+    """a glass cube of the given ARefractiveIndex (Schott / Cauchy / mixed formulas: src/ASchottFormula.cxx:43-55,
+    src/ACauchyFormula.cxx:40-46, include/AMixedRefractiveIndex.h:36-45) in the world of the unit tests"""
+    manager, lens = lens_box(index, half)
+    manager.SetLimit(30)
+    return manager, lens

@@ -1,5 +1,6 @@
 """BASELINE.json configs 2-5 at their full single-GPU sizes (-m gpu): the oracle cannot trace 1e8 rays in seconds, so these
-tests check size-independent properties of the result — conservation, invariants of each terminal status, symmetry of
+tests re-trace a random 1e6-ray sample of every full-size run with the oracle (exact replay: Philox is keyed by the global ray id)
+and check size-independent properties of the whole result — conservation, invariants of each terminal status, symmetry of
 the on-axis beams, and the order-independence that multi-GPU sharding, the wavefront and the coherence sort rely on
 (same rays traced as one batch, as shards with ray_id_offset, single-launch / wavefront, sorted / unsorted index list)."""
 import ctypes as C
@@ -58,6 +59,32 @@ class DeviceBatch:
         self.R.rbg_scene_destroy(self.h)
 
 
+def sampled_oracle_parity(b, oracle, ex, id_offset=0, windows=256, width=4096, pick=2, **kw):
+    """Oracle check at full size: `windows` random windows of `width` consecutive rays (1.05e6 rays by default) of the batch
+    just traced on the device are re-traced by the CPU oracle from the same inputs with the same global ray ids (Philox is
+    keyed by seed and global id, so a window is an exact replay whatever the batch, the wavefront or the sort did around
+    it) and compared per ray: status, npoints, last node identical, position <= 1e-7 cm, direction <= 1e-9 rad."""
+    rng = np.random.default_rng(pick)  # `pick` chooses the windows; kw are the trace options (seed = Philox seed, ...)
+    starts = np.sort(rng.choice(max(1, (b.n - width) // width), size=min(windows, max(1, (b.n - width) // width)), replace=False)) * width
+    worst = dict(bad=0, status_mismatch=0, npoints_mismatch=0, node_mismatch=0, max_dpos=0.0, max_dang=0.0, n=0)
+    for lo in starts:
+        lo = int(lo)
+        hi = min(b.n, lo + width)
+        ref = H.Rays(b.inp[:, lo:hi].cpu().numpy().T)
+        H.trace_with(oracle.orc_trace, ex, ref, H.opts(ray_id_offset=id_offset + lo, **kw), nthreads=os.cpu_count() or 4)
+        got = H.Rays(np.zeros((hi - lo, 8)))
+        got.out[:] = b.out[:, lo:hi].cpu().numpy()
+        got.iout[:] = b.iout[:, lo:hi].cpu().numpy()
+        rep = H.compare(ref, got)
+        for k in ("bad", "status_mismatch", "npoints_mismatch", "node_mismatch", "n"):
+            worst[k] += rep[k]
+        worst["max_dpos"] = max(worst["max_dpos"], rep["max_dpos"])
+        worst["max_dang"] = max(worst["max_dang"], rep["max_dang"])
+    assert worst["n"] >= min(b.n, 1_000_000) * 0.99, worst
+    assert worst["bad"] == 0 and worst["status_mismatch"] == 0 and worst["npoints_mismatch"] == 0 and worst["node_mismatch"] == 0, worst
+    return worst
+
+
 def common_invariants(b, limit=100):
     t = b.torch
     st, npts = b.iout[0], b.iout[2]
@@ -73,7 +100,7 @@ def common_invariants(b, limit=100):
     return cnt
 
 
-def test_config2_davies_cotton_1e8(R):
+def test_config2_davies_cotton_1e8(R, oracle):
     """DaviesCotton.C, 9 field angles x 3334^2 = 1.0004e8 rays (the bench workload), traced angle by angle"""
     mgr, _k = configs.davies_cotton()
     ex = mgr.ExportScene()
@@ -85,6 +112,8 @@ def test_config2_davies_cotton_1e8(R):
         b.trace(disable_fresnel=1, id_offset=k * n)
         cnt = common_invariants(b)
         total += cnt
+        # 9 x 29 windows x 4096 rays = 1.07e6 oracle-checked rays over the sweep
+        sampled_oracle_parity(b, oracle, ex, id_offset=k * n, windows=29, pick=100 + k, disable_fresnel=1)
         foc = b.iout[0] == 3
         if th == 0.0:
             dg = b.digest()
@@ -111,13 +140,14 @@ def test_config2_davies_cotton_1e8(R):
     assert total.sum() == 9 * n and total[3] > 0.4 * total.sum()
 
 
-def test_config3_schwarzschild_couder_1e8(R):
+def test_config3_schwarzschild_couder_1e8(R, oracle):
     mgr, _k = configs.schwarzschild_couder()
     ex = mgr.ExportScene()
     n = 10000 * 10000
     b = DeviceBatch(R, ex, configs.beam(3, 0.0), n)
     b.trace()
     cnt = common_invariants(b)
+    sampled_oracle_parity(b, oracle, ex, pick=3)
     foc = b.iout[0] == 3
     assert cnt[3] > 0.05 * n and cnt[4] == 0 and cnt[5] == 0
     assert abs(b.out[0][foc].mean().item()) < 1e-6 and abs(b.out[1][foc].mean().item()) < 1e-6
@@ -132,7 +162,7 @@ def test_config3_schwarzschild_couder_1e8(R):
     b.close()
 
 
-def test_config4_schmidt_cassegrain_3e7(R):
+def test_config4_schmidt_cassegrain_3e7(R, oracle):
     """stochastic config (Fresnel + bulk absorption, polychromatic): counts obey conservation, and the result is a pure
     function of (seed, global ray id) — independent of sharding, launch granularity and the order of the index list"""
     mgr, _k = configs.schmidt_cassegrain()
@@ -142,6 +172,7 @@ def test_config4_schmidt_cassegrain_3e7(R):
     b.trace(seed=20180601)
     cnt = common_invariants(b)
     assert cnt[3] > 0.4 * n and cnt[5] > 0 and cnt[1] > 0
+    sampled_oracle_parity(b, oracle, ex, pick=4, seed=20180601)
     dg = b.digest()
     b.out.zero_(); b.iout.zero_()
     b.trace(0, n // 4, seed=20180601)
@@ -160,7 +191,7 @@ def test_config4_schmidt_cassegrain_3e7(R):
     b.close()
 
 
-def test_config5_hex_winston_cone_1p25e8(R):
+def test_config5_hex_winston_cone_1p25e8(R, oracle):
     """one GPU's share of the 1e9-ray config (1.25e8 rays, 331 cells, multilayer-coated walls, RandomSquare beam at 20 deg)"""
     mgr, _k = configs.hex_winston_cone(rings=10)
     ex = mgr.ExportScene()
@@ -170,6 +201,7 @@ def test_config5_hex_winston_cone_1p25e8(R):
     b.trace(seed=20110306, id_offset=rank * n)
     cnt = common_invariants(b)
     assert cnt[3] > 0.3 * n and cnt[5] > 0.01 * n
+    sampled_oracle_parity(b, oracle, ex, id_offset=rank * n, pick=5, seed=20110306)
     foc = b.iout[0] == 3
     assert (b.out[2][foc].max() - b.out[2][foc].min()).item() < 0.002  # all PMT windows lie in one plane (0.01 mm thick)
     dg = b.digest()

@@ -673,3 +673,50 @@ def test_arb8_and_xtru_from_points_place_the_solid_on_its_corners(R, oracle):
             inside_flags = np.array([w for _t, w in rays])
             stopped = batch.status == 1
             assert (stopped[inside_flags]).all() and not (stopped[~inside_flags] & (np.linalg.norm(batch.out[:3].T - inp[:, :3], axis=1)[~inside_flags] < 0.5)).any(), (kind, trial)
+
+
+# ----------------------------------------------------------------------------- daughter-box trees (round 2)
+@pytest.mark.parametrize("cfg,theta,nside,kw", [(1, 1.0, 60, {}), (2, 0.0, 70, {}), (2, 3.0, 70, {}), (3, 2.0, 60, {}), (4, 0.1, 50, {}),
+                                                (5, 0.0, 50, dict(rings=2)), (5, 25.0, 60, dict(rings=4))])
+def test_voxel_lookup_is_bit_identical_to_the_full_daughter_walk(oracle, cfg, theta, nside, kw):
+    """the oracle's daughter-box trees (the role of TGeoVoxelFinder) only skip daughters that could not have changed the step:
+    every output bit equals the walk over all daughters (src/AOpticsManager.cxx:363 -> TGeoNavigator::FindNextBoundaryAndStep)"""
+    from robast_b200 import configs
+    mgr, _keep = configs.BUILDERS[cfg](**kw)
+    ex = mgr.ExportScene()
+    side = {2: 40.0, 4: 75.0}.get(kw.get("rings"))
+    beam = configs.beam(cfg, theta, n_side=nside if cfg <= 3 else side)
+    n = nside * nside
+    o = H.opts(disable_fresnel=1 if cfg == 2 else 0, seed=31)
+    out = []
+    try:
+        for vox in (0, 1):
+            oracle.orc_set_voxels(vox)
+            out.append(H.trace_with(oracle.orc_trace, ex, H.make_rays(oracle, beam, 0, n), o, nthreads=2))
+    finally:
+        oracle.orc_set_voxels(1)
+    a, b = out
+    assert np.array_equal(a.out, b.out) and np.array_equal(a.iout, b.iout)
+    assert len(np.unique(a.status)) >= 2
+
+
+def test_voxel_lookup_with_overlapping_nodes_and_history(oracle):
+    """MANY nodes (cluster look-up goes through next_daughter_holding with `from` > 0) and a scene with 12 sisters"""
+    import scenes
+    mgr, _keep = scenes.overlapping_frame(nested=True)
+    ex = mgr.ExportScene()
+    rng = np.random.default_rng(8)
+    n = 3000
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    inp = np.zeros((n, 8))
+    inp[:, 0:3] = 150 * (rng.random((n, 3)) - 0.5)
+    inp[:, 4:7], inp[:, 7] = v, 400e-7
+    out = []
+    try:
+        for vox in (0, 1):
+            oracle.orc_set_voxels(vox)
+            out.append(H.trace_with(oracle.orc_trace, ex, H.Rays(inp), H.opts(seed=3, limit=20)))
+    finally:
+        oracle.orc_set_voxels(1)
+    assert np.array_equal(out[0].out, out[1].out) and np.array_equal(out[0].iout, out[1].iout)
