@@ -1,0 +1,9 @@
+mkdir -p gpurun_out/r2k
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_parity_branches.py -m gpu -x -q > gpurun_out/r2k/pytest.log 2>&1
+tail -3 gpurun_out/r2k/pytest.log
+for coop in 1 0; do
+for c in "1 0 9000000 3" "2 1 11115556 3" "3 0 9000000 3" "4 0 10000000 3" "5 20 10000000 3 rings=10"; do
+  RB_COOP=$coop timeout 300 python profiles/trace_one.py $c 2>&1 | sed "s/^/coop=$coop /" | cut -c1-170 >> gpurun_out/r2k/survey.log
+done
+done
+cat gpurun_out/r2k/survey.log

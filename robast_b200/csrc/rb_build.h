@@ -64,6 +64,7 @@ struct SceneBuilder {
   std::vector<int> shape_depth;
   std::vector<DNode> nodes;
   std::vector<DBvh> bvh;
+  std::vector<DBox> boxes;
   std::vector<std::string> names;
 
   DMat mat(int id) const {
@@ -238,6 +239,27 @@ struct SceneBuilder {
       shape_box[i] = b;
     }
   }
+  // which flat evaluator can take the shape (RB_LEAF_*, rb_scene.h)
+  int leaf_kind(int sh) const {
+    auto prim = [&](int i) { return shapes[i].type < RBG_SHAPE_UNION || shapes[i].type > RBG_SHAPE_SUBTRACTION; };
+    auto general_poly = [&](int i) {  // hollow or azimuthally cut TGeoPgon/TGeoPcon: flag behind the edge table (see build_shapes)
+      if (shapes[i].type != RBG_SHAPE_PGON && shapes[i].type != RBG_SHAPE_PCON) return false;
+      const double* P = dpar.data() + shapes[i].ipar;
+      return P[4 + 3 * (int)P[3] + 2 * (int)P[2]] != 0.;
+    };
+    if (prim(sh)) return RB_LEAF_PRIM;
+    const DShape& s = shapes[sh];
+    if (prim(s.left) && prim(s.right)) {
+      if (general_poly(s.left) || general_poly(s.right)) return RB_LEAF_GENERIC;
+      return RB_LEAF_BOOL2 | (s.type << 4) | (shapes[s.left].type << 8) | (shapes[s.right].type << 12);
+    }
+    int i = sh, levels = 0;
+    while (!prim(i)) {  // ((a + b) + c) + d
+      if (shapes[i].type != RBG_SHAPE_UNION || !prim(shapes[i].right) || ++levels > 6) return RB_LEAF_GENERIC;
+      i = shapes[i].left;
+    }
+    return RB_LEAF_UNIONS;
+  }
   // DFS pre-order flattening of placed nodes into physical paths
   int flatten(int vol, const DMat& g, int mother, int overlap, const std::string& name) {
     if (vol < 0 || vol >= D->nvolumes) throw Invalid("bad volume id");
@@ -252,7 +274,16 @@ struct SceneBuilder {
     n.mother = mother;
     n.overlap = overlap;
     n.level = mother < 0 ? 0 : nodes[mother].level + 1;
+    n.leaf = leaf_kind(n.shape);
     nodes.push_back(n);
+    {
+      Box wb = world_box(id);
+      for (int k = 0; k < 3; k++) {  // same outward rounding + padding as the BVH leaves (bvh_rec)
+        double pad = 2e-3 + 4e-7 * std::max(fabs(wb.lo[k]), fabs(wb.hi[k]));
+        nodes[id].blo[k] = std::nextafterf((float)(wb.lo[k] - pad), -INFINITY);
+        nodes[id].bhi[k] = std::nextafterf((float)(wb.hi[k] + pad), INFINITY);
+      }
+    }
     names.push_back(name);
     const rbg_volume& v = D->volumes[vol];
     std::vector<int> kids;
@@ -336,6 +367,16 @@ struct SceneBuilder {
     for (int i = first; i < end; i++)
       if (bvh[i].skip >= end) bvh[i].skip = -1;
     nodes[node].bvh_count = end - first;
+    nodes[node].box_first = (int)boxes.size();
+    for (int i = first; i < end; i++)
+      if (bvh[i].child >= 0) {
+        DBox b;
+        memset(&b, 0, sizeof(b));
+        for (int k = 0; k < 3; k++) { b.lo[k] = bvh[i].lo[k]; b.hi[k] = bvh[i].hi[k]; }
+        b.child = bvh[i].child;
+        boxes.push_back(b);
+      }
+    nodes[node].box_count = (int)boxes.size() - nodes[node].box_first;
   }
 };
 

@@ -33,15 +33,14 @@
 #define RB_PH_MIRROR_TABLE 32u /* AMirror reflectance != constant */
 #define RB_PH_OVERLAP 64u     /* AddNodeOverlap ("MANY") nodes: overlap-cluster point location, sister candidates */
 #define RB_PH_ALL 0xffu
-// TAG: distinguishes experiment instantiations whose other parameters coincide (same type = same kernel symbol across
-// translation units, whatever macros the unit was compiled with)
-template <int D, unsigned S, unsigned P, int MINB = 1, int STEP_THREADS = 512, int STEP_MINB = 2, int TAG = 0> struct TraceCfg {
+template <class... Cs> struct Combos;
+template <int D, unsigned S, unsigned P, int THREADS = 128, int MINB = 4, class CL = Combos<>> struct TraceCfg {
+  typedef CL combos;  // two-primitive booleans evaluated by typed inline code (Bool2), e.g. Combos<B2<RBG_SHAPE_INTERSECTION, RBG_SHAPE_SPHERE, RBG_SHAPE_PGON>>
   static constexpr int depth = D;
   static constexpr unsigned shapes = S;
   static constexpr unsigned phys = P;
-  static constexpr int min_blocks = MINB;            // k_trace: __launch_bounds__(128, MINB) (register cap)
-  static constexpr int step_threads = STEP_THREADS;  // k_step: block size and min resident blocks per SM
-  static constexpr int step_min_blocks = STEP_MINB;
+  static constexpr int threads = THREADS;   // k_trace: __launch_bounds__(THREADS, MINB) — block size and register cap
+  static constexpr int min_blocks = MINB;
 };
 
 #define RB_BIG 1e30
@@ -275,18 +274,25 @@ template <int NP> RB_HD inline void tmm_coherent_multi(const DScene& sc, int fir
   for (int i = 0; i < N; i++) {
     const rbg_layer L = sc.layers[first + (reverse ? b - i : a + i)];
     Cx ni = cx(index_n(sc, L.index, lam), index_k(sc, L.index, lam));
-    Cx thi;
+    // Snell's law (AMultilayer::ListSnell): the reference takes theta_i = asin(n0 sin(theta0) / n_i), corrects the first and the
+    // last layer to the forward-travelling solution (theta -> pi - theta) and then only ever uses cos(theta_i).  On the principal
+    // branches cos(asin z) = sqrt(1 - z^2), and theta -> pi - theta flips the sign of the cosine: the same numbers without a
+    // complex asin (sqrt, log, atan2) and a complex cos (cos, sin, cosh, sinh) per layer.
     if (i == 0) {
       n0 = ni;
-      n0s = ni * csin_(th0);
-      thi = casin_(n0s / ni);
-      if (!tmm_is_forward(ni, thi)) thi = cx(RB_PI - thi.re, -thi.im);
-      cprev = ccos_(thi);
-    } else {
-      thi = casin_(n0s / ni);
-      if (i == N - 1 && !tmm_is_forward(ni, thi)) thi = cx(RB_PI - thi.re, -thi.im);
+      n0s = th0.im == 0 ? cx(ni.re * sin(th0.re), ni.im * sin(th0.re)) : ni * csin_(th0);
+    }
+    const Cx zs = n0s / ni;
+    Cx ccur = csqrt_(cx(1, 0) - zs * zs);
+    if (i == 0 || i == N - 1) {
+      const Cx nc = ni * ccur;  // IsForwardAngle (src/AMultilayer.cxx:26-56)
+      const bool forward = fabs(nc.im) > 100 * 2.220446049250313e-16 ? nc.im > 0 : nc.re > 0;
+      if (!forward) ccur = cx(-ccur.re, -ccur.im);
+    }
+    if (i == 0) cprev = ccur;
+    else {
       // interface (i-1) -> i
-      Cx ci = cprev, cf = ccos_(thi);
+      Cx ci = cprev, cf = ccur;
       Cx ii = nprev * ci;
       Cx em = cx(1, 0), ep = cx(1, 0);
       if (i > 1) {
@@ -327,7 +333,7 @@ template <int NP> RB_HD inline void tmm_coherent_multi(const DScene& sc, int fir
     n_last = ni;
     c_last = cprev;
   }
-  Cx cf = c_last, ci = ccos_(th0);
+  Cx cf = c_last, ci = th0.im == 0 ? cx(cos(th0.re), 0) : ccos_(th0);
 #pragma unroll
   for (int q = 0; q < NP; q++) {
     const int pol = NP == 1 ? pol0 : q;
@@ -649,17 +655,18 @@ RB_HD inline V3 para_normal(const double* P, V3 p, V3 d) {
 }
 
 // ---- TGeoSphere  P: rmin,rmax,th1,th2,ph1,ph2(deg), c1,s1,c2,s2, cp1,sp1,cp2,sp2, flags
+static RB_HD RB_NOINLINE bool sphere_phi_outside(const double* P, V3 p) {  // azimuthal segment (rare): kept out of line, atan2 is large
+  double phi = rb_atan2(p.y, p.x) * 180. / RB_PI;
+  while (phi < P[4]) phi += 360.;
+  return phi - P[4] > P[5] - P[4];
+}
 RB_HD inline bool sphere_contains(const double* P, V3 p) {
   double r2 = dot(p, p);
   if (P[0] > 0 && r2 < P[0] * P[0]) return false;
   if (r2 > P[1] * P[1]) return false;
   if (r2 < 1E-20) return true;
   int flags = (int)P[14];
-  if (flags & 4) {
-    double phi = rb_atan2(p.y, p.x) * 180. / RB_PI;
-    while (phi < P[4]) phi += 360.;
-    if (phi - P[4] > P[5] - P[4]) return false;
-  }
+  if ((flags & 4) && sphere_phi_outside(P, p)) return false;
   if (flags & 3) {
     double ct = p.z / sqrt(r2);  // theta >= th1 <=> cos(theta) <= cos(th1)
     if ((flags & 1) && ct > P[6]) return false;
@@ -672,6 +679,41 @@ RB_HD inline double sphere_dist(const double* P, V3 p, V3 d, bool from_inside) {
 #pragma unroll
   for (int k = 0; k < 10; k++) c[k] = RB_BIG;
   double a = dot(d, d), b = 2 * dot(p, d), pp = dot(p, p);
+  if (!from_inside && P[0] > 0 && pp < P[0] * P[0] && ((int)P[14] & 4) == 0) {
+    // Start point in the hollow of a shell (every ray that meets a mirror facet from its concave side, and every ray leaving
+    // one): the solid lies between the two spheres, so it can only be entered where the ray leaves the inner sphere, at E, or —
+    // if E is outside the polar range — through a cone while the ray crosses the shell between E and its exit from the outer
+    // sphere at X; after X it never comes back.  One quadratic settles the first case, two more the second; same root
+    // formulas as the general candidate scan below, which takes whatever is left.
+    const int flags = (int)P[14];
+    double e0, e1;
+    cand_quadratic(a, b, pp - P[0] * P[0], e0, e1);
+    const double tE = rb_min(e0, e1);
+    if (tE < 1e29) {
+      const double ct = (p.z + tE * d.z) / P[0];
+      if (!(((flags & 1) && ct > P[6]) || ((flags & 2) && ct < P[8]))) {
+        // E is in the polar range with a margin? (on the edge of the range the interval classification of the scan decides)
+        const double m = 1e-9;
+        if (!(((flags & 1) && ct > P[6] - m) || ((flags & 2) && ct < P[8] + m))) return tE;
+      } else {
+        double x0, x1;
+        cand_quadratic(a, b, pp - P[1] * P[1], x0, x1);
+        const double tX = rb_min(x0, x1);
+        bool cone_in_window = false;
+        const double dxy = d.x * d.x + d.y * d.y, pdxy = p.x * d.x + p.y * d.y, pxy = p.x * p.x + p.y * p.y;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (!(flags & (1 << k))) continue;
+          const double c2 = P[6 + 2 * k] * P[6 + 2 * k], s2 = P[7 + 2 * k] * P[7 + 2 * k];
+          double t0, t1;
+          cand_quadratic(dxy * c2 - d.z * d.z * s2, 2 * (pdxy * c2 - p.z * d.z * s2), pxy * c2 - p.z * p.z * s2, t0, t1);
+          const double lo = tE - 1e-9, hi = tX + 1e-9;
+          cone_in_window = cone_in_window || (t0 >= lo && t0 <= hi) || (t1 >= lo && t1 <= hi);
+        }
+        if (!cone_in_window && tX < 1e29) return RB_BIG;
+      }
+    }
+  }
   if (P[0] > 0) cand_quadratic(a, b, pp - P[0] * P[0], c[0], c[1]);
   cand_quadratic(a, b, pp - P[1] * P[1], c[2], c[3]);
   int flags = (int)P[14];
@@ -905,7 +947,7 @@ template <bool CONE> RB_HD inline V3 poly_normal(const double* P, V3 p, V3 d) {
 // between two consecutive candidates is classified by Contains() at its midpoint.
 RB_HD inline const double* polyg_tail(const double* P) { return P + 4 + 3 * (int)P[3] + 2 * (int)P[2]; }
 RB_HD inline bool poly_is_general(const double* P) { return polyg_tail(P)[0] != 0.; }
-template <bool CONE> RB_HD inline bool polyg_contains(const double* P, V3 p) {
+template <bool CONE> RB_HD RB_NOINLINE bool polyg_contains(const double* P, V3 p) {
   int ne = (int)P[2], nz = (int)P[3];
   const double* sec = P + 4;
   const double* cs = P + 4 + 3 * nz;
@@ -987,7 +1029,7 @@ template <bool CONE> RB_HD inline double polyg_next(const double* P, V3 p, V3 d,
     }
   return best;
 }
-template <bool CONE> RB_HD inline double polyg_dist(const double* P, V3 p, V3 d, bool from_inside) {
+template <bool CONE> RB_HD RB_NOINLINE double polyg_dist(const double* P, V3 p, V3 d, bool from_inside) {
   double prev = 0, last = 0;
   for (int it = 0; it < 4096; it++) {
     double t = polyg_next<CONE>(P, p, d, last);
@@ -1000,7 +1042,7 @@ template <bool CONE> RB_HD inline double polyg_dist(const double* P, V3 p, V3 d,
   }
   return from_inside ? prev : RB_BIG;
 }
-template <bool CONE> RB_HD inline V3 polyg_normal(const double* P, V3 p, V3 d) {
+template <bool CONE> RB_HD RB_NOINLINE V3 polyg_normal(const double* P, V3 p, V3 d) {
   int ne = (int)P[2], nz = (int)P[3];
   const double* sec = P + 4;
   const double* cs = P + 4 + 3 * nz;
@@ -1833,6 +1875,271 @@ template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE V3 Csg<DEPTH, SM>::normal(co
   return m < 0 ? ln : to_master_vec(sc.mats[m], ln);
 }
 
+// ================================================================== flat leaf evaluators
+// The shapes of real telescopes are almost always a primitive, a boolean of two primitives (mirror facet = sphere * polygon,
+// light guide = polygon - Winston cone, camera housing = box - box) or a chain of unions (spider = box + box + box + tube).
+// Leaf<K> evaluates these without the generic walk's recursion of non-inlined calls:
+//   * a primitive is dispatched to its code directly;
+//   * a boolean of two primitives whose (operation, left type, right type) is in the instantiation's list K::combos is
+//     evaluated by Bool2<...>: TGeoIntersection / TGeoSubtraction / TGeoUnion with both operands inlined and their types known
+//     at compile time (one copy of each primitive routine, no dispatch, everything in registers);
+//   * a chain of unions is evaluated as a flat loop over its primitives.
+// Everything else goes to Csg<DEPTH>.  The flat paths perform exactly the arithmetic of the generic walk (same operations in the
+// same order, TGeoBoolNode algorithms included), so both give identical bits; SceneBuilder::leaf_kind classifies the nodes.
+template <int T> struct PrimT;  // primitive routines by compile-time type (P = the shape's parameter block)
+#define RB_PRIMT(T, CONTAINS, DIN, DOUT, NORMAL)                                                          \
+  template <> struct PrimT<T> {                                                                            \
+    static RB_HD inline bool contains(const double* P, V3 p) { return CONTAINS; }                          \
+    static RB_HD inline double dist_in(const double* P, V3 p, V3 d) { return DIN; }                        \
+    static RB_HD inline double dist_out(const double* P, V3 p, V3 d, double step) { (void)step; return DOUT; } \
+    static RB_HD inline V3 normal(const double* P, V3 p, V3 d) { return NORMAL; }                          \
+  };
+RB_PRIMT(RBG_SHAPE_BBOX, bbox_contains(P, p), bbox_dist_in(P, p, d), bbox_dist_out(P, p, d, step), bbox_normal(P, p, d))
+RB_PRIMT(RBG_SHAPE_TUBE, tube_contains(P, p), tube_dist_in(P[0], P[1], P[2], p, d), tube_dist_out(P[0], P[1], P[2], p, d), tube_normal(P, p, d))
+RB_PRIMT(RBG_SHAPE_SPHERE, sphere_contains(P, p), sphere_dist(P, p, d, true), sphere_dist(P, p, d, false), sphere_normal(P, p, d))
+RB_PRIMT(RBG_SHAPE_PARABOLOID, para_contains(P, p), para_dist_in(P, p, d), para_dist_out(P, p, d), para_normal(P, p, d))
+// polygons / polycones reach the typed path only in their convex form (rmin = 0, full azimuth): leaf_kind sees to that
+RB_PRIMT(RBG_SHAPE_PGON, poly_contains<false>(P, p), poly_dist_in<false>(P, p, d), poly_dist_out<false>(P, p, d), poly_normal<false>(P, p, d))
+RB_PRIMT(RBG_SHAPE_PCON, poly_contains<true>(P, p), poly_dist_in<true>(P, p, d), poly_dist_out<true>(P, p, d), poly_normal<true>(P, p, d))
+RB_PRIMT(RBG_SHAPE_ASPHERE, asph_contains(P, p), asph_dist4(P, p, d), asph_dist_out(P, p, d, step), asph_normal(P, p, d))
+RB_PRIMT(RBG_SHAPE_WINSTON2D, win_contains(P, false, p), win_dist_in(P, false, p, d), win_dist_out(P, false, p, d), win_normal(P, false, p, d))
+RB_PRIMT(RBG_SHAPE_WINSTONPOLY, win_contains(P, true, p), win_dist_in(P, true, p, d), win_dist_out(P, true, p, d), win_normal(P, true, p, d))
+#undef RB_PRIMT
+
+// leaf code of a placed node: class in the low 4 bits; for RB_LEAF_BOOL2 the operation and the operand types above them
+#define RB_LEAF_CODE(OP, TL, TR) (RB_LEAF_BOOL2 | ((OP) << 4) | ((TL) << 8) | ((TR) << 12))
+template <int OP_, int TL_, int TR_> struct B2 {
+  static constexpr int OP = OP_, TL = TL_, TR = TR_, code = RB_LEAF_CODE(OP_, TL_, TR_);
+};
+template <class... Cs> struct Combos {};
+
+// boolean of two primitives of known types: ROOT's TGeoBoolNode algorithms (as in Csg<DEPTH>) on inlined operands
+template <class C> struct Bool2 {
+  typedef PrimT<C::TL> PL;
+  typedef PrimT<C::TR> PR;
+  static RB_HD inline bool contains(const DScene& sc, const DShape& s, V3 p) {
+    const double *A = sc.dpar + sc.shapes[s.left].ipar, *B = sc.dpar + sc.shapes[s.right].ipar;
+    bool l = PL::contains(A, op_point(sc, s.lmat, p));
+    if (C::OP == RBG_SHAPE_UNION) return l || PR::contains(B, op_point(sc, s.rmat, p));
+    if (!l) return false;
+    bool r = PR::contains(B, op_point(sc, s.rmat, p));
+    return C::OP == RBG_SHAPE_INTERSECTION ? r : !r;
+  }
+  // TGeoIntersection / TGeoSubtraction :: DistFromInside (a union's is iterative and rare: left to the generic walk)
+  static RB_HD inline double dist_in(const DScene& sc, const DShape& s, V3 p, V3 d, int& sel) {
+    const double *A = sc.dpar + sc.shapes[s.left].ipar, *B = sc.dpar + sc.shapes[s.right].ipar;
+    V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p), ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
+    double d1 = PL::dist_in(A, lp, ld);
+    double d2 = C::OP == RBG_SHAPE_INTERSECTION ? PR::dist_in(B, rp, rd) : PR::dist_out(B, rp, rd, RB_BIG);
+    if (d1 < d2) { sel = 1; return d1; }
+    sel = 2;
+    return d2;
+  }
+  // returns false when the case is left to the generic walk (start point inside an intersection: not a navigation case)
+  static RB_HD inline bool dist_out(const DScene& sc, const DShape& s, V3 p, V3 d, double step, int& sel, double& out) {
+    const double *A = sc.dpar + sc.shapes[s.left].ipar, *B = sc.dpar + sc.shapes[s.right].ipar;
+    sel = 0;
+    V3 ld = op_vec(sc, s.lmat, d), rd = op_vec(sc, s.rmat, d);
+    V3 lp = op_point(sc, s.lmat, p), rp = op_point(sc, s.rmat, p);
+    if (C::OP == RBG_SHAPE_UNION) {
+      double d1 = PL::dist_out(A, lp, ld, step), d2 = PR::dist_out(B, rp, rd, step);
+      if (d1 < d2) { sel = 1; out = d1; }
+      else { sel = 2; out = d2; }
+      return true;
+    }
+    V3 master = p;
+    if (C::OP == RBG_SHAPE_INTERSECTION) {
+      bool inl = PL::contains(A, lp), inr = PR::contains(B, rp);
+      if (inl && inr) return false;
+      // either operand missing means no hit: the cheaper primitive goes first, in the order the generic walk uses
+      constexpr bool right_first = C::TR < C::TL ? false : C::TR != RBG_SHAPE_SPHERE;
+      double snext = 0.0;
+      out = RB_BIG;
+      for (int guard = 0; guard < 64; guard++) {
+        double d1 = 0, d2 = 0;
+        if (right_first && !inr) {
+          d2 = rb_max(PR::dist_out(B, rp, rd, RB_BIG), RB_TOL);
+          if (d2 > 1E20) return true;
+        }
+        if (!inl) {
+          d1 = rb_max(PL::dist_out(A, lp, ld, RB_BIG), RB_TOL);
+          if (d1 > 1E20) return true;
+        }
+        if (!right_first && !inr) {
+          d2 = rb_max(PR::dist_out(B, rp, rd, RB_BIG), RB_TOL);
+          if (d2 > 1E20) return true;
+        }
+        const bool left_entered = d1 > d2;
+        const double adv = left_entered ? d1 : d2;
+        snext += adv;
+        sel = left_entered ? 1 : 2;
+        master = along(master, d, adv);
+        lp = op_point(sc, s.lmat, master);
+        rp = op_point(sc, s.rmat, master);
+        if (left_entered) {
+          inl = true;
+          inr = PR::contains(B, along(rp, rd, RB_TOL));
+          if (inr) { out = snext; return true; }
+        } else {
+          inr = true;
+          inl = PL::contains(A, along(lp, ld, RB_TOL));
+          if (inl) { out = snext; return true; }
+        }
+      }
+      return true;
+    }
+    // TGeoSubtraction::DistFromOutside
+    bool inside = PR::contains(B, rp);
+    double snxt = 0., epsil = 0.;
+    out = RB_BIG;
+    for (int guard = 0; guard < 64; guard++) {
+      if (inside) {
+        double d1 = PR::dist_in(B, rp, rd);
+        sel = 2;
+        snxt += d1 + epsil;
+        master = along(master, d, d1 + 1E-8);
+        epsil = 1.E-8;
+        if (PL::contains(A, op_point(sc, s.lmat, master))) { out = snxt; return true; }
+      }
+      lp = op_point(sc, s.lmat, master);
+      double d2 = PL::dist_out(A, lp, ld, RB_BIG);
+      if (d2 > 1E20) return true;
+      rp = op_point(sc, s.rmat, master);
+      double d1 = PR::dist_out(B, rp, rd, RB_BIG);
+      if (d2 < d1 - RB_TOL) {
+        sel = 1;
+        out = snxt + d2 + epsil;
+        return true;
+      }
+      snxt += d1 + epsil;
+      master = along(master, d, d1 + 1E-8);
+      epsil = 1.E-8;
+      rp = op_point(sc, s.rmat, master);
+      inside = true;
+    }
+    return true;
+  }
+  static RB_HD inline V3 normal(const DScene& sc, const DShape& s, V3 p, V3 d, int side) {
+    const int m = side == 1 ? s.lmat : s.rmat;
+    const double* P = sc.dpar + sc.shapes[side == 1 ? s.left : s.right].ipar;
+    V3 lp = op_point(sc, m, p), ld = op_vec(sc, m, d);
+    V3 ln = side == 1 ? PL::normal(P, lp, ld) : PR::normal(P, lp, ld);
+    return m < 0 ? ln : to_master_vec(sc.mats[m], ln);
+  }
+};
+
+template <class K> struct Leaf {
+  typedef Csg<K::depth, K::shapes> G;
+  typedef Csg<0, K::shapes> G0;
+  static constexpr unsigned SM = K::shapes;
+
+  // ---- chain of unions ((a + b) + c) + d: operands visited from the outermost right operand inwards; on equal distances
+  // TGeoUnion keeps the right operand, i.e. the outer one.  `sel` is the selection path the generic walk would record.
+  static RB_HD RB_NOINLINE bool unions_contains(const DScene& sc, int sh, V3 p) {
+    while (true) {
+      const DShape s = sc.shapes[sh];
+      if (!rb_is_bool(s.type)) return G0::contains(sc, sh, p);
+      if (G0::contains(sc, s.right, op_point(sc, s.rmat, p))) return true;
+      p = op_point(sc, s.lmat, p);
+      sh = s.left;
+    }
+  }
+  static RB_HD RB_NOINLINE double unions_dist_out(const DScene& sc, int sh, V3 p, V3 d, double step, int& sel) {
+    double best = RB_BIG;
+    int path = 0, shift = 0, dummy = 0;
+    sel = 0;
+    bool first = true;
+    while (true) {
+      const DShape s = sc.shapes[sh];
+      if (!rb_is_bool(s.type)) {
+        double t = G0::dist_out(sc, sh, p, d, step, dummy);
+        if (first || t < best) { best = t; sel = path; }
+        return best;
+      }
+      double t = G0::dist_out(sc, s.right, op_point(sc, s.rmat, p), op_vec(sc, s.rmat, d), step, dummy);
+      if (first || t < best) { best = t; sel = path | (2 << shift); }
+      first = false;
+      path |= 1 << shift;
+      shift += 2;
+      p = op_point(sc, s.lmat, p);
+      d = op_vec(sc, s.lmat, d);
+      sh = s.left;
+    }
+  }
+
+  // ---- typed two-primitive booleans: try every combination of the instantiation's list
+  template <class... Cs> static RB_HD inline bool combo_contains(Combos<Cs...>, int code, const DScene& sc, const DShape& s, V3 p, bool& out) {
+    return ((code == Cs::code ? (out = Bool2<Cs>::contains(sc, s, p), true) : false) || ...);
+  }
+  template <class... Cs> static RB_HD inline bool combo_dist_in(Combos<Cs...>, int code, const DScene& sc, const DShape& s, V3 p, V3 d, int& sel, double& out) {
+    return ((code == Cs::code && Cs::OP != RBG_SHAPE_UNION ? (out = Bool2<Cs>::dist_in(sc, s, p, d, sel), true) : false) || ...);
+  }
+  template <class... Cs>
+  static RB_HD inline bool combo_dist_out(Combos<Cs...>, int code, const DScene& sc, const DShape& s, V3 p, V3 d, double step, int& sel, double& out) {
+    return ((code == Cs::code ? Bool2<Cs>::dist_out(sc, s, p, d, step, sel, out) : false) || ...);
+  }
+  template <class... Cs> static RB_HD inline bool combo_normal(Combos<Cs...>, int code, const DScene& sc, const DShape& s, V3 p, V3 d, int side, V3& out) {
+    return ((code == Cs::code ? (out = Bool2<Cs>::normal(sc, s, p, d, side), true) : false) || ...);
+  }
+
+  // ---- dispatch on the node's class
+  static RB_HD inline bool contains(const DScene& sc, int leaf, int sh, V3 p) {
+    if (leaf == RB_LEAF_PRIM) return prim_contains<SM>(sc, sc.shapes[sh], p);
+    if constexpr (K::depth > 0) {
+      if ((leaf & 15) == RB_LEAF_BOOL2) {
+        bool out;
+        if (combo_contains(typename K::combos(), leaf, sc, sc.shapes[sh], p, out)) return out;
+      }
+      if ((SM & RB_SBIT(RBG_SHAPE_UNION)) != 0 && leaf == RB_LEAF_UNIONS) return unions_contains(sc, sh, p);
+    }
+    return G::contains(sc, sh, p);
+  }
+  static RB_HD inline double dist_in(const DScene& sc, int leaf, int sh, V3 p, V3 d, int& sel) {
+    sel = 0;
+    if (leaf == RB_LEAF_PRIM) return prim_dist_in<SM>(sc, sc.shapes[sh], p, d);
+    if constexpr (K::depth > 0) {
+      if ((leaf & 15) == RB_LEAF_BOOL2) {
+        double out;
+        if (combo_dist_in(typename K::combos(), leaf, sc, sc.shapes[sh], p, d, sel, out)) return out;
+      }
+    }
+    return G::dist_in(sc, sh, p, d, sel);
+  }
+  static RB_HD inline double dist_out(const DScene& sc, int leaf, int sh, V3 p, V3 d, double step, int& sel) {
+    sel = 0;
+    if (leaf == RB_LEAF_PRIM) return prim_dist_out<SM>(sc, sc.shapes[sh], p, d, step);
+    if constexpr (K::depth > 0) {
+      if ((leaf & 15) == RB_LEAF_BOOL2) {
+        double out;
+        if (combo_dist_out(typename K::combos(), leaf, sc, sc.shapes[sh], p, d, step, sel, out)) return out;
+      }
+      if ((SM & RB_SBIT(RBG_SHAPE_UNION)) != 0 && leaf == RB_LEAF_UNIONS) return unions_dist_out(sc, sh, p, d, step, sel);
+    }
+    return G::dist_out(sc, sh, p, d, step, sel);
+  }
+  static RB_HD inline V3 normal(const DScene& sc, int leaf, int sh, V3 p, V3 d, int sel) {
+    if (leaf == RB_LEAF_PRIM) return prim_normal<SM>(sc, sc.shapes[sh], p, d);
+    if constexpr (K::depth > 0) {
+      if ((leaf & 15) == RB_LEAF_BOOL2 && (sel & 3) != 0) {  // side 0 = no boundary recorded (start on the surface): generic
+        V3 out;
+        if (combo_normal(typename K::combos(), leaf, sc, sc.shapes[sh], p, d, sel & 3, out)) return out;
+      }
+    }
+    return G::normal(sc, sh, p, d, sel);
+  }
+};
+
+// point test of a placed node (world coordinates); not inlined: it has many call sites (point location, relocation after a
+// reflection), none of them inside the distance loops
+template <class K> RB_HD RB_NOINLINE bool node_contains(const DScene& sc, int node, V3 q) {
+  const DNode& nd = sc.nodes[node];
+  return Leaf<K>::contains(sc, nd.leaf, nd.shape, to_local(nd.g, q));
+}
+RB_HD inline bool node_box_holds(const DNode& nd, V3 q) {
+  const float x = (float)q.x, y = (float)q.y, z = (float)q.z;  // the boxes are padded for this rounding
+  return x >= nd.blo[0] && x <= nd.bhi[0] && y >= nd.blo[1] && y <= nd.bhi[1] && z >= nd.blo[2] && z <= nd.bhi[2];
+}
+
 // ================================================================== flattened navigation
 struct RayReg {           // register-resident ray state
   V3 p, d;
@@ -1856,8 +2163,7 @@ template <class K> RB_HD inline int child_containing(const DScene& sc, int node,
     if (b.child >= 0) {
       int c = b.child;
       if (c != skip && c > after && (best < 0 || c < best)) {
-        const DNode& cn = sc.nodes[c];
-        if (Csg<K::depth, K::shapes>::contains(sc, cn.shape, to_local(cn.g, q))) best = c;
+        if (node_contains<K>(sc, c, q)) best = c;
       }
       i = b.skip;
     } else i = i + 1;
@@ -1898,7 +2204,7 @@ template <class K> RB_HD inline int search_node(const DScene& sc, int node, V3 q
     while (true) {
       if (node < 0) return -1;
       const DNode& nd = sc.nodes[node];
-      bool inside = node == skip ? true : Csg<K::depth, K::shapes>::contains(sc, nd.shape, to_local(nd.g, q));
+      bool inside = node == skip ? true : node_contains<K>(sc, node, q);
       if constexpr ((K::phys & RB_PH_OVERLAP) != 0) {
         // GotoSafeLevel: the search restarts from the first ordinary node above a run of overlapping ones
         if (inside && nd.overlap && nd.mother >= 0) {
@@ -1927,7 +2233,8 @@ struct StepOut {
   int sel;         // boolean-operand selection path of the crossed shape
   int from;        // node the step started in (-1 outside)
   int nvis;        // daughters of `from` whose padded AABB the ray touched before the boundary; -1 = not recorded
-  int vis[RB_MAXVIS];
+  int vis[RB_MAXVIS];     // ... ordered by the parameter at which the ray enters the box
+  float tin[RB_MAXVIS];
 };
 
 RB_HD inline double locate_extra(const DScene& sc, int node, double step) {
@@ -1949,6 +2256,9 @@ struct NavStep {
   int mode;      // 0 = finished in nb_begin, 1 = daughters to examine
   int bvh_next;  // >= 0: traversal stopped because o.vis was full; resume here after evaluating the batch
   int xkind, xnode, xsel;  // overlap extension (nb_many): 0 none, 1 = left the mother `xnode` of an overlapping node, 2 = met its sister `xnode`
+  // point location behind the crossed boundary, requested by nb_begin / nb_finish and done at one place (nb_locate):
+  // search_node(loc_node, point pushed by locate_extra(loc_node), loc_skip, loc_check, loc_prefer); loc_node = -2: none pending
+  int loc_node, loc_skip, loc_check, loc_prefer;
 };
 
 // phase A: boundary push, outside-world entry, DistFromInside of the current shape
@@ -1958,18 +2268,23 @@ template <class K> RB_HD inline void nb_begin(const DScene& sc, RayReg& r, bool 
   o.sel = 0;
   o.from = r.cur;
   o.nvis = -1;
+  o.next = -1;
   st.mode = 0;
   st.bvh_next = -1;
   st.enter = -1;
   st.esel = 0;
   st.xkind = 0;
+  st.loc_node = -2;
+  st.loc_skip = -1;
+  st.loc_check = 0;
+  st.loc_prefer = -1;
   double extra = (r.on_boundary && push_quirk) ? RB_TOL : 0.0;
   st.extra = extra;
   r.on_boundary = 0;
   r.p = along(r.p, r.d, extra);
   if (r.cur < 0) {
     int sel = 0;
-    double s = Csg<K::depth, K::shapes>::dist_out(sc, sc.top_shape, r.p, r.d, RB_BIG, sel);
+    double s = Leaf<K>::dist_out(sc, sc.top_leaf, sc.top_shape, r.p, r.d, RB_BIG, sel);
     if (s > 1e29) { o.step = RB_BIG; o.next = -1; return; }
     if (s <= 0) { s = 0.0; o.step = 0.0; r.p = along(r.p, r.d, -extra); }
     else o.step = s + extra;
@@ -1977,12 +2292,12 @@ template <class K> RB_HD inline void nb_begin(const DScene& sc, RayReg& r, bool 
     r.on_boundary = 1;
     o.crossed = 0;
     o.sel = sel;
-    o.next = search_node<K>(sc, 0, along(r.p, r.d, locate_extra(sc, 0, o.step)), -1, false);
+    st.loc_node = 0;
     return;
   }
   const DNode& cn = sc.nodes[r.cur];
   st.sel_exit = 0;
-  st.s_exit = Csg<K::depth, K::shapes>::dist_in(sc, cn.shape, to_local(cn.g, r.p), to_local_vec(cn.g, r.d), st.sel_exit);
+  st.s_exit = Leaf<K>::dist_in(sc, cn.leaf, cn.shape, to_local(cn.g, r.p), to_local_vec(cn.g, r.d), st.sel_exit);
   if (st.s_exit <= RB_TOL) {
     o.step = RB_TOL;
     r.p = along(r.p, r.d, o.step);
@@ -1990,7 +2305,9 @@ template <class K> RB_HD inline void nb_begin(const DScene& sc, RayReg& r, bool 
     o.crossed = r.cur;
     o.sel = st.sel_exit;
     if (cn.mother < 0) { o.next = -1; return; }
-    o.next = search_node<K>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
+    st.loc_node = cn.mother;
+    st.loc_skip = r.cur;
+    st.loc_check = 1;
     return;
   }
   st.best = RB_BIG;
@@ -2000,31 +2317,55 @@ template <class K> RB_HD inline void nb_begin(const DScene& sc, RayReg& r, bool 
   st.bvh_next = cn.bvh_count > 0 ? cn.bvh_first : -1;
 }
 
-// phase B: threaded-BVH walk over the daughters of the current node; only collects candidates (postponed leaf
-// intersection).  fp32 slab test against padded boxes: one FFMA per plane, FMNMX min/max.
+// fp32 slab test of one ray against padded boxes: one FFMA per plane, FMNMX min/max
+struct RayBox {
+  float ix, iy, iz, ox, oy, oz, fx, fy, fz, bestf;
+  bool px, py, pz;
+};
+RB_HD inline RayBox raybox_prepare(V3 p, V3 d, double best) {
+  RayBox q;
+  q.ix = (float)(1. / d.x); q.iy = (float)(1. / d.y); q.iz = (float)(1. / d.z);
+  q.ox = -(float)p.x * q.ix; q.oy = -(float)p.y * q.iy; q.oz = -(float)p.z * q.iz;
+  q.px = isfinite(q.ix) && isfinite(q.ox); q.py = isfinite(q.iy) && isfinite(q.oy); q.pz = isfinite(q.iz) && isfinite(q.oz);
+  q.fx = (float)p.x; q.fy = (float)p.y; q.fz = (float)p.z;
+  q.bestf = best > 1e29 ? 3.0e38f : (float)best * 1.000001f + 1e-3f;
+  return q;
+}
+RB_HD inline bool raybox_test(const RayBox& q, const float* lo, const float* hi, float& tmin) {
+  tmin = 0.f;
+  float tmax = q.bestf;
+  bool hit = true;
+  if (q.px) { float t0 = fmaf(lo[0], q.ix, q.ox), t1 = fmaf(hi[0], q.ix, q.ox); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
+  else hit = hit && q.fx >= lo[0] && q.fx <= hi[0];
+  if (q.py) { float t0 = fmaf(lo[1], q.iy, q.oy), t1 = fmaf(hi[1], q.iy, q.oy); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
+  else hit = hit && q.fy >= lo[1] && q.fy <= hi[1];
+  if (q.pz) { float t0 = fmaf(lo[2], q.iz, q.oz), t1 = fmaf(hi[2], q.iz, q.oz); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
+  else hit = hit && q.fz >= lo[2] && q.fz <= hi[2];
+  return hit && tmin <= tmax * 1.000002f + 1e-4f;
+}
+// candidate list, nearest box first: the step found in the first candidates lets nb_eval drop the farther ones unevaluated
+RB_HD inline void cand_insert(StepOut& o, int first, int child, float tmin) {
+  int k = o.nvis++;
+  while (k > first && o.tin[k - 1] > tmin) { o.vis[k] = o.vis[k - 1]; o.tin[k] = o.tin[k - 1]; k--; }
+  o.vis[k] = child;
+  o.tin[k] = tmin;
+}
+
+// phase B: threaded-BVH walk over the daughters of the current node; only collects candidates (postponed leaf intersection)
 template <class K> RB_HD inline void nb_collect(const DScene& sc, const RayReg& r, NavStep& st) {
   StepOut& o = st.o;
   int i = st.bvh_next;
   if (st.mode != 1 || i < 0) { st.bvh_next = -1; return; }
-  const float ix = (float)(1. / r.d.x), iy = (float)(1. / r.d.y), iz = (float)(1. / r.d.z);
-  const float ox = -(float)r.p.x * ix, oy = -(float)r.p.y * iy, oz = -(float)r.p.z * iz;
-  const bool px = isfinite(ix) && isfinite(ox), py = isfinite(iy) && isfinite(oy), pz = isfinite(iz) && isfinite(oz);
-  const float fx = (float)r.p.x, fy = (float)r.p.y, fz = (float)r.p.z;
-  const float bestf = st.best > 1e29 ? 3.0e38f : (float)st.best * 1.000001f + 1e-3f;
+  const RayBox q = raybox_prepare(r.p, r.d, st.best);
+  const int first = o.nvis;
   while (i >= 0 && o.nvis < RB_MAXVIS) {
     const DBvh& b = sc.bvh[i];
-    float tmin = 0.f, tmax = bestf;
-    bool hit = true;
-    if (px) { float t0 = fmaf(b.lo[0], ix, ox), t1 = fmaf(b.hi[0], ix, ox); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
-    else hit = hit && fx >= b.lo[0] && fx <= b.hi[0];
-    if (py) { float t0 = fmaf(b.lo[1], iy, oy), t1 = fmaf(b.hi[1], iy, oy); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
-    else hit = hit && fy >= b.lo[1] && fy <= b.hi[1];
-    if (pz) { float t0 = fmaf(b.lo[2], iz, oz), t1 = fmaf(b.hi[2], iz, oz); tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1)); }
-    else hit = hit && fz >= b.lo[2] && fz <= b.hi[2];
-    hit = hit && tmin <= tmax * 1.000002f + 1e-4f;
-    if (!hit) { i = b.skip; continue; }
-    if (b.child >= 0) { o.vis[o.nvis++] = b.child; i = b.skip; }
-    else i = i + 1;
+    float tmin;
+    if (!raybox_test(q, b.lo, b.hi, tmin)) { i = b.skip; continue; }
+    if (b.child >= 0) {
+      cand_insert(o, first, b.child, tmin);
+      i = b.skip;
+    } else i = i + 1;
   }
   st.bvh_next = i;  // >= 0 only if the candidate buffer filled up
 }
@@ -2033,9 +2374,12 @@ template <class K> RB_HD inline void nb_collect(const DScene& sc, const RayReg& 
 // tolerance: on (near-)ties the lowest daughter index wins regardless of the visiting order.
 template <class K> RB_HD inline void nb_eval(const DScene& sc, const RayReg& r, NavStep& st, int k) {
   int c = st.o.vis[k];
+  // the ray enters this daughter's box (padded by >= 2e-3) beyond the step already found: its DistFromOutside cannot be
+  // nearer than the best one, nor tie with it within the tolerance
+  if (st.o.tin[k] > (float)st.best * 1.000001f + 1e-3f) return;
   const DNode& dn = sc.nodes[c];
   int sel = 0;
-  double s = Csg<K::depth, K::shapes>::dist_out(sc, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), st.best + 2 * RB_TOL, sel);
+  double s = Leaf<K>::dist_out(sc, dn.leaf, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), st.best + 2 * RB_TOL, sel);
   if (s < st.best - RB_TOL || (st.enter >= 0 && c < st.enter && s <= st.best + RB_TOL)) { st.best = s; st.enter = c; st.esel = sel; }
 }
 
@@ -2068,47 +2412,70 @@ template <class K> RB_HD inline void nb_many(const DScene& sc, const RayReg& r, 
   }
 }
 
-// phase D: move to the boundary and locate the node behind it (CrossBoundaryAndLocate)
-template <class K> RB_HD inline void nb_finish(const DScene& sc, RayReg& r, NavStep& st) {
-  if (st.mode != 1) return;
+// phase D: move to the boundary (nb_arrive) and locate the node behind it (nb_locate) — CrossBoundaryAndLocate
+template <class K> RB_HD inline void nb_arrive(const DScene& sc, RayReg& r, NavStep& st) {
   StepOut& o = st.o;
-  const DNode& cn = sc.nodes[r.cur];
-  if constexpr ((K::phys & RB_PH_OVERLAP) != 0) {
-    if (sc.has_many) {
-      nb_many<K>(sc, r, st);
-      o.nvis = -1;  // relocate_back must not take its sibling shortcut in a scene with overlapping nodes
-      if (st.xkind != 0) {
-        r.p = along(r.p, r.d, st.best);
-        o.step = st.best + st.extra;
-        r.on_boundary = 1;
-        o.crossed = st.xnode;
-        o.sel = st.xsel;
-        const int y = sc.nodes[st.xnode].mother;  // left node: relocate above it; met sister: relocate from the common mother
-        if (y < 0) { o.next = -1; return; }
-        o.next = search_node<K>(sc, y, along(r.p, r.d, locate_extra(sc, y, o.step)), st.xkind == 1 ? st.xnode : -1, true, st.xkind == 2 ? st.xnode : -1);
-        return;
-      }
-    }
-  }
-  r.p = along(r.p, r.d, st.best);
-  o.step = st.best + st.extra;
-  r.on_boundary = 1;
-  if (st.enter >= 0) {
-    o.crossed = st.enter;
-    o.sel = st.esel;
+  if (st.mode == 1) {
+    const DNode& cn = sc.nodes[r.cur];
+    bool done = false;
     if constexpr ((K::phys & RB_PH_OVERLAP) != 0) {
-      if (sc.nodes[st.enter].overlap) {  // an overlapping daughter: an ordinary sister holding the point has priority
-        o.next = search_node<K>(sc, r.cur, along(r.p, r.d, locate_extra(sc, r.cur, o.step)), -1, true, st.enter);
-        return;
+      if (sc.has_many) {
+        nb_many<K>(sc, r, st);
+        o.nvis = -1;  // relocate_back must not take its sibling shortcut in a scene with overlapping nodes
+        if (st.xkind != 0) {
+          r.p = along(r.p, r.d, st.best);
+          o.step = st.best + st.extra;
+          r.on_boundary = 1;
+          o.crossed = st.xnode;
+          o.sel = st.xsel;
+          const int y = sc.nodes[st.xnode].mother;  // left node: relocate above it; met sister: relocate from the common mother
+          if (y < 0) o.next = -1;
+          else {
+            st.loc_node = y;
+            st.loc_skip = st.xkind == 1 ? st.xnode : -1;
+            st.loc_check = 1;
+            st.loc_prefer = st.xkind == 2 ? st.xnode : -1;
+          }
+          done = true;
+        }
       }
     }
-    o.next = search_node<K>(sc, st.enter, along(r.p, r.d, locate_extra(sc, st.enter, o.step)), -1, false);
-    return;
+    if (!done) {
+      r.p = along(r.p, r.d, st.best);
+      o.step = st.best + st.extra;
+      r.on_boundary = 1;
+      if (st.enter >= 0) {
+        o.crossed = st.enter;
+        o.sel = st.esel;
+        st.loc_node = st.enter;
+        if constexpr ((K::phys & RB_PH_OVERLAP) != 0) {
+          if (sc.nodes[st.enter].overlap) {  // an overlapping daughter: an ordinary sister holding the point has priority
+            st.loc_node = r.cur;
+            st.loc_check = 1;
+            st.loc_prefer = st.enter;
+          }
+        }
+      } else {
+        o.crossed = r.cur;
+        o.sel = st.sel_exit;
+        if (cn.mother < 0) o.next = -1;
+        else {
+          st.loc_node = cn.mother;
+          st.loc_skip = r.cur;
+          st.loc_check = 1;
+        }
+      }
+    }
   }
-  o.crossed = r.cur;
-  o.sel = st.sel_exit;
-  if (cn.mother < 0) { o.next = -1; return; }
-  o.next = search_node<K>(sc, cn.mother, along(r.p, r.d, locate_extra(sc, cn.mother, o.step)), r.cur, true);
+}
+// point location behind the crossed boundary, as requested by nb_begin / nb_arrive (loc_node = -2: nothing to do, o.next is set)
+template <class K> RB_HD inline int nb_locate(const DScene& sc, V3 p, V3 d, double step, int loc_node, int loc_skip, int loc_check, int loc_prefer, int next) {
+  if (loc_node > -2) return search_node<K>(sc, loc_node, along(p, d, locate_extra(sc, loc_node, step)), loc_skip, loc_check != 0, loc_prefer);
+  return next;
+}
+template <class K> RB_HD inline void nb_finish(const DScene& sc, RayReg& r, NavStep& st) {
+  nb_arrive<K>(sc, r, st);
+  st.o.next = nb_locate<K>(sc, r.p, r.d, st.o.step, st.loc_node, st.loc_skip, st.loc_check, st.loc_prefer, st.o.next);
 }
 
 // the phases run back to back for one thread (per-ray loop kernel, host emulation)
@@ -2157,7 +2524,7 @@ struct Hit {       // context of one boundary interaction
 template <class K> RB_HD inline V3 geometric_normal(const DScene& sc, const RayReg& r, const Hit& h, V3 dir) {
   if (h.crossed < 0) return v3(0, 0, 1);
   const DNode& nd = sc.nodes[h.crossed];
-  V3 ln = Csg<K::depth, K::shapes>::normal(sc, nd.shape, to_local(nd.g, r.p), to_local_vec(nd.g, dir), h.sel);
+  V3 ln = Leaf<K>::normal(sc, nd.leaf, nd.shape, to_local(nd.g, r.p), to_local_vec(nd.g, dir), h.sel);
   return to_master_vec(nd.g, ln);
 }
 
@@ -2224,31 +2591,30 @@ RB_HD inline void set_direction(RayReg& r, V3 d2) {
 // so.vis — no second BVH walk is needed.  Everything else takes the generic SearchNode path.
 template <class K> RB_HD inline int relocate_back(const DScene& sc, const Hit& h, V3 back) {
   const StepOut& so = *h.so;
-  typedef Csg<K::depth, K::shapes> G;
+  int start = h.next_node < 0 ? 0 : h.next_node;
+  bool check = true;
   if (so.nvis >= 0 && so.from >= 0 && so.next >= 0 && so.next == so.crossed && sc.nodes[so.next].mother == so.from && so.step > 4e-6) {
-    const DNode& en = sc.nodes[so.next];
-    if (G::contains(sc, en.shape, to_local(en.g, back))) return search_node<K>(sc, so.next, back, -1, false);
-    const DNode& fn = sc.nodes[so.from];
-    if (G::contains(sc, fn.shape, to_local(fn.g, back))) {
+    if (node_contains<K>(sc, so.next, back)) { start = so.next; check = false; }
+    else if (node_contains<K>(sc, so.from, back)) {
       int best = -1;
       for (int k = 0; k < so.nvis; k++) {
         int c = so.vis[k];
         if (c == so.next || (best >= 0 && c > best)) continue;
-        const DNode& cn = sc.nodes[c];
-        if (G::contains(sc, cn.shape, to_local(cn.g, back))) best = c;
+        if (!node_box_holds(sc.nodes[c], back)) continue;  // a point outside the (padded) box is outside the shape
+        if (node_contains<K>(sc, c, back)) best = c;
       }
-      return best < 0 ? so.from : search_node<K>(sc, best, back, -1, false);
+      if (best < 0) return so.from;
+      start = best;
+      check = false;
     }
   }
-  return search_node<K>(sc, h.next_node < 0 ? 0 : h.next_node, back, -1, true);
+  return search_node<K>(sc, start, back, -1, check);
 }
 
 // AOpticsManager::DoReflection.  `pos` is the boundary point; r.p still holds the segment start.
+// (`n` is the facet normal, drawn by the caller: trace_shade evaluates GetFacetNormal at one place for all its users)
 template <class K> RB_HD inline void do_reflection(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1,
-                                                    Philox& g, const V3* normal_in) {
-  RayReg at = r;
-  at.p = pos;
-  V3 n = normal_in ? *normal_in : facet_normal<K>(sc, at, h, g);
+                                                    Philox& g, V3 n) {
   V3 d1 = r.d;
   double cos1 = dot(d1, n);
   bool absorbed = false;
@@ -2297,12 +2663,10 @@ template <class K> RB_HD inline void do_reflection(const DScene& sc, const DTrac
   r.on_boundary = 0;
 }
 
-// AOpticsManager::DoFresnel
-template <class K> RB_HD inline void do_fresnel(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, int& loc, const Hit& h, double n1, double n2,
-                                                 double k2, Philox& g) {
-  RayReg at = r;
-  at.p = pos;
-  V3 n = facet_normal<K>(sc, at, h, g);
+// AOpticsManager::DoFresnel.  Returns true when the ray is to be reflected instead (multilayer reflection, total internal
+// reflection, Fresnel reflection: the reference calls DoReflection from here, :91, :100, :138) — the caller does that.
+template <class K> RB_HD inline bool do_fresnel(const DScene& sc, const DTraceParams& tp, RayReg& r, V3& pos, const Hit& h, double n1, double n2,
+                                                 double k2, Philox& g, V3 n) {
   V3 d1 = r.d;
   double cos1 = dot(d1, n), sin1 = sqrt(1 - cos1 * cos1), sin2 = n1 * sin1 / n2, cos2 = sqrt(1 - sin2 * sin2);
   bool absorbed = false, decided = false;
@@ -2312,13 +2676,13 @@ template <class K> RB_HD inline void do_fresnel(const DScene& sc, const DTracePa
       double R, T;
       tmm_mixed(sc, c->multilayer, rb_acos(cos1), r.lambda, R, T);
       double rnd = rng_uniform(g);
-      if (rnd < R) { do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+      if (rnd < R) return true;
       decided = true;
       if (!(rnd < R + T)) absorbed = true;
     }
   }
   if (!decided) {
-    if (sin2 > 1.) { do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+    if (sin2 > 1.) return true;
     if (!tp.disable_fresnel) {
       double Rs, Rp;
       if (k2 <= 0.) {
@@ -2335,7 +2699,7 @@ template <class K> RB_HD inline void do_fresnel(const DScene& sc, const DTracePa
         Rs = (sqr(x1S - x2S) + sqr(y2S)) / (sqr(x1S + x2S) + sqr(y2S));
         Rp = (sqr(x1P - x2P) + sqr(y2P)) / (sqr(x1P + x2P) + sqr(y2P));
       }
-      if (rng_uniform(g) < (Rs + Rp) / 2.) { do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, &n); return; }
+      if (rng_uniform(g) < (Rs + Rp) / 2.) return true;
     }
   }
   V3 d2 = d1;
@@ -2346,6 +2710,7 @@ template <class K> RB_HD inline void do_fresnel(const DScene& sc, const DTracePa
   add_point(r, pos, r.t + h.step / (RB_C_CM / n1), h.next_node, h.hs);
   if (absorbed) r.status = RBG_ABSORB;
   else set_direction(r, d2);
+  return false;
 }
 
 // One iteration of the while(ray->IsRunning()) loop, src/AOpticsManager.cxx:359-518
@@ -2391,27 +2756,41 @@ RB_HD inline void trace_shade(const DScene& sc, const DTraceParams& tp, RayReg& 
   }
   bool curVac = typeCurrent == RBG_NULL || typeCurrent == RBG_OPT || typeCurrent == RBG_OTHER;
   bool curLens = kLens && typeCurrent == RBG_LENS;
-  if ((curVac || curLens) && typeNext == RBG_MIRROR) {
-    double n1 = 1.;
-    if constexpr (kLens) n1 = curLens ? index_n(sc, sc.volumes[cur_vol].index, lambda) : 1.;
-    do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, nullptr);
-  } else if ((curVac || curLens) && (typeNext == RBG_OBS || typeNext == RBG_FOCUS)) {
-    double speed = RB_C_CM;
-    if constexpr (kLens) speed = curLens ? RB_C_CM / index_n(sc, sc.volumes[cur_vol].index, lambda) : RB_C_CM;
-    add_point(r, pos, t1 + so.step / speed, so.next, hs);
-  } else if (curVac && (typeNext == RBG_OTHER || typeNext == RBG_OPT)) {
-    add_point(r, pos, t1 + so.step / RB_C_CM, so.next, hs);
-  } else if constexpr (kLens) {
-    if (curVac && typeNext == RBG_LENS) {
-      int ix = sc.volumes[h.next_vol].index;
-      do_fresnel<K>(sc, tp, r, pos, loc, h, 1., index_n(sc, ix, lambda), index_k(sc, ix, lambda), g);
-    } else if (curLens && typeNext == RBG_LENS) {
-      int i1 = sc.volumes[cur_vol].index, i2 = sc.volumes[h.next_vol].index;
-      do_fresnel<K>(sc, tp, r, pos, loc, h, index_n(sc, i1, lambda), index_n(sc, i2, lambda), index_k(sc, i2, lambda), g);
-    } else if (curLens && (typeNext == RBG_NULL || typeNext == RBG_OPT || typeNext == RBG_OTHER)) {
-      do_fresnel<K>(sc, tp, r, pos, loc, h, index_n(sc, sc.volumes[cur_vol].index, lambda), 1., 0., g);
+  const bool nextVac = typeNext == RBG_NULL || typeNext == RBG_OPT || typeNext == RBG_OTHER;
+  bool reflect = (curVac || curLens) && typeNext == RBG_MIRROR;
+  const bool fresnel = kLens && ((curVac && typeNext == RBG_LENS) || (curLens && (typeNext == RBG_LENS || nextVac)));
+  // QE(theta) of a focal surface needs the facet normal as well (src/AOpticsManager.cxx:495-505); none of the branches leading
+  // there draws a random number before it, so GetFacetNormal can be evaluated here, once, for whichever branch wants it
+  bool qe_angle = false;
+  if constexpr ((K::phys & RB_PH_QE) != 0) {
+    if (typeNext == RBG_FOCUS && !(typeCurrent == RBG_FOCUS || typeCurrent == RBG_OBS || typeCurrent == RBG_MIRROR)) {
+      const int fo = sc.volumes[h.next_vol].focal;
+      qe_angle = fo >= 0 && sc.focals[fo].qe_angle >= 0;
     }
   }
+  V3 n = v3(0, 0, 1);
+  if (reflect || fresnel || qe_angle) {
+    RayReg at = r;
+    at.p = pos;
+    n = facet_normal<K>(sc, at, h, g);
+  }
+  double n1 = 1.;
+  if constexpr (kLens) n1 = curLens ? index_n(sc, sc.volumes[cur_vol].index, lambda) : 1.;
+  if (fresnel) {
+    if constexpr (kLens) {
+      double n2 = 1., k2 = 0.;
+      if (typeNext == RBG_LENS) {
+        const int ix = sc.volumes[h.next_vol].index;
+        n2 = index_n(sc, ix, lambda);
+        k2 = index_k(sc, ix, lambda);
+      }
+      reflect = do_fresnel<K>(sc, tp, r, pos, h, n1, n2, k2, g, n);
+    }
+  } else if (!reflect) {
+    if ((curVac || curLens) && (typeNext == RBG_OBS || typeNext == RBG_FOCUS)) add_point(r, pos, t1 + so.step / (RB_C_CM / n1), so.next, hs);
+    else if (curVac && (typeNext == RBG_OTHER || typeNext == RBG_OPT)) add_point(r, pos, t1 + so.step / RB_C_CM, so.next, hs);
+  }
+  if (reflect) do_reflection<K>(sc, tp, r, pos, loc, h, n1, g, n);
   // termination (evaluated after the interaction, src/AOpticsManager.cxx:485-513)
   if (typeNext == RBG_NULL) {
     add_point(r, pos, t1 + so.step / RB_C_CM, so.next, hs);
@@ -2419,19 +2798,14 @@ RB_HD inline void trace_shade(const DScene& sc, const DTraceParams& tp, RayReg& 
   } else if (typeCurrent == RBG_FOCUS || typeCurrent == RBG_OBS || typeCurrent == RBG_MIRROR || typeNext == RBG_OBS) {
     r.status = RBG_STOP;
   } else if (typeNext == RBG_FOCUS) {
-    const rbg_volume& fv = sc.volumes[h.next_vol];
     double qe = 1.;
-    if constexpr ((K::phys & RB_PH_QE) != 0) if (fv.focal >= 0) {
-      const rbg_focal f = sc.focals[fv.focal];
-      double angle = 0.;
-      if (f.qe_angle >= 0) {
-        RayReg at = r;
-        at.p = pos;
-        V3 n = facet_normal<K>(sc, at, h, g);
-        angle = rb_acos(dot(r.d, n));
+    if constexpr ((K::phys & RB_PH_QE) != 0) {
+      const rbg_volume& fv = sc.volumes[h.next_vol];
+      if (fv.focal >= 0) {
+        const rbg_focal f = sc.focals[fv.focal];
+        if (f.qe_lambda >= 0) qe = graph_eval(sc, f.qe_lambda, lambda);
+        if (f.qe_angle >= 0) qe *= graph_eval(sc, f.qe_angle, rb_acos(dot(r.d, n)));
       }
-      if (f.qe_lambda >= 0) qe = graph_eval(sc, f.qe_lambda, lambda);
-      if (f.qe_angle >= 0) qe *= graph_eval(sc, f.qe_angle, angle);
     }
     if (qe == 1 || rng_uniform(g) < qe) r.status = RBG_FOCUSED;
     else r.status = RBG_STOP;

@@ -12,8 +12,6 @@
 //  k_tmm            AMultilayer::CoherentTMMMixed per (theta, lambda) pair.
 #include <cuda_runtime.h>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -79,8 +77,8 @@ struct ProfScope {
   bool on;
   ProfScope(cudaStream_t s, int k) : st(s), kind(k), on(g_profile != 0) {
     if (on) {
-      cudaEventCreate(&e.a);
-      cudaEventCreate(&e.b);
+      if (cudaEventCreate(&e.a) != cudaSuccess) { on = false; cudaGetLastError(); return; }
+      if (cudaEventCreate(&e.b) != cudaSuccess) { on = false; cudaEventDestroy(e.a); cudaGetLastError(); return; }
       e.kind = kind;
       cudaEventRecord(e.a, st);
     }
@@ -98,18 +96,30 @@ struct ProfScope {
 // ---- stream compaction (single pass, decoupled look-back, stable)
 // One tile = 256 threads x 16 rays, blocked so that every thread reads 64 contiguous bytes (4 x 128-bit loads).
 // Tile prefixes are published as (flag << 32 | value) words; warp 0 looks back over 32 predecessor tiles at a time.
+// The number of input entries comes from device memory (`count_in`, the previous compaction's output; null: n_max), so the
+// host never reads a counter back; the grid covers n_max and the surplus tiles leave at once.  The survivor count goes to
+// device memory for the next bounce and, as a fraction of the batch, to pinned host memory for the next call's launch plan.
 #define CP_THREADS 256
 #define CP_ITEMS 16
 #define CP_TILE (CP_THREADS * CP_ITEMS)
-__global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restrict__ live_in, int n_in, const int32_t* __restrict__ status,
-                                                       int32_t* __restrict__ live_out, int32_t* count_out, unsigned long long* tile_state,
-                                                       int32_t* tile_counter, int ntiles, int vec_ok) {
+__global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restrict__ live_in, const int32_t* __restrict__ count_in, int n_max,
+                                                       const int32_t* __restrict__ status, int32_t* __restrict__ live_out, int32_t* count_out,
+                                                       float* frac_out, float inv_batch, unsigned long long* tile_state, int32_t* tile_counter, int vec_ok) {
   __shared__ int s_tile, s_prefix;
   __shared__ int s_warp[CP_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_in = count_in ? *count_in : n_max;
+  const int ntiles = (n_in + CP_TILE - 1) / CP_TILE;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1);  // tiles are numbered in the order they start: no deadlock in the look-back
   __syncthreads();
   const int tile = s_tile;
+  if (tile >= ntiles) {
+    if (n_in == 0 && tile == 0 && tid == 0) {
+      *count_out = 0;
+      if (frac_out) *frac_out = 0.f;
+    }
+    return;
+  }
   const int base = tile * CP_TILE + tid * CP_ITEMS;
   int idx[CP_ITEMS];
   unsigned alive = 0;
@@ -184,7 +194,10 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restric
     if (lane == 0) {
       atomicExch(&tile_state[tile], (2ull << 32) | (unsigned)(excl + total));  // INCLUSIVE PREFIX
       s_prefix = excl;
-      if (tile == ntiles - 1) { *count_out = excl + total; __threadfence_system(); }
+      if (tile == ntiles - 1) {
+        *count_out = excl + total;
+        if (frac_out) { *frac_out = (float)(excl + total) * inv_batch; __threadfence_system(); }
+      }
     }
   }
   __syncthreads();
@@ -194,55 +207,133 @@ __global__ void __launch_bounds__(CP_THREADS) k_compact(const int32_t* __restric
     if (alive & (1u << k)) live_out[pos++] = idx[k];
 }
 
-// ---- coherence sort key: 30-bit Morton code of the point where the ray enters the bounding box of the top volume's
-// daughters (fp32 is plenty for a sort key).  Rays that miss the box sort last.  Also counts adjacent input rays whose
-// keys share the 12 leading bits: an already ordered beam (grid shooters) keeps its order and skips the sort.
-__device__ inline uint32_t morton_spread10(uint32_t v) {
-  v &= 0x3ffu;
-  v = (v | (v << 16)) & 0x030000ffu;
-  v = (v | (v << 8)) & 0x0300f00fu;
-  v = (v | (v << 4)) & 0x030c30c3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
+// ---- coherence binning of the first bounce's index list.
+// A beam whose neighbouring rays are far apart (random shooters) makes every warp walk 32 different pieces of geometry.  The
+// rays stay where they are; the wavefront visits them through an index list, and that list is put into the order of the cell
+// (64 x 64 grid over the two long sides of the box around the top volume's daughters, Z-order) in which each ray enters the
+// box: a counting sort in three small kernels (cell + histogram, scan of the 4096 counters, scatter).  Results do not depend
+// on the order of the list (outputs stay in input order, Philox streams are keyed by the ray id).
+#define SB_BINS 4096
+#define SB_THREADS 256
+struct BinFrame {
+  float lo[3], hi[3];
+  int ax0, ax1;  // the two axes the cells are laid over
+};
+__device__ inline uint32_t sb_interleave(uint32_t a, uint32_t b) {  // Z-order of two 6-bit cell coordinates
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) r |= ((a >> k) & 1u) << (2 * k) | ((b >> k) & 1u) << (2 * k + 1);
+  return r;
 }
-__global__ void k_sortkey(long long n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                          const double* __restrict__ dx, const double* __restrict__ dy, const double* __restrict__ dz, float3 lo, float3 hi,
-                          uint32_t* __restrict__ keys, int32_t* __restrict__ iota, unsigned long long* coherent_pairs, int block_stride) {
-  // block_stride > 1: sampling pass (every block_stride-th run of 256 rays, nothing written but the counter)
-  long long i = (long long)blockIdx.x * block_stride * blockDim.x + threadIdx.x;
-  uint32_t key = 0x3fffffffu;
-  if (i < n) {
-    float px = (float)x[i], py = (float)y[i], pz = (float)z[i], vx = (float)dx[i], vy = (float)dy[i], vz = (float)dz[i];
-    float t0 = 0.f, t1 = 3.0e38f;
-    bool hit = true;
-    const float p[3] = {px, py, pz}, v[3] = {vx, vy, vz}, l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+__device__ inline uint32_t sb_cell(const BinFrame& f, double x, double y, double z, double dx, double dy, double dz) {
+  const float p[3] = {(float)x, (float)y, (float)z}, v[3] = {(float)dx, (float)dy, (float)dz};
+  float t0 = 0.f, t1 = 3.0e38f;
+  bool hit = true;
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      if (v[a] != 0.f) {
-        float inv = 1.f / v[a], ta = (l[a] - p[a]) * inv, tb = (h[a] - p[a]) * inv;
-        t0 = fmaxf(t0, fminf(ta, tb));
-        t1 = fminf(t1, fmaxf(ta, tb));
-      } else hit = hit && p[a] >= l[a] && p[a] <= h[a];
-    }
-    if (hit && t0 <= t1) {
-      uint32_t q[3];
+  for (int a = 0; a < 3; a++) {
+    if (v[a] != 0.f) {
+      float inv = 1.f / v[a], ta = (f.lo[a] - p[a]) * inv, tb = (f.hi[a] - p[a]) * inv;
+      t0 = fmaxf(t0, fminf(ta, tb));
+      t1 = fminf(t1, fmaxf(ta, tb));
+    } else hit = hit && p[a] >= f.lo[a] && p[a] <= f.hi[a];
+  }
+  if (!(hit && t0 <= t1)) return SB_BINS - 1;  // rays that miss the box go last
+  uint32_t q[2];
 #pragma unroll
-      for (int a = 0; a < 3; a++) {
-        float u = (p[a] + t0 * v[a] - l[a]) / fmaxf(h[a] - l[a], 1e-30f);
-        q[a] = (uint32_t)fminf(fmaxf(u * 1024.f, 0.f), 1023.f);
+  for (int k = 0; k < 2; k++) {
+    const int a = k == 0 ? f.ax0 : f.ax1;
+    float u = (p[a] + t0 * v[a] - f.lo[a]) / fmaxf(f.hi[a] - f.lo[a], 1e-30f);
+    q[k] = (uint32_t)fminf(fmaxf(u * 64.f, 0.f), 63.f);
+  }
+  return sb_interleave(q[0], q[1]);
+}
+// cell of every ray + global histogram (shared-memory privatised); with `cells` == null it is the sampling pass of the
+// coherence probe: counts the pairs of neighbouring input rays that enter through the same or an adjacent cell
+__global__ void __launch_bounds__(SB_THREADS) k_bin_count(long long n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                                          const double* __restrict__ dx, const double* __restrict__ dy, const double* __restrict__ dz, BinFrame f,
+                                                          uint16_t* __restrict__ cells, uint32_t* __restrict__ hist, unsigned long long* probe, long long per_block,
+                                                          long long block_stride) {
+  __shared__ uint32_t sh[SB_BINS];
+  if (cells) {
+    for (int b = threadIdx.x; b < SB_BINS; b += SB_THREADS) sh[b] = 0;
+    __syncthreads();
+  }
+  const long long first = (long long)blockIdx.x * block_stride * per_block, last = min(n, first + per_block);
+  unsigned long long coherent = 0, pairs = 0;
+  for (long long i0 = first; i0 < last; i0 += SB_THREADS) {
+    long long i = i0 + threadIdx.x;
+    uint32_t c = SB_BINS - 1;
+    if (i < last) {
+      c = sb_cell(f, x[i], y[i], z[i], dx[i], dy[i], dz[i]);
+      if (cells) {
+        cells[i] = (uint16_t)c;
+        atomicAdd(&sh[c], 1u);
       }
-      key = morton_spread10(q[0]) | (morton_spread10(q[1]) << 1) | (morton_spread10(q[2]) << 2);
     }
-    if (keys) {
-      keys[i] = key;
-      iota[i] = (int32_t)i;
+    if (probe) {
+      uint32_t prev = __shfl_up_sync(0xffffffffu, c, 1);
+      bool have = i < last && (threadIdx.x & 31) != 0;
+      // Z-order cells: the same cell, or cells that differ in the lowest bit pair only, count as neighbours
+      bool coh = have && (c >> 2) == (prev >> 2);
+      coherent += __popc(__ballot_sync(0xffffffffu, coh));
+      pairs += __popc(__ballot_sync(0xffffffffu, have));
     }
   }
-  // neighbours in input order: lane k compares with lane k-1 (block edges are ignored)
-  uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-  bool coh = i < n && (threadIdx.x & 31) != 0 && (key >> 18) == (prev >> 18);
-  unsigned m = __ballot_sync(0xffffffffu, coh);
-  if ((threadIdx.x & 31) == 0 && m && coherent_pairs) atomicAdd(coherent_pairs, (unsigned long long)__popc(m));
+  if (probe && (threadIdx.x & 31) == 0 && pairs) {
+    atomicAdd(&probe[0], coherent);
+    atomicAdd(&probe[1], pairs);
+  }
+  if (cells) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < SB_BINS; b += SB_THREADS)
+      if (sh[b]) atomicAdd(&hist[b], sh[b]);
+  }
+}
+// exclusive scan of the 4096 cell counters (one block): hist[] becomes the write cursor of every cell
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* hist) {
+  __shared__ uint32_t s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t v[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = hist[4 * tid + k]; sum += v[k]; }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane], iw = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, iw, o);
+      if (lane >= o) iw += u;
+    }
+    s_warp[lane] = iw - w;
+  }
+  __syncthreads();
+  uint32_t run = s_warp[warp] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { hist[4 * tid + k] = run; run += v[k]; }
+}
+// scatter: every block counts the cells of its slice, reserves a range per cell from the global cursors and writes the ray
+// indices there (the order inside a cell is not defined; nothing depends on it)
+__global__ void __launch_bounds__(SB_THREADS) k_bin_scatter(long long n, const uint16_t* __restrict__ cells, uint32_t* cursor, int32_t* __restrict__ out,
+                                                            long long per_block) {
+  __shared__ uint32_t sh[SB_BINS];
+  for (int b = threadIdx.x; b < SB_BINS; b += SB_THREADS) sh[b] = 0;
+  __syncthreads();
+  const long long first = (long long)blockIdx.x * per_block, last = min(n, first + per_block);
+  for (long long i = first + threadIdx.x; i < last; i += SB_THREADS) atomicAdd(&sh[cells[i]], 1u);
+  __syncthreads();
+  for (int b = threadIdx.x; b < SB_BINS; b += SB_THREADS) {
+    uint32_t c = sh[b];
+    sh[b] = c ? atomicAdd(&cursor[b], c) : 0u;
+  }
+  __syncthreads();
+  for (long long i = first + threadIdx.x; i < last; i += SB_THREADS) out[atomicAdd(&sh[cells[i]], 1u)] = (int32_t)i;
 }
 
 // largest npoints of a batch, written to pinned host memory (how many rows of a polyline record hold data)
@@ -254,11 +345,11 @@ __global__ void k_max_npoints(const int32_t* __restrict__ np, long long n, int32
 }
 
 // copies a device counter into pinned (UVA-mapped) host memory with a plain store: no copy-engine queueing
-__global__ void k_publish(const unsigned long long* d, unsigned long long* h) {
-  *h = *d;
+__global__ void k_publish_probe(const unsigned long long* d, unsigned long long* h) {
+  h[0] = d[0];
+  h[1] = d[1];
   __threadfence_system();
 }
-
 __global__ void k_publish32(const int32_t* d, int32_t* h) {
   *h = *d;
   __threadfence_system();
@@ -443,7 +534,8 @@ __global__ void k_tmm_general(DScene sc, int ml, int mode, int pol, int reverse,
 }
 
 // ------------------------------------------------------------------------------------------------ host: scene
-#define RB_HOST_STREAMS 8  // chunks in flight on the host-buffer path of rbg_trace (one worker thread + stream + stage each)
+#define RB_HOST_STREAMS 8   // chunks in flight on the host-buffer path of rbg_trace (one worker thread + stream + stage each)
+#define RB_MAX_ROUNDS 24    // wavefront bounces planned ahead at most; whatever survives them is finished by one run-to-the-end launch
 struct rbg_scene {
   int device = 0;
   int depth = 0;
@@ -451,15 +543,17 @@ struct rbg_scene {
   DScene d;
   std::vector<void*> allocs;
   std::vector<std::string> node_names;
-  // per-scene scratch for the wavefront loop and host staging
-  void* scratch = nullptr;
-  size_t scratch_bytes = 0;
+  // host staging of the host-buffer path
   void* stage[RB_HOST_STREAMS] = {};
   size_t stage_bytes[RB_HOST_STREAMS] = {};
   cudaStream_t streams[RB_HOST_STREAMS] = {};
   int32_t* d_count = nullptr;
   int32_t* h_count = nullptr;  // pinned
-  unsigned long long* h_pairs = nullptr;  // pinned, one per host stream: coherence counter of k_sortkey
+  // launch plan of the wavefront, learned from the calls before (pinned, written by the device without any host wait):
+  // h_frac[b] = share of the batch still running after bounce b; h_probe = {coherent, sampled} neighbour pairs of the last beam
+  float* h_frac = nullptr;
+  unsigned long long* h_probe = nullptr;
+  std::atomic<int> calls{0};
   float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};  // bounding box of the top volume's daughters
   bool has_root = false;
   int top_daughters = 0;
@@ -483,25 +577,42 @@ template <class T> static const T* upload(rbg_scene* s, const T* src, size_t n) 
 static void scene_free(rbg_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
+  cudaDeviceSynchronize();  // traces enqueued on caller streams may still read the tables
   for (void* p : s->allocs) cudaFree(p);
-  if (s->scratch) cudaFree(s->scratch);
   for (int i = 0; i < RB_HOST_STREAMS; i++) {
     if (s->stage[i]) cudaFree(s->stage[i]);
     if (s->streams[i]) cudaStreamDestroy(s->streams[i]);
   }
   if (s->d_count) cudaFree(s->d_count);
   if (s->h_count) cudaFreeHost(s->h_count);
-  if (s->h_pairs) cudaFreeHost(s->h_pairs);
+  if (s->h_frac) cudaFreeHost(s->h_frac);
+  if (s->h_probe) cudaFreeHost(s->h_probe);
   if (s->pin) cudaFreeHost(s->pin);
   delete s;
 }
 
+// the stream-ordered pool must keep its memory between calls: with the default release threshold (0) every synchronisation
+// hands it back to the driver and the next cudaMallocAsync pays a device allocation
+static void keep_pool(int device) {
+  static std::atomic<unsigned> pool_kept{0};
+  if (device >= 0 && device < 32 && !(pool_kept.fetch_or(1u << device) & (1u << device))) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host: trace driver
-#ifdef RB_EXPERIMENTS
-// experiment translation units (make EXP=1) register their instantiations from static initialisers
-static std::vector<const rb_variant*>& x_variants() { static std::vector<const rb_variant*> v; return v; }
-int rb_register_x_variant(const rb_variant* v) { x_variants().push_back(v); return 0; }
-#endif
+int rb_coop_search() {
+  static const int on = getenv("RB_COOP") ? atoi(getenv("RB_COOP")) : 1;
+  return on;
+}
+// launch-bound tuning units (make TUNE=1, rb_trace_t_*.cu) register extra instantiations from static initialisers
+static std::vector<const rb_variant*>& extra_variants() { static std::vector<const rb_variant*> v; return v; }
+int rb_register_variant(const rb_variant* v) { extra_variants().push_back(v); return 0; }
 static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys) {
   const char* force = getenv("RB_FORCE_GENERIC");
   const rb_variant* best = nullptr;
@@ -509,10 +620,8 @@ static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys)
   if (const char* want = getenv("RB_VARIANT")) {  // experiments: force a named (compatible) instantiation
     for (const rb_variant* v : rb_variants)
       if (!strcmp(v->name, want) && v->depth >= depth && !(shapes & ~v->shapes) && !(phys & ~v->phys)) return v;
-#ifdef RB_EXPERIMENTS
-    for (const rb_variant* v : x_variants())
+    for (const rb_variant* v : extra_variants())
       if (!strcmp(v->name, want) && v->depth >= depth && !(shapes & ~v->shapes) && !(phys & ~v->phys)) return v;
-#endif
   }
   for (const rb_variant* v : rb_variants) {
     if (v->depth < depth || (shapes & ~v->shapes) || (phys & ~v->phys)) continue;
@@ -523,30 +632,36 @@ static const rb_variant* pick_variant(int depth, unsigned shapes, unsigned phys)
   if (!best) throw NotSupported("boolean composite nesting deeper than 6 is not supported");
   return best;
 }
-static void launch_trace(const rb_variant* v, const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, long long n, int init,
-                         int keep, cudaStream_t st) {
-  if (n <= 0) return;
+static void launch_phase(const rb_variant* v, int phase, const DScene& sc, const DTraceParams& tp, const DRays& R, const DNavOut& N, const int32_t* live,
+                         const int32_t* count, long long n_grid, long long n_max, cudaStream_t st) {
+  if (n_max <= 0) return;
   ProfScope ps(st, 0);
-  static const bool no_lockstep = getenv("RB_NO_LOCKSTEP") != nullptr;
-  // wavefront launches of exactly one boundary step use the block-lock-step kernel
-  int rc = (tp.max_steps == 1 && keep && !no_lockstep) ? v->launch_step(sc, tp, R, live, n, init, keep, st) : v->launch(sc, tp, R, live, n, init, keep, st);
+  int rc = v->launch_phase(phase, sc, tp, R, N, live, count, n_grid, n_max, st);
+  g_launches++;
+  if (rc != 0) throw std::runtime_error(std::string("cuda: bounce kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+}
+static void launch_trace(const rb_variant* v, const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, const int32_t* count,
+                         long long n_grid, long long n_max, int init, int keep, cudaStream_t st) {
+  if (n_max <= 0) return;
+  ProfScope ps(st, 0);
+  int rc = v->launch(sc, tp, R, live, count, n_grid, n_max, init, keep, st);
   g_launches++;
   if (rc != 0) throw std::runtime_error(std::string("cuda: k_trace launch: ") + cudaGetErrorString((cudaError_t)rc));
 }
 
-static void ensure_scratch(rbg_scene* s, size_t bytes) {
-  if (bytes <= s->scratch_bytes) return;
-  if (s->scratch) CK(cudaFree(s->scratch));
-  s->scratch = nullptr;
-  s->scratch_bytes = 0;
-  CK(cudaMalloc(&s->scratch, bytes));
-  s->scratch_bytes = bytes;
+static size_t wavefront_scratch_bytes(long long n) {
+  size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
+  // cur, ndraw, liveA, liveB, cells (uint16), the nav record (6 x 16 B) + bounce counters + tile state + tile counter + cell histogram
+  return 4 * ((size_t)n * 4 + 256) + ((size_t)n * 2 + 256) + 6 * ((size_t)n * 16 + 256) + 256 + ntile * 8 + 256 + 256 + SB_BINS * 4 + 512;
 }
 
-static size_t sort_temp_bytes(long long n);
-// device-resident trace of n rays (n < 2^31) on stream st
-static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long long n, unsigned long long id_offset, cudaStream_t st, void* scratch,
-                         int32_t* d_count, int32_t* h_count, unsigned long long* h_pairs) {
+// Device-resident trace of n rays (n < 2^31) enqueued on stream st; never waits for the device.
+// Single launch: every ray runs to its terminal status in registers.  Wavefront (large batches): one boundary step per launch
+// over the compacted list of survivors.  The survivor counts stay on the device (k_compact -> k_trace), so the sequence of
+// launches is planned ahead: `rounds` bounces (how many is learned from the shares of survivors the earlier calls on this
+// scene reported), then one run-to-the-end launch over whatever is left.  A plan that is too short only moves work into the
+// last launch; one that is too long adds a few empty launches.
+static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long long n, unsigned long long id_offset, cudaStream_t st) {
   if (n <= 0) return;
   if (n > 0x7fffff00LL) throw Invalid("at most 2^31-256 rays per call on the device path; shard the batch");
   DTraceParams tp;
@@ -556,114 +671,131 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   // steps_per_launch: > 0 as given; 0 = auto (wavefront with one boundary step per bounce kernel for large
   // batches, where compaction pays for itself; a single launch for small ones); < 0 = single launch
   tp.max_steps = o->steps_per_launch > 0 ? o->steps_per_launch : (o->steps_per_launch == 0 && n >= 262144 ? 1 : 0);
-  if (R.hist.x) tp.max_steps = 0;  // the polyline record is written by the per-ray loop kernel only
+  if (R.hist.x) tp.max_steps = 0;  // the polyline record is written by the single-launch mode only
   tp.seed = o->seed;
   tp.ray_id_offset = id_offset;
-  if (tp.max_steps <= 0) {  // one launch, every ray runs to its terminal status in registers
+  if (tp.max_steps <= 0) {
     R.cur = nullptr;
     R.ndraw = nullptr;
-    launch_trace(s->variant, s->d, tp, R, nullptr, n, 1, 0, st);
+    launch_trace(s->variant, s->d, tp, R, nullptr, nullptr, n, n, 1, 0, st);
     return;
   }
-  // wavefront: bounce kernel -> compaction of survivors -> next bounce
-  size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
-  char* base = (char*)scratch;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 255) & ~size_t(255); return p; };
-  R.cur = (int32_t*)take(n * 4);
-  R.ndraw = (uint32_t*)take(n * 4);
-  int32_t* liveA = (int32_t*)take(n * 4);
-  int32_t* liveB = (int32_t*)take(n * 4);
-  unsigned long long* tile_state = (unsigned long long*)take(ntile * 8);
-  int32_t* tile_counter = (int32_t*)take(256);
-  const int32_t* live = nullptr;
-  long long nlive = n;
-  int init = 1;
-  // Coherence sort (first bounce): a beam whose neighbouring rays are far apart (random shooters) makes every warp walk
-  // 32 different pieces of geometry — warp execution efficiency of 8/32 on the Winston-cone array (profiles/).  The rays
-  // stay where they are; only the order in which the index list visits them changes (outputs keep the input order).
-  static const int sort_mode = getenv("RB_SORT") ? atoi(getenv("RB_SORT")) : -1;  // -1 auto, 0 never, 1 always
-  // auto: only scenes with many daughters under the top volume can scatter a warp over different geometry, and only
-  // beams whose input order is not already spatially coherent need the sort (a sampled pass decides)
-  if (s->has_root && sort_mode != 0 && (sort_mode == 1 || s->top_daughters >= 32)) {
-    float3 lo = make_float3(s->root_lo[0], s->root_lo[1], s->root_lo[2]), hi = make_float3(s->root_hi[0], s->root_hi[1], s->root_hi[2]);
-    bool do_sort = sort_mode == 1;
-    static const int coarse_bits = getenv("RB_SORT_COARSE_BITS") ? std::min(30, atoi(getenv("RB_SORT_COARSE_BITS"))) : 21;
-    static const int full_bits = getenv("RB_SORT_FULL_BITS") ? std::min(30, std::max(1, atoi(getenv("RB_SORT_FULL_BITS")))) : 30;
-    int sort_bits = full_bits;
-    if (!do_sort) {
-      unsigned long long* d_pairs = (unsigned long long*)take(256);
-      CK(cudaMemsetAsync(d_pairs, 0, 8, st));
-      long long blocks = (n + 255) / 256;
-      int stride = (int)std::max<long long>(1, blocks / 512);
-      long long sblocks = blocks / stride;  // full runs only
-      k_sortkey<<<(unsigned)sblocks, 256, 0, st>>>(n, R.x, R.y, R.z, R.dx, R.dy, R.dz, lo, hi, nullptr, nullptr, d_pairs, stride);
-      k_publish<<<1, 1, 0, st>>>(d_pairs, h_pairs);
-      g_launches += 2;
-      CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(st));
-      do_sort = (double)*h_pairs < 0.5 * (double)sblocks * 256. * 31. / 32.;
-      // A beam that is coherent along its input order (grid shooters: a block of 512 rays is a 2 m strip of one grid row
-      // and crosses several facets) still gains from square tiles: every warp of a block then walks the same facet and the
-      // phase barriers of k_step wait less.  A coarse key is enough for that (top bits only = fewer radix passes, input
-      // order kept inside a cell so the ray loads stay contiguous); large batches only, the sort is launch-bound on small ones.
-      static const long long coarse_min = getenv("RB_SORT_COARSE_MIN") ? atoll(getenv("RB_SORT_COARSE_MIN")) : (1ll << 20);
-      if (!do_sort && coarse_bits > 0 && n >= coarse_min) {
-        do_sort = true;
-        sort_bits = coarse_bits;
+  keep_pool(s->device);
+  const int call = s->calls.fetch_add(1);
+  char* base = nullptr;
+  CK(cudaMallocAsync((void**)&base, wavefront_scratch_bytes(n), st));
+  try {
+    size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 255) & ~size_t(255); return p; };
+    R.cur = (int32_t*)take(n * 4);
+    R.ndraw = (uint32_t*)take(n * 4);
+    int32_t* liveA = (int32_t*)take(n * 4);
+    int32_t* liveB = (int32_t*)take(n * 4);
+    uint16_t* cells = (uint16_t*)take(n * 2);
+    DNavOut N;
+    N.pxy = (double2*)take(n * 16); N.pzs = (double2*)take(n * 16);
+    N.loc = (int4*)take(n * 16); N.hit = (int4*)take(n * 16); N.vis = (int4*)take(2 * n * 16);
+    N.n = n;
+    int32_t* d_counts = (int32_t*)take((RB_MAX_ROUNDS + 2) * 4);
+    unsigned long long* tile_state = (unsigned long long*)take(ntile * 8);
+    int32_t* tile_counter = (int32_t*)take(4);
+    uint32_t* cell_hist = (uint32_t*)take(SB_BINS * 4);
+    unsigned long long* d_probe = (unsigned long long*)take(16);
+    const int32_t* live = nullptr;
+    const int32_t* count = nullptr;
+    // ---- coherence binning of the index list (first bounce).  Only scenes with many daughters under the top volume can
+    // scatter a warp over different geometry, and only beams whose input order is not already spatially coherent need it.
+    // The verdict on the beam comes from a sampled probe; it is read from the call before (pinned memory, no wait) — the
+    // first call on a scene waits for its own probe once.
+    static const int sort_mode = getenv("RB_SORT") ? atoi(getenv("RB_SORT")) : -1;  // -1 auto, 0 never, 1 always
+    if (s->has_root && sort_mode != 0 && (sort_mode == 1 || s->top_daughters >= 32)) {
+      BinFrame f;
+      int ax[3] = {0, 1, 2};
+      std::sort(ax, ax + 3, [&](int a, int b) { return s->root_hi[a] - s->root_lo[a] > s->root_hi[b] - s->root_lo[b]; });
+      for (int k = 0; k < 3; k++) { f.lo[k] = s->root_lo[k]; f.hi[k] = s->root_hi[k]; }
+      f.ax0 = std::min(ax[0], ax[1]);
+      f.ax1 = std::max(ax[0], ax[1]);
+      bool do_sort = sort_mode == 1;
+      if (!do_sort) {
+        // sampled probe of this beam: every stride-th run of 256 rays
+        long long runs = (n + SB_THREADS - 1) / SB_THREADS;
+        long long stride = std::max<long long>(1, runs / 512);
+        CK(cudaMemsetAsync(d_probe, 0, 16, st));
+        k_bin_count<<<(unsigned)(runs / stride), SB_THREADS, 0, st>>>(n, R.x, R.y, R.z, R.dx, R.dy, R.dz, f, nullptr, nullptr, d_probe, SB_THREADS, stride);
+        if (call == 0) {
+          k_publish_probe<<<1, 1, 0, st>>>(d_probe, s->h_probe);
+          CK(cudaStreamSynchronize(st));
+        }
+        unsigned long long coh = s->h_probe[0], pairs = s->h_probe[1];
+        do_sort = pairs > 0 && (double)coh < 0.5 * (double)pairs;
+        if (call != 0) k_publish_probe<<<1, 1, 0, st>>>(d_probe, s->h_probe);  // plain stores into pinned memory, for the next call
+        g_launches += 2;
+        CK(cudaGetLastError());
+      }
+      if (do_sort) {
+        ProfScope ps(st, 1);
+        long long blocks = std::min<long long>((n + 4095) / 4096, 148 * 8);
+        long long per_block = ((n + blocks - 1) / blocks + SB_THREADS - 1) / SB_THREADS * SB_THREADS;
+        blocks = (n + per_block - 1) / per_block;
+        CK(cudaMemsetAsync(cell_hist, 0, SB_BINS * 4, st));
+        k_bin_count<<<(unsigned)blocks, SB_THREADS, 0, st>>>(n, R.x, R.y, R.z, R.dx, R.dy, R.dz, f, cells, cell_hist, nullptr, per_block, 1);
+        k_bin_scan<<<1, 1024, 0, st>>>(cell_hist);
+        k_bin_scatter<<<(unsigned)blocks, SB_THREADS, 0, st>>>(n, cells, cell_hist, liveA, per_block);
+        g_launches += 3;
+        CK(cudaGetLastError());
+        live = liveA;
       }
     }
-    if (do_sort) {
-      uint32_t* keys = (uint32_t*)take(n * 4);
-      uint32_t* keys_out = (uint32_t*)take(n * 4);
-      size_t tb = sort_temp_bytes(n);
-      void* temp = take(tb);
-      k_sortkey<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, R.x, R.y, R.z, R.dx, R.dy, R.dz, lo, hi, keys, liveB, nullptr, 1);
-      g_launches++;
-      CK(cudaGetLastError());
-      CK(cub::DeviceRadixSort::SortPairs(temp, tb, (const uint32_t*)keys, keys_out, (const int32_t*)liveB, liveA, (int)n, 30 - sort_bits, 30, st));
-      g_launches += (sort_bits + 7) / 8;
-      live = liveA;
+    // ---- launch plan
+    const long long tail = std::max<long long>(4096, n / 512);  // survivors below this finish in the run-to-the-end launch
+    float frac[RB_MAX_ROUNDS];
+    for (int b = 0; b < RB_MAX_ROUNDS; b++) frac[b] = call == 0 ? -1.f : s->h_frac[b];
+    int rounds = RB_MAX_ROUNDS;
+    for (int b = 0; b < RB_MAX_ROUNDS; b++)
+      if (frac[b] >= 0.f && (double)frac[b] * (double)n <= (double)tail) { rounds = b + 1; break; }
+    if (tp.limit - 1 < rounds) rounds = std::max(1, tp.limit - 1);  // a ray takes at most limit - 1 steps
+    static const int max_rounds_env = getenv("RB_MAX_ROUNDS") ? atoi(getenv("RB_MAX_ROUNDS")) : RB_MAX_ROUNDS;
+    rounds = std::min(rounds, std::max(1, max_rounds_env));
+    auto estimate = [&](int b) -> long long {  // rays expected to be alive when bounce b starts
+      if (b == 0) return n;
+      float fr = frac[b - 1];
+      if (fr < 0.f) return n;
+      return std::min<long long>(n, (long long)((double)fr * 1.25 * (double)n) + 4096);
+    };
+    const float inv_batch = 1.f / (float)n;
+    const int vec_ok = (reinterpret_cast<uintptr_t>(R.status) & 15) == 0;
+    const int tiles = (int)ntile;
+    static const bool fused = getenv("RB_FUSED_BOUNCE") != nullptr;  // experiments: the whole step in one kernel (k_trace, max_steps = 1)
+    for (int b = 0; b < rounds; b++) {
+      if (fused) launch_trace(s->variant, s->d, tp, R, live, count, estimate(b), n, b == 0, 1, st);
+      else {
+        if (b == 0) launch_phase(s->variant, 0, s->d, tp, R, N, nullptr, nullptr, n, n, st);
+        launch_phase(s->variant, 1, s->d, tp, R, N, live, count, estimate(b), n, st);
+        launch_phase(s->variant, 2, s->d, tp, R, N, live, count, estimate(b), n, st);
+      }
+      CK(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
+      CK(cudaMemsetAsync(tile_counter, 0, 4, st));
+      int32_t* out = (live == liveA) ? liveB : liveA;
+      {
+        ProfScope ps(st, 1);
+        // the grid has to cover the true count, which only the device knows: one tile per 4096 rays of the batch, the surplus
+        // tiles leave at once
+        k_compact<<<tiles, CP_THREADS, 0, st>>>(live, count, (int)n, R.status, out, d_counts + b, s->h_frac + b, inv_batch, tile_state, tile_counter, vec_ok);
+        g_launches++;
+        CK(cudaGetLastError());
+      }
+      live = out;
+      count = d_counts + b;
     }
+    DTraceParams tl = tp;
+    tl.max_steps = 0;
+    launch_trace(s->variant, s->d, tl, R, live, count, std::max<long long>(estimate(rounds), tail), n, 0, 1, st);
+  } catch (...) {
+    cudaFreeAsync(base, st);
+    throw;
   }
-  const long long tail = std::max<long long>(4096, n / 512);  // survivors below this finish in one per-ray-loop launch
-  for (int iter = 0; nlive > 0; iter++) {
-    if (iter > 100000) throw std::runtime_error("wavefront did not terminate");
-    if (iter > 0 && nlive <= tail) {
-      DTraceParams tl = tp;
-      tl.max_steps = 0;
-      launch_trace(s->variant, s->d, tl, R, live, nlive, 0, 1, st);
-      break;
-    }
-    launch_trace(s->variant, s->d, tp, R, live, nlive, init, 1, st);
-    init = 0;
-    int tiles = (int)((nlive + CP_TILE - 1) / CP_TILE);
-    CK(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
-    CK(cudaMemsetAsync(tile_counter, 0, 4, st));
-    int32_t* out = (live == liveA) ? liveB : liveA;
-    {
-      ProfScope ps(st, 1);
-      // the survivor count is written straight into pinned host memory (UVA-mapped): a 4-byte cudaMemcpyAsync would
-      // queue behind the other chunks' multi-MB result copies on the D2H copy engine and stall every bounce
-      k_compact<<<tiles, CP_THREADS, 0, st>>>(live, (int)nlive, R.status, out, h_count, tile_state, tile_counter, tiles,
-                                              (reinterpret_cast<uintptr_t>(R.status) & 15) == 0);
-      g_launches++;
-      CK(cudaGetLastError());
-    }
-    CK(cudaStreamSynchronize(st));
-    nlive = *h_count;
-    live = out;
-  }
-}
-static size_t sort_temp_bytes(long long n) {
-  size_t tb = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 30);
-  return tb;
-}
-static size_t wavefront_scratch_bytes(long long n) {
-  size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
-  // cur, ndraw, liveA, liveB (+ sort keys in/out) + tile state + counter + radix-sort temporary
-  return 6 * ((size_t)n * 4 + 256) + ntile * 8 + 256 + 512 + sort_temp_bytes(n) + 768;
+  CK(cudaFreeAsync(base, st));
 }
 
 // ================================================================================================ C ABI
@@ -687,7 +819,12 @@ int rbg_profile_enable(int on) {
 }
 int rbg_profile_read(double* bounce_ms, int64_t* bounce_launches, double* compact_ms, int64_t* compact_launches) {
   return guard([&] {
-    for (auto& e : g_prof_events) {
+    std::vector<ProfEvt> evts;
+    {
+      std::lock_guard<std::mutex> lk(g_prof_mutex);
+      evts.swap(g_prof_events);
+    }
+    for (auto& e : evts) {
       CK(cudaEventSynchronize(e.b));
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, e.a, e.b));
@@ -696,7 +833,6 @@ int rbg_profile_read(double* bounce_ms, int64_t* bounce_launches, double* compac
       cudaEventDestroy(e.a);
       cudaEventDestroy(e.b);
     }
-    g_prof_events.clear();
     if (bounce_ms) *bounce_ms = g_prof_ms[0];
     if (bounce_launches) *bounce_launches = g_prof_n[0];
     if (compact_ms) *compact_ms = g_prof_ms[1];
@@ -732,6 +868,7 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     memset(&s->d, 0, sizeof(s->d));
     s->d.nodes = upload(s, B.nodes);
     s->d.bvh = upload(s, B.bvh);
+    s->d.boxes = upload(s, B.boxes);
     s->d.shapes = upload(s, B.shapes);
     s->d.dpar = upload(s, B.dpar);
     s->d.mats = upload(s, B.mats);
@@ -758,10 +895,14 @@ int rbg_scene_create(const rbg_scene_desc* D, int device, rbg_scene** out) {
     s->d.ndpar = (int)B.dpar.size();
     s->d.nmats = (int)B.mats.size();
     s->d.top_shape = D->top_volume >= 0 ? D->volumes[D->top_volume].shape : -1;
+    s->d.top_leaf = s->d.top_shape >= 0 ? B.leaf_kind(s->d.top_shape) : RB_LEAF_GENERIC;
     s->d.has_many = (need_phys & RB_PH_OVERLAP) != 0;
     CK(cudaMalloc((void**)&s->d_count, RB_HOST_STREAMS * sizeof(int32_t)));
     CK(cudaMallocHost((void**)&s->h_count, RB_HOST_STREAMS * sizeof(int32_t)));
-    CK(cudaMallocHost((void**)&s->h_pairs, RB_HOST_STREAMS * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void**)&s->h_frac, RB_MAX_ROUNDS * sizeof(float)));
+    CK(cudaMallocHost((void**)&s->h_probe, 2 * sizeof(unsigned long long)));
+    for (int b = 0; b < RB_MAX_ROUNDS; b++) s->h_frac[b] = -1.f;
+    s->h_probe[0] = s->h_probe[1] = 0;
     if (!B.nodes.empty() && B.nodes[0].bvh_count > 0) {
       const DBvh& rb = B.bvh[B.nodes[0].bvh_first];
       for (int k = 0; k < 3; k++) { s->root_lo[k] = rb.lo[k]; s->root_hi[k] = rb.hi[k]; }
@@ -816,8 +957,7 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         R.hist.stride = rays->n;
         R.hist.max_points = hpts;
       }
-      if (o->steps_per_launch >= 0 && hpts == 0) ensure_scratch(s, wavefront_scratch_bytes(rays->n));
-      trace_device(s, o, R, rays->n, o->ray_id_offset, st, s->scratch, s->d_count, s->h_count, s->h_pairs);
+      trace_device(s, o, R, rays->n, o->ray_id_offset, st);
       return;
     }
     // small batches (the tutorial / MINUIT-loop regime, thousands of calls of 1e3..1e5 rays): latency matters, not bandwidth.
@@ -828,8 +968,7 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
       if (!s->streams[0]) CK(cudaStreamCreateWithFlags(&s->streams[0], cudaStreamNonBlocking));
       cudaStream_t st = s->streams[0];
       const size_t in_b = (size_t)n * 64, out_b = (size_t)n * 68, hist_b = (size_t)n * hpts * 36;
-      const size_t scr = o->steps_per_launch > 0 ? wavefront_scratch_bytes(n) : 0;
-      const size_t dev_b = in_b + out_b + 512 + scr + hist_b + 1024;
+      const size_t dev_b = in_b + out_b + 512 + hist_b + 1024;
       if (s->stage_bytes[0] < dev_b) {
         if (s->stage[0]) CK(cudaFree(s->stage[0]));
         s->stage[0] = nullptr;
@@ -861,8 +1000,7 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
       R.status = diout; R.last_node = diout + n; R.npoints = diout + 2 * n;
       R.cur = nullptr; R.ndraw = nullptr;
       memset(&R.hist, 0, sizeof(R.hist));
-      char* scratch = base + ((in_b + out_b + 511) & ~size_t(255));
-      char* hb = scratch + ((scr + 255) & ~size_t(255));
+      char* hb = base + ((in_b + out_b + 511) & ~size_t(255));
       if (hpts > 0) {
         size_t plane = (size_t)n * hpts * 8;
         R.hist.x = (double*)hb; R.hist.y = (double*)(hb + plane); R.hist.z = (double*)(hb + 2 * plane); R.hist.t = (double*)(hb + 3 * plane);
@@ -870,7 +1008,7 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         R.hist.stride = n;
         R.hist.max_points = hpts;
       }
-      trace_device(s, o, R, n, o->ray_id_offset, st, scratch, s->d_count, s->h_count, s->h_pairs);
+      trace_device(s, o, R, n, o->ray_id_offset, st);
       if (hpts > 0) {
         CK(cudaMemsetAsync(s->d_count + 1, 0, 4, st));
         k_max_npoints<<<(unsigned)std::min<long long>((n + 255) / 256, 296), 256, 0, st>>>(R.npoints, n, s->d_count + 1);
@@ -903,7 +1041,7 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
     static const long long CH = getenv("RB_HOST_CHUNK") ? std::max(4096LL, atoll(getenv("RB_HOST_CHUNK"))) : (1LL << 20);
     long long chunk = std::min<long long>(rays->n, CH);
     size_t per_ray = 8 * 8 + 7 * 8 + 3 * 4;  // in + out
-    size_t bytes = (size_t)chunk * per_ray + 4096 + (o->steps_per_launch >= 0 ? wavefront_scratch_bytes(chunk) : 0) + (size_t)chunk * hpts * 36 + 1024;
+    size_t bytes = (size_t)chunk * per_ray + 4096 + (size_t)chunk * hpts * 36 + 1024;
     // chunk list: sizes ramp up from chunk/8 at the start and down again at the end, so that the un-overlapped
     // pipeline fill (first H2D) and drain (last D2H) of the call are short
     std::vector<std::pair<long long, long long>> chunks;  // (first ray, count)
@@ -960,16 +1098,15 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         R.status = diout[0]; R.last_node = diout[1]; R.npoints = diout[2];
         R.cur = nullptr; R.ndraw = nullptr;
         memset(&R.hist, 0, sizeof(R.hist));
-        size_t scratch_off = off;
-        if (hpts > 0) {  // history stage: 4 double planes + 1 int plane of hpts x chunk, placed after the wavefront scratch
-          char* hb = base + off + ((o->steps_per_launch >= 0 ? wavefront_scratch_bytes(chunk) : 0) + 255) / 256 * 256;
+        if (hpts > 0) {  // history stage: 4 double planes + 1 int plane of hpts x chunk
+          char* hb = base + off;
           size_t plane = (size_t)chunk * hpts * 8;
           R.hist.x = (double*)hb; R.hist.y = (double*)(hb + plane); R.hist.z = (double*)(hb + 2 * plane); R.hist.t = (double*)(hb + 3 * plane);
           R.hist.node = (int32_t*)(hb + 4 * plane);
           R.hist.stride = chunk;
           R.hist.max_points = hpts;
         }
-        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st, base + scratch_off, s->d_count + k, s->h_count + k, s->h_pairs + k);
+        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, st);
         if (hpts > 0) {
           double* hd[4] = {hist->hx, hist->hy, hist->hz, hist->ht};
           double* dd[4] = {R.hist.x, R.hist.y, R.hist.z, R.hist.t};
@@ -1145,18 +1282,7 @@ int rbg_containment_radius(int32_t nhist, const unsigned long long* hist, int32_
     if (nhist < 0 || nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin) || !hist || !stats || !out) throw Invalid("bad containment-radius arguments");
     if (nhist == 0) return;
     CK(cudaSetDevice(device));
-    // Stream-ordered scratch for the per-row running sums.  With the default release threshold (0) the pool hands its memory back
-    // to the driver at every synchronisation — rbg_trace synchronises after each bounce — and this call then pays a fresh
-    // device allocation (seen as 30-700 ms stalls of a 78 ms bench step whenever anything else held the driver lock): keep it.
-    static std::atomic<unsigned> pool_kept{0};
-    if (device >= 0 && device < 32 && !(pool_kept.fetch_or(1u << device) & (1u << device))) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      cudaGetLastError();
-    }
+    keep_pool(device);  // stream-ordered scratch for the per-row running sums
     double* prefix = nullptr;
     CK(cudaMallocAsync((void**)&prefix, (size_t)nhist * (nx + 1) * ny * sizeof(double), (cudaStream_t)stream));
     int rc = rb_launch_containment_u64(nhist, hist, nx, xmin, xmax, ny, ymin, ymax, stats, fraction, out, prefix, (cudaStream_t)stream);

@@ -35,12 +35,31 @@ struct DNode {
   int32_t bvh_count;
   int32_t overlap;   // placed with AddNodeOverlap ("MANY")
   int32_t level;     // depth in the physical tree (top = 0)
+  int32_t leaf;      // RB_LEAF_*: which flat evaluator handles this node's shape (rb_device.cuh, Leaf<K>)
+  float blo[3], bhi[3];  // padded world AABB of the node's shape (same box as its BVH leaf): cheap rejection of point tests
+  int32_t box_first; // this node's daughters as a flat list of boxes: slice [box_first, box_first + box_count) of DScene::boxes
+  int32_t box_count;
+  int32_t pad_[3];
 };
+
+// Leaf evaluator classes.  A node's shape is a boolean tree of primitives; the generic evaluator walks it through a
+// depth-bounded template recursion of non-inlined calls (Csg<DEPTH>).  Almost every shape of a real telescope is one of three
+// flat patterns, which are evaluated inline instead, with the same sequence of arithmetic operations as the generic walk:
+#define RB_LEAF_GENERIC 0  /* anything else: Csg<DEPTH> */
+#define RB_LEAF_PRIM 1     /* a primitive */
+#define RB_LEAF_BOOL2 2    /* union / intersection / subtraction of two primitives (mirror facets, cones, camera boxes) */
+#define RB_LEAF_UNIONS 3   /* left-associated chain of unions whose right operands (and the innermost left one) are primitives */
 
 struct DBvh {   // 32 B; boxes are fp32, rounded outwards and padded, traversal is fp32-conservative
   float lo[3], hi[3];
   int32_t child;     // >= 0: leaf holding this physical node id; -1: internal
   int32_t skip;      // absolute index of the next BVH entry when this subtree is done/missed (-1 = end)
+};
+
+struct DBox {   // 32 B: padded fp32 AABB of one daughter (the leaves of the mother's BVH, in BVH order)
+  float lo[3], hi[3];
+  int32_t child;
+  int32_t pad_;
 };
 
 struct DShape {
@@ -53,6 +72,7 @@ struct DShape {
 struct DScene {
   const DNode* nodes;
   const DBvh* bvh;
+  const DBox* boxes;
   const DShape* shapes;
   const double* dpar;
   const DMat* mats;
@@ -75,9 +95,9 @@ struct DScene {
   const double* g2z;
   int32_t nnodes;
   int32_t top_shape;
+  int32_t top_leaf;  // RB_LEAF_* of the top volume's shape
   int32_t has_many;  // some node is placed with AddNodeOverlap
-  int32_t nbvh, nshapes, ndpar, nmats;  // table lengths (shared-memory staging of the geometry tables)
-  int32_t pad_;
+  int32_t nbvh, nshapes, ndpar, nmats;  // table lengths
 };
 
 #define RB_MAX_TMM_LAYERS 16

@@ -1,3 +1,4 @@
-// bounce-kernel instantiations (k_trace + k_step): SimpleParabolicTelescope-class scenes
+// bounce-kernel instantiation: paraboloid mirrors (SimpleParabolicTelescope)
 #include "rb_trace_kernel.cuh"
-RB_DEFINE_TRACE_VARIANT(cfg1_parabolic, 1, (RB_SBIT(RBG_SHAPE_BBOX)|RB_SBIT(RBG_SHAPE_TUBE)|RB_SBIT(RBG_SHAPE_PARABOLOID)|RB_SBIT(RBG_SHAPE_SUBTRACTION)), (0u), 4, 512, 2)
+typedef Combos<B2<RBG_SHAPE_SUBTRACTION, RBG_SHAPE_PARABOLOID, RBG_SHAPE_PARABOLOID>> rb_combos_cfg1_parabolic;
+RB_DEFINE_TRACE_VARIANT(cfg1_parabolic, 1, (RB_SBIT(RBG_SHAPE_BBOX)|RB_SBIT(RBG_SHAPE_TUBE)|RB_SBIT(RBG_SHAPE_PARABOLOID)|RB_SBIT(RBG_SHAPE_SUBTRACTION)), (0u), 256, 4, rb_combos_cfg1_parabolic)

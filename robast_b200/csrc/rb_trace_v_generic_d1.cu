@@ -1,3 +1,4 @@
-// bounce-kernel instantiations (k_trace + k_step): any scene, composites nested 1 level
+// bounce-kernel instantiation: every shape and every physics branch, boolean nesting up to 1
 #include "rb_trace_kernel.cuh"
-RB_DEFINE_TRACE_VARIANT(generic_d1, 1, (RB_SHAPES_ALL), (RB_PH_ALL), 2, 256, 2)
+typedef Combos<> rb_combos_generic_d1;
+RB_DEFINE_TRACE_VARIANT(generic_d1, 1, (RB_SHAPES_ALL), (RB_PH_ALL), 128, 4, rb_combos_generic_d1)

@@ -9,6 +9,12 @@
 #include "../../robast_b200/csrc/rb_device.cuh"
 
 namespace {
+// the typed two-primitive booleans the scene-specialised kernels carry (rb_trace_v_*.cu), so that the host build runs them too
+typedef Combos<B2<RBG_SHAPE_INTERSECTION, RBG_SHAPE_SPHERE, RBG_SHAPE_PGON>, B2<RBG_SHAPE_INTERSECTION, RBG_SHAPE_SPHERE, RBG_SHAPE_TUBE>,
+               B2<RBG_SHAPE_SUBTRACTION, RBG_SHAPE_BBOX, RBG_SHAPE_BBOX>, B2<RBG_SHAPE_SUBTRACTION, RBG_SHAPE_PGON, RBG_SHAPE_WINSTONPOLY>,
+               B2<RBG_SHAPE_SUBTRACTION, RBG_SHAPE_PARABOLOID, RBG_SHAPE_PARABOLOID>, B2<RBG_SHAPE_SUBTRACTION, RBG_SHAPE_PGON, RBG_SHAPE_PGON>,
+               B2<RBG_SHAPE_SUBTRACTION, RBG_SHAPE_PCON, RBG_SHAPE_PCON>>
+    EmulCombos;
 template <class K> void run(const DScene& sc, const DTraceParams& tp, const rbg_rays* R, const rbg_history* H) {
   DHist dh;
   memset(&dh, 0, sizeof(dh));
@@ -58,22 +64,23 @@ extern "C" __attribute__((visibility("default"))) int emul_trace_history(const r
     B.flatten(D->top_volume, mat_identity(), -1, 0, "top_1");
     DScene sc;
     memset(&sc, 0, sizeof(sc));
-    sc.nodes = B.nodes.data(); sc.bvh = B.bvh.data(); sc.shapes = B.shapes.data(); sc.dpar = B.dpar.data(); sc.mats = B.mats.data();
+    sc.nodes = B.nodes.data(); sc.bvh = B.bvh.data(); sc.boxes = B.boxes.data(); sc.shapes = B.shapes.data(); sc.dpar = B.dpar.data(); sc.mats = B.mats.data();
     sc.volumes = D->volumes; sc.borders = D->borders; sc.graphs = D->graphs; sc.gx = D->gx; sc.gy = D->gy; sc.th2 = D->th2; sc.th2v = D->th2v;
     sc.indices = D->indices; sc.mirrors = D->mirrors; sc.focals = D->focals; sc.multilayers = D->multilayers; sc.layers = D->layers;
     sc.graph2d = D->graph2d; sc.tri = D->tri; sc.g2x = D->g2x; sc.g2y = D->g2y; sc.g2z = D->g2z;
     sc.nnodes = (int)B.nodes.size();
     sc.top_shape = D->volumes[D->top_volume].shape;
+    sc.top_leaf = B.leaf_kind(sc.top_shape);
     for (const DNode& nd : B.nodes) sc.has_many |= nd.overlap != 0;
     DTraceParams tp;
     tp.limit = o->limit > 0 ? o->limit : 100; tp.disable_fresnel = o->disable_fresnel; tp.quirks = o->quirks; tp.max_steps = 0;
     tp.seed = o->seed; tp.ray_id_offset = o->ray_id_offset;
     switch (scene_depth_needed(B)) {
-      case 0: run<TraceCfg<0, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
-      case 1: run<TraceCfg<1, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
-      case 2: run<TraceCfg<2, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
-      case 3: run<TraceCfg<3, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
-      case 4: case 5: case 6: run<TraceCfg<6, RB_SHAPES_ALL, RB_PH_ALL>>(sc, tp, R, H); break;
+      case 0: run<TraceCfg<0, RB_SHAPES_ALL, RB_PH_ALL, 128, 4, EmulCombos>>(sc, tp, R, H); break;
+      case 1: run<TraceCfg<1, RB_SHAPES_ALL, RB_PH_ALL, 128, 4, EmulCombos>>(sc, tp, R, H); break;
+      case 2: run<TraceCfg<2, RB_SHAPES_ALL, RB_PH_ALL, 128, 4, EmulCombos>>(sc, tp, R, H); break;
+      case 3: run<TraceCfg<3, RB_SHAPES_ALL, RB_PH_ALL, 128, 4, EmulCombos>>(sc, tp, R, H); break;
+      case 4: case 5: case 6: run<TraceCfg<6, RB_SHAPES_ALL, RB_PH_ALL, 128, 4, EmulCombos>>(sc, tp, R, H); break;
       default: return RBG_ENOTSUP;
     }
     return RBG_OK;
