@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — rays/s of TraceNonSequential on BASELINE.json's headline configuration.
+"""bench.py — rays/s of TraceNonSequential on BASELINE.json's configurations.
 
-Workload (config.workload): configs[1], DaviesCotton.C — 88-facet Davies-Cotton reflector, 9 field
-angles 0..4 deg, each ARayShooter::Square(400 nm, 14 m, n=3334) = 11 115 556 rays, 100 040 004 rays
-per step.  One "step" = one TraceNonSequential pass over all nine batches plus the
-on-device PSF reducers (histogram + moments per field angle).
+Headline (`value`, `e2e`, `roofline`, `cpu_baseline`): configs[1], DaviesCotton.C — 88-facet Davies-Cotton reflector, 9 field
+angles 0..4 deg, each ARayShooter::Square(400 nm, 14 m, n=3334) = 11 115 556 rays, 100 040 004 rays per step.
+One "step" = one TraceNonSequential pass over all nine batches plus the on-device PSF reducers (histogram + moments + D80 per
+field angle).
 
-  value : rays/s, inputs resident in HBM (rays generated on device by rbg_shoot before the timed region)
-  e2e   : rays/s through the C ABI with HOST (pinned) buffers; H2D of the 64 B/ray inputs and D2H of the
-          68 B/ray results are inside the timed region
-  roofline : k_trace<1>, algorithmic 132 B/ray (64 in + 68 out) / CUDA-event launch time vs measured HBM peak
-  cpu_baseline : the CPU oracle (reference algorithm restated; ROOT is unavailable) on all host threads,
-          bounded sample of the same workload
-Multi-GPU (torchrun): rays shard across ranks (each rank traces its own field-angle sweep, geometry
-replicated), no data-path collective; the PSF histograms/moments are all-reduced with NCCL at the end
-of each step.  Scaling is weak (per-GPU work fixed).
+  value    : rays/s, inputs resident in HBM (rays generated on device by rbg_shoot before the timed region)
+  e2e      : rays/s through the C ABI with HOST (pinned) buffers; H2D of the 64 B/ray inputs and D2H of the 68 B/ray results are
+             inside the timed region
+  roofline : the navigation kernel k_nav (dominant): algorithmic 132 B/ray (64 in + 68 out) over the CUDA-event time of the
+             bounce kernels of a pass, against the measured HBM peak
+  cpu_baseline : the CPU oracle (reference algorithm restated; ROOT is unavailable) on all host threads, on a sample of
+             windows spread evenly over the whole beam, with the daughter-box trees that play TGeoVoxelFinder's role
+             ("port+voxels"); the walk over all daughters ("port") is reported next to it
+  configs  : the same figures for every BASELINE config (1-5) at its BASELINE size on one GPU, each with its own bounce-kernel
+             time, roofline fraction, CPU row and host-buffer (e2e) rate
+  cfg5_strong (torchrun, or 1 GPU): the 1e9-ray HexWinstonCone run of configs[4], rays [rank * 1e9/N, (rank+1) * 1e9/N) per
+             rank by shard_range, global ray ids and seeds, generated / traced / reduced on the device batch by batch
 
-`--impl reference` times the reference arm: the reference's own implementation cannot be built here
-(needs CERN ROOT), so it is the oracle port on all host threads (cpu_baseline.kind = "port").
+Multi-GPU (torchrun): rays shard across ranks (each rank traces its own field-angle sweep, geometry replicated), no data-path
+collective; the PSF histograms/moments are all-reduced with NCCL at the end of each step.  The headline scales weakly (per-GPU
+work fixed), cfg5_strong strongly (total work fixed).
+
+`--impl reference` times the reference arm: the reference's own implementation cannot be built here (needs CERN ROOT), so it is
+the oracle port on all host threads (cpu_baseline.kind = "port+voxels"), on the same spread-out sample of the same workload.
 """
 import argparse
 import ctypes as C
@@ -36,6 +43,19 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 N_SIDE = 3334
 ANGLES = [0.5 * i for i in range(9)]
 BYTES_IN, BYTES_OUT = 64, 68
+FP64_PEAK_TFLOPS = 34.19  # DFMA peak measured on this pool (profiles/r1j_fp64_peak.json, profiles/fp64_peak.cu)
+
+# the five BASELINE configs at their BASELINE sizes on one GPU: (cfg, field angle, rays, builder kwargs, beam side for cfg 5)
+CONFIGS = {
+    1: dict(name="SimpleParabolicTelescope.C", theta=0.0, n=1000 * 1000, kw={}, what="on-axis Square(400 nm, 5 m, n=1000)"),
+    2: dict(name="DaviesCotton.C", theta=2.0, n=N_SIDE * N_SIDE, kw={}, what="one field angle (2 deg) of the headline sweep, Square(400 nm, 14 m, n=3334)"),
+    3: dict(name="SchwarzschildCouder.C", theta=0.0, n=10000 * 10000, kw={}, what="on-axis Square(400 nm, 20 m, n=10000)"),
+    4: dict(name="SchmidtCassegrain.C", theta=0.0, n=10_000_000, kw={}, what="RandomCircle(12.5 in), 300-700 nm, Fresnel + absorption on"),
+    5: dict(name="HexWinstonCone.C", theta=20.0, n=125_000_000, kw=dict(rings=10), side=84.0,
+            what="331 cells, multilayer-coated walls (direct TMM), RandomSquare at 20 deg: one GPU's share (1/8) of the 1e9-ray run"),
+}
+CFG5_TOTAL = 1_000_000_000
+CFG5_BATCH = 125_000_000
 
 
 def make_clock_reader():
@@ -94,28 +114,82 @@ def clocks_summary(samples):
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": reasons, "samples": len(samples)}
 
 
-def oracle_rate(oracle, H, export, params, n, threads, opts):
-    rays = H.make_rays(oracle, params, 0, n)
-    t0 = time.perf_counter()
-    H.trace_with(oracle.orc_trace, export, rays, opts, nthreads=threads)
-    return n / (time.perf_counter() - t0)
+# ------------------------------------------------------------------------------------------------ CPU rows (the oracle as checker / baseline only)
+def load_cpu_oracle():
+    """the oracle built for this host's cores (-march=native, built here on first use) if the compiler is around, else the
+    portable build that travelled with the repo"""
+    import helpers as H
+    try:
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "native"], check=True, timeout=240, capture_output=True)
+        native = os.path.join(ROOT, "oracle", "_build", "liboracle_native.so")
+        if os.path.exists(native):
+            H.ORACLE_SO = native
+            return H.load_oracle(), "-O3 -march=native"
+    except Exception:
+        pass
+    return H.load_oracle(), "-O3"
+
+
+def spread_sample(oracle, H, beam, n_total, n_sample, windows=64):
+    """`windows` windows of consecutive rays at evenly spaced offsets over the whole beam (not its busiest rows)"""
+    import numpy as np
+    windows = max(1, min(windows, n_sample // 64 or 1))
+    w = max(1, n_sample // windows)
+    parts = []
+    for k in range(windows):
+        first = int((k + 0.5) * n_total / windows) - w // 2
+        first = max(0, min(n_total - w, first))
+        parts.append(H.make_rays(oracle, beam, first, w).inp)
+    return np.concatenate(parts, axis=1)
+
+
+def cpu_rows(oracle, H, export, beam, n_total, opts, threads, seconds, flags):
+    """-> (cpu_baseline dict with voxels, dict of the full daughter walk): rays/s of the oracle on `threads` host threads on a
+    spread-out sample sized for about `seconds` of work each"""
+    import numpy as np
+    rows = {}
+    for vox in (1, 0):
+        oracle.orc_set_voxels(vox)
+        try:
+            probe = H.Rays(spread_sample(oracle, H, beam, n_total, 4096 * 4).T)
+            t0 = time.perf_counter()
+            H.trace_with(oracle.orc_trace, export, probe, opts, nthreads=threads)
+            rate = probe.n / (time.perf_counter() - t0)
+            ns = int(min(8e6, max(20000, rate * (seconds if vox else seconds / 3))))
+            rays = H.Rays(spread_sample(oracle, H, beam, n_total, ns).T)
+            t0 = time.perf_counter()
+            H.trace_with(oracle.orc_trace, export, rays, opts, nthreads=threads)
+            dt = time.perf_counter() - t0
+            rows[vox] = {"value": rays.n / dt, "unit": "rays/s", "cores": threads, "per_thread": rays.n / dt / threads,
+                         "kind": "port+voxels" if vox else "port",
+                         "sample": "%d rays in 64 windows spread evenly over the beam, %.1f s; reference algorithm restated in C++ (oracle/, %s), ROOT unavailable%s"
+                                   % (rays.n, dt, flags, "; daughter-box trees in TGeoVoxelFinder's role, results bit-identical to the full walk" if vox else
+                                      "; every daughter of a volume examined at every step")}
+        finally:
+            oracle.orc_set_voxels(1)
+    return rows[1], rows[0]
 
 
 def run_reference(args):
-    """reference arm: CPU oracle (port of the reference algorithm) with all host threads"""
+    """reference arm: CPU oracle (port of the reference algorithm) with all host threads, same workload, spread-out sample"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import helpers as H
+    import numpy as np
     from robast_b200 import configs
-    oracle = H.load_oracle()
+    oracle, flags = load_cpu_oracle()
     mgr, _k = configs.davies_cotton()
     export = mgr.ExportScene()
     threads = os.cpu_count() or 1
     opts = H.opts(disable_fresnel=1)
-    rate = oracle_rate(oracle, H, export, configs.beam(2, 0.0, n_side=N_SIDE), 20000, threads, opts)
-    per_angle = max(2000, int(rate * 4.0 / len(ANGLES)))  # ~4 s per step
-    batches = [H.make_rays(oracle, configs.beam(2, th, n_side=N_SIDE), (N_SIDE * N_SIDE) // 2 - per_angle // 2, per_angle) for th in ANGLES]
+    n = N_SIDE * N_SIDE
+    probe = H.Rays(spread_sample(oracle, H, configs.beam(2, 2.0, n_side=N_SIDE), n, 65536).T)
+    t0 = time.perf_counter()
+    H.trace_with(oracle.orc_trace, export, probe, opts, nthreads=threads)
+    rate = probe.n / (time.perf_counter() - t0)
+    per_angle = max(4096, int(rate * 4.0 / len(ANGLES)))  # ~4 s per step
+    batches = [H.Rays(spread_sample(oracle, H, configs.beam(2, th, n_side=N_SIDE), n, per_angle).T) for th in ANGLES]
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -124,17 +198,194 @@ def run_reference(args):
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    nrays = per_angle * len(ANGLES)
+    nrays = sum(b.n for b in batches)
     value = nrays * args.steps / total
-    sample = "%d rays per field angle (central rows of each 3334^2 grid) x 9 angles per step" % per_angle
+    sample = "%d rays per field angle (64 windows spread evenly over each 3334^2 grid) x 9 angles per step; oracle with daughter-box trees, %s" % (batches[0].n, flags)
     print(json.dumps({
         "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "DaviesCotton.C 88 hex facets, 9 field angles 0-4 deg, Square(400 nm, 14 m, n=3334) each; bounded CPU sample", "rays_per_step": nrays},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": "DaviesCotton.C (BASELINE configs[1]): 88 hex facets + camera + masts, 9 field angles 0-4 deg, Square(400 nm, 14 m, n=3334) each; bounded CPU sample",
+                   "rays_per_step": nrays},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "per_thread": value / threads, "kind": "port+voxels", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference itself needs CERN ROOT (absent); this is the restated reference algorithm (oracle/) on all host threads",
     }))
+
+
+# ------------------------------------------------------------------------------------------------ device helpers
+class Batch:
+    """device-resident SoA ray batch + its rbg_rays view"""
+
+    def __init__(self, R, torch, dev, n):
+        self.n = n
+        self.inp = torch.empty((8, n), dtype=torch.float64, device=dev)
+        self.out = torch.empty((7, n), dtype=torch.float64, device=dev)
+        self.iout = torch.empty((3, n), dtype=torch.int32, device=dev)
+        r = R.rbg_rays()
+        r.n, r.on_device = n, 1
+        for i, key in enumerate(["x", "y", "z", "t", "dx", "dy", "dz", "lambda_"]):
+            setattr(r, key, self.inp[i].data_ptr())
+        for i, key in enumerate(["ox", "oy", "oz", "ot", "odx", "ody", "odz"]):
+            setattr(r, key, self.out[i].data_ptr())
+        for i, key in enumerate(["status", "last_node", "npoints"]):
+            setattr(r, key, self.iout[i].data_ptr())
+        self.struct = r
+
+
+def profile_reset(R):
+    bm, bn, cm, cn = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
+    R.rbg_profile_read(C.byref(bm), C.byref(bn), C.byref(cm), C.byref(cn))
+    return bm.value, bn.value, cm.value, cn.value
+
+
+def roofline_of(n_rays_traced, bounce_ms, hbm_peak, flops_per_ray=None):
+    """algorithmic 132 B/ray over the summed CUDA-event time of the bounce kernels"""
+    if bounce_ms <= 0:
+        return None
+    achieved = (BYTES_IN + BYTES_OUT) * n_rays_traced / (bounce_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+         "algorithmic_bytes_per_ray": BYTES_IN + BYTES_OUT, "bounce_kernel_ms": bounce_ms}
+    if flops_per_ray:
+        tf = flops_per_ray * n_rays_traced / (bounce_ms * 1e-3) / 1e12
+        r["fp64"] = {"algorithmic_kflop_per_ray": flops_per_ray / 1e3, "achieved_tflops": tf, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tf / FP64_PEAK_TFLOPS,
+                     "note": "SURVEY.md 8d flop estimate x rays / bounce-kernel time; the measured pipe utilisation is in profiles/ (ncu)"}
+    return r
+
+
+KFLOP = {1: 0.6e3, 2: 2.5e3, 3: 6e3, 4: 10e3, 5: 9e3}  # SURVEY.md §8d algorithmic flop estimates per ray
+
+
+def bench_one_config(R, torch, H, configs, dev, local, stream, cfg, reps, hbm_peak, oracle, flags, cpu_seconds, e2e_cap):
+    """device-resident rays/s, bounce-kernel roofline, host-buffer rate and CPU rows of one BASELINE config on this GPU"""
+    c = CONFIGS[cfg]
+    mgr, _keep = configs.BUILDERS[cfg](**c["kw"])
+    export = mgr.ExportScene()
+    scene = C.c_void_p()
+    R.check(R.rbg_scene_create(export.desc_ptr(), local, C.byref(scene)))
+    n = c["n"]
+    nside = int(round(n ** 0.5)) if cfg <= 3 else c.get("side")
+    beam = configs.beam(cfg, c["theta"], n_side=nside)
+    b = Batch(R, torch, dev, n)
+    d = H.shoot_desc(beam)
+    R.check(R.rbg_shoot(C.byref(d), 0, n, *[b.inp[i].data_ptr() for i in range(8)], local, stream))
+    opts = H.opts(disable_fresnel=1 if cfg == 2 else 0, seed=20180601 if cfg != 5 else 20110306)
+    for _ in range(2):
+        R.check(R.rbg_trace(scene, C.byref(opts), C.byref(b.struct), stream))
+    torch.cuda.synchronize()
+    R.rbg_profile_enable(1)
+    profile_reset(R)
+    l0 = R.rbg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        R.check(R.rbg_trace(scene, C.byref(opts), C.byref(b.struct), stream))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bm, bn, cm, cn = profile_reset(R)
+    R.rbg_profile_enable(0)
+    launches = (R.rbg_launch_count() - l0) // reps
+    counts = torch.bincount(b.iout[0].to(torch.int64), minlength=6).cpu().numpy().tolist()
+    res = {"workload": "%s: %s" % (c["name"], c["what"]), "rays": n, "value": n / (ms * 1e-3), "unit": "rays/s", "ms_per_trace": ms,
+           "kernel_variant": R.rbg_scene_kernel_variant(scene).decode(), "gpu_launches_per_trace": int(launches),
+           "bounce_kernel_ms_per_trace": bm / reps, "compaction_and_sort_ms_per_trace": cm / reps,
+           "roofline": roofline_of(n, bm / reps, hbm_peak, KFLOP[cfg]), "status_counts": counts, "mean_npoints": float(b.iout[2].float().mean().item())}
+    # host-buffer rate (pinned), bounded size
+    ne = min(n, e2e_cap)
+    if ne > 0:
+        hin = torch.empty((8, ne), dtype=torch.float64).pin_memory()
+        hin.copy_(b.inp[:, :ne].cpu())
+        hout = torch.empty((7, ne), dtype=torch.float64).pin_memory()
+        hiout = torch.empty((3, ne), dtype=torch.int32).pin_memory()
+        r = R.rbg_rays()
+        r.n, r.on_device = ne, 0
+        for i, key in enumerate(["x", "y", "z", "t", "dx", "dy", "dz", "lambda_"]):
+            setattr(r, key, hin[i].data_ptr())
+        for i, key in enumerate(["ox", "oy", "oz", "ot", "odx", "ody", "odz"]):
+            setattr(r, key, hout[i].data_ptr())
+        for i, key in enumerate(["status", "last_node", "npoints"]):
+            setattr(r, key, hiout[i].data_ptr())
+        R.check(R.rbg_trace(scene, C.byref(opts), C.byref(r), None))
+        t0 = time.perf_counter()
+        for _ in range(2):
+            R.check(R.rbg_trace(scene, C.byref(opts), C.byref(r), None))
+        dt = (time.perf_counter() - t0) / 2
+        same = bool((hiout[0] == b.iout[0, :ne].cpu()).all().item())
+        res["e2e"] = {"value": ne / dt, "unit": "rays/s", "rays": ne, "h2d_bytes_per_trace": BYTES_IN * ne, "d2h_bytes_per_trace": BYTES_OUT * ne,
+                      "statuses_equal_device_path": same}
+        del hin, hout, hiout
+    del b
+    torch.cuda.empty_cache()
+    if oracle is not None:
+        vox, brute = cpu_rows(oracle, H, export, beam, n, opts, os.cpu_count() or 1, cpu_seconds, flags)
+        res["cpu_baseline"] = vox
+        res["cpu_baseline_full_walk"] = brute
+    R.rbg_scene_destroy(scene)
+    return res
+
+
+def bench_cfg5_strong(R, torch, H, configs, sharding, dev, local, stream, rank, world, dist, steps):
+    """configs[4] as BASELINE states it: 1e9 RandomSquare rays over the ranks (contiguous ranges, global ray ids), generated on
+    the device, traced and reduced to the PMT-plane histogram + status counters batch by batch; nothing but the reducers leaves
+    the GPU.  Strong scaling: the total is fixed, each rank takes 1e9 / N rays."""
+    c = CONFIGS[5]
+    mgr, _keep = configs.BUILDERS[5](**c["kw"])
+    export = mgr.ExportScene()
+    scene = C.c_void_p()
+    R.check(R.rbg_scene_create(export.desc_ptr(), local, C.byref(scene)))
+    beam = configs.beam(5, c["theta"], n_side=c["side"])
+    d = H.shoot_desc(beam)
+    lo, hi = sharding.shard_range(CFG5_TOTAL, rank, world)
+    nb = min(CFG5_BATCH, hi - lo)
+    b = Batch(R, torch, dev, nb)
+    hist = torch.zeros(200 * 200, dtype=torch.int64, device=dev)
+    mom = torch.zeros(8, dtype=torch.float64, device=dev)
+    cnt = torch.zeros(6, dtype=torch.int64, device=dev)
+    opts = H.opts(seed=20110306)
+
+    def step():
+        hist.zero_(); mom.zero_(); cnt.zero_()
+        first = lo
+        while first < hi:
+            m = min(nb, hi - first)
+            R.check(R.rbg_shoot(C.byref(d), first, m, *[b.inp[i].data_ptr() for i in range(8)], local, stream))
+            b.struct.n = m
+            opts.ray_id_offset = first
+            R.check(R.rbg_trace(scene, C.byref(opts), C.byref(b.struct), stream))
+            R.check(R.rbg_hist2d(m, b.out[0].data_ptr(), b.out[1].data_ptr(), b.iout[0].data_ptr(), R.RBG_FOCUSED, 200, -45., 45., 200, -45., 45., hist.data_ptr(), local, stream))
+            R.check(R.rbg_moments(m, b.out[0].data_ptr(), b.out[1].data_ptr(), b.out[3].data_ptr(), b.iout[0].data_ptr(), R.RBG_FOCUSED, mom.data_ptr(), cnt.data_ptr(), local, stream))
+            first += m
+        if dist is not None:
+            dist.all_reduce(hist)
+            dist.all_reduce(mom)
+            dist.all_reduce(cnt)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item()) / steps
+    counts = cnt.cpu().numpy().tolist()
+    res = {"workload": "HexWinstonCone.C (BASELINE configs[4]): 1e9 RandomSquare rays at 20 deg on 331 multilayer-coated cells, generated, traced and reduced on device",
+           "rays_total": CFG5_TOTAL, "rays_per_gpu": hi - lo, "batch": nb, "n_gpus": world, "scaling": "strong", "value": CFG5_TOTAL / (ms * 1e-3), "unit": "rays/s",
+           "ms_per_step": ms, "steps": steps, "status_counts": counts, "focused_fraction": counts[R.RBG_FOCUSED] / float(max(1, sum(counts))),
+           "histogram_entries": int(hist.sum().item())}
+    R.rbg_scene_destroy(scene)
+    del b
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -148,6 +399,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=int(os.environ.get("RB_E2E_THREADS", "1")), help="TraceNonSequential calls in flight on the host-buffer path")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (configs 1-5) and the cfg5 strong-scaling run")
+    ap.add_argument("--latency", action="store_true", help="also measure the small-batch latency per config")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -155,7 +408,7 @@ def main():
     import numpy as np
     import torch
     import robast_b200 as R
-    from robast_b200 import configs
+    from robast_b200 import configs, sharding
     import helpers as H
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -239,8 +492,7 @@ def main():
         step()
     barrier()
     R.rbg_profile_enable(1)
-    bm, bn, cm_, cn = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
-    R.rbg_profile_read(C.byref(bm), C.byref(bn), C.byref(cm_), C.byref(cn))  # reset
+    profile_reset(R)
     stop, samples = threading.Event(), []
     th_clock = threading.Thread(target=sample_clocks, args=(stop, samples, clock_reader), daemon=True)
     th_clock.start()
@@ -265,7 +517,7 @@ def main():
     ms = e0.elapsed_time(e1)
     step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
     launches = R.rbg_launch_count() - launches0
-    R.rbg_profile_read(C.byref(bm), C.byref(bn), C.byref(cm_), C.byref(cn))
+    bm, bn, cm_, cn = profile_reset(R)
     R.rbg_profile_enable(0)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -354,21 +606,17 @@ def main():
             R.rbg_scene_destroy(h)
         del hin, hout, hiout
 
-    # ---- CPU baseline (rank 0, N=1): the oracle on all host threads, bounded sample
-    cpu = None
+    variant = R.rbg_scene_kernel_variant(scene).decode()
+    R.rbg_scene_destroy(scene)
+    del inp, out, iout
+    torch.cuda.empty_cache()
+
+    # ---- CPU baseline (rank 0, N=1): the oracle on all host threads, bounded spread-out sample of the same workload
+    cpu = cpu_full = None
+    oracle = flags = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        oracle = H.load_oracle()
-        threads = os.cpu_count() or 1
-        o = H.opts(disable_fresnel=1)
-        rate = oracle_rate(oracle, H, export, configs.beam(2, 0.0, n_side=N_SIDE), 20000, threads, o)
-        ns = int(min(4e6, max(20000, rate * 15.0)))
-        first = n // 2 - ns // 2
-        rays = H.make_rays(oracle, configs.beam(2, 2.0, n_side=N_SIDE), first, ns)
-        t0 = time.perf_counter()
-        H.trace_with(oracle.orc_trace, export, rays, o, nthreads=threads)
-        dtc = time.perf_counter() - t0
-        cpu = {"value": ns / dtc, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": "%d rays (central rows of the 2.0 deg 3334^2 grid), %.1f s; reference algorithm restated in C++ (oracle/), ROOT unavailable" % (ns, dtc)}
+        oracle, flags = load_cpu_oracle()
+        cpu, cpu_full = cpu_rows(oracle, H, export, configs.beam(2, 2.0, n_side=N_SIDE), N_SIDE * N_SIDE, H.opts(disable_fresnel=1), os.cpu_count() or 1, 12.0, flags)
 
     peaks = {}
     try:
@@ -376,30 +624,30 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    kernel_ms = bm.value / max(1, bn.value)
-    # one bounce launch processes the live rays of one field angle; per TraceNonSequential pass the algorithmic bytes are
-    # 132 B/ray (64 in + 68 out), and the bounce kernel runs `launches per pass` times per pass
     passes = args.steps * nang
-    achieved = (BYTES_IN + BYTES_OUT) * n * passes / (bm.value * 1e-3) / 1e9 if bm.value > 0 else None
-    variant = R.rbg_scene_kernel_variant(scene).decode()
-    roof = {"bound": "hbm", "kernel": "k_step<%s> (wavefront bounce kernel; k_trace<%s> finishes the tail)" % (variant, variant), "achieved": achieved, "peak": hbm_peak,
-            "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-            "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "of fallback", "algorithmic_bytes_per_ray": BYTES_IN + BYTES_OUT,
-            "algorithmic_bytes_per_pass": (BYTES_IN + BYTES_OUT) * n, "bounce_ms_per_pass": bm.value / passes, "bounce_launches_per_pass": bn.value / passes,
-            "kernel_ms_per_launch": kernel_ms, "kernel_launches": bn.value, "kernel_share_of_step": bm.value / ms if ms else None,
-            "compact": {"ms_per_launch": cm_.value / max(1, cn.value), "launches": cn.value, "share_of_step": cm_.value / ms if ms else None},
-            "note": "achieved = 132 B/ray x rays of a pass / summed CUDA-event time of that pass's bounce launches. The bounce kernel is bound by FP64/"
-                    "instruction issue, not HBM: see roofline.fp64 and profiles/"}
-    for fn, key in (("traffic_k_step.json", "traffic"),):
-        try:
-            roof[key] = json.load(open(os.path.join(ROOT, "profiles", fn))).get("dram_bytes_per_pass")
-        except Exception:
-            pass
-    try:
-        fp = json.load(open(os.path.join(ROOT, "profiles", "fp64_roofline.json")))
-        roof["fp64"] = fp
+    roof = roofline_of(n * passes, bm, hbm_peak, KFLOP[2]) or {}
+    roof.update({"kernel": "k_nav<%s> + k_shade<%s> (the two halves of the wavefront bounce; k_init locates the start points, k_trace finishes the tail)" % (variant, variant),
+                 "peak_source": "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "of fallback",
+                 "algorithmic_bytes_per_pass": (BYTES_IN + BYTES_OUT) * n, "bounce_ms_per_pass": bm / passes, "bounce_launches_per_pass": bn / passes,
+                 "kernel_ms_per_launch": bm / max(1, bn), "kernel_launches": bn, "kernel_share_of_step": bm / ms if ms else None,
+                 "compact": {"ms_per_launch": cm_ / max(1, cn), "launches": cn, "share_of_step": cm_ / ms if ms else None},
+                 "note": "achieved = 132 B/ray x rays of a pass / summed CUDA-event time of that pass's bounce launches. The bounce kernels are bound by "
+                         "instruction issue / latency, not by HBM: see roofline.fp64 and profiles/ (ncu)"})
+    try:  # DRAM bytes per pass from the ncu capture committed with this code (stamped with the commit it was taken at)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic_k_nav.json")))
+        roof["traffic"] = tr.get("dram_bytes_per_pass")
+        roof["traffic_source"] = tr.get("source")
     except Exception:
         pass
+
+    # ---- every BASELINE config on one GPU (rank 0 reports; under torchrun every rank runs them so the GPUs stay in step)
+    per_config = strong = None
+    if not args.no_configs:
+        per_config = {}
+        for cfg in (1, 2, 3, 4, 5):
+            per_config["cfg%d" % cfg] = bench_one_config(R, torch, H, configs, dev, local, stream, cfg, 3, hbm_peak,
+                                                         oracle if (rank == 0 and world == 1) else None, flags, 4.0, 30_000_000 if not args.no_e2e else 0)
+        strong = bench_cfg5_strong(R, torch, H, configs, sharding, dev, local, stream, rank, world, dist, 2 if world < 4 else 3)
 
     if rank == 0:
         print(json.dumps({
@@ -408,10 +656,11 @@ def main():
             "config": {"workload": "DaviesCotton.C (BASELINE configs[1]): 88 hex facets + camera + masts, 9 field angles 0-4 deg, Square(400 nm, 14 m, n=3334) each",
                        "rays_per_step_per_gpu": n * nang, "rays_per_step": rays_per_step, "l2_policy": "inputs (711 MB per batch) larger than L2, no flush",
                        "steps_per_launch": args.steps_per_launch, "parallelism": "rays sharded over %d GPU(s), geometry replicated" % world},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks_summary(samples), "step_ms": step_ms,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_full_walk": cpu_full, "clocks": clocks_summary(samples),
+            "step_ms": step_ms,
             "check": {"focused_fraction": focused_frac, "status_counts": counts, "d80_cm_by_angle": [round(v, 4) for v in d80[:, 0].cpu().numpy().tolist()]},
+            "configs": per_config, "cfg5_strong": strong,
         }))
-    R.rbg_scene_destroy(scene)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -80,7 +80,7 @@ def sampled_oracle_parity(b, oracle, ex, id_offset=0, windows=256, width=4096, p
             worst[k] += rep[k]
         worst["max_dpos"] = max(worst["max_dpos"], rep["max_dpos"])
         worst["max_dang"] = max(worst["max_dang"], rep["max_dang"])
-    assert worst["n"] >= min(b.n, 1_000_000) * 0.99, worst
+    assert worst["n"] >= min(b.n, windows * width) * 0.99, worst
     assert worst["bad"] == 0 and worst["status_mismatch"] == 0 and worst["npoints_mismatch"] == 0 and worst["node_mismatch"] == 0, worst
     return worst
 
