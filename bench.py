@@ -314,6 +314,16 @@ def bench_one_config(R, torch, H, configs, dev, local, stream, cfg, reps, hbm_pe
         res["e2e"] = {"value": ne / dt, "unit": "rays/s", "rays": ne, "h2d_bytes_per_trace": BYTES_IN * ne, "d2h_bytes_per_trace": BYTES_OUT * ne,
                       "statuses_equal_device_path": same}
         del hin, hout, hiout
+    # the MINUIT-loop regime (tutorials/Optimize.C, optimize_multilayer.C): 1000-ray calls with host arrays, one after another
+    nl = 1000
+    small = H.Rays(b.inp[:, :: max(1, n // nl)][:, :nl].cpu().numpy().T)
+    rs = small.struct()
+    for _ in range(5):
+        R.check(R.rbg_trace(scene, C.byref(opts), C.byref(rs), None))
+    t0 = time.perf_counter()
+    for _ in range(200):
+        R.check(R.rbg_trace(scene, C.byref(opts), C.byref(rs), None))
+    res["latency_us_1k_rays"] = (time.perf_counter() - t0) / 200 * 1e6
     del b
     torch.cuda.empty_cache()
     if oracle is not None:

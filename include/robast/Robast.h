@@ -52,8 +52,8 @@ class ARefractiveIndex : public TObject {
   virtual std::complex<Double_t> GetComplexRefractiveIndex(Double_t lambda) const {
     return std::complex<Double_t>(GetRefractiveIndex(lambda), GetExtinctionCoefficient(lambda));
   }
-  virtual void SetExtinctionCoefficient(std::shared_ptr<TGraph> graph) { fExtinctionCoefficient = graph; }
-  virtual void SetRefractiveIndex(std::shared_ptr<TGraph> graph) { fRefractiveIndex = graph; }
+  virtual void SetExtinctionCoefficient(std::shared_ptr<TGraph> graph) { RbGeomTouch(); fExtinctionCoefficient = graph; }
+  virtual void SetRefractiveIndex(std::shared_ptr<TGraph> graph) { RbGeomTouch(); fRefractiveIndex = graph; }
   std::shared_ptr<TGraph> GetRefractiveIndexGraph() const { return fRefractiveIndex; }
   std::shared_ptr<TGraph> GetExtinctionCoefficientGraph() const { return fExtinctionCoefficient; }
   static Double_t AbsorptionLengthToExtinctionCoefficient(Double_t a, Double_t lambda) { return lambda / (4 * TMath::Pi() * a); }
@@ -128,7 +128,7 @@ class AMixedRefractiveIndex : public ARefractiveIndex {
   Double_t GetExtinctionCoefficient(Double_t lambda) const override {
     return fMaterialA->GetExtinctionCoefficient(lambda) * fFractionA + fMaterialB->GetExtinctionCoefficient(lambda) * fFractionB;
   }
-  void SetFraction(Double_t fa, Double_t fb) {
+  void SetFraction(Double_t fa, Double_t fb) { RbGeomTouch();
     fFractionA = fa / (fa + fb);
     fFractionB = fb / (fa + fb);
   }
@@ -322,7 +322,7 @@ class AGeoAsphericDisk : public TGeoBBox {
     ComputeBBox();
   }
   EKind Kind() const override { return kAsphere; }
-  void SetAsphDimensions(Double_t z1, Double_t curve1, Double_t z2, Double_t curve2, Double_t rmax, Double_t rmin) {
+  void SetAsphDimensions(Double_t z1, Double_t curve1, Double_t z2, Double_t curve2, Double_t rmax, Double_t rmin) { RbGeomTouch();
     if (z1 < z2) { fZ1 = z1; fZ2 = z2; fCurve1 = curve1; fCurve2 = curve2; }
     else { fZ1 = z2; fZ2 = z1; fCurve1 = curve2; fCurve2 = curve1; }
     rmax = std::fabs(rmax); rmin = std::fabs(rmin);
@@ -336,11 +336,11 @@ class AGeoAsphericDisk : public TGeoBBox {
     fDX = fDY = fRmax;
     fDZ = (zmax - zmin) / 2;
   }
-  void SetConicConstants(Double_t conic1, Double_t conic2) {
+  void SetConicConstants(Double_t conic1, Double_t conic2) { RbGeomTouch();
     fConic1 = conic1; fConic2 = conic2; fKappa1 = conic1 + 1; fKappa2 = conic2 + 1;
     ComputeBBox();
   }
-  void SetPolynomials(Int_t n1, const Double_t* k1, Int_t n2, const Double_t* k2) {
+  void SetPolynomials(Int_t n1, const Double_t* k1, Int_t n2, const Double_t* k2) { RbGeomTouch();
     fK1.assign(k1 ? k1 : nullptr, k1 ? k1 + (n1 > 0 ? n1 : 0) : nullptr);
     fK2.assign(k2 ? k2 : nullptr, k2 ? k2 + (n2 > 0 ? n2 : 0) : nullptr);
     ComputeBBox();
@@ -384,7 +384,7 @@ class AGeoWinstonCone2D : public TGeoBBox {
  protected:
   Double_t fR1, fR2, fF, fTheta;
 
-  void SetBase(Double_t r1, Double_t r2) {
+  void SetBase(Double_t r1, Double_t r2) { RbGeomTouch();
     fR1 = std::max(std::fabs(r1), std::fabs(r2));
     fR2 = std::min(std::fabs(r1), std::fabs(r2));
     fTheta = std::asin(fR2 / fR1);
@@ -419,7 +419,7 @@ class AGeoWinstonCone2D : public TGeoBBox {
 // reference src/AGeoWinstonConePoly.cxx:30-64,356-386
 class AGeoWinstonConePoly : public AGeoWinstonCone2D {
   Int_t fPolyN;
-  void SetPoly(Double_t r1, Double_t r2, Int_t n) {
+  void SetPoly(Double_t r1, Double_t r2, Int_t n) { RbGeomTouch();
     SetBase(r1, r2);
     fPolyN = n >= 3 ? n : 3;
     Double_t r = r1 / std::cos(TMath::Pi() / n);
@@ -460,12 +460,12 @@ template <class Base> class ABezierSections : public Base {
       z = u * u * u * p0z + 3 * u * u * t * c1z + 3 * u * t * t * c2z + t * t * t * pLz;
     }
   }
-  void SetControlPoints(Double_t r1, Double_t z1) { fNcontrol = 1; fPr[0] = r1; fPz[0] = z1; SetSections(); }
-  void SetControlPoints(Double_t r1, Double_t z1, Double_t r2, Double_t z2) {
+  void SetControlPoints(Double_t r1, Double_t z1) { RbGeomTouch(); fNcontrol = 1; fPr[0] = r1; fPz[0] = z1; SetSections(); }
+  void SetControlPoints(Double_t r1, Double_t z1, Double_t r2, Double_t z2) { RbGeomTouch();
     fNcontrol = 2; fPr[0] = r1; fPz[0] = z1; fPr[1] = r2; fPz[1] = z2;
     SetSections();
   }
-  void SetSections() {
+  void SetSections() { RbGeomTouch();
     for (Int_t i = 0; i < this->fNz; i++) {
       Double_t t = Double_t(i) / (this->fNz - 1), r, z;
       Bezier(t, r, z);
@@ -599,12 +599,12 @@ class AMultilayer : public TObject {
     fThicknessList = {inf, inf};
     fCoherentList = {kFALSE, kFALSE};
   }
-  void AddLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t coherent = kTRUE) {
+  void AddLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t coherent = kTRUE) { RbGeomTouch();
     fRefractiveIndexList.insert(fRefractiveIndexList.begin() + 1, idx);
     fThicknessList.insert(fThicknessList.begin() + 1, thickness);
     fCoherentList.insert(fCoherentList.begin() + 1, coherent);
   }
-  void InsertLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t coherent = kTRUE) {
+  void InsertLayer(std::shared_ptr<ARefractiveIndex> idx, Double_t thickness, Bool_t coherent = kTRUE) { RbGeomTouch();
     fRefractiveIndexList.insert(fRefractiveIndexList.end() - 1, idx);
     fThicknessList.insert(fThicknessList.end() - 1, thickness);
     fCoherentList.insert(fCoherentList.end() - 1, coherent);
@@ -632,7 +632,7 @@ class AMultilayer : public TObject {
   static std::complex<Double_t> Snell(std::complex<Double_t> n_1, std::complex<Double_t> n_2, std::complex<Double_t> th_1) {
     return std::asin(n_1 * std::sin(th_1) / n_2);
   }
-  void ChangeThickness(std::size_t i, Double_t thickness) {
+  void ChangeThickness(std::size_t i, Double_t thickness) { RbGeomTouch();
     if (i < 1 || i > fThicknessList.size() - 2) Error("ChangeThickness", "Cannot change the thickness of the %luth layer", (unsigned long)i);
     else fThicknessList[i] = thickness;
   }
@@ -664,7 +664,7 @@ class AMultilayer : public TObject {
     if (!lam_vac.empty()) DeviceTMM((Int_t)lam_vac.size(), th.data(), lam_vac.data(), reflectance.data(), transmittance.data());
   }
   // reference include/AMultilayer.h:243-262 — λ×θ table at bin centres, one device launch
-  void PreCalculateCoherentTMM(Int_t lam_nbins, Double_t lam_min, Double_t lam_max, Int_t th_nbins, Double_t th_min, Double_t th_max) {
+  void PreCalculateCoherentTMM(Int_t lam_nbins, Double_t lam_min, Double_t lam_max, Int_t th_nbins, Double_t th_min, Double_t th_max) { RbGeomTouch();
     auto R = std::make_shared<TH2D>("", "", lam_nbins, lam_min, lam_max, th_nbins, th_min, th_max);
     auto T = std::make_shared<TH2D>("", "", lam_nbins, lam_min, lam_max, th_nbins, th_min, th_max);
     std::vector<Double_t> th, lam;
@@ -687,7 +687,7 @@ class AMultilayer : public TObject {
     fPreCalculatedTransmittanceMixed = T;
   }
   // reference include/AMultilayer.h:263-282: the same table filled by IncoherentTMMMixed
-  void PreCalculateIncoherentTMM(Int_t lam_nbins, Double_t lam_min, Double_t lam_max, Int_t th_nbins, Double_t th_min, Double_t th_max) {
+  void PreCalculateIncoherentTMM(Int_t lam_nbins, Double_t lam_min, Double_t lam_max, Int_t th_nbins, Double_t th_min, Double_t th_max) { RbGeomTouch();
     auto R = std::make_shared<TH2D>("", "", lam_nbins, lam_min, lam_max, th_nbins, th_min, th_max);
     auto T = std::make_shared<TH2D>("", "", lam_nbins, lam_min, lam_max, th_nbins, th_min, th_max);
     std::vector<std::complex<Double_t>> th;
@@ -721,7 +721,7 @@ class AOpticalComponent : public TGeoVolume {
   AOpticalComponent() {}
   AOpticalComponent(const char* name, const TGeoShape* shape, const TGeoMedium* med = nullptr) : TGeoVolume(name, shape, med) {}
   virtual Int_t OpticalType() const { return RBG_OPT; }
-  void AddBorderSurfaceCondition(ABorderSurfaceCondition* c) { fBorders.push_back(c); }
+  void AddBorderSurfaceCondition(ABorderSurfaceCondition* c) { RbGeomTouch(); fBorders.push_back(c); }
   ABorderSurfaceCondition* FindBorderSurfaceCondition(AOpticalComponent* component2);
   const std::vector<ABorderSurfaceCondition*>& GetBorders() const { return fBorders; }
 };
@@ -742,11 +742,11 @@ class ABorderSurfaceCondition : public TObject {
   AOpticalComponent* GetComponent1() { return fComponent[0]; }
   AOpticalComponent* GetComponent2() { return fComponent[1]; }
   Double_t GetGaussianRoughness() const { return fSigma; }
-  void SetGaussianRoughness(Double_t sigma) { fSigma = std::fabs(sigma); }
-  void SetMultilayer(std::shared_ptr<AMultilayer> layer) { fMultilayer = layer; }
+  void SetGaussianRoughness(Double_t sigma) { RbGeomTouch(); fSigma = std::fabs(sigma); }
+  void SetMultilayer(std::shared_ptr<AMultilayer> layer) { RbGeomTouch(); fMultilayer = layer; }
   std::shared_ptr<AMultilayer> GetMultilayer() const { return fMultilayer; }
   Bool_t IsLambertian() const { return fLambertian; }
-  void EnableLambertian(Bool_t mode) { fLambertian = mode; }
+  void EnableLambertian(Bool_t mode) { RbGeomTouch(); fLambertian = mode; }
 };
 inline ABorderSurfaceCondition* AOpticalComponent::FindBorderSurfaceCondition(AOpticalComponent* component2) {
   for (auto* b : fBorders)
@@ -764,7 +764,7 @@ class ALens : public AOpticalComponent {
   Double_t GetAbsorptionLength(Double_t lambda) const { return fIndex ? fIndex->GetAbsorptionLength(lambda) : std::numeric_limits<Double_t>::infinity(); }
   Double_t GetExtinctionCoefficient(Double_t lambda) const { return fIndex ? fIndex->GetExtinctionCoefficient(lambda) : 0; }
   Double_t GetRefractiveIndex(Double_t lambda) const { return fIndex ? fIndex->GetRefractiveIndex(lambda) : 1.; }
-  void SetRefractiveIndex(std::shared_ptr<ARefractiveIndex> index) { fIndex = index; }
+  void SetRefractiveIndex(std::shared_ptr<ARefractiveIndex> index) { RbGeomTouch(); fIndex = index; }
   std::shared_ptr<ARefractiveIndex> GetIndex() const { return fIndex; }
 };
 
@@ -778,10 +778,10 @@ class AMirror : public AOpticalComponent {
  public:
   AMirror(const char* name, const TGeoShape* shape, const TGeoMedium* med = nullptr) : AOpticalComponent(name, shape, med) {}
   Int_t OpticalType() const override { return RBG_MIRROR; }
-  void SetReflectance(Double_t ref) { fReflectance = ref; }
-  void SetReflectance(std::shared_ptr<TGraph> ref) { fReflectance1D = ref; }
-  void SetReflectance(std::shared_ptr<TGraph2D> ref) { fReflectance2D = ref; }
-  void SetReflectance(std::shared_ptr<TH2> ref) { fReflectanceTH2 = ref; }
+  void SetReflectance(Double_t ref) { RbGeomTouch(); fReflectance = ref; }
+  void SetReflectance(std::shared_ptr<TGraph> ref) { RbGeomTouch(); fReflectance1D = ref; }
+  void SetReflectance(std::shared_ptr<TGraph2D> ref) { RbGeomTouch(); fReflectance2D = ref; }
+  void SetReflectance(std::shared_ptr<TH2> ref) { RbGeomTouch(); fReflectanceTH2 = ref; }
   // src/AMirror.cxx:39-60: priority TGraph2D > TH2 > TGraph > constant, clamped to [0, 1]
   Double_t GetReflectance(Double_t lambda, Double_t angle) const {
     Double_t ret = fReflectance;
@@ -805,8 +805,8 @@ class AFocalSurface : public AOpticalComponent {
   AFocalSurface(const char* name, const TGeoShape* shape, const TGeoMedium* med = nullptr) : AOpticalComponent(name, shape, med) {}
   Int_t OpticalType() const override { return RBG_FOCUS; }
   Bool_t HasQEAngle() const { return fQuantumEfficiencyAngle != nullptr; }
-  void SetQuantumEfficiency(TGraph* qe) { fQuantumEfficiencyLambda = qe; }
-  void SetQuantumEfficiencyAngle(TGraph* qe) { fQuantumEfficiencyAngle = qe; }
+  void SetQuantumEfficiency(TGraph* qe) { RbGeomTouch(); fQuantumEfficiencyLambda = qe; }
+  void SetQuantumEfficiencyAngle(TGraph* qe) { RbGeomTouch(); fQuantumEfficiencyAngle = qe; }
   TGraph* GetQELambdaGraph() const { return fQuantumEfficiencyLambda; }
   TGraph* GetQEAngleGraph() const { return fQuantumEfficiencyAngle; }
   Double_t GetQuantumEfficiency(Double_t lambda) const { return fQuantumEfficiencyLambda ? fQuantumEfficiencyLambda->Eval(lambda) : 1.; }
@@ -1626,7 +1626,10 @@ class AOpticsManager : public TGeoManager {
   std::vector<Double_t> fHistBuf;     // receive buffers of rbg_trace_history, reused across calls
   std::vector<int32_t> fHistNodeBuf;
   rbg_scene* fScene = nullptr;
+  rbg_multi* fMulti = nullptr;             // scene replicas on several GPUs (GetNumberOfGPUs() > 1)
   std::string fSceneKey;
+  std::shared_ptr<ASceneExport> fExport;   // flattened scene of the geometry epoch fExportEpoch
+  unsigned long long fExportEpoch = 0;
   std::shared_ptr<std::vector<std::string>> fNodeNames;
 
   static std::string Key(const ASceneExport& e) {
@@ -1649,6 +1652,7 @@ class AOpticsManager : public TGeoManager {
   AOpticsManager(const char* name, const char* title) : TGeoManager(name, title) {}
   ~AOpticsManager() override {
     if (fScene) rbg_scene_destroy(fScene);
+    if (fMulti) rbg_multi_destroy(fMulti);
   }
   static Double_t km() { return 1e3 * m(); }
   static Double_t m() { return 1e2 * cm(); }
@@ -1686,6 +1690,16 @@ class AOpticsManager : public TGeoManager {
   // unless a depth is requested here), 0 = never.
   void SetHistoryDepth(Int_t n) { fHistoryDepth = n; }
   Int_t GetHistoryDepth() const { return fHistoryDepth; }
+  // The flattened scene (export + device tables) is kept across calls until a mutator of a shape, matrix, volume, table or
+  // optical property ran anywhere (RbGeomEpoch, RootCompat.h).  InvalidateScene() forces a re-export, for changes made behind
+  // the classes' backs (writes through raw pointers); RB_NO_SCENE_CACHE=1 re-exports on every call like round 1 did.
+  void InvalidateScene() { fExport.reset(); }
+  // SetMaxThreads(n) + SetMultiThread(true) is how a ROBAST macro asks for n workers (src/AOpticsManager.cxx:529-568): here the
+  // workers are GPUs — min(n, visible devices) of them, rays in contiguous chunks, geometry replicated (rbg_multi_trace).
+  Int_t GetNumberOfGPUs() const {
+    Int_t g = IsMultiThread() ? std::min<Int_t>(GetMaxThreads(), rbg_device_count()) : 1;
+    return g < 1 ? 1 : g;
+  }
   std::shared_ptr<ASceneExport> ExportScene() const {
     if (!fTopVolume) throw std::runtime_error("AOpticsManager: no top volume");
     auto e = std::make_shared<ASceneExport>();
@@ -1700,7 +1714,14 @@ class AOpticsManager : public TGeoManager {
     for (size_t i = 0; i < T.size(); i++)
       if (T.status[i] == RBG_RUN) run.push_back(i);
     if (run.empty()) return;
-    auto ex = ExportScene();
+    static const bool no_cache = getenv("RB_NO_SCENE_CACHE") != nullptr;
+    const unsigned long long epoch = RbGeomEpoch().load(std::memory_order_relaxed);
+    const bool fresh = !fExport || epoch != fExportEpoch || no_cache;
+    if (fresh) {
+      fExport = ExportScene();
+      fExportEpoch = epoch;
+    }
+    const std::shared_ptr<ASceneExport>& ex = fExport;
     size_t n = run.size();
     bool contiguous = run.back() - run.front() + 1 == n;
     std::vector<Double_t> buf;
@@ -1740,10 +1761,12 @@ class AOpticsManager : public TGeoManager {
     fRayCounter += n;
     int rc;
     {  // the CUDA library is the only trace path: no CPU fallback, no pluggable tracer
-      std::string key = Key(*ex);
+      std::string key = (fresh || !fScene) ? Key(*ex) : fSceneKey;  // untouched geometry: same tables, nothing to compare
       if (!fScene || key != fSceneKey) {
         if (fScene) rbg_scene_destroy(fScene);
         fScene = nullptr;
+        if (fMulti) rbg_multi_destroy(fMulti);
+        fMulti = nullptr;
         if (rbg_scene_create(&ex->desc, fDevice, &fScene) != RBG_OK)
           throw std::runtime_error(std::string("AOpticsManager::TraceNonSequential: ") + rbg_last_error());
         fSceneKey = key;
@@ -1763,7 +1786,13 @@ class AOpticsManager : public TGeoManager {
         hist.ht = fHistBuf.data() + (size_t)3 * depth * n;
         hist.hnode = fHistNodeBuf.data();
       }
-      rc = rbg_trace_history(fScene, &opts, &r, depth > 0 ? &hist : nullptr, nullptr);
+      const Int_t ngpu = GetNumberOfGPUs();
+      if (ngpu > 1 && depth == 0 && n >= (size_t)ngpu * 262144) {  // fan out over the GPUs of the box
+        if (fMulti && rbg_multi_num_devices(fMulti) != ngpu) { rbg_multi_destroy(fMulti); fMulti = nullptr; }
+        if (!fMulti && rbg_multi_create(&ex->desc, ngpu, nullptr, &fMulti) != RBG_OK)
+          throw std::runtime_error(std::string("AOpticsManager::TraceNonSequential: ") + rbg_last_error());
+        rc = rbg_multi_trace(fMulti, &opts, &r);
+      } else rc = rbg_trace_history(fScene, &opts, &r, depth > 0 ? &hist : nullptr, nullptr);
       if (rc != RBG_OK) throw std::runtime_error(std::string("AOpticsManager::TraceNonSequential: ") + rbg_last_error());
       if (depth > 0 || T.HasHistory()) {  // rebuild the packed per-ray records: traced rays get their new polyline
         T.EnsureHistoryOffsets();
@@ -1819,9 +1848,30 @@ class AOpticsManager : public TGeoManager {
     if (fresh && T.HistCount(0) > 0) ray.SetHistory(&T.hpts[0], T.HistCount(0), &T.hnode[0], fNodeNames.get());
   }
   void TraceNonSequential(ARay* ray) { TraceNonSequential(*ray); }
+  // a TObjArray of ARay (src/AOpticsManager.cxx:335): the running rays go through the batch path in ONE call
   void TraceNonSequential(TObjArray* array) {
-    for (Int_t i = 0; i <= array->GetLast(); i++)
-      if (auto* r = dynamic_cast<ARay*>(array->At(i))) TraceNonSequential(*r);
+    std::vector<ARay*> rays;
+    ARayArray tmp;
+    for (Int_t i = 0; i <= array->GetLast(); i++) {
+      auto* r = dynamic_cast<ARay*>(array->At(i));
+      if (!r || !r->IsRunning()) continue;
+      Double_t p[4], d[3];
+      r->GetLastPoint(p);
+      r->GetDirection(d);
+      tmp.AddRaw(p[0], p[1], p[2], p[3], d[0], d[1], d[2], r->GetLambda());
+      rays.push_back(r);
+    }
+    if (rays.empty()) return;
+    TraceNonSequential(tmp);
+    const ARayArray::Table& T = tmp.GetTable();
+    for (size_t j = 0; j < rays.size(); j++) {
+      ARay& ray = *rays[j];
+      Double_t last[4] = {T.x[j], T.y[j], T.z[j], T.t[j]}, dir[3] = {T.dx[j], T.dy[j], T.dz[j]};
+      const char* nn = (fNodeNames && T.last_node[j] >= 0) ? (*fNodeNames)[T.last_node[j]].c_str() : nullptr;
+      const bool was_fresh = ray.GetNpoints() == 1;
+      ray.SetTraced(last, dir, T.status[j], ray.GetNpoints() + T.npoints[j] - 1, nn);
+      if (was_fresh && T.HistCount(j) > 0) ray.SetHistory(&T.hpts[4 * T.hoff[j]], T.HistCount(j), &T.hnode[T.hoff[j]], fNodeNames.get());
+    }
   }
 };
 

@@ -8,6 +8,7 @@
 #define ROBAST_ROOTCOMPAT_H
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <ctime>
@@ -122,6 +123,23 @@ template <class T> inline Long64_t LocMax(Long64_t n, const T* a) {
 }  // namespace TMath
 
 // ---------------------------------------------------------------------------- TObject & co
+// Geometry epoch: every mutator of a shape, matrix, volume, table or optical property bumps it, so that AOpticsManager can keep
+// its flattened scene (export + device tables) across TraceNonSequential calls for as long as nothing was touched.
+inline std::atomic<unsigned long long>& RbGeomEpoch() {
+  static std::atomic<unsigned long long> e{1};
+  return e;
+}
+// a constructor that fills its members through its own setters is not a change of the geometry: the object is new, it gets
+// into a scene only through AddNode / RegisterYourself / a Set... call on something else, and those bump the epoch
+struct RbGeomQuiet {
+  static int& Depth() { thread_local int d = 0; return d; }
+  RbGeomQuiet() { ++Depth(); }
+  ~RbGeomQuiet() { --Depth(); }
+};
+inline void RbGeomTouch() {
+  if (RbGeomQuiet::Depth() == 0) RbGeomEpoch().fetch_add(1, std::memory_order_relaxed);
+}
+
 class TObject {
  public:
   virtual ~TObject() {}
@@ -339,7 +357,7 @@ class TGeoMatrix : public TNamed {
   const Double_t* GetRotationMatrix() const { return fRot; }
   const Double_t* GetTranslation() const { return fTr; }
   // ROOT keeps every registered matrix in gGeoManager's list, where composite-shape expressions find them by name
-  virtual void RegisterYourself() {
+  virtual void RegisterYourself() { RbGeomTouch();
     if (!fName.empty()) RobastRegistry::Get().matrices[fName] = this;
   }
   virtual ~TGeoMatrix() {}
@@ -369,7 +387,7 @@ class TGeoMatrix : public TNamed {
     l[0] = r[0]; l[1] = r[1]; l[2] = r[2];
   }
   // this = this * right  (apply `right` first, then the old `this`)
-  void MultiplyRight(const TGeoMatrix& b) {
+  void MultiplyRight(const TGeoMatrix& b) { RbGeomTouch();
     Double_t r[9], t[3];
     for (int i = 0; i < 3; i++) {
       for (int j = 0; j < 3; j++) r[3 * i + j] = fRot[3 * i] * b.fRot[j] + fRot[3 * i + 1] * b.fRot[3 + j] + fRot[3 * i + 2] * b.fRot[6 + j];
@@ -382,25 +400,25 @@ class TGeoMatrix : public TNamed {
     memcpy(fRot, o.fRot, sizeof(fRot));
     memcpy(fTr, o.fTr, sizeof(fTr));
   }
-  void SetRotationArray(const Double_t* r) { memcpy(fRot, r, sizeof(fRot)); }
-  void SetTranslationArray(const Double_t* t) { memcpy(fTr, t, sizeof(fTr)); }
+  void SetRotationArray(const Double_t* r) { RbGeomTouch(); memcpy(fRot, r, sizeof(fRot)); }
+  void SetTranslationArray(const Double_t* t) { RbGeomTouch(); memcpy(fTr, t, sizeof(fTr)); }
 };
 
 class TGeoTranslation : public TGeoMatrix {
  public:
   TGeoTranslation() {}
-  TGeoTranslation(Double_t dx, Double_t dy, Double_t dz) { SetTranslation(dx, dy, dz); }
-  TGeoTranslation(const char* name, Double_t dx, Double_t dy, Double_t dz) : TGeoMatrix(name) { SetTranslation(dx, dy, dz); }
-  void SetTranslation(Double_t dx, Double_t dy, Double_t dz) { fTr[0] = dx; fTr[1] = dy; fTr[2] = dz; }
+  TGeoTranslation(Double_t dx, Double_t dy, Double_t dz) { RbGeomQuiet q; SetTranslation(dx, dy, dz); }
+  TGeoTranslation(const char* name, Double_t dx, Double_t dy, Double_t dz) : TGeoMatrix(name) { RbGeomQuiet q; SetTranslation(dx, dy, dz); }
+  void SetTranslation(Double_t dx, Double_t dy, Double_t dz) { RbGeomTouch(); fTr[0] = dx; fTr[1] = dy; fTr[2] = dz; }
 };
 
 class TGeoRotation : public TGeoMatrix {
  public:
   TGeoRotation() {}
   TGeoRotation(const char* name) : TGeoMatrix(name) {}
-  TGeoRotation(const char* name, Double_t phi, Double_t theta, Double_t psi) : TGeoMatrix(name) { SetAngles(phi, theta, psi); }
+  TGeoRotation(const char* name, Double_t phi, Double_t theta, Double_t psi) : TGeoMatrix(name) { RbGeomQuiet q; SetAngles(phi, theta, psi); }
   // Euler Z-X-Z in degrees: R = Rz(phi) Rx(theta) Rz(psi)   
-  void SetAngles(Double_t phi, Double_t theta, Double_t psi) {
+  void SetAngles(Double_t phi, Double_t theta, Double_t psi) { RbGeomTouch();
     const Double_t degrad = TMath::Pi() / 180.;
     Double_t sinphi = std::sin(degrad * phi), cosphi = std::cos(degrad * phi);
     Double_t sinthe = std::sin(degrad * theta), costhe = std::cos(degrad * theta);
@@ -415,9 +433,9 @@ class TGeoRotation : public TGeoMatrix {
     fRot[7] = cospsi * sinthe;
     fRot[8] = costhe;
   }
-  void RotateX(Double_t angle) { TGeoRotation r("", 0, angle, 0); MultiplyBy(&r, kFALSE); }
-  void RotateZ(Double_t angle) { TGeoRotation r("", angle, 0, 0); MultiplyBy(&r, kFALSE); }
-  void RotateY(Double_t angle) {
+  void RotateX(Double_t angle) { RbGeomTouch(); TGeoRotation r("", 0, angle, 0); MultiplyBy(&r, kFALSE); }
+  void RotateZ(Double_t angle) { RbGeomTouch(); TGeoRotation r("", angle, 0, 0); MultiplyBy(&r, kFALSE); }
+  void RotateY(Double_t angle) { RbGeomTouch();
     Double_t a = angle * TMath::DegToRad(), c = std::cos(a), s = std::sin(a);
     TGeoRotation r;
     Double_t m[9] = {c, 0, s, 0, 1, 0, -s, 0, c};
@@ -425,7 +443,7 @@ class TGeoRotation : public TGeoMatrix {
     MultiplyBy(&r, kFALSE);
   }
   // after=true: this = this*rot ; after=false: this = rot*this
-  void MultiplyBy(const TGeoRotation* rot, Bool_t after = kTRUE) {
+  void MultiplyBy(const TGeoRotation* rot, Bool_t after = kTRUE) { RbGeomTouch();
     const Double_t *a = after ? fRot : rot->fRot, *b = after ? rot->fRot : fRot;
     Double_t r[9];
     for (int i = 0; i < 3; i++)
@@ -452,7 +470,7 @@ class TGeoCombiTrans : public TGeoMatrix {
   }
   // TGeoCombiTrans::RegisterYourself also registers the rotation it was built from (tutorials/AshraOptics.C:865-866 relies on
   // it: "30_rot3" is only ever handed to a TGeoCombiTrans that AddNode registers, and is then named in a composite expression)
-  void RegisterYourself() override {
+  void RegisterYourself() override { RbGeomTouch();
     TGeoMatrix::RegisterYourself();
     if (fRotation) fRotation->RegisterYourself();
   }
@@ -472,7 +490,7 @@ class TGeoHMatrix : public TGeoMatrix {
     return h;
   }
   TGeoHMatrix& operator*=(const TGeoMatrix& right) { MultiplyRight(right); return *this; }
-  void Multiply(const TGeoMatrix* right) { MultiplyRight(*right); }
+  void Multiply(const TGeoMatrix* right) { RbGeomTouch(); MultiplyRight(*right); }
 };
 inline TGeoHMatrix operator*(const TGeoMatrix& a, const TGeoMatrix& b) {
   TGeoHMatrix h(a);
@@ -507,7 +525,7 @@ class TGeoBBox : public TGeoShape {
   TGeoBBox(const char* name, Double_t dx, Double_t dy, Double_t dz, Double_t* origin = nullptr) : TGeoShape(name) {
     SetBoxDimensions(dx, dy, dz, origin);
   }
-  void SetBoxDimensions(Double_t dx, Double_t dy, Double_t dz, Double_t* origin = nullptr) {
+  void SetBoxDimensions(Double_t dx, Double_t dy, Double_t dz, Double_t* origin = nullptr) { RbGeomTouch();
     fDX = dx; fDY = dy; fDZ = dz;
     if (origin) memcpy(fOrigin, origin, sizeof(fOrigin));
   }
@@ -526,7 +544,7 @@ class TGeoTube : public TGeoBBox {
   TGeoTube() {}
   TGeoTube(Double_t rmin, Double_t rmax, Double_t dz) { Set(rmin, rmax, dz); }
   TGeoTube(const char* name, Double_t rmin, Double_t rmax, Double_t dz) { SetName(name); Set(rmin, rmax, dz); }
-  void Set(Double_t rmin, Double_t rmax, Double_t dz) {
+  void Set(Double_t rmin, Double_t rmax, Double_t dz) { RbGeomTouch();
     fRmin = rmin; fRmax = rmax; fDz = dz;
     fDX = fDY = rmax; fDZ = dz;
   }
@@ -547,7 +565,7 @@ class TGeoSphere : public TGeoBBox {
     SetName(name);
     Set(rmin, rmax, theta1, theta2, phi1, phi2);
   }
-  void Set(Double_t rmin, Double_t rmax, Double_t t1, Double_t t2, Double_t p1, Double_t p2) {
+  void Set(Double_t rmin, Double_t rmax, Double_t t1, Double_t t2, Double_t p1, Double_t p2) { RbGeomTouch();
     fRmin = rmin; fRmax = rmax; fTheta1 = t1; fTheta2 = t2; fPhi1 = p1; fPhi2 = p2;
     if (fPhi1 < 0) fPhi1 += 360.;
     while (fPhi2 <= fPhi1) fPhi2 += 360.;
@@ -587,7 +605,7 @@ class TGeoPcon : public TGeoBBox {
  public:
   TGeoPcon(Double_t phi, Double_t dphi, Int_t nz) : fPhi1(phi), fDphi(dphi), fNz(nz), fZ(nz), fRmin(nz), fRmax(nz) {}
   TGeoPcon(const char* name, Double_t phi, Double_t dphi, Int_t nz) : fPhi1(phi), fDphi(dphi), fNz(nz), fZ(nz), fRmin(nz), fRmax(nz) { SetName(name); }
-  virtual void DefineSection(Int_t snum, Double_t z, Double_t rmin, Double_t rmax) {
+  virtual void DefineSection(Int_t snum, Double_t z, Double_t rmin, Double_t rmax) { RbGeomTouch();
     if (snum < 0 || snum >= fNz) return;
     fZ[snum] = z; fRmin[snum] = rmin; fRmax[snum] = rmax;
     if (snum == fNz - 1) {
@@ -642,12 +660,12 @@ class TGeoArb8 : public TGeoBBox {
       for (int i = 0; i < 8; i++) { fXY[i][0] = vertices[2 * i]; fXY[i][1] = vertices[2 * i + 1]; }
     Box();
   }
-  void SetVertex(Int_t vnum, Double_t x, Double_t y) {
+  void SetVertex(Int_t vnum, Double_t x, Double_t y) { RbGeomTouch();
     if (vnum < 0 || vnum > 7) return;
     fXY[vnum][0] = x; fXY[vnum][1] = y;
     Box();
   }
-  void SetDz(Double_t dz) { fDz = dz; Box(); }
+  void SetDz(Double_t dz) { RbGeomTouch(); fDz = dz; Box(); }
   EKind Kind() const override { return kArb8; }
   Double_t GetDz() const { return fDz; }
   Double_t* GetVertices() { return &fXY[0][0]; }
@@ -672,14 +690,14 @@ class TGeoXtru : public TGeoBBox {
 
  public:
   TGeoXtru(Int_t nz) : fNz(nz), fZ(nz, 0.), fX0(nz, 0.), fY0(nz, 0.), fScale(nz, 1.) {}
-  Bool_t DefinePolygon(Int_t nvert, const Double_t* xv, const Double_t* yv) {
+  Bool_t DefinePolygon(Int_t nvert, const Double_t* xv, const Double_t* yv) { RbGeomTouch();
     if (nvert < 3) return kFALSE;
     fX.assign(xv, xv + nvert);
     fY.assign(yv, yv + nvert);
     Box();
     return kTRUE;
   }
-  virtual void DefineSection(Int_t snum, Double_t z, Double_t x0 = 0., Double_t y0 = 0., Double_t scale = 1.) {
+  virtual void DefineSection(Int_t snum, Double_t z, Double_t x0 = 0., Double_t y0 = 0., Double_t scale = 1.) { RbGeomTouch();
     if (snum < 0 || snum >= fNz) return;
     fZ[snum] = z; fX0[snum] = x0; fY0[snum] = y0; fScale[snum] = scale;
     Box();
@@ -820,11 +838,11 @@ class TGeoVolume : public TNamed {
   TGeoVolume() {}
   TGeoVolume(const char* name, const TGeoShape* shape, const TGeoMedium* = nullptr) : TNamed(name), fShape(const_cast<TGeoShape*>(shape)) {}
   TGeoShape* GetShape() const { return fShape; }
-  virtual void AddNode(TGeoVolume* vol, Int_t copy_no, TGeoMatrix* mat = nullptr, Option_t* = "") {
+  virtual void AddNode(TGeoVolume* vol, Int_t copy_no, TGeoMatrix* mat = nullptr, Option_t* = "") { RbGeomTouch();
     if (mat) mat->RegisterYourself();  // TGeoVolume::AddNode registers the placement matrix
     fNodes.push_back(new TGeoNode(vol, copy_no, mat, kFALSE));
   }
-  virtual void AddNodeOverlap(TGeoVolume* vol, Int_t copy_no, TGeoMatrix* mat = nullptr, Option_t* = "") {
+  virtual void AddNodeOverlap(TGeoVolume* vol, Int_t copy_no, TGeoMatrix* mat = nullptr, Option_t* = "") { RbGeomTouch();
     if (mat) mat->RegisterYourself();
     fNodes.push_back(new TGeoNode(vol, copy_no, mat, kTRUE));
   }
@@ -850,9 +868,9 @@ class TGeoManager : public TNamed {
   TGeoManager();
   TGeoManager(const char* name, const char* title);
   virtual ~TGeoManager();
-  void SetTopVolume(TGeoVolume* v) { fTopVolume = v; }
+  void SetTopVolume(TGeoVolume* v) { RbGeomTouch(); fTopVolume = v; }
   TGeoVolume* GetTopVolume() const { return fTopVolume; }
-  virtual void CloseGeometry(Option_t* = "d") { fClosed = kTRUE; }
+  virtual void CloseGeometry(Option_t* = "d") { RbGeomTouch(); fClosed = kTRUE; }
   Bool_t IsClosed() const { return fClosed; }
   void SetNsegments(Int_t) {}
   void SetMaxThreads(Int_t n) { fMaxThreads = n; fMultiThread = n >= 1; }
@@ -916,11 +934,11 @@ class TGraph : public TNamed {
   TGraph() {}
   TGraph(Int_t n) : fX(n), fY(n) {}
   TGraph(Int_t n, const Double_t* x, const Double_t* y) : fX(x, x + n), fY(y, y + n) {}
-  void SetPoint(Int_t i, Double_t x, Double_t y) {
+  void SetPoint(Int_t i, Double_t x, Double_t y) { RbGeomTouch();
     if (i >= (Int_t)fX.size()) { fX.resize(i + 1); fY.resize(i + 1); }
     fX[i] = x; fY[i] = y;
   }
-  void AddPoint(Double_t x, Double_t y) { SetPoint(GetN(), x, y); }
+  void AddPoint(Double_t x, Double_t y) { RbGeomTouch(); SetPoint(GetN(), x, y); }
   // drawing is out of scope; with ROBAST_DRAW_SUMMARY set, Draw() prints the points the plot would have shown
   void Draw(Option_t* = "") override {
     if (!getenv("ROBAST_DRAW_SUMMARY")) return;
@@ -1036,12 +1054,12 @@ class TGraph2D : public TNamed {
  public:
   TGraph2D() {}
   TGraph2D(Int_t n, const Double_t* x, const Double_t* y, const Double_t* z) : fX(x, x + n), fY(y, y + n), fZ(z, z + n) {}
-  void SetPoint(Int_t i, Double_t x, Double_t y, Double_t z) {
+  void SetPoint(Int_t i, Double_t x, Double_t y, Double_t z) { RbGeomTouch();
     if (i >= (Int_t)fX.size()) { fX.resize(i + 1); fY.resize(i + 1); fZ.resize(i + 1); }
     fX[i] = x; fY[i] = y; fZ[i] = z;
     fTriValid = kFALSE;
   }
-  void AddPoint(Double_t x, Double_t y, Double_t z) { SetPoint(GetN(), x, y, z); }
+  void AddPoint(Double_t x, Double_t y, Double_t z) { RbGeomTouch(); SetPoint(GetN(), x, y, z); }
   Int_t GetN() const { return (Int_t)fX.size(); }
   const Double_t* GetX() const { return fX.data(); }
   const Double_t* GetY() const { return fY.data(); }
@@ -1114,7 +1132,7 @@ class TH1D : public TH1 {
   TH1D(const char* name, const char* title, Int_t n, Double_t lo, Double_t hi) : TH1(name, title), fC(n + 2, 0.) {
     fXaxis.fN = n; fXaxis.fMin = lo; fXaxis.fMax = hi;
   }
-  Int_t Fill(Double_t x, Double_t w = 1) {
+  Int_t Fill(Double_t x, Double_t w = 1) { RbGeomTouch();
     Int_t b = fXaxis.FindFixBin(x);
     fC[b] += w;
     fEntries += 1;
@@ -1124,7 +1142,7 @@ class TH1D : public TH1 {
   Int_t GetNbinsX() const { return fXaxis.fN; }
   TAxis* GetXaxis() { return &fXaxis; }
   Double_t GetBinContent(Int_t b) const { return fC[b]; }
-  void SetBinContent(Int_t b, Double_t v) { fC[b] = v; }
+  void SetBinContent(Int_t b, Double_t v) { RbGeomTouch(); fC[b] = v; }
   Double_t GetBinCenter(Int_t b) const { return fXaxis.GetBinCenter(b); }
   Double_t GetMean(Int_t = 1) const { return fSw ? fSwx / fSw : 0; }
   Double_t GetStdDev(Int_t = 1) const {
@@ -1158,7 +1176,7 @@ class TH2 : public TH1 {
     fYaxis.fN = ny; fYaxis.fMin = ylo; fYaxis.fMax = yhi;
   }
   Int_t GetBin(Int_t bx, Int_t by) const { return bx + (fXaxis.fN + 2) * by; }
-  Int_t Fill(Double_t x, Double_t y, Double_t w = 1) {
+  Int_t Fill(Double_t x, Double_t y, Double_t w = 1) { RbGeomTouch();
     Int_t bx = fXaxis.FindFixBin(x), by = fYaxis.FindFixBin(y);
     fC[GetBin(bx, by)] += w;
     fEntries += 1;
@@ -1174,7 +1192,7 @@ class TH2 : public TH1 {
   const TAxis* GetXaxis() const { return &fXaxis; }
   const TAxis* GetYaxis() const { return &fYaxis; }
   Double_t GetBinContent(Int_t bx, Int_t by) const { return fC[GetBin(bx, by)]; }
-  void SetBinContent(Int_t bx, Int_t by, Double_t v) { fC[GetBin(bx, by)] = v; }
+  void SetBinContent(Int_t bx, Int_t by, Double_t v) { RbGeomTouch(); fC[GetBin(bx, by)] = v; }
   Double_t GetMean(Int_t axis = 1) const { return !fSw ? 0 : (axis == 1 ? fSwx / fSw : fSwy / fSw); }
   Double_t GetStdDev(Int_t axis = 1) const {
     if (!fSw) return 0;

@@ -224,7 +224,12 @@ const char* rbg_scene_node_name(const rbg_scene* scene, int node);
 /* TraceNonSequential over a ray batch (src/AOpticsManager.cxx:335-520,523-587).
  * `stream` is a cudaStream_t (NULL = default stream). With host pointers the call performs the
  * H2D/D2H copies itself, chunked and overlapped, and returns after completion.  With device
- * pointers the work is enqueued on `stream` and the call returns without synchronising. */
+ * pointers the whole trace — every bounce, the compactions between them, the scratch it needs
+ * (stream-ordered allocation) — is enqueued on `stream` and the call returns without waiting for the
+ * device: the survivor counts that size each bounce stay in device memory.  Several calls on the same
+ * scene may be in flight on different streams.  (One exception: the very first large batch a scene sees,
+ * when the scene has 32 or more daughters under its top volume, waits once for the probe that tells a
+ * coherent beam from a scattered one.) */
 int rbg_trace(rbg_scene* scene, const rbg_trace_opts* opts, const rbg_rays* rays, void* stream);
 
 /* Optional polyline record of every ray (ARay's TGeoTrack points and node history, reference
@@ -268,6 +273,30 @@ typedef struct {
 } rbg_shoot_desc;
 int rbg_shoot(const rbg_shoot_desc* d, int64_t first, int64_t n, double* x, double* y, double* z,
               double* t, double* dx, double* dy, double* dz, double* lambda, int device, void* stream);
+
+/* ---------------------------------------------------------------- several GPUs of one box, one process
+ * The reference fans a batch out over threads inside TraceNonSequential (src/AOpticsManager.cxx:529-568: contiguous chunks,
+ * one TGeoNavigator per thread, ordered Merge).  Here the chunks go to GPUs: the geometry is replicated on every device,
+ * device k traces rays [k n/G, (k+1) n/G) (the last one takes the remainder, :533-541), Philox ray ids are global, so the
+ * result is bit-identical to the single-GPU one whatever G is. */
+typedef struct rbg_multi rbg_multi;
+/* devices == NULL: devices 0 .. ndev-1 */
+int rbg_multi_create(const rbg_scene_desc* desc, int ndev, const int* devices, rbg_multi** out);
+int rbg_multi_destroy(rbg_multi* m);
+int rbg_multi_num_devices(const rbg_multi* m);
+/* TraceNonSequential over a HOST batch, sharded over the devices (one host thread per device, each running the chunked
+ * H2D -> trace -> D2H pipeline of rbg_trace on its range) */
+int rbg_multi_trace(rbg_multi* m, const rbg_trace_opts* opts, const rbg_rays* host_rays);
+/* The 1e9-ray pattern of BASELINE configs[4]: generate (rbg_shoot), trace and reduce on the devices — n_total rays of `shoot`
+ * split over the devices, at most `batch` rays resident per device at a time, nothing but the reducers ever leaves a GPU.
+ * hist (nx*ny uint64, bin (i,j) at i + nx*j) is the PSF histogram of the rays with status `sel`; it lives on the first device
+ * and every device's histogram kernel adds its block-private bins straight into it through peer memory (NVLink atomics: the
+ * cross-GPU reduction is part of the histogram kernel, there is no separate collective; without peer access the partial
+ * histograms are copied over and added).  moments: the 8 doubles of rbg_moments; counts: 6 status counters.  All three are
+ * HOST pointers, written when the call returns. */
+int rbg_multi_shoot_trace_reduce(rbg_multi* m, const rbg_trace_opts* opts, const rbg_shoot_desc* shoot, int64_t n_total,
+                                 int64_t batch, int32_t sel, int32_t nx, double xmin, double xmax, int32_t ny, double ymin,
+                                 double ymax, unsigned long long* hist, double* moments, long long* counts);
 
 /* CORSIKA IACT photon bunches -> rays on the device: ACorsikaIACTFile::GetRayArray (src/ACorsikaIACTFile.cxx:71-133) for the
  * bunches of one telescope.  Bunch arrays are HOST pointers in CORSIKA units (x,y cm at the observation level relative to the

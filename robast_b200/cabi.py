@@ -71,10 +71,17 @@ rbg_moments = _proto("rbg_moments", C.c_int, [C.c_int64, _dp, _dp, _dp, _dp, C.c
 rbg_tmm = _proto("rbg_tmm", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, C.c_void_p])
 rbg_tmm_general_host = _proto("rbg_tmm_general_host", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _dp])
 rbg_tmm_host = _proto("rbg_tmm_host", C.c_int, [C.c_void_p, C.c_int, C.c_int64, _dp, _dp, _dp, _dp])
+rbg_multi_create = _proto("rbg_multi_create", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)])
+rbg_multi_destroy = _proto("rbg_multi_destroy", C.c_int, [C.c_void_p])
+rbg_multi_num_devices = _proto("rbg_multi_num_devices", C.c_int, [C.c_void_p])
+rbg_multi_trace = _proto("rbg_multi_trace", C.c_int, [C.c_void_p, C.POINTER(rbg_trace_opts), C.POINTER(rbg_rays)])
+rbg_multi_shoot_trace_reduce = _proto("rbg_multi_shoot_trace_reduce", C.c_int, [C.c_void_p, C.POINTER(rbg_trace_opts), C.POINTER(rbg_shoot_desc), C.c_int64, C.c_int64, C.c_int32,
+                                                                              C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, _dp, _dp, _dp])
 
 ABI_SYMBOLS = ["rbg_abi_version", "rbg_last_error", "rbg_device_count", "rbg_scene_create", "rbg_scene_destroy",
                "rbg_scene_num_nodes", "rbg_scene_node_name", "rbg_scene_kernel_variant", "rbg_trace", "rbg_trace_history", "rbg_launch_count", "rbg_profile_enable",
-               "rbg_profile_read", "rbg_shoot", "rbg_bunch_rays", "rbg_shoot_bunches", "rbg_hist2d", "rbg_hist2d_stats", "rbg_containment_radius", "rbg_containment_radius_host", "rbg_moments", "rbg_tmm", "rbg_tmm_host", "rbg_tmm_general_host"]
+               "rbg_profile_read", "rbg_shoot", "rbg_bunch_rays", "rbg_shoot_bunches", "rbg_hist2d", "rbg_hist2d_stats", "rbg_containment_radius", "rbg_containment_radius_host", "rbg_moments", "rbg_tmm", "rbg_tmm_host", "rbg_tmm_general_host",
+               "rbg_multi_create", "rbg_multi_destroy", "rbg_multi_num_devices", "rbg_multi_trace", "rbg_multi_shoot_trace_reduce"]
 
 
 class RbgError(RuntimeError):

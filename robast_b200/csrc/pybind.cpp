@@ -34,6 +34,8 @@ PYBIND11_MODULE(_robast, m) {
       .def("__getitem__", [](const TVector3& v, int i) { return v[i]; });
 
   py::class_<TObjArray, TObject, Raw<TObjArray>>(m, "TObjArray")
+      .def(py::init<>())
+      .def("Add", [](TObjArray& a, TObject* o) { a.Add(o); }, py::keep_alive<1, 2>())
       .def("GetLast", &TObjArray::GetLast).def("GetEntries", &TObjArray::GetEntries).def("GetEntriesFast", &TObjArray::GetEntriesFast)
       .def("At", &TObjArray::At, py::return_value_policy::reference)
       .def("__getitem__", &TObjArray::At, py::return_value_policy::reference)
@@ -58,7 +60,8 @@ PYBIND11_MODULE(_robast, m) {
       .def("LocalToMasterVect", [](const TGeoMatrix& t, std::array<double, 3> l) { std::array<double, 3> o; t.LocalToMasterVect(l.data(), o.data()); return o; });
   py::class_<TGeoTranslation, TGeoMatrix, Raw<TGeoTranslation>>(m, "TGeoTranslation")
       .def(py::init<double, double, double>())
-      .def(py::init<const char*, double, double, double>());
+      .def(py::init<const char*, double, double, double>())
+      .def("SetTranslation", &TGeoTranslation::SetTranslation);
   py::class_<TGeoRotation, TGeoMatrix, Raw<TGeoRotation>>(m, "TGeoRotation")
       .def(py::init<>())
       .def(py::init<const char*>())
@@ -131,6 +134,8 @@ PYBIND11_MODULE(_robast, m) {
       .def(py::init<const char*, double, double, int, double, double, double>())
       .def("SetControlPoints", (void(AGeoBezierPcon::*)(double, double)) & AGeoBezierPcon::SetControlPoints)
       .def("SetControlPoints", (void(AGeoBezierPcon::*)(double, double, double, double)) & AGeoBezierPcon::SetControlPoints);
+  m.def("RbGeomEpoch", []() { return (unsigned long long)RbGeomEpoch().load(); },
+        "geometry epoch: bumped by every mutator of a shape / matrix / volume / table / optical property (scene cache of AOpticsManager)");
   m.def("ContainmentRadius", [](TH2* h, double fraction) {
     double r, x, y;
     AGeoUtil::ContainmentRadius(h, fraction, r, x, y);
@@ -375,6 +380,8 @@ PYBIND11_MODULE(_robast, m) {
       .def("SetSeed", &AOpticsManager::SetSeed).def("SetQuirks", &AOpticsManager::SetQuirks).def("SetDevice", &AOpticsManager::SetDevice)
       .def("SetHistoryDepth", &AOpticsManager::SetHistoryDepth).def("GetHistoryDepth", &AOpticsManager::GetHistoryDepth)
       .def("ExportScene", &AOpticsManager::ExportScene)
+      .def("InvalidateScene", &AOpticsManager::InvalidateScene).def("GetNumberOfGPUs", &AOpticsManager::GetNumberOfGPUs)
+      .def("TraceNonSequential", [](AOpticsManager& mg, TObjArray* a) { mg.TraceNonSequential(a); })
       .def("TraceNonSequential", [](AOpticsManager& mg, ARayArray& a) { py::gil_scoped_release rel; mg.TraceNonSequential(a); })
       .def("TraceNonSequential", [](AOpticsManager& mg, ARay& r) { mg.TraceNonSequential(r); });
 }

@@ -798,6 +798,38 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   CK(cudaFreeAsync(base, st));
 }
 
+// ================================================================================================ several GPUs, one process
+struct rbg_multi {
+  std::vector<rbg_scene*> scenes;  // one replica per device
+  std::vector<int> devices;
+  bool peer = false;               // device 0 can be written by every other device
+};
+__global__ void k_add_u64(unsigned long long* dst, const unsigned long long* src, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+// contiguous ranges, the last device takes the remainder (src/AOpticsManager.cxx:533-541)
+static void multi_range(long long n, int k, int G, long long& b, long long& e) {
+  long long chunk = n / G;
+  b = chunk * k;
+  e = k == G - 1 ? n : chunk * (k + 1);
+}
+template <class F> static void multi_run(rbg_multi* m, F f) {
+  const int G = (int)m->scenes.size();
+  std::vector<std::string> errs(G);
+  std::vector<int> rcs(G, RBG_OK);
+  std::vector<std::thread> th;
+  for (int k = 0; k < G; k++)
+    th.emplace_back([&, k] {
+      rcs[k] = guard([&] { f(k); });
+      if (rcs[k] != RBG_OK) errs[k] = g_err;  // g_err is thread-local: carry it over
+    });
+  for (auto& t : th) t.join();
+  for (int k = 0; k < G; k++)
+    if (rcs[k] != RBG_OK) throw std::runtime_error(errs[k].rfind("cuda", 0) == 0 ? errs[k] : "device " + std::to_string(m->devices[k]) + ": " + errs[k]);
+}
+
+
 // ================================================================================================ C ABI
 #pragma GCC visibility push(default)
 extern "C" {
@@ -1140,6 +1172,167 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         for (int j = 0; j < nst; j++) cudaStreamSynchronize(s->streams[j]);
         std::rethrow_exception(errs[k]);
       }
+    }
+  });
+}
+
+// ---- several GPUs, one process
+int rbg_multi_create(const rbg_scene_desc* D, int ndev, const int* devices, rbg_multi** out) {
+  rbg_multi* m = nullptr;
+  int rc = guard([&] {
+    if (!out) throw Invalid("null output handle");
+    *out = nullptr;
+    int have = rbg_device_count();
+    if (have <= 0) throw std::runtime_error("cuda: no CUDA device available — the tracer has no CPU fallback");
+    if (ndev < 1 || ndev > have) throw Invalid("bad device count");
+    m = new rbg_multi;
+    for (int k = 0; k < ndev; k++) {
+      int d = devices ? devices[k] : k;
+      if (d < 0 || d >= have) throw Invalid("bad device index");
+      for (int j : m->devices)
+        if (j == d) throw Invalid("device listed twice");
+      m->devices.push_back(d);
+      rbg_scene* s = nullptr;
+      if (rbg_scene_create(D, d, &s) != RBG_OK) throw std::runtime_error(g_err);
+      m->scenes.push_back(s);
+    }
+    // peer access towards the first device (the reducers' home): remote atomics over NVLink
+    m->peer = ndev > 1;
+    for (int k = 1; k < ndev && m->peer; k++) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, m->devices[k], m->devices[0]));
+      if (!can) { m->peer = false; break; }
+      CK(cudaSetDevice(m->devices[k]));
+      cudaError_t e = cudaDeviceEnablePeerAccess(m->devices[0], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) m->peer = false;
+      cudaGetLastError();
+    }
+    if (getenv("RB_NO_PEER")) m->peer = false;
+    *out = m;
+    m = nullptr;
+  });
+  if (m) {
+    for (rbg_scene* s : m->scenes) scene_free(s);
+    delete m;
+  }
+  return rc;
+}
+int rbg_multi_destroy(rbg_multi* m) {
+  return guard([&] {
+    if (!m) return;
+    for (rbg_scene* s : m->scenes) scene_free(s);
+    delete m;
+  });
+}
+int rbg_multi_num_devices(const rbg_multi* m) { return m ? (int)m->scenes.size() : 0; }
+
+int rbg_multi_trace(rbg_multi* m, const rbg_trace_opts* o, const rbg_rays* rays) {
+  return guard([&] {
+    if (!m || !o || !rays) throw Invalid("null argument");
+    if (rays->on_device) throw Invalid("rbg_multi_trace takes host arrays (a device batch lives on one GPU: use rbg_trace)");
+    if (rays->n <= 0) return;
+    const int G = (int)m->scenes.size();
+    multi_run(m, [&](int k) {
+      long long b, e;
+      multi_range(rays->n, k, G, b, e);
+      if (e <= b) return;
+      rbg_rays r = *rays;
+      r.n = e - b;
+      r.x += b; r.y += b; r.z += b; r.t += b; r.dx += b; r.dy += b; r.dz += b; r.lambda += b;
+      r.ox += b; r.oy += b; r.oz += b; r.ot += b; r.odx += b; r.ody += b; r.odz += b;
+      r.status += b; r.last_node += b; r.npoints += b;
+      rbg_trace_opts ok = *o;
+      ok.ray_id_offset = o->ray_id_offset + (unsigned long long)b;
+      if (rbg_trace(m->scenes[k], &ok, &r, nullptr) != RBG_OK) throw std::runtime_error(g_err);
+    });
+  });
+}
+
+int rbg_multi_shoot_trace_reduce(rbg_multi* m, const rbg_trace_opts* o, const rbg_shoot_desc* shoot, int64_t n_total, int64_t batch, int32_t sel, int32_t nx,
+                                 double xmin, double xmax, int32_t ny, double ymin, double ymax, unsigned long long* hist, double* moments, long long* counts) {
+  return guard([&] {
+    if (!m || !o || !shoot || !hist || !moments || !counts) throw Invalid("null argument");
+    if (nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin)) throw Invalid("bad histogram axes");
+    if (n_total < 0 || batch < 1) throw Invalid("bad ray counts");
+    const int G = (int)m->scenes.size();
+    const size_t nb = (size_t)nx * ny;
+    // the histogram's home: device 0
+    unsigned long long* d_hist0 = nullptr;
+    CK(cudaSetDevice(m->devices[0]));
+    CK(cudaMalloc((void**)&d_hist0, nb * 8 * (m->peer ? 1 : G)));
+    CK(cudaMemset(d_hist0, 0, nb * 8 * (m->peer ? 1 : G)));
+    std::vector<double> mom((size_t)G * 8, 0.);
+    std::vector<long long> cnt((size_t)G * 6, 0);
+    try {
+      multi_run(m, [&](int k) {
+        long long b, e;
+        multi_range(n_total, k, G, b, e);
+        const int dev = m->devices[k];
+        CK(cudaSetDevice(dev));
+        rbg_scene* s = m->scenes[k];
+        if (!s->streams[0]) CK(cudaStreamCreateWithFlags(&s->streams[0], cudaStreamNonBlocking));
+        cudaStream_t st = s->streams[0];
+        const long long cap = std::min<long long>(batch, std::max<long long>(e - b, 1));
+        char* buf = nullptr;
+        // rays (8 in + 7 out doubles, 3 ints) + local reducers
+        const size_t bytes = (size_t)cap * (15 * 8 + 3 * 4) + 1024 + nb * 8 + 256;
+        CK(cudaMalloc((void**)&buf, bytes));
+        try {
+          double* in = (double*)buf;
+          double* out = in + 8 * cap;
+          int32_t* io = (int32_t*)(out + 7 * cap);
+          char* tail = (char*)(((uintptr_t)(io + 3 * cap) + 255) & ~uintptr_t(255));
+          double* d_mom = (double*)tail;
+          unsigned long long* d_cnt = (unsigned long long*)(tail + 64);
+          unsigned long long* d_hist = (unsigned long long*)(tail + 256);  // used without peer access only
+          CK(cudaMemsetAsync(tail, 0, 256 + (m->peer ? 0 : nb * 8), st));
+          unsigned long long* target = (m->peer || k == 0) ? d_hist0 : d_hist;
+          const int use_smem = (long long)nx * ny <= HIST_SMEM_BINS;
+          for (long long first = b; first < e; first += cap) {
+            const long long n = std::min<long long>(cap, e - first);
+            k_shoot<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(*shoot, first, n, in, in + cap, in + 2 * cap, in + 3 * cap, in + 4 * cap, in + 5 * cap,
+                                                                 in + 6 * cap, in + 7 * cap);
+            DRays R;
+            R.x = in; R.y = in + cap; R.z = in + 2 * cap; R.t = in + 3 * cap; R.dx = in + 4 * cap; R.dy = in + 5 * cap; R.dz = in + 6 * cap; R.lambda = in + 7 * cap;
+            R.ox = out; R.oy = out + cap; R.oz = out + 2 * cap; R.ot = out + 3 * cap; R.odx = out + 4 * cap; R.ody = out + 5 * cap; R.odz = out + 6 * cap;
+            R.status = io; R.last_node = io + cap; R.npoints = io + 2 * cap;
+            R.cur = nullptr; R.ndraw = nullptr;
+            memset(&R.hist, 0, sizeof(R.hist));
+            trace_device(s, o, R, n, o->ray_id_offset + (unsigned long long)first, st);
+            const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+            // with peer access `target` is device 0's histogram: the flush of the block-private bins is the cross-GPU reduction
+            k_hist2d<<<blocks, 256, 0, st>>>(n, out, out + cap, io, sel, nx, xmin, xmax, ny, ymin, ymax, target, use_smem, nullptr, 0., 0.);
+            k_moments<<<blocks, 256, 0, st>>>(n, out, out + cap, out + 3 * cap, io, sel, d_mom, d_cnt);
+            g_launches += 3;
+            CK(cudaGetLastError());
+          }
+          CK(cudaMemcpyAsync(&mom[(size_t)k * 8], d_mom, 7 * 8, cudaMemcpyDeviceToHost, st));
+          CK(cudaMemcpyAsync(&cnt[(size_t)k * 6], d_cnt, 6 * 8, cudaMemcpyDeviceToHost, st));
+          if (!m->peer && k > 0) CK(cudaMemcpyPeerAsync(d_hist0 + (size_t)k * nb, m->devices[0], d_hist, dev, nb * 8, st));
+          CK(cudaStreamSynchronize(st));
+        } catch (...) {
+          cudaFree(buf);
+          throw;
+        }
+        CK(cudaFree(buf));
+      });
+      CK(cudaSetDevice(m->devices[0]));
+      if (!m->peer)
+        for (int k = 1; k < G; k++) {
+          k_add_u64<<<(unsigned)std::min<size_t>((nb + 255) / 256, 1024), 256>>>(d_hist0, d_hist0 + (size_t)k * nb, (long long)nb);
+          g_launches++;
+        }
+      CK(cudaMemcpy(hist, d_hist0, nb * 8, cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cudaFree(d_hist0);
+      throw;
+    }
+    CK(cudaFree(d_hist0));
+    for (int a = 0; a < 8; a++) moments[a] = 0;
+    for (int a = 0; a < 6; a++) counts[a] = 0;
+    for (int k = 0; k < G; k++) {
+      for (int a = 0; a < 7; a++) moments[a] += mom[(size_t)k * 8 + a];
+      for (int a = 0; a < 6; a++) counts[a] += cnt[(size_t)k * 6 + a];
     }
   });
 }
