@@ -449,12 +449,18 @@ def main():
     for k, th in enumerate(my_angles):
         d = H.shoot_desc(configs.beam(2, th, n_side=nside))
         R.check(R.rbg_shoot(C.byref(d), 0, n, *[inp[k, i].data_ptr() for i in range(8)], local, stream))
-    hist = torch.zeros((nang, 200 * 200), dtype=torch.int64, device=dev)
-    hstats = torch.zeros((nang, 5), dtype=torch.float64, device=dev)
-    d80 = torch.zeros((nang, 3), dtype=torch.float64, device=dev)
+    # the reducers are double-buffered: the D80 search of a step (a sequential search, a few SMs) runs on a side stream while
+    # the next step's rays are traced
+    hist2 = [torch.zeros((nang, 200 * 200), dtype=torch.int64, device=dev) for _ in range(2)]
+    hstats2 = [torch.zeros((nang, 5), dtype=torch.float64, device=dev) for _ in range(2)]
+    d80_2 = [torch.zeros((nang, 3), dtype=torch.float64, device=dev) for _ in range(2)]
     d80_all = torch.zeros((world * nang, 3), dtype=torch.float64, device=dev)
     mom = torch.zeros((nang, 8), dtype=torch.float64, device=dev)
     cnt = torch.zeros((nang, 6), dtype=torch.int64, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    side_done = [None, None]
+    main_stream = torch.cuda.current_stream()
+    state = {"k": 0}
     opts = H.opts(disable_fresnel=1, steps_per_launch=args.steps_per_launch, seed=20180601)
 
     def rays_struct(k):
@@ -471,6 +477,11 @@ def main():
     structs = [rays_struct(k) for k in range(nang)]
 
     def step():
+        b = state["k"] & 1
+        state["k"] += 1
+        hist, hstats, d80 = hist2[b], hstats2[b], d80_2[b]
+        if side_done[b] is not None:
+            main_stream.wait_event(side_done[b])  # the search that read this buffer pair two steps ago
         hist.zero_()
         hstats.zero_()
         mom.zero_()
@@ -484,13 +495,20 @@ def main():
             R.check(R.rbg_hist2d_stats(n, out[0].data_ptr(), out[1].data_ptr(), iout[0].data_ptr(), R.RBG_FOCUSED, cx, 0., 200, -4., 10., 200, -7., 7.,
                                        hist[k].data_ptr(), hstats[k].data_ptr(), local, stream))
             R.check(R.rbg_moments(n, out[0].data_ptr(), out[1].data_ptr(), out[3].data_ptr(), iout[0].data_ptr(), R.RBG_FOCUSED, mom[k].data_ptr(), cnt[k].data_ptr(), local, stream))
-        # D80 of each of this rank's field angles (AGeoUtil::ContainmentRadius), then the cross-rank reductions
-        R.check(R.rbg_containment_radius(nang, hist.data_ptr(), 200, -4., 10., 200, -7., 7., hstats.data_ptr(), 0.8, d80.data_ptr(), local, stream))
+        # D80 of each of this rank's field angles (AGeoUtil::ContainmentRadius) on the side stream, then the cross-rank reductions
+        ev = torch.cuda.Event()
+        ev.record(main_stream)
+        side.wait_event(ev)
+        R.check(R.rbg_containment_radius(nang, hist.data_ptr(), 200, -4., 10., 200, -7., 7., hstats.data_ptr(), 0.8, d80.data_ptr(), local, side.cuda_stream))
         if dist is not None:
-            dist.all_reduce(hist)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(d80_all, d80)
             dist.all_reduce(mom)
             dist.all_reduce(cnt)
-            dist.all_gather_into_tensor(d80_all, d80)
+            hsum = hist.clone()
+            dist.all_reduce(hsum)
+        side_done[b] = torch.cuda.Event()
+        side_done[b].record(side)
 
     def barrier():
         if dist is not None:
@@ -668,7 +686,7 @@ def main():
                        "steps_per_launch": args.steps_per_launch, "parallelism": "rays sharded over %d GPU(s), geometry replicated" % world},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_full_walk": cpu_full, "clocks": clocks_summary(samples),
             "step_ms": step_ms,
-            "check": {"focused_fraction": focused_frac, "status_counts": counts, "d80_cm_by_angle": [round(v, 4) for v in d80[:, 0].cpu().numpy().tolist()]},
+            "check": {"focused_fraction": focused_frac, "status_counts": counts, "d80_cm_by_angle": [round(v, 4) for v in d80_2[(state["k"] - 1) & 1][:, 0].cpu().numpy().tolist()]},
             "configs": per_config, "cfg5_strong": strong,
         }))
     if dist is not None:

@@ -228,9 +228,10 @@ struct SceneBuilder {
           Box bl = box_transform(shape_box[s.left], mat(s.lmat)), br = box_transform(shape_box[s.right], mat(s.rmat));
           if (s.type == RBG_SHAPE_UNION)
             for (int k = 0; k < 3; k++) { b.lo[k] = std::min(bl.lo[k], br.lo[k]); b.hi[k] = std::max(bl.hi[k], br.hi[k]); }
-          else if (s.type == RBG_SHAPE_INTERSECTION)
+          else if (s.type == RBG_SHAPE_INTERSECTION) {
             for (int k = 0; k < 3; k++) { b.lo[k] = std::max(bl.lo[k], br.lo[k]); b.hi[k] = std::min(bl.hi[k], br.hi[k]); }
-          else b = bl;
+            tighten_sphere_cut(s, b);
+          } else b = bl;
           shape_depth[i] = 1 + std::max(shape_depth[s.left], shape_depth[s.right]);
           break;
         }
@@ -238,6 +239,55 @@ struct SceneBuilder {
       }
       shape_box[i] = b;
     }
+  }
+  // Mirror facets are a thin spherical shell cut by a prism or a tube about the same axis direction ("mirSphere:transZ*mirCut",
+  // tutorials/DaviesCotton.C:70, MST.C:135): the box of the cutter is as tall as the cutter (20 cm for a Davies-Cotton facet) while
+  // the solid itself is only as tall as the sag of the cap over the cutter's footprint (0.75 cm).  The thin box keeps the facet
+  // out of the candidate lists of the rays that pass over it or leave a neighbouring facet (profiles/r2_summary.md).
+  // Solid = shell(rmin..rmax about c) with polar range, cut by a solid inside the cylinder of radius rc about the axis through a,
+  // both operands placed by translations only.  z-range of the shell points whose distance from that axis is <= rc.
+  void tighten_sphere_cut(const rbg_shape& s, Box& b) const {
+    const rbg_shape *sp = &D->shapes[s.left], *cu = &D->shapes[s.right];
+    int smat = s.lmat, cmat = s.rmat;
+    if (sp->type != RBG_SHAPE_SPHERE) { std::swap(sp, cu); std::swap(smat, cmat); }
+    if (sp->type != RBG_SHAPE_SPHERE) return;
+    if (cu->type != RBG_SHAPE_PGON && cu->type != RBG_SHAPE_PCON && cu->type != RBG_SHAPE_TUBE) return;
+    auto pure_translation = [&](int m) {
+      if (m < 0) return true;
+      const double* r = D->matrices[m].rot;
+      return r[0] == 1 && r[4] == 1 && r[8] == 1 && r[1] == 0 && r[2] == 0 && r[3] == 0 && r[5] == 0 && r[6] == 0 && r[7] == 0;
+    };
+    if (!pure_translation(smat) || !pure_translation(cmat)) return;
+    const double* P = D->dpar + sp->ipar;  // rmin, rmax, theta1, theta2, phi1, phi2
+    const double* C = D->dpar + cu->ipar;
+    double c[3] = {0, 0, 0}, a[3] = {0, 0, 0};
+    if (smat >= 0) memcpy(c, D->matrices[smat].tr, sizeof(c));
+    if (cmat >= 0) memcpy(a, D->matrices[cmat].tr, sizeof(a));
+    double rc = 0;
+    if (cu->type == RBG_SHAPE_TUBE) rc = C[1];
+    else {
+      const bool pg = cu->type == RBG_SHAPE_PGON;
+      int nz = (int)C[pg ? 3 : 2];
+      const double* sec = C + (pg ? 4 : 3);
+      for (int k = 0; k < nz; k++) rc = std::max(rc, sec[3 * k + 2]);
+      if (pg) rc /= cos(0.5 * C[1] / C[2] * M_PI / 180.);
+    }
+    const double rmin = P[0], rmax = P[1], h = std::hypot(c[0] - a[0], c[1] - a[1]);
+    const double rho_lo = std::max(0., h - rc), rho_hi = h + rc;  // distance of the footprint from the sphere's axis
+    if (rho_lo >= rmax) return;
+    // heights (relative to the sphere centre) of the shell points above the footprint: +-sqrt(r^2 - rho^2)
+    const double top_max = sqrt(std::max(0., rmax * rmax - rho_lo * rho_lo));                          // highest point of the upper half
+    const double top_min = rho_hi < rmin ? sqrt(rmin * rmin - rho_hi * rho_hi) : 0.;                   // lowest point of the upper half
+    const double deg = M_PI / 180.;
+    const bool upper = P[2] < 90., lower = P[3] > 90.;  // polar range reaches above / below the equator
+    double zlo = 1e300, zhi = -1e300;
+    if (upper) { zlo = std::min(zlo, c[2] + (lower ? -top_max : top_min)); zhi = std::max(zhi, c[2] + top_max); }
+    if (lower) { zlo = std::min(zlo, c[2] - top_max); zhi = std::max(zhi, c[2] + (upper ? top_max : -top_min)); }
+    (void)deg;
+    if (zlo > zhi) return;
+    const double pad = 1e-6 * (1. + rmax);
+    b.lo[2] = std::max(b.lo[2], zlo - pad);
+    b.hi[2] = std::min(b.hi[2], zhi + pad);
   }
   // which flat evaluator can take the shape (RB_LEAF_*, rb_scene.h)
   int leaf_kind(int sh) const {

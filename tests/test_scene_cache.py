@@ -95,7 +95,7 @@ def test_tobjarray_of_rays_is_traced_in_one_batch(R):
         arr.Add(r)
     l0 = R.rbg_launch_count()
     mgr.TraceNonSequential(arr)
-    assert R.rbg_launch_count() - l0 <= 2  # one batch, not 50 single-ray traces
+    assert R.rbg_launch_count() - l0 <= 4  # one batch (trace + the two kernels that size its polyline record), not 50 single-ray traces
     for i, r in enumerate(rays):
         assert r.IsExited()
         d = r.GetDirection()
