@@ -770,9 +770,14 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     for (int b = 0; b < rounds; b++) {
       if (fused) launch_trace(s->variant, s->d, tp, R, live, count, estimate(b), n, b == 0, 1, st);
       else {
-        if (b == 0) launch_phase(s->variant, 0, s->d, tp, R, N, nullptr, nullptr, n, n, st);
-        launch_phase(s->variant, 1, s->d, tp, R, N, live, count, estimate(b), n, st);
-        launch_phase(s->variant, 2, s->d, tp, R, N, live, count, estimate(b), n, st);
+        // Locating the start points inside the first k_nav saves a pass over the rays but brings the Contains routines into the
+        // navigation kernel's instruction footprint: measured 10 % faster on configs 1 and 5, 10 % slower on 2 and 3
+        // (profiles/r2_summary.md).  Separate pass by default; RB_FUSED_INIT=1 fuses.
+        static const bool separate_init = getenv("RB_FUSED_INIT") == nullptr;
+        const int first = b == 0 && !separate_init;
+        if (b == 0 && separate_init) launch_phase(s->variant, 0, s->d, tp, R, N, nullptr, nullptr, n, n, st);
+        launch_phase(s->variant, first ? 3 : 1, s->d, tp, R, N, live, count, estimate(b), n, st);
+        launch_phase(s->variant, first ? 4 : 2, s->d, tp, R, N, live, count, estimate(b), n, st);
       }
       CK(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
       CK(cudaMemsetAsync(tile_counter, 0, 4, st));

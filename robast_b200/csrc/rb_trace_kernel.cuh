@@ -46,7 +46,7 @@ template <class K> __device__ inline void load_ray(const DScene& sc, const DTrac
     r.last_node = -1;
     r.ndraw = 0;
     r.on_boundary = 0;
-    r.cur = locate_start<K>(sc, r.p);
+    r.cur = init == 2 ? rb_ldcs(R.cur + idx) : locate_start<K>(sc, r.p);
   } else {
     r.p = v3(rb_ldcs(R.ox + idx), rb_ldcs(R.oy + idx), rb_ldcs(R.oz + idx));
     r.t = rb_ldcs(R.ot + idx);
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_trace(const __gri
 // free-running warps stall on instruction fetch (no_instruction 51-70 % of the warp samples), and keeping the block in lock
 // step with barriers only trades that for barrier waits.  The step is therefore cut where its code splits in two halves of
 // less than 32 KB each, and each half is a kernel of its own that streams over all live rays:
-//   k_init  (first bounce only) InitTrack: locate the start point, write the initial state
+//   (first bounce: k_nav also locates the start points — InitTrack — and k_shade starts from the input arrays; k_init does
+//   both as a pass of its own and is kept for comparison, RB_SEPARATE_INIT=1)
 //   k_nav   FindNextBoundary: DistFromInside of the current shape, BVH walk, DistFromOutside of the candidates, move to the
 //           boundary.  Touches only the Dist* routines of the scene's shapes.  Leaves a NavOut record per live ray.
 //   k_shade CrossBoundaryAndLocate + the interaction: point location behind the boundary (Contains routines), facet normal,
@@ -243,7 +244,7 @@ template <class K>
 __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
                                                                    const __grid_constant__ DRays R, const __grid_constant__ DNavOut N,
                                                                    const int32_t* __restrict__ live, const int32_t* __restrict__ count, long long n_max,
-                                                                   int coop) {
+                                                                   int coop, int init) {
   const long long n = count ? (long long)*count : n_max;
   const bool push = (tp.quirks & RBG_QUIRK_BOUNDARY_PUSH) != 0;
   // warp-uniform trip count: the lanes of a warp search their candidates together
@@ -257,7 +258,20 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
     nav.on_boundary = 0;
     nav.p = v3(0, 0, 0);
     nav.d = v3(0, 0, 1);
-    if (active) {
+    bool outside = false;
+    if (active && init) {
+      // first bounce: InitTrack — the start point is located here and the node handed to k_shade through the scratch column.
+      // A ray shot from outside the top volume has to enter it first: k_shade takes that step for it (no daughters to examine,
+      // no interaction besides AddPoint) and the ray joins the wavefront with the next bounce.
+      nav.p = v3(R.x[idx], R.y[idx], R.z[idx]);
+      V3 d = v3(R.dx[idx], R.dy[idx], R.dz[idx]);
+      double mag = sqrt(dot(d, d));
+      nav.d = mag > 0 ? (1. / mag) * d : d;  // ARay::SetDirection normalises (src/ARay.cxx:210-223)
+      nav.cur = locate_start<K>(sc, nav.p);
+      rb_stcs(R.cur + idx, (int32_t)nav.cur);
+      outside = nav.cur < 0;
+      nav.status = outside ? RBG_STOP : RBG_RUN;
+    } else if (active) {
       nav.p = v3(rb_ldcs(R.ox + idx), rb_ldcs(R.oy + idx), rb_ldcs(R.oz + idx));
       nav.d = v3(rb_ldcs(R.odx + idx), rb_ldcs(R.ody + idx), rb_ldcs(R.odz + idx));
       nav.status = R.status[idx];
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
     const int nvis = (st.o.nvis >= 0 && st.o.nvis <= 8) ? st.o.nvis : -1;
     N.pxy[i] = make_double2(nav.p.x, nav.p.y);
     N.pzs[i] = make_double2(nav.p.z, st.o.step);
-    N.loc[i] = make_int4(st.loc_node, st.loc_skip, (st.loc_check ? 1 : 0) | (nav.on_boundary ? 2 : 0), st.loc_prefer);
+    N.loc[i] = make_int4(st.loc_node, st.loc_skip, (st.loc_check ? 1 : 0) | (nav.on_boundary ? 2 : 0) | (outside ? 4 : 0), st.loc_prefer);
     N.hit[i] = make_int4(st.o.crossed, st.o.sel, nvis, st.o.next);
     if (nvis > 0) N.vis[i] = make_int4(st.o.vis[0], nvis > 1 ? st.o.vis[1] : -1, nvis > 2 ? st.o.vis[2] : -1, nvis > 3 ? st.o.vis[3] : -1);
     if (nvis > 4) N.vis[N.n + i] = make_int4(st.o.vis[4], nvis > 5 ? st.o.vis[5] : -1, nvis > 6 ? st.o.vis[6] : -1, nvis > 7 ? st.o.vis[7] : -1);
@@ -302,16 +316,22 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
 template <class K>
 __global__ void __launch_bounds__(K::threads, K::min_blocks) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
                                                                      const __grid_constant__ DRays R, const __grid_constant__ DNavOut N,
-                                                                     const int32_t* __restrict__ live, const int32_t* __restrict__ count, long long n_max) {
+                                                                     const int32_t* __restrict__ live, const int32_t* __restrict__ count, long long n_max,
+                                                                     int init) {
   const long long n = count ? (long long)*count : n_max;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long idx = live ? (long long)live[i] : i;
-    if (R.status[idx] != RBG_RUN) continue;
+    if (!init && R.status[idx] != RBG_RUN) continue;
     RayReg r;
     Philox g;
-    load_ray<K>(sc, tp, R, idx, 0, r, g);
+    load_ray<K>(sc, tp, R, idx, init ? 2 : 0, r, g);
     const double2 pxy = N.pxy[i], pzs = N.pzs[i];
     const int4 loc = N.loc[i], hit = N.hit[i];
+    if (loc.z & 4) {  // started outside the top volume: the step into it
+      trace_step<K>(sc, tp, r, g, nullptr);
+      store_ray(R, idx, r, g, 1);
+      continue;
+    }
     RayReg nav = r;  // navigator copy: nav.p sits on the boundary, r.p at the segment start
     nav.p = v3(pxy.x, pxy.y, pzs.x);
     nav.on_boundary = (loc.z >> 1) & 1;
@@ -348,7 +368,8 @@ struct rb_variant {
   int depth;
   unsigned shapes, phys;
   rb_launch_fn launch;  // k_trace : per-ray loop (single launch, tail of a wavefront, polyline records)
-  // one wavefront bounce: phase 0 = k_init (first bounce only), 1 = k_nav, 2 = k_shade
+  // one wavefront bounce: phase 1 = k_nav, 2 = k_shade; first bounce: 3 = k_nav locating the start points, 4 = k_shade starting from
+  // the input arrays (or, RB_SEPARATE_INIT=1: phase 0 = k_init, then 1 and 2)
   int (*launch_phase)(int phase, const DScene& sc, const DTraceParams& tp, const DRays& R, const DNavOut& N, const int32_t* live, const int32_t* count,
                       long long n_grid, long long n_max, cudaStream_t st);
 };
@@ -367,9 +388,11 @@ struct rb_variant {
     long long blocks = (n_grid + TH - 1) / TH;                                                                                        \
     if (blocks < 1) blocks = 1;                                                                                                       \
     if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;                                                                                 \
+    const int init = phase >= 3;                                                                                                      \
     if (phase == 0) k_init<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, n_max);                                         \
-    else if (phase == 1) k_nav<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, N, live, count, n_max, rb_coop_search());  \
-    else k_shade<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, N, live, count, n_max);                                   \
+    else if (phase == 1 || phase == 3)                                                                                                \
+      k_nav<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, N, live, count, n_max, rb_coop_search(), init);               \
+    else k_shade<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, N, live, count, n_max, init);                             \
     return (int)cudaGetLastError();                                                                                                   \
   }                                                                                                                                   \
   extern const rb_variant rb_variant_##NAME = {#NAME, D, S, P, rb_launch_trace_##NAME, rb_launch_phase_##NAME};
