@@ -1,7 +1,7 @@
 # Host-buffer path of rbg_trace: nine calls of 1.11e7 rays (the bench's e2e arm) against one call of 1.0e8 rays over the same
 # pinned buffers — separates the pipeline's fill/drain per call from its steady state.
 import sys, time, ctypes as C
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import os; _r = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, _r); sys.path.insert(0, os.path.join(_r, 'tests'))
 import torch
 import robast_b200 as R
 from robast_b200 import configs

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -547,6 +548,8 @@ struct rbg_scene {
   void* stage[RB_HOST_STREAMS] = {};
   size_t stage_bytes[RB_HOST_STREAMS] = {};
   cudaStream_t streams[RB_HOST_STREAMS] = {};
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer pipeline: all H2D on one stream, all D2H on another
+  cudaEvent_t ev_in[RB_HOST_STREAMS] = {}, ev_cmp[RB_HOST_STREAMS] = {}, ev_out[RB_HOST_STREAMS] = {};
   int32_t* d_count = nullptr;
   int32_t* h_count = nullptr;  // pinned
   // launch plan of the wavefront, learned from the calls before (pinned, written by the device without any host wait):
@@ -582,7 +585,12 @@ static void scene_free(rbg_scene* s) {
   for (int i = 0; i < RB_HOST_STREAMS; i++) {
     if (s->stage[i]) cudaFree(s->stage[i]);
     if (s->streams[i]) cudaStreamDestroy(s->streams[i]);
+    if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+    if (s->ev_cmp[i]) cudaEventDestroy(s->ev_cmp[i]);
+    if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
   }
+  if (s->copy_in) cudaStreamDestroy(s->copy_in);
+  if (s->copy_out) cudaStreamDestroy(s->copy_out);
   if (s->d_count) cudaFree(s->d_count);
   if (s->h_count) cudaFreeHost(s->h_count);
   if (s->h_frac) cudaFreeHost(s->h_frac);
@@ -1075,7 +1083,20 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
     // the H2D of chunk c+1, the bounce kernels of chunk c and the D2H of chunk c-1 overlap (PCIe is full duplex).
     // chunk size: small enough that a 1e7-ray call has a steady state (H2D, kernels and D2H of different chunks
     // overlapping), large enough that a bounce launch still fills the 148 SMs many times over
-    static const long long CH = getenv("RB_HOST_CHUNK") ? std::max(4096LL, atoll(getenv("RB_HOST_CHUNK"))) : (1LL << 20);
+    bool pinned = hpts == 0 && getenv("RB_HOST_THREADS_PIPELINE") == nullptr;
+    {
+      const void* probe[4] = {rays->x, rays->lambda, rays->ox, rays->status};
+      for (int a = 0; a < 4 && pinned; a++) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, probe[a]) != cudaSuccess || at.type != cudaMemoryTypeHost) pinned = false;
+        cudaGetLastError();
+      }
+    }
+    // chunk size: small enough that a 1e7-ray call has a steady state (H2D, kernels and D2H of different chunks overlapping) and
+    // a short fill and drain, large enough that a bounce launch still fills the 148 SMs.  Measured on the nine 1.1e7-ray calls
+    // of the bench (profiles/r2_summary.md): pinned pipeline 256 Ki rays x 8 stage buffers, no ramp; threaded pipeline 1 Mi x 6.
+    static const long long CH_env = getenv("RB_HOST_CHUNK") ? std::max(4096LL, atoll(getenv("RB_HOST_CHUNK"))) : 0;
+    const long long CH = CH_env ? CH_env : (pinned ? (1LL << 18) : (1LL << 20));
     long long chunk = std::min<long long>(rays->n, CH);
     size_t per_ray = 8 * 8 + 7 * 8 + 3 * 4;  // in + out
     size_t bytes = (size_t)chunk * per_ray + 4096 + (size_t)chunk * hpts * 36 + 1024;
@@ -1085,7 +1106,9 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
     {
       long long head = 0, tail = rays->n;
       std::vector<std::pair<long long, long long>> back;
-      for (long long sz = std::max<long long>(chunk / 8, 65536); sz < chunk && tail - head > 4 * chunk; sz *= 2) {
+      static const int ramp_env = getenv("RB_HOST_RAMP") ? atoi(getenv("RB_HOST_RAMP")) : 0;  // first / last chunk = chunk / ramp
+      const int ramp = ramp_env ? ramp_env : (pinned ? 1 : 8);
+      for (long long sz = std::max<long long>(chunk / std::max(1, ramp), 65536); sz < chunk && tail - head > 4 * chunk; sz *= 2) {
         chunks.emplace_back(head, sz);
         head += sz;
         back.emplace_back(tail - sz, sz);
@@ -1099,7 +1122,8 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
       chunks.insert(chunks.end(), back.rbegin(), back.rend());
     }
     long long nchunks = (long long)chunks.size();
-    static const int max_streams = getenv("RB_HOST_NSTREAMS") ? std::min(RB_HOST_STREAMS, std::max(1, atoi(getenv("RB_HOST_NSTREAMS")))) : 6;
+    static const int streams_env = getenv("RB_HOST_NSTREAMS") ? std::min(RB_HOST_STREAMS, std::max(1, atoi(getenv("RB_HOST_NSTREAMS")))) : 0;
+    const int max_streams = streams_env ? streams_env : (pinned ? 8 : 6);
     int nst = (int)std::min<long long>(nchunks, max_streams);
     for (int k = 0; k < nst; k++) {
       if (!s->streams[k]) CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
@@ -1111,7 +1135,83 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         s->stage_bytes[k] = bytes;
       }
     }
+    // Pinned host arrays: three-stage pipeline driven by this thread alone (nothing below waits for the device until the end).
+    // Every H2D copy goes to one stream, in chunk order, every D2H copy to another, the traces to one stream per stage
+    // buffer; events chain copy-in -> trace -> copy-out per chunk and free a stage buffer for the chunk `nst` later.  Both copy
+    // engines always have their next transfer queued, so the two PCIe directions stay busy together for the whole call instead
+    // of idling whenever a stream that owns a chunk end to end (the scheme below) sits in one of its other two stages
+    // (profiles/r2_summary.md: 59 -> 7x GB/s H2D + D2H per 1.1e7-ray call).
+    if (pinned) {
+      if (!s->copy_in) CK(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+      if (!s->copy_out) CK(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+      for (int k = 0; k < nst; k++) {
+        if (!s->ev_in[k]) CK(cudaEventCreateWithFlags(&s->ev_in[k], cudaEventDisableTiming));
+        if (!s->ev_cmp[k]) CK(cudaEventCreateWithFlags(&s->ev_cmp[k], cudaEventDisableTiming));
+        if (!s->ev_out[k]) CK(cudaEventCreateWithFlags(&s->ev_out[k], cudaEventDisableTiming));
+      }
+      const double* hin[8] = {rays->x, rays->y, rays->z, rays->t, rays->dx, rays->dy, rays->dz, rays->lambda};
+      double* hout[7] = {rays->ox, rays->oy, rays->oz, rays->ot, rays->odx, rays->ody, rays->odz};
+      int32_t* hiout[3] = {rays->status, rays->last_node, rays->npoints};
+      // columns laid out at one constant pitch (the rows of one matrix): one 2-D copy per chunk and direction instead of 8 + 10
+      auto pitch_of = [](const char* const* p, int cnt, long long min_bytes) -> long long {
+        const long long d = p[1] - p[0];
+        if (d < min_bytes) return 0;
+        for (int a = 2; a < cnt; a++)
+          if (p[a] - p[a - 1] != d) return 0;
+        return d;
+      };
+      const char* pin_[8]; const char* pout_[7]; const char* piout_[3];
+      for (int a = 0; a < 8; a++) pin_[a] = (const char*)hin[a];
+      for (int a = 0; a < 7; a++) pout_[a] = (const char*)hout[a];
+      for (int a = 0; a < 3; a++) piout_[a] = (const char*)hiout[a];
+      static const bool no2d = getenv("RB_HOST_NO2D") != nullptr;
+      const long long in_pitch = no2d ? 0 : pitch_of(pin_, 8, rays->n * 8), out_pitch = no2d ? 0 : pitch_of(pout_, 7, rays->n * 8),
+                      iout_pitch = no2d ? 0 : pitch_of(piout_, 3, rays->n * 4);
+      for (long long ci = 0; ci < nchunks; ci++) {
+        const int k = (int)(ci % nst);
+        const long long b = chunks[ci].first, m = chunks[ci].second;
+        char* base = (char*)s->stage[k];
+        double* din[8];
+        double* dout[7];
+        int32_t* diout[3];
+        size_t off = 0;
+        for (int a = 0; a < 8; a++) { din[a] = (double*)(base + off); off += (size_t)chunk * 8; }
+        for (int a = 0; a < 7; a++) { dout[a] = (double*)(base + off); off += (size_t)chunk * 8; }
+        for (int a = 0; a < 3; a++) { diout[a] = (int32_t*)(base + off); off += (size_t)chunk * 4; }
+        if (ci >= nst) CK(cudaStreamWaitEvent(s->copy_in, s->ev_out[k], 0));  // the stage buffer's previous chunk has left
+        if (in_pitch > 0) CK(cudaMemcpy2DAsync(din[0], (size_t)chunk * 8, hin[0] + b, (size_t)in_pitch, (size_t)m * 8, 8, cudaMemcpyHostToDevice, s->copy_in));
+        else
+          for (int a = 0; a < 8; a++) CK(cudaMemcpyAsync(din[a], hin[a] + b, (size_t)m * 8, cudaMemcpyHostToDevice, s->copy_in));
+        CK(cudaEventRecord(s->ev_in[k], s->copy_in));
+        CK(cudaStreamWaitEvent(s->streams[k], s->ev_in[k], 0));
+        DRays R;
+        R.x = din[0]; R.y = din[1]; R.z = din[2]; R.t = din[3]; R.dx = din[4]; R.dy = din[5]; R.dz = din[6]; R.lambda = din[7];
+        R.ox = dout[0]; R.oy = dout[1]; R.oz = dout[2]; R.ot = dout[3]; R.odx = dout[4]; R.ody = dout[5]; R.odz = dout[6];
+        R.status = diout[0]; R.last_node = diout[1]; R.npoints = diout[2];
+        R.cur = nullptr; R.ndraw = nullptr;
+        memset(&R.hist, 0, sizeof(R.hist));
+        trace_device(s, o, R, m, o->ray_id_offset + (unsigned long long)b, s->streams[k]);
+        CK(cudaEventRecord(s->ev_cmp[k], s->streams[k]));
+        CK(cudaStreamWaitEvent(s->copy_out, s->ev_cmp[k], 0));
+        if (out_pitch > 0) CK(cudaMemcpy2DAsync(hout[0] + b, (size_t)out_pitch, dout[0], (size_t)chunk * 8, (size_t)m * 8, 7, cudaMemcpyDeviceToHost, s->copy_out));
+        else
+          for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(hout[a] + b, dout[a], (size_t)m * 8, cudaMemcpyDeviceToHost, s->copy_out));
+        if (iout_pitch > 0) CK(cudaMemcpy2DAsync(hiout[0] + b, (size_t)iout_pitch, diout[0], (size_t)chunk * 4, (size_t)m * 4, 3, cudaMemcpyDeviceToHost, s->copy_out));
+        else
+          for (int a = 0; a < 3; a++) CK(cudaMemcpyAsync(hiout[a] + b, diout[a], (size_t)m * 4, cudaMemcpyDeviceToHost, s->copy_out));
+        CK(cudaEventRecord(s->ev_out[k], s->copy_out));
+      }
+      CK(cudaStreamSynchronize(s->copy_out));
+      return;
+    }
+    // Pageable host arrays (and polyline records): a cudaMemcpyAsync from pageable memory blocks its caller while the driver
+    // stages the data, so every chunk in flight gets its own host thread, stream and stage buffer.
+    static const bool time_host = getenv("RB_TIME_HOST") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    double t_enq[RB_HOST_STREAMS] = {}, t_wait[RB_HOST_STREAMS] = {};
     auto work = [&](int k) {
+      const auto t_w = std::chrono::steady_clock::now();
       CK(cudaSetDevice(s->device));
       cudaStream_t st = s->streams[k];
       char* base = (char*)s->stage[k];
@@ -1155,7 +1255,9 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(hout[a] + b, dout[a], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
         for (int a = 0; a < 3; a++) CK(cudaMemcpyAsync(hiout[a] + b, diout[a], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
       }
+      t_enq[k] = since(t_w);
       CK(cudaStreamSynchronize(st));
+      t_wait[k] = since(t_w);
     };
     if (nst == 1) {
       work(0);
@@ -1172,6 +1274,11 @@ int rbg_trace_history(rbg_scene* s, const rbg_trace_opts* o, const rbg_rays* ray
         }
       });
     for (auto& w : workers) w.join();
+    if (time_host) {
+      fprintf(stderr, "rbg_trace host path: n=%lld chunks=%lld streams=%d total %.2f ms; per worker enqueue/done:", (long long)rays->n, nchunks, nst, since(t_call));
+      for (int k = 0; k < nst; k++) fprintf(stderr, " %.2f/%.2f", t_enq[k], t_wait[k]);
+      fprintf(stderr, "\n");
+    }
     for (int k = 0; k < nst; k++) {
       if (errs[k]) {
         for (int j = 0; j < nst; j++) cudaStreamSynchronize(s->streams[j]);
