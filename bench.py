@@ -654,7 +654,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     passes = args.steps * nang
     roof = roofline_of(n * passes, bm, hbm_peak, KFLOP[2]) or {}
-    roof.update({"kernel": "k_nav<%s> + k_shade<%s> (the two halves of the wavefront bounce; k_init locates the start points, k_trace finishes the tail)" % (variant, variant),
+    roof.update({"kernel": "k_nav<%s> + k_shade<%s> (the two halves of the wavefront bounce; the first k_nav also locates the start points, k_trace finishes the tail)" % (variant, variant),
                  "peak_source": "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "of fallback",
                  "algorithmic_bytes_per_pass": (BYTES_IN + BYTES_OUT) * n, "bounce_ms_per_pass": bm / passes, "bounce_launches_per_pass": bn / passes,
                  "kernel_ms_per_launch": bm / max(1, bn), "kernel_launches": bn, "kernel_share_of_step": bm / ms if ms else None,

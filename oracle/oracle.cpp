@@ -2741,7 +2741,7 @@ int orc_shoot_bunches(const rbg_bunches* b, int64_t first, int64_t n, double* x,
         Rng r;
         r.key[0] = (uint32_t)b->seed; r.key[1] = (uint32_t)(b->seed >> 32);
         r.id[0] = (uint32_t)ray; r.id[1] = (uint32_t)((uint64_t)ray >> 32);
-        r.ndraw = 0;
+        r.ndraw = 0x40000000u;  // shooter draws live in their own counter range (as orc_shoot)
         lam = 1. / (1. / b->lambda_min_nm - r.uniform() * (1. / b->lambda_min_nm - 1. / b->lambda_max_nm));
       }
       x[out] = px; y[out] = py; z[out] = b->z; t[out] = pt;

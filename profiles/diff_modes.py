@@ -1,4 +1,4 @@
-"""per-ray difference between the wavefront (k_init/k_nav/k_shade) and the single-launch (k_trace) modes on one config"""
+"""per-ray difference between the wavefront (k_nav/k_shade) and the single-launch (k_trace) modes on one config"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,0 +1,24 @@
+# deepest-box-first order for boxes holding the start point + step limit inside the typed booleans
+mkdir -p gpurun_out/r3d
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_parity_branches.py tests/test_gpu_full_size.py -m gpu -x -q > gpurun_out/r3d/pytest.log 2>&1
+tail -3 gpurun_out/r3d/pytest.log
+python profiles/diff_modes.py 2 0 4000000; python profiles/diff_modes.py 5 20 2000000
+for e in "RB_INIT=1"; do
+for c in "1 0 9000000 3" "2 1 11115556 3" "3 0 9000000 3" "4 0 10000000 3" "5 20 10000000 3 rings=10"; do
+  env $e timeout 300 python profiles/trace_one.py $c 2>&1 | sed "s/^/$e /" | cut -c1-170 >> gpurun_out/r3d/survey.log
+done
+done
+cat gpurun_out/r3d/survey.log
+for c in "5 20 10000000 2 rings=10"; do
+RB_INIT=1 timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_nav|k_shade|k_locate|k_trace" -s 49 -c 7 --csv --log-file gpurun_out/r3d/m.csv python profiles/trace_one.py $c > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows = list(csv.reader(l for l in open('gpurun_out/r3d/m.csv') if l.startswith('"')))
+hdr = rows[0]; iK = hdr.index('Kernel Name'); iM = hdr.index('Metric Name'); iV = hdr.index('Metric Value'); iI = hdr.index('ID')
+cur = {}
+for r in rows[1:]:
+    cur.setdefault((int(r[iI]), r[iK][:14]), {})[r[iM]] = float(r[iV].replace(',',''))
+for k, v in sorted(cur.items()):
+    print(k, 'ms %.2f inst %.0fM rd %.2f GB wr %.2f GB' % (v['gpu__time_duration.sum']/1e6, v['smsp__inst_executed.sum']/1e6, v['dram__bytes_read.sum']/1e9, v['dram__bytes_write.sum']/1e9))
+PY
+done

@@ -333,6 +333,12 @@ struct SceneBuilder {
         nodes[id].blo[k] = std::nextafterf((float)(wb.lo[k] - pad), -INFINITY);
         nodes[id].bhi[k] = std::nextafterf((float)(wb.hi[k] + pad), INFINITY);
       }
+      const Box& lb = shape_box[n.shape];
+      for (int k = 0; k < 3; k++) {
+        const double c = 0.5 * (lb.lo[k] + lb.hi[k]), h = 0.5 * (lb.hi[k] - lb.lo[k]);
+        nodes[id].lc[k] = (float)c;
+        nodes[id].lh[k] = std::nextafterf((float)(h + fabs(c - (double)(float)c) + 2e-3 + 4e-7 * (fabs(c) + h)), INFINITY);
+      }
     }
     names.push_back(name);
     const rbg_volume& v = D->volumes[vol];

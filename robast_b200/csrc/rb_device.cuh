@@ -66,6 +66,12 @@ RB_HD inline double rb_atan2(double y, double x) {  // TMath::ATan2
   if (y == 0) return 0;
   return y > 0 ? RB_PI / 2 : -RB_PI / 2;
 }
+// a / b, bit for bit.  The compiler's inline fp64 division handles a zero (or denormal) numerator through an out-of-line routine
+// of ~90 instructions and ~20 local-memory accesses; numerators that are exactly zero are structural in this code (imaginary
+// parts of lossless layers, flat surfaces, prisms of constant radius): 30 such calls per ray in the multilayer reflectance, a
+// tenth of all instructions of the interaction kernel on BASELINE config 5 (profiles/r2_summary.md).  IEEE gives 0 / b = +-0 with
+// the sign of a xor b for every b but 0 and NaN.
+RB_HD inline double rb_div(double a, double b) { return (a == 0. && b != 0. && b == b) ? a * copysign(1., b) : a / b; }
 RB_HD inline double rb_acos(double x) { return x < -1. ? RB_PI : (x > 1. ? 0 : acos(x)); }
 RB_HD inline double rb_asin(double x) { return x < -1. ? -RB_PI / 2 : (x > 1. ? RB_PI / 2 : asin(x)); }
 
@@ -222,11 +228,11 @@ RB_HD inline Cx operator*(Cx a, Cx b) { return cx(a.re * b.re - a.im * b.im, a.r
 RB_HD inline Cx operator*(double s, Cx a) { return cx(s * a.re, s * a.im); }
 RB_HD inline Cx operator/(Cx a, Cx b) {  // Smith's algorithm
   if (fabs(b.re) >= fabs(b.im)) {
-    double r = b.im / b.re, den = b.re + b.im * r;
-    return cx((a.re + a.im * r) / den, (a.im - a.re * r) / den);
+    double r = rb_div(b.im, b.re), den = b.re + b.im * r;
+    return cx(rb_div(a.re + a.im * r, den), rb_div(a.im - a.re * r, den));
   }
-  double r = b.re / b.im, den = b.re * r + b.im;
-  return cx((a.re * r + a.im) / den, (a.im * r - a.re) / den);
+  double r = rb_div(b.re, b.im), den = b.re * r + b.im;
+  return cx(rb_div(a.re * r + a.im, den), rb_div(a.im * r - a.re, den));
 }
 RB_HD inline double cabs2(Cx a) { return a.re * a.re + a.im * a.im; }
 RB_HD inline Cx cconj(Cx a) { return cx(a.re, -a.im); }
@@ -234,7 +240,7 @@ RB_HD inline Cx csqrt_(Cx z) {  // principal branch
   double m = hypot(z.re, z.im);
   if (m == 0) return cx(0, 0);
   double s = sqrt(0.5 * (m + fabs(z.re)));
-  double o = z.im / (2 * s);
+  double o = rb_div(z.im, 2 * s);
   if (z.re >= 0) return cx(s, o);
   return cx(fabs(o), z.im >= 0 ? s : -s);
 }
@@ -264,86 +270,76 @@ RB_HD inline bool tmm_is_forward(Cx n, Cx theta) {
 // unpolarised CoherentTMMMixed costs one set of transcendentals instead of two.  Per polarisation the arithmetic is the same
 // sequence of operations either way.
 template <int NP> RB_HD inline void tmm_coherent_multi(const DScene& sc, int first, int a, int b, bool reverse, int pol0, Cx th0, double lam, double* R, double* T) {
-  int N = b - a + 1;
-  Cx n0 = cx(1, 0), nprev = cx(1, 0), n_last = cx(1, 0);
-  Cx n0s = cx(0, 0);
-  Cx cprev = cx(1, 0), c_last = cx(1, 0);  // cos of the Snell angle in the previous / last layer
-  Cx m00[NP], m01[NP], m10[NP], m11[NP], r0[NP], t0[NP];
-#pragma unroll
-  for (int q = 0; q < NP; q++) { m00[q] = cx(1, 0); m01[q] = cx(0, 0); m10[q] = cx(0, 0); m11[q] = cx(1, 0); r0[q] = cx(0, 0); t0[q] = cx(1, 0); }
-  for (int i = 0; i < N; i++) {
-    const rbg_layer L = sc.layers[first + (reverse ? b - i : a + i)];
-    Cx ni = cx(index_n(sc, L.index, lam), index_k(sc, L.index, lam));
-    // Snell's law (AMultilayer::ListSnell): the reference takes theta_i = asin(n0 sin(theta0) / n_i), corrects the first and the
-    // last layer to the forward-travelling solution (theta -> pi - theta) and then only ever uses cos(theta_i).  On the principal
-    // branches cos(asin z) = sqrt(1 - z^2), and theta -> pi - theta flips the sign of the cosine: the same numbers without a
-    // complex asin (sqrt, log, atan2) and a complex cos (cos, sin, cosh, sinh) per layer.
-    if (i == 0) {
-      n0 = ni;
-      n0s = th0.im == 0 ? cx(ni.re * sin(th0.re), ni.im * sin(th0.re)) : ni * csin_(th0);
-    }
+  // r = M10 / M00 and t = 1 / M00 need only the first column of M = B_01 M_1 ... M_{N-2}: the product is applied to the unit
+  // vector from the last layer towards the first — two complex numbers of state per polarisation instead of a 2x2 matrix plus
+  // the first interface's coefficients (the kernels run at 64 registers; the matrix form lived in local memory).
+  const int N = b - a + 1;
+  const rbg_layer L0 = sc.layers[first + (reverse ? b : a)];
+  const Cx n0 = cx(index_n(sc, L0.index, lam), index_k(sc, L0.index, lam));
+  const Cx n0s = th0.im == 0 ? cx(n0.re * sin(th0.re), n0.im * sin(th0.re)) : n0 * csin_(th0);
+  // Snell's law (AMultilayer::ListSnell): the reference takes theta_i = asin(n0 sin(theta0) / n_i), corrects the first and the
+  // last layer to the forward-travelling solution (theta -> pi - theta) and then only ever uses cos(theta_i).  On the principal
+  // branches cos(asin z) = sqrt(1 - z^2), and theta -> pi - theta flips the sign of the cosine: the same numbers without a
+  // complex asin (sqrt, log, atan2) and a complex cos (cos, sin, cosh, sinh) per layer.
+  auto snell_cos = [&](Cx ni, bool end) {
     const Cx zs = n0s / ni;
-    Cx ccur = csqrt_(cx(1, 0) - zs * zs);
-    if (i == 0 || i == N - 1) {
-      const Cx nc = ni * ccur;  // IsForwardAngle (src/AMultilayer.cxx:26-56)
+    Cx c = csqrt_(cx(1, 0) - zs * zs);
+    if (end) {
+      const Cx nc = ni * c;  // IsForwardAngle (src/AMultilayer.cxx:26-56)
       const bool forward = fabs(nc.im) > 100 * 2.220446049250313e-16 ? nc.im > 0 : nc.re > 0;
-      if (!forward) ccur = cx(-ccur.re, -ccur.im);
+      if (!forward) c = cx(-c.re, -c.im);
     }
-    if (i == 0) cprev = ccur;
-    else {
-      // interface (i-1) -> i
-      Cx ci = cprev, cf = ccur;
-      Cx ii = nprev * ci;
-      Cx em = cx(1, 0), ep = cx(1, 0);
-      if (i > 1) {
-        // layer i-1 is an inner layer: M_{i-1} = (1/t) diag(e^{-iδ}, e^{iδ}) [[1,r],[r,1]]
-        Cx kz = ((2 * RB_PI) * (nprev * ci));
-        kz = cx(kz.re / lam, kz.im / lam);
-        double d = sc.layers[first + (reverse ? b - (i - 1) : a + i - 1)].thickness;
-        Cx delta = cx(kz.re * d, kz.im * d);
-        if (delta.im > 35) delta.im = 35;
-        em = cexp_(cx(delta.im, -delta.re));  // exp(-iδ)
-        ep = cexp_(cx(-delta.im, delta.re));  // exp(iδ)
-      }
+    return c;
+  };
+  const rbg_layer LN = sc.layers[first + (reverse ? a : b)];
+  const Cx n_last = cx(index_n(sc, LN.index, lam), index_k(sc, LN.index, lam));
+  const Cx c_last = snell_cos(n_last, true);
+  Cx nf = n_last, cf = c_last;  // the layer behind the interface being added
+  Cx v0[NP], v1[NP];
 #pragma unroll
-      for (int q = 0; q < NP; q++) {
-        const int pol = NP == 1 ? pol0 : q;
-        Cx r, t;
-        if (pol == 0) {
-          Cx ff = ni * cf;
-          r = (ii - ff) / (ii + ff);
-          t = (2. * ii) / (ii + ff);
-        } else {
-          Cx fi = ni * ci, i_f = nprev * cf;
-          r = (fi - i_f) / (fi + i_f);
-          t = (2. * ii) / (fi + i_f);
-        }
-        if (i == 1) { r0[q] = r; t0[q] = t; }
-        else {
-          Cx s = cx(1, 0) / t;
-          Cx d00 = s * em, d11 = s * ep;
-          Cx a00 = d00, a01 = d00 * r, a10 = d11 * r, a11 = d11;
-          Cx q00 = m00[q] * a00 + m01[q] * a10, q01 = m00[q] * a01 + m01[q] * a11, q10 = m10[q] * a00 + m11[q] * a10, q11 = m10[q] * a01 + m11[q] * a11;
-          m00[q] = q00; m01[q] = q01; m10[q] = q10; m11[q] = q11;
-        }
-      }
-      cprev = cf;
+  for (int q = 0; q < NP; q++) { v0[q] = cx(1, 0); v1[q] = cx(0, 0); }
+  for (int i = N - 2; i >= 0; i--) {
+    const rbg_layer L = sc.layers[first + (reverse ? b - i : a + i)];
+    const Cx ni = i == 0 ? n0 : cx(index_n(sc, L.index, lam), index_k(sc, L.index, lam));
+    const Cx ci = snell_cos(ni, i == 0);
+    const Cx ii = ni * ci;
+    Cx em = cx(1, 0), ep = cx(1, 0);
+    if (i > 0) {
+      // an inner layer: M_i = (1/t) diag(e^{-i delta}, e^{i delta}) [[1,r],[r,1]]
+      Cx delta = cx((2 * RB_PI) * ii.re / lam * L.thickness, rb_div((2 * RB_PI) * ii.im, lam) * L.thickness);
+      if (delta.im > 35) delta.im = 35;
+      em = cexp_(cx(delta.im, -delta.re));  // exp(-i delta)
+      ep = cexp_(cx(-delta.im, delta.re));  // exp(i delta)
     }
-    nprev = ni;
-    n_last = ni;
-    c_last = cprev;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      const int pol = NP == 1 ? pol0 : q;
+      Cx r, s;  // interface i -> i+1: reflection coefficient and 1 / transmission coefficient
+      if (pol == 0) {
+        const Cx ff = nf * cf;
+        r = (ii - ff) / (ii + ff);
+        s = (ii + ff) / (2. * ii);
+      } else {
+        const Cx fi = nf * ci, i_f = ni * cf;
+        r = (fi - i_f) / (fi + i_f);
+        s = (fi + i_f) / (2. * ii);
+      }
+      const Cx w0 = v0[q] + r * v1[q], w1 = r * v0[q] + v1[q];
+      v0[q] = (s * em) * w0;
+      v1[q] = (s * ep) * w1;
+    }
+    nf = ni;
+    cf = ci;
   }
-  Cx cf = c_last, ci = th0.im == 0 ? cx(cos(th0.re), 0) : ccos_(th0);
+  const Cx c0 = th0.im == 0 ? cx(cos(th0.re), 0) : ccos_(th0);
 #pragma unroll
   for (int q = 0; q < NP; q++) {
     const int pol = NP == 1 ? pol0 : q;
-    Cx b00 = cx(1, 0) / t0[q], b01 = r0[q] / t0[q];
-    Cx q00 = b00 * m00[q] + b01 * m10[q], q10 = b01 * m00[q] + b00 * m10[q];
-    Cx r = q10 / q00, t = cx(1, 0) / q00;
+    const Cx r = v1[q] / v0[q], t = cx(1, 0) / v0[q];
     R[q] = cabs2(r);
-    double tt = cabs2(t);  // |t*t| = |t|^2
-    if (pol == 0) T[q] = tt * ((n_last * cf).re / (n0 * ci).re);
-    else T[q] = tt * ((n_last * cconj(cf)).re / (n0 * cconj(ci)).re);
+    const double tt = cabs2(t);  // |t*t| = |t|^2
+    if (pol == 0) T[q] = tt * ((n_last * c_last).re / (n0 * c0).re);
+    else T[q] = tt * ((n_last * cconj(c_last)).re / (n0 * cconj(c0)).re);
   }
 }
 RB_HD inline void tmm_coherent_sub(const DScene& sc, int first, int a, int b, bool reverse, int pol, Cx th0, double lam, double& R, double& T) {
@@ -820,7 +816,7 @@ template <bool CONE> RB_HD inline bool poly_slab(const double* P, int k, V3 p, V
     tout = rb_max(ta, tb);
   } else if (p.z < z0 || p.z > z1) return false;
   if (tout <= 1e-11) return false;  // the whole slab lies behind the ray: no caller uses such an interval
-  double s = (r1 - r0) / dz, base = r0 + (p.z - z0) * s;
+  double s = rb_div(r1 - r0, dz), base = r0 + (p.z - z0) * s;
   if constexpr (CONE) {
     // inside the frustum: f(t) = |xy(t)|^2 - (base + s dz t)^2 <= 0 on the nappe with non-negative radius, which is
     // the only one the z slab can reach (r0, r1 >= 0)
@@ -1097,7 +1093,7 @@ RB_HD inline bool asph_F(const double* P, int s, double r, double& out) {
   if (1 - pp < 0) return false;
   double poly = 0;
   for (int i = n - 1; i >= 0; i--) poly = (poly + K[i]) * r2;  // sum K_i r^(2(i+1)), Horner in r^2
-  out = z0 + r2 * c / (1 + sqrt(1 - pp)) + poly;
+  out = z0 + rb_div(r2 * c, 1 + sqrt(1 - pp)) + poly;
   return true;
 }
 RB_HD inline bool asph_dF(const double* P, int s, double r, double& out) {
@@ -1108,7 +1104,7 @@ RB_HD inline bool asph_dF(const double* P, int s, double r, double& out) {
   if (1 - pp <= 0) return false;
   double poly = 0;
   for (int i = n - 1; i >= 0; i--) poly = poly * r2 + 2 * (i + 1) * K[i];  // sum 2(i+1) K_i r^(2i), then * r
-  out = r * c / sqrt(1 - pp) + poly * r;
+  out = rb_div(r * c, sqrt(1 - pp)) + poly * r;
   return true;
 }
 RB_HD inline bool asph_contains(const double* P, V3 p) {
@@ -1127,9 +1123,9 @@ RB_HD inline double asph_surface(const double* P, int s, V3 pt, V3 dir) {
   double p = -(zr * dir.z + pt.x * dir.x + pt.y * dir.y);
   double M = p * dir.z + zr, M2 = zr * zr + H2 - p * p;
   double w = (M2 * curve - 2 * M);
-  double check = 1 - w * curve / dir.z / dir.z;
+  double check = 1 - rb_div(rb_div(w * curve, dir.z), dir.z);
   if (check < 0) return RB_BIG;
-  double q = p + w / (dir.z * (1 + sqrt(check)));
+  double q = p + rb_div(w, dir.z * (1 + sqrt(check)));
   double nx = pt.x + q * dir.x, ny = pt.y + q * dir.y, nz = pt.z + q * dir.z - d;
   double ck = curve * kappa, cc = kappa * curve * curve;
   for (int i = 0;; i++) {
@@ -1148,7 +1144,7 @@ RB_HD inline double asph_surface(const double* P, int s, V3 pt, V3 dir) {
     l *= inv; m *= inv; n *= inv;
     check = dir.z * l + dir.x * m + dir.y * n;
     if (check == 0) return RB_BIG;
-    double e = l * (x - nz) / check;
+    double e = rb_div(l * (x - nz), check);
     nx += e * dir.x; ny += e * dir.y; nz += e * dir.z;
     if (fabs(e) < 1e-10) break;
   }
@@ -1209,14 +1205,14 @@ RB_HD inline V3 asph_normal(const double* P, V3 p, V3 d) {
   double dfs = 0;
   for (int k = 1; k <= 2; k++) {
     double saf = RB_BIG;
-    if (asph_F(P, k, r, f) && asph_dF(P, k, r, df)) saf = fabs(f - p.z) / sqrt(1 + df * df);
+    if (asph_F(P, k, r, f) && asph_dF(P, k, r, df)) saf = rb_div(fabs(f - p.z), sqrt(1 + df * df));
     if (saf < best) { best = saf; which = 1 + k; dfs = df; }
   }
   double nx = 0, nz = 0;
   if (which < 2) nx = 1;
   else if (dfs == 0) nz = 1;
   else { double inv = 1. / sqrt(1 + dfs * dfs); nx = dfs * inv; nz = -inv; }
-  V3 n = r > 0 ? v3(nx * p.x / r, nx * p.y / r, nz) : v3(nx, 0, nz);  // RotateZ(atan2(y, x))
+  V3 n = r > 0 ? v3(rb_div(nx * p.x, r), rb_div(nx * p.y, r), nz) : v3(nx, 0, nz);  // RotateZ(atan2(y, x))
   if (dot(n, d) < 0) n = v3(-n.x, -n.y, -n.z);
   return n;
 }
@@ -1972,6 +1968,7 @@ template <class C> struct Bool2 {
         const bool left_entered = d1 > d2;
         const double adv = left_entered ? d1 : d2;
         snext += adv;
+        if (snext > step) return true;  // the solid starts beyond the caller's limit (the step already found): no crossing to report
         sel = left_entered ? 1 : 2;
         master = along(master, d, adv);
         lp = op_point(sc, s.lmat, master);
@@ -2003,7 +2000,7 @@ template <class C> struct Bool2 {
       }
       lp = op_point(sc, s.lmat, master);
       double d2 = PL::dist_out(A, lp, ld, RB_BIG);
-      if (d2 > 1E20) return true;
+      if (d2 > 1E20 || snxt + d2 > step) return true;  // misses the left solid, or reaches it beyond the caller's limit
       rp = op_point(sc, s.rmat, master);
       double d1 = PR::dist_out(B, rp, rd, RB_BIG);
       if (d2 < d1 - RB_TOL) {
@@ -2134,6 +2131,19 @@ template <class K> struct Leaf {
 template <class K> RB_HD RB_NOINLINE bool node_contains(const DScene& sc, int node, V3 q) {
   const DNode& nd = sc.nodes[node];
   return Leaf<K>::contains(sc, nd.leaf, nd.shape, to_local(nd.g, q));
+}
+// The line through lp along ld against the node's own box (separating axes d x e_k, no division), and the box entirely behind
+// the start point.  fp32 on local coordinates: the margins cover the roundings (|lp| relative) on top of the padded widths.
+RB_HD inline bool local_box_missed(const DNode& nd, V3 lp, V3 ld) {
+  const float px = (float)lp.x - nd.lc[0], py = (float)lp.y - nd.lc[1], pz = (float)lp.z - nd.lc[2];
+  const float dx = (float)ld.x, dy = (float)ld.y, dz = (float)ld.z;
+  const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+  const float eps = (2e-6f * (fabsf(px) + fabsf(py) + fabsf(pz)) + 1e-3f) * (ax + ay + az);
+  const float hx = nd.lh[0], hy = nd.lh[1], hz = nd.lh[2];
+  if (fabsf(py * dz - pz * dy) > hy * az + hz * ay + eps) return true;
+  if (fabsf(pz * dx - px * dz) > hz * ax + hx * az + eps) return true;
+  if (fabsf(px * dy - py * dx) > hx * ay + hy * ax + eps) return true;
+  return px * dx + py * dy + pz * dz > hx * ax + hy * ay + hz * az + eps;
 }
 RB_HD inline bool node_box_holds(const DNode& nd, V3 q) {
   const float x = (float)q.x, y = (float)q.y, z = (float)q.z;  // the boxes are padded for this rounding
@@ -2343,6 +2353,15 @@ RB_HD inline bool raybox_test(const RayBox& q, const float* lo, const float* hi,
   else hit = hit && q.fz >= lo[2] && q.fz <= hi[2];
   return hit && tmin <= tmax * 1.000002f + 1e-4f;
 }
+// Boxes that hold the start point all enter the list with parameter 0; among them the one the point sits deepest in goes first
+// (key = minus the distance to the nearest face).  That is the cell the ray is flying through — a Winston cone's own wall, a
+// facet's own shell — while its neighbours' boxes only reach the point with a corner: once the own cell has given the step,
+// the neighbours are dropped after their cheapest operand (Bool2::dist_out's step limit) instead of being evaluated in full.
+RB_HD inline float cand_key(const RayBox& q, const float* lo, const float* hi, float tmin) {
+  if (tmin > 0.f) return tmin;
+  const float depth = fminf(fminf(fminf(q.fx - lo[0], hi[0] - q.fx), fminf(q.fy - lo[1], hi[1] - q.fy)), fminf(q.fz - lo[2], hi[2] - q.fz));
+  return depth > 0.f ? -depth : 0.f;
+}
 // candidate list, nearest box first: the step found in the first candidates lets nb_eval drop the farther ones unevaluated
 RB_HD inline void cand_insert(StepOut& o, int first, int child, float tmin) {
   int k = o.nvis++;
@@ -2363,7 +2382,7 @@ template <class K> RB_HD inline void nb_collect(const DScene& sc, const RayReg& 
     float tmin;
     if (!raybox_test(q, b.lo, b.hi, tmin)) { i = b.skip; continue; }
     if (b.child >= 0) {
-      cand_insert(o, first, b.child, tmin);
+      cand_insert(o, first, b.child, cand_key(q, b.lo, b.hi, tmin));
       i = b.skip;
     } else i = i + 1;
   }
@@ -2372,14 +2391,28 @@ template <class K> RB_HD inline void nb_collect(const DScene& sc, const RayReg& 
 
 // phase C: DistFromOutside of candidate k.  TGeo scans daughters in order and keeps the first one within
 // tolerance: on (near-)ties the lowest daughter index wins regardless of the visiting order.
+#if defined(RB_EMUL_STATS) && !defined(__CUDACC__)
+// host-side analysis build (profiles/cand_stats.py): what happens to the candidates of a step, per step number of the ray
+struct RbEvalStats { long long steps[8], listed[8], culled[8], boxed[8], evaluated[8], hits[8]; };
+inline RbEvalStats g_eval_stats;
+inline int g_eval_step = 0;
+#define RB_STAT(field) g_eval_stats.field[g_eval_step < 7 ? g_eval_step : 7]++
+#else
+#define RB_STAT(field) ((void)0)
+#endif
 template <class K> RB_HD inline void nb_eval(const DScene& sc, const RayReg& r, NavStep& st, int k) {
   int c = st.o.vis[k];
+  RB_STAT(listed);
   // the ray enters this daughter's box (padded by >= 2e-3) beyond the step already found: its DistFromOutside cannot be
   // nearer than the best one, nor tie with it within the tolerance
-  if (st.o.tin[k] > (float)st.best * 1.000001f + 1e-3f) return;
+  if (st.o.tin[k] > (float)st.best * 1.000001f + 1e-3f) { RB_STAT(culled); return; }
   const DNode& dn = sc.nodes[c];
   int sel = 0;
-  double s = Leaf<K>::dist_out(sc, dn.leaf, dn.shape, to_local(dn.g, r.p), to_local_vec(dn.g, r.d), st.best + 2 * RB_TOL, sel);
+  const V3 lp = to_local(dn.g, r.p), ld = to_local_vec(dn.g, r.d);
+  if (local_box_missed(dn, lp, ld)) { RB_STAT(boxed); return; }  // DistFromOutside would report no crossing
+  double s = Leaf<K>::dist_out(sc, dn.leaf, dn.shape, lp, ld, st.best + 2 * RB_TOL, sel);
+  RB_STAT(evaluated);
+  if (s < 1e29) RB_STAT(hits);
   if (s < st.best - RB_TOL || (st.enter >= 0 && c < st.enter && s <= st.best + RB_TOL)) { st.best = s; st.enter = c; st.esel = sel; }
 }
 

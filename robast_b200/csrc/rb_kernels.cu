@@ -660,7 +660,7 @@ static void launch_trace(const rb_variant* v, const DScene& sc, const DTracePara
 static size_t wavefront_scratch_bytes(long long n) {
   size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
   // cur, ndraw, liveA, liveB, cells (uint16), the nav record (6 x 16 B) + bounce counters + tile state + tile counter + cell histogram
-  return 4 * ((size_t)n * 4 + 256) + ((size_t)n * 2 + 256) + 6 * ((size_t)n * 16 + 256) + 256 + ntile * 8 + 256 + 256 + SB_BINS * 4 + 512;
+  return 4 * ((size_t)n * 4 + 256) + ((size_t)n * 2 + 256) + 6 * ((size_t)n * 16 + 256) + ((size_t)n * 8 + 256) + 256 + ntile * 8 + 256 + 256 + SB_BINS * 4 + 512;
 }
 
 // Device-resident trace of n rays (n < 2^31) enqueued on stream st; never waits for the device.
@@ -704,6 +704,7 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     DNavOut N;
     N.pxy = (double2*)take(n * 16); N.pzs = (double2*)take(n * 16);
     N.loc = (int4*)take(n * 16); N.hit = (int4*)take(n * 16); N.vis = (int4*)take(2 * n * 16);
+    N.ent = (double*)take(n * 8);
     N.n = n;
     int32_t* d_counts = (int32_t*)take((RB_MAX_ROUNDS + 2) * 4);
     unsigned long long* tile_state = (unsigned long long*)take(ntile * 8);
@@ -778,14 +779,10 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     for (int b = 0; b < rounds; b++) {
       if (fused) launch_trace(s->variant, s->d, tp, R, live, count, estimate(b), n, b == 0, 1, st);
       else {
-        // Locating the start points inside the first k_nav saves a pass over the rays but brings the Contains routines into the
-        // navigation kernel's instruction footprint: measured 10 % faster on configs 1 and 5, 10 % slower on 2 and 3
-        // (profiles/r2_summary.md).  Separate pass by default; RB_FUSED_INIT=1 fuses.
-        static const bool separate_init = getenv("RB_FUSED_INIT") == nullptr;
-        const int first = b == 0 && !separate_init;
-        if (b == 0 && separate_init) launch_phase(s->variant, 0, s->d, tp, R, N, nullptr, nullptr, n, n, st);
-        launch_phase(s->variant, first ? 3 : 1, s->d, tp, R, N, live, count, estimate(b), n, st);
-        launch_phase(s->variant, first ? 4 : 2, s->d, tp, R, N, live, count, estimate(b), n, st);
+        // first bounce: k_nav locates the start points (InitTrack), takes the step into the top volume for rays shot from outside
+        // it, and reads the input arrays; k_shade starts from the input arrays too
+        launch_phase(s->variant, b == 0 ? 3 : 1, s->d, tp, R, N, live, count, estimate(b), n, st);
+        launch_phase(s->variant, b == 0 ? 4 : 2, s->d, tp, R, N, live, count, estimate(b), n, st);
       }
       CK(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
       CK(cudaMemsetAsync(tile_counter, 0, 4, st));
@@ -1490,7 +1487,7 @@ __global__ void k_shoot_bunches(long long nb, const long long* __restrict__ offs
     Philox g;
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
     g.id0 = (uint32_t)ray; g.id1 = (uint32_t)((unsigned long long)ray >> 32);
-    g.ndraw = 0;
+    g.ndraw = 0x40000000u;  // the shooters' counter range (k_shoot): a trace of the same rays with the same seed starts at 0
     lam = 1. / (1. / lmin - rng_uniform(g) * (1. / lmin - 1. / lmax));
   }
   x[j] = bx[lo] * cm - tel_dist * cx;

@@ -39,7 +39,9 @@ struct DNode {
   float blo[3], bhi[3];  // padded world AABB of the node's shape (same box as its BVH leaf): cheap rejection of point tests
   int32_t box_first; // this node's daughters as a flat list of boxes: slice [box_first, box_first + box_count) of DScene::boxes
   int32_t box_count;
-  int32_t pad_[3];
+  float lc[3], lh[3];  // box of the shape in the node's own frame (centre, padded half-widths): nb_eval drops a candidate whose
+                       // box the ray misses before any of its Dist* code runs — the world box of a tilted thin solid is mostly air
+  int32_t pad_[1];
 };
 
 // Leaf evaluator classes.  A node's shape is a boolean tree of primitives; the generic evaluator walks it through a

@@ -115,8 +115,9 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_trace(const __gri
 // free-running warps stall on instruction fetch (no_instruction 51-70 % of the warp samples), and keeping the block in lock
 // step with barriers only trades that for barrier waits.  The step is therefore cut where its code splits in two halves of
 // less than 32 KB each, and each half is a kernel of its own that streams over all live rays:
-//   (first bounce: k_nav also locates the start points — InitTrack — and k_shade starts from the input arrays; k_init does
-//   both as a pass of its own and is kept for comparison, RB_SEPARATE_INIT=1)
+//   (first bounce: k_nav also locates the start points — InitTrack — and takes the step into the top volume for rays shot from
+//   outside it; k_shade starts from the input arrays.  A pass of its own for that, k_init / k_locate, was measured slower on
+//   every config once the entry step stopped costing a bounce: profiles/r2_summary.md)
 //   k_nav   FindNextBoundary: DistFromInside of the current shape, BVH walk, DistFromOutside of the candidates, move to the
 //           boundary.  Touches only the Dist* routines of the scene's shapes.  Leaves a NavOut record per live ray.
 //   k_shade CrossBoundaryAndLocate + the interaction: point location behind the boundary (Contains routines), facet normal,
@@ -128,22 +129,9 @@ struct DNavOut {       // SoA over the slots of the live list (16-byte vectors: 
   int4* loc;           // loc_node, loc_skip, loc_check | on_boundary << 1, loc_prefer
   int4* hit;           // crossed, sel, nvis (-1: not recorded), next (valid when loc_node == -2)
   int4* vis;           // daughters whose box the ray touched (relocate_back's shortcut): entries 0-3 at [i], 4-7 at [n + i];
+  double* ent;         // first bounce, ray shot from outside the top volume (loc.z & 8): the step that took it inside
   long long n;         // more than eight => recorded as nvis = -1 (relocate_back then searches from the top)
 };
-
-template <class K>
-__global__ void __launch_bounds__(K::threads, K::min_blocks) k_init(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
-                                                                    const __grid_constant__ DRays R, long long n) {
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    RayReg r;
-    Philox g;
-    load_ray<K>(sc, tp, R, idx, 1, r, g);
-    // a ray shot from outside the top volume first has to enter it (no daughters to examine, no interaction besides AddPoint):
-    // that step is taken here instead of spending a whole bounce on it
-    if (r.cur < 0) trace_step<K>(sc, tp, r, g, nullptr);
-    store_ray(R, idx, r, g, 1);
-  }
-}
 
 // ---- warp-cooperative candidate search.  The rays of a warp are neighbours of one beam: they sit in the same mother volume
 // and go through the same few daughter boxes, yet each of them walks the mother's BVH on its own, node after node, every node a
@@ -228,7 +216,7 @@ template <class K> __device__ inline bool nb_collect_warp(const DScene& sc, cons
         float tmin;
         if (mine && !ovf && raybox_test(q, bx.lo, bx.hi, tmin)) {
           if (st.o.nvis >= RB_MAXVIS) ovf = true;
-          else cand_insert(st.o, 0, bx.child, tmin);
+          else cand_insert(st.o, 0, bx.child, cand_key(q, bx.lo, bx.hi, tmin));
         }
       }
     }
@@ -258,11 +246,10 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
     nav.on_boundary = 0;
     nav.p = v3(0, 0, 0);
     nav.d = v3(0, 0, 1);
-    bool outside = false;
+    bool outside = false, entered = false;
     if (active && init) {
-      // first bounce: InitTrack — the start point is located here and the node handed to k_shade through the scratch column.
-      // A ray shot from outside the top volume has to enter it first: k_shade takes that step for it (no daughters to examine,
-      // no interaction besides AddPoint) and the ray joins the wavefront with the next bounce.
+      // first bounce: InitTrack — the start point is located here and the node handed to k_shade through
+      // the scratch column
       nav.p = v3(R.x[idx], R.y[idx], R.z[idx]);
       V3 d = v3(R.dx[idx], R.dy[idx], R.dz[idx]);
       double mag = sqrt(dot(d, d));
@@ -271,6 +258,31 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
       rb_stcs(R.cur + idx, (int32_t)nav.cur);
       outside = nav.cur < 0;
       nav.status = outside ? RBG_STOP : RBG_RUN;
+      // A ray shot from outside the top volume has to enter it first.  Common case — it arrives in a plain (non-optical) volume:
+      // that step has no effect but AddPoint (trace_shade, curVac -> OPT/OTHER), so it is taken right here and the ray goes
+      // on to its first real boundary in the same pass; k_shade rebuilds the entry point from the recorded step length.
+      // Anything else (the ray misses the world, or lands in a mirror / lens / obscuration placed flush with the world's
+      // surface) is left to k_shade, which spends this bounce on the entry step alone.
+      if (outside && tp.limit > 2) {
+        int sel = 0;
+        double s_in = Leaf<K>::dist_out(sc, sc.top_leaf, sc.top_shape, nav.p, nav.d, RB_BIG, sel);
+        if (s_in <= 1e29) {
+          if (s_in <= 0) s_in = 0.0;
+          const V3 q = along(nav.p, nav.d, s_in);
+          const int nx = search_node<K>(sc, 0, along(q, nav.d, locate_extra(sc, 0, s_in)), -1, false);
+          const int ty = nx < 0 ? RBG_NULL : sc.nodes[nx].type;
+          if (ty == RBG_OPT || ty == RBG_OTHER) {
+            entered = true;
+            outside = false;
+            N.ent[i] = s_in;
+            rb_stcs(R.cur + idx, (int32_t)nx);
+            nav.p = q;
+            nav.cur = nx;
+            nav.on_boundary = 1;
+            nav.status = RBG_RUN;
+          }
+        }
+      }
     } else if (active) {
       nav.p = v3(rb_ldcs(R.ox + idx), rb_ldcs(R.oy + idx), rb_ldcs(R.oz + idx));
       nav.d = v3(rb_ldcs(R.odx + idx), rb_ldcs(R.ody + idx), rb_ldcs(R.odz + idx));
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
     st.mode = 0; st.bvh_next = -1; st.best = 0;
     st.o.next = -1; st.o.crossed = -1; st.o.sel = 0; st.o.nvis = -1; st.o.step = 0;
     st.loc_node = -2; st.loc_skip = -1; st.loc_check = 0; st.loc_prefer = -1;
-    const bool run = active && nav.status == RBG_RUN;  // (the first bounce also sees rays that ended in k_init)
+    const bool run = active && nav.status == RBG_RUN;  // (the first bounce also sees rays left to k_shade: outside the top volume)
     if (run) nb_begin<K>(sc, nav, push, st);
     const bool want = run && st.mode == 1 && st.bvh_next >= 0;
     const bool listed = coop ? nb_collect_warp<K>(sc, nav, st, want) : false;
@@ -306,7 +318,7 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
     const int nvis = (st.o.nvis >= 0 && st.o.nvis <= 8) ? st.o.nvis : -1;
     N.pxy[i] = make_double2(nav.p.x, nav.p.y);
     N.pzs[i] = make_double2(nav.p.z, st.o.step);
-    N.loc[i] = make_int4(st.loc_node, st.loc_skip, (st.loc_check ? 1 : 0) | (nav.on_boundary ? 2 : 0) | (outside ? 4 : 0), st.loc_prefer);
+    N.loc[i] = make_int4(st.loc_node, st.loc_skip, (st.loc_check ? 1 : 0) | (nav.on_boundary ? 2 : 0) | (outside ? 4 : 0) | (entered ? 8 : 0), st.loc_prefer);
     N.hit[i] = make_int4(st.o.crossed, st.o.sel, nvis, st.o.next);
     if (nvis > 0) N.vis[i] = make_int4(st.o.vis[0], nvis > 1 ? st.o.vis[1] : -1, nvis > 2 ? st.o.vis[2] : -1, nvis > 3 ? st.o.vis[3] : -1);
     if (nvis > 4) N.vis[N.n + i] = make_int4(st.o.vis[4], nvis > 5 ? st.o.vis[5] : -1, nvis > 6 ? st.o.vis[6] : -1, nvis > 7 ? st.o.vis[7] : -1);
@@ -331,6 +343,10 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_shade(const __gri
       trace_step<K>(sc, tp, r, g, nullptr);
       store_ray(R, idx, r, g, 1);
       continue;
+    }
+    if (loc.z & 8) {  // k_nav took the step into the top volume (r.cur is already the node it arrived in): AddPoint
+      const double s_in = N.ent[i];
+      add_point(r, along(r.p, r.d, s_in), r.t + s_in / RB_C_CM, r.cur, nullptr);
     }
     RayReg nav = r;  // navigator copy: nav.p sits on the boundary, r.p at the segment start
     nav.p = v3(pxy.x, pxy.y, pzs.x);
@@ -369,7 +385,7 @@ struct rb_variant {
   unsigned shapes, phys;
   rb_launch_fn launch;  // k_trace : per-ray loop (single launch, tail of a wavefront, polyline records)
   // one wavefront bounce: phase 1 = k_nav, 2 = k_shade; first bounce: 3 = k_nav locating the start points, 4 = k_shade starting from
-  // the input arrays (or, RB_SEPARATE_INIT=1: phase 0 = k_init, then 1 and 2)
+  // the input arrays
   int (*launch_phase)(int phase, const DScene& sc, const DTraceParams& tp, const DRays& R, const DNavOut& N, const int32_t* live, const int32_t* count,
                       long long n_grid, long long n_max, cudaStream_t st);
 };
@@ -389,8 +405,7 @@ struct rb_variant {
     if (blocks < 1) blocks = 1;                                                                                                       \
     if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;                                                                                 \
     const int init = phase >= 3;                                                                                                      \
-    if (phase == 0) k_init<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, n_max);                                         \
-    else if (phase == 1 || phase == 3)                                                                                                \
+    if (phase == 1 || phase == 3)                                                                                                     \
       k_nav<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, N, live, count, n_max, rb_coop_search(), init);               \
     else k_shade<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, N, live, count, n_max, init);                             \
     return (int)cudaGetLastError();                                                                                                   \

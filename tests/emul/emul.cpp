@@ -41,7 +41,11 @@ template <class K> void run(const DScene& sc, const DTraceParams& tp, const rbg_
     sink.idx = idx;
     const HistSink* hs = dh.x ? &sink : nullptr;
     if (hs) { dh.x[idx] = r.p.x; dh.y[idx] = r.p.y; dh.z[idx] = r.p.z; dh.t[idx] = r.t; dh.node[idx] = -1; }
+#ifdef RB_EMUL_STATS
+    for (g_eval_step = 0; r.status == RBG_RUN; g_eval_step++) { RB_STAT(steps); trace_step<K>(sc, tp, r, g, hs); }
+#else
     while (r.status == RBG_RUN) trace_step<K>(sc, tp, r, g, hs);
+#endif
     R->ox[idx] = r.p.x; R->oy[idx] = r.p.y; R->oz[idx] = r.p.z; R->ot[idx] = r.t;
     R->odx[idx] = r.d.x; R->ody[idx] = r.d.y; R->odz[idx] = r.d.z;
     R->status[idx] = r.status; R->last_node[idx] = r.last_node; R->npoints[idx] = r.npoints;
@@ -89,6 +93,12 @@ extern "C" __attribute__((visibility("default"))) int emul_trace_history(const r
     return RBG_EINTERNAL;
   }
 }
+#ifdef RB_EMUL_STATS
+extern "C" __attribute__((visibility("default"))) void emul_stats(long long* out, int reset) {
+  memcpy(out, &g_eval_stats, sizeof(g_eval_stats));
+  if (reset) memset(&g_eval_stats, 0, sizeof(g_eval_stats));
+}
+#endif
 extern "C" __attribute__((visibility("default"))) int emul_tmm(const rbg_scene_desc* D, int ml, int pol, double th, double lam, double* R, double* T) {
   DScene sc;
   memset(&sc, 0, sizeof(sc));

@@ -100,6 +100,48 @@ def test_rays_starting_outside_world_and_inside_volumes(oracle):
     assert rep["bad"] == 0 and rep["status_mismatch"] == 0, (rep, ref.status, got.status)
 
 
+def test_wavefront_entry_step_from_outside_the_world(R, oracle):
+    """Rays shot from outside the top volume (tutorials/DaviesCotton.C:198-205 starts its beam above the world box).  The first
+    k_nav takes the step into the world itself when the ray lands in a plain volume; rays that land in a mirror / obscuration
+    placed flush with the world's surface, or miss the world, are left to k_shade.  Both routes, both launch modes, per ray."""
+    import scenes
+    mgr = scenes.make_the_world()  # 20 m half-width box
+    world = mgr.GetTopVolume()
+    m = 100.0
+    mirror = R.AMirror("mirror", R.TGeoBBox("mbox", 5 * m, 5 * m, 1 * m))
+    world.AddNode(mirror, 1, R.TGeoTranslation("t1", -10 * m, 0, 19 * m))   # flush with the top face
+    obs = R.AObscuration("obs", R.TGeoBBox("obox", 3 * m, 3 * m, 1 * m))
+    world.AddNode(obs, 1, R.TGeoTranslation("t2", 12 * m, 0, 19 * m))
+    lens = R.ALens("lens", R.TGeoBBox("lbox", 3 * m, 3 * m, 1 * m))
+    idx = R.ARefractiveIndex(1.5)
+    lens.SetRefractiveIndex(idx)
+    world.AddNode(lens, 1, R.TGeoTranslation("t3", 0, 12 * m, 19 * m))
+    focal = R.AFocalSurface("focal", R.TGeoBBox("fbox", 15 * m, 15 * m, 0.1))
+    world.AddNode(focal, 1, R.TGeoTranslation("t4", 0, 0, -10 * m))
+    box = R.AOpticalComponent("frame", R.TGeoBBox("cbox", 2 * m, 2 * m, 2 * m))
+    world.AddNode(box, 1, R.TGeoTranslation("t5", 0, -12 * m, 18 * m))     # a plain volume flush with the top face
+    mgr.CloseGeometry()
+    ex = mgr.ExportScene()
+    rng = np.random.default_rng(21)
+    n = 6000
+    inp = np.zeros((n, 8))
+    inp[:, 0:2] = (rng.random((n, 2)) - 0.5) * 50 * m      # some start beside the world's footprint
+    inp[:, 2] = 30 * m
+    tilt = (rng.random((n, 2)) - 0.5) * 0.4
+    inp[:, 4:6] = tilt
+    inp[:, 6] = -1.0
+    inp[n // 2:, 2] = -5 * m                                # the second half starts inside the world
+    inp[:, 7] = 4e-5
+    inp[:40, 6] = 1.0                                       # and a few fly away from it
+    for limit in (100, 2):
+        ref = H.trace_with(oracle.orc_trace, ex, H.Rays(inp), H.opts(seed=3, limit=limit), nthreads=4)
+        for steps in (-1, 1):
+            got = H.trace_gpu(ex, H.Rays(inp), H.opts(seed=3, limit=limit, steps_per_launch=steps))
+            rep = H.compare(ref, got)
+            assert rep["bad"] == 0 and rep["status_mismatch"] == 0 and rep["npoints_mismatch"] == 0 and rep["node_mismatch"] == 0, (limit, steps, rep)
+    assert len(set(ref.status.tolist())) >= 2
+
+
 def test_tmm_kernel_matches_oracle_and_golden(R, oracle):
     med1, med2, med3, med4 = R.ARefractiveIndex(1.), R.ARefractiveIndex(2., 4.), R.ARefractiveIndex(3., .3), R.ARefractiveIndex(1., .1)
     multi = R.AMultilayer(med1, med4)
