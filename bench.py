@@ -533,12 +533,18 @@ def main():
         step()
         marks.append(torch.cuda.Event(enable_timing=True))
         marks[-1].record()
-        if clock_reader.inline:
+    e1.record()
+    # rbg_trace only queues work, so the steps above are all in the stream long before the GPU is through the first one: the
+    # clocks are read now, while it works on them, and no NVML call sits between two steps' launches.
+    if clock_reader.inline:
+        while True:
             try:
                 samples.append(clock_reader())
             except Exception:
                 pass
-    e1.record()
+            if e1.query() or len(samples) >= 200:
+                break
+            time.sleep(0.02)
     barrier()
     stop.set()
     th_clock.join()

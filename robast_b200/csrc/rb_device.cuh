@@ -670,7 +670,7 @@ RB_HD inline bool sphere_contains(const double* P, V3 p) {
   }
   return true;
 }
-RB_HD inline double sphere_dist(const double* P, V3 p, V3 d, bool from_inside) {
+RB_HD inline double sphere_dist(const double* P, V3 p, V3 d, bool from_inside, double limit = RB_BIG) {
   double c[10];
 #pragma unroll
   for (int k = 0; k < 10; k++) c[k] = RB_BIG;
@@ -685,6 +685,7 @@ RB_HD inline double sphere_dist(const double* P, V3 p, V3 d, bool from_inside) {
     double e0, e1;
     cand_quadratic(a, b, pp - P[0] * P[0], e0, e1);
     const double tE = rb_min(e0, e1);
+    if (tE > limit && tE < 1e29) return RB_BIG;  // the shell starts beyond the caller's limit (the step already found)
     if (tE < 1e29) {
       const double ct = (p.z + tE * d.z) / P[0];
       if (!(((flags & 1) && ct > P[6]) || ((flags & 2) && ct < P[8]))) {
@@ -1892,7 +1893,7 @@ template <int T> struct PrimT;  // primitive routines by compile-time type (P = 
   };
 RB_PRIMT(RBG_SHAPE_BBOX, bbox_contains(P, p), bbox_dist_in(P, p, d), bbox_dist_out(P, p, d, step), bbox_normal(P, p, d))
 RB_PRIMT(RBG_SHAPE_TUBE, tube_contains(P, p), tube_dist_in(P[0], P[1], P[2], p, d), tube_dist_out(P[0], P[1], P[2], p, d), tube_normal(P, p, d))
-RB_PRIMT(RBG_SHAPE_SPHERE, sphere_contains(P, p), sphere_dist(P, p, d, true), sphere_dist(P, p, d, false), sphere_normal(P, p, d))
+RB_PRIMT(RBG_SHAPE_SPHERE, sphere_contains(P, p), sphere_dist(P, p, d, true), sphere_dist(P, p, d, false, step), sphere_normal(P, p, d))
 RB_PRIMT(RBG_SHAPE_PARABOLOID, para_contains(P, p), para_dist_in(P, p, d), para_dist_out(P, p, d), para_normal(P, p, d))
 // polygons / polycones reach the typed path only in their convex form (rmin = 0, full azimuth): leaf_kind sees to that
 RB_PRIMT(RBG_SHAPE_PGON, poly_contains<false>(P, p), poly_dist_in<false>(P, p, d), poly_dist_out<false>(P, p, d), poly_normal<false>(P, p, d))
@@ -1953,16 +1954,19 @@ template <class C> struct Bool2 {
       out = RB_BIG;
       for (int guard = 0; guard < 64; guard++) {
         double d1 = 0, d2 = 0;
+        // (the operands get what is left of the caller's limit: one that starts beyond it reports no crossing, and so does the
+        // intersection — the same outcome as the `snext > step` test below, reached earlier)
+        const double left = step - snext;
         if (right_first && !inr) {
-          d2 = rb_max(PR::dist_out(B, rp, rd, RB_BIG), RB_TOL);
+          d2 = rb_max(PR::dist_out(B, rp, rd, left), RB_TOL);
           if (d2 > 1E20) return true;
         }
         if (!inl) {
-          d1 = rb_max(PL::dist_out(A, lp, ld, RB_BIG), RB_TOL);
+          d1 = rb_max(PL::dist_out(A, lp, ld, left), RB_TOL);
           if (d1 > 1E20) return true;
         }
         if (!right_first && !inr) {
-          d2 = rb_max(PR::dist_out(B, rp, rd, RB_BIG), RB_TOL);
+          d2 = rb_max(PR::dist_out(B, rp, rd, left), RB_TOL);
           if (d2 > 1E20) return true;
         }
         const bool left_entered = d1 > d2;

@@ -613,6 +613,28 @@ static void keep_pool(int device) {
   }
 }
 
+// Scratch of the reducers comes from a pool of its own.  Taken from the device's default pool on a second stream it shares
+// address space with the wavefront's GB-sized scratch blocks of the main stream, whose stream-ordered frees are still pending
+// when the host runs ahead: now and then the allocator had to rearrange the pool, which blocks the host until the device is
+// idle — a step of 62 ms came out at 95-330 ms in one bench run out of four (profiles/r2_summary.md).
+static cudaMemPool_t small_pool(int device) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[32] = {};
+  if (device < 0 || device >= 32) throw Invalid("bad device index");
+  std::lock_guard<std::mutex> lk(mu);
+  if (!pools[device]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CK(cudaMemPoolCreate(&pools[device], &props));
+    uint64_t keep = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  return pools[device];
+}
+
 // ------------------------------------------------------------------------------------------------ host: trace driver
 int rb_coop_search() {
   static const int on = getenv("RB_COOP") ? atoi(getenv("RB_COOP")) : 1;
@@ -1584,9 +1606,8 @@ int rbg_containment_radius(int32_t nhist, const unsigned long long* hist, int32_
     if (nhist < 0 || nx < 1 || ny < 1 || !(xmax > xmin) || !(ymax > ymin) || !hist || !stats || !out) throw Invalid("bad containment-radius arguments");
     if (nhist == 0) return;
     CK(cudaSetDevice(device));
-    keep_pool(device);  // stream-ordered scratch for the per-row running sums
-    double* prefix = nullptr;
-    CK(cudaMallocAsync((void**)&prefix, (size_t)nhist * (nx + 1) * ny * sizeof(double), (cudaStream_t)stream));
+    double* prefix = nullptr;  // stream-ordered scratch for the per-row running sums
+    CK(cudaMallocFromPoolAsync((void**)&prefix, (size_t)nhist * (nx + 1) * ny * sizeof(double), small_pool(device), (cudaStream_t)stream));
     int rc = rb_launch_containment_u64(nhist, hist, nx, xmin, xmax, ny, ymin, ymax, stats, fraction, out, prefix, (cudaStream_t)stream);
     cudaFreeAsync(prefix, (cudaStream_t)stream);
     CK((cudaError_t)rc);
