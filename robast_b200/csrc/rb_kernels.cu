@@ -797,7 +797,9 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     const float inv_batch = 1.f / (float)n;
     const int vec_ok = (reinterpret_cast<uintptr_t>(R.status) & 15) == 0;
     const int tiles = (int)ntile;
-    static const bool fused = getenv("RB_FUSED_BOUNCE") != nullptr;  // experiments: the whole step in one kernel (k_trace, max_steps = 1)
+    // RB_FUSED_BOUNCE=1 / 0 overrides the instantiation's choice between one k_trace launch per bounce and k_nav + k_shade
+    static const int fused_env = getenv("RB_FUSED_BOUNCE") ? atoi(getenv("RB_FUSED_BOUNCE")) : -1;
+    const bool fused = fused_env >= 0 ? fused_env != 0 : s->variant->fused_bounce != 0;
     for (int b = 0; b < rounds; b++) {
       if (fused) launch_trace(s->variant, s->d, tp, R, live, count, estimate(b), n, b == 0, 1, st);
       else {

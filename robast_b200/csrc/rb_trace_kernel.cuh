@@ -388,7 +388,14 @@ struct rb_variant {
   // the input arrays
   int (*launch_phase)(int phase, const DScene& sc, const DTraceParams& tp, const DRays& R, const DNavOut& N, const int32_t* live, const int32_t* count,
                       long long n_grid, long long n_max, cudaStream_t st);
+  // 1: the wavefront takes a bounce as one k_trace launch.  Scenes of a few plain shapes have a step small enough for the
+  // instruction cache; skipping the record between k_nav and k_shade (176 B per ray and bounce) is then worth 7-35 %
+  // (SimpleParabolicTelescope, SchwarzschildCouder).  The Davies-Cotton dish loses 3 % that way, the Schmidt-Cassegrain 25 %.
+  int fused_bounce;
 };
+#ifndef RB_VARIANT_FUSED
+#define RB_VARIANT_FUSED 0
+#endif
 #define RB_DEFINE_TRACE_VARIANT(NAME, D, S, P, TH, MB, CL)                                                                                \
   typedef TraceCfg<D, S, P, TH, MB, CL> rb_cfg_##NAME;                                                                                 \
   int rb_launch_trace_##NAME(const DScene& sc, const DTraceParams& tp, const DRays& R, const int32_t* live, const int32_t* count,     \
@@ -410,7 +417,7 @@ struct rb_variant {
     else k_shade<rb_cfg_##NAME><<<(unsigned)blocks, TH, 0, st>>>(sc, tp, R, N, live, count, n_max, init);                             \
     return (int)cudaGetLastError();                                                                                                   \
   }                                                                                                                                   \
-  extern const rb_variant rb_variant_##NAME = {#NAME, D, S, P, rb_launch_trace_##NAME, rb_launch_phase_##NAME};
+  extern const rb_variant rb_variant_##NAME = {#NAME, D, S, P, rb_launch_trace_##NAME, rb_launch_phase_##NAME, RB_VARIANT_FUSED};
 // tuning units add themselves to the RB_VARIANT=<name> lookup
 int rb_register_variant(const rb_variant* v);
 #define RB_DEFINE_TUNE_VARIANT(NAME, D, S, P, TH, MB, CL) \
