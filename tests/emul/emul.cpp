@@ -99,6 +99,7 @@ extern "C" __attribute__((visibility("default"))) void emul_stats(long long* out
   if (reset) memset(&g_eval_stats, 0, sizeof(g_eval_stats));
 }
 #endif
+extern "C" __attribute__((visibility("default"))) double emul_div(double a, double b) { return rb_div(a, b); }
 extern "C" __attribute__((visibility("default"))) int emul_tmm(const rbg_scene_desc* D, int ml, int pol, double th, double lam, double* R, double* T) {
   DScene sc;
   memset(&sc, 0, sizeof(sc));

@@ -68,6 +68,8 @@ def load_emul():
     lib.emul_trace.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.c_int]
     lib.emul_trace_history.restype = C.c_int
     lib.emul_trace_history.argtypes = [C.c_void_p, C.POINTER(R.rbg_trace_opts), C.POINTER(R.rbg_rays), C.POINTER(R.rbg_history), C.c_int]
+    lib.emul_div.restype = C.c_double
+    lib.emul_div.argtypes = [C.c_double, C.c_double]
     lib.emul_tmm.restype = C.c_int
     lib.emul_tmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return lib

@@ -227,3 +227,20 @@ def test_overlapping_nodes_match_oracle(oracle, emul, nested, tilt):
     st = np.bincount(got.status, minlength=6)
     assert st[3] > 200 and st[1] > 200, st  # focused via plate + mirror; stopped on the holder's bars or the overlapping stop ring
     assert got.npoints[got.status == 3].max() >= 6  # start, plate in/out, mirror, plate in/out, focal plane
+
+
+def test_zero_numerator_division_shortcut_is_ieee_exact(emul):
+    """rb_div (rb_device.cuh) keeps zero numerators away from the compiler's out-of-line fp64 division; its result has to be the
+    IEEE quotient bit for bit, signs of zero, infinities and NaNs included"""
+    import struct
+    inf, nan = float("inf"), float("nan")
+    vals = [0.0, -0.0, 1.0, -1.0, 3.5, -2.25e-300, 1e300, 5e-324, -5e-324, inf, -inf, nan]
+    for a in vals:
+        for b in vals:
+            got = emul.emul_div(a, b)
+            with np.errstate(all="ignore"):
+                want = float(np.float64(a) / np.float64(b))
+            if want != want:
+                assert got != got, (a, b, got)
+            else:
+                assert struct.pack("<d", got) == struct.pack("<d", want), (a, b, got, want)
