@@ -455,8 +455,9 @@ def main():
     hstats2 = [torch.zeros((nang, 5), dtype=torch.float64, device=dev) for _ in range(2)]
     d80_2 = [torch.zeros((nang, 3), dtype=torch.float64, device=dev) for _ in range(2)]
     d80_all = torch.zeros((world * nang, 3), dtype=torch.float64, device=dev)
-    mom = torch.zeros((nang, 8), dtype=torch.float64, device=dev)
-    cnt = torch.zeros((nang, 6), dtype=torch.int64, device=dev)
+    mom2 = [torch.zeros((nang, 8), dtype=torch.float64, device=dev) for _ in range(2)]
+    cnt2 = [torch.zeros((nang, 6), dtype=torch.int64, device=dev) for _ in range(2)]
+    hsum2 = [torch.zeros_like(hist2[0]) for _ in range(2)]
     side = torch.cuda.Stream(device=dev)
     side_done = [None, None]
     main_stream = torch.cuda.current_stream()
@@ -479,7 +480,8 @@ def main():
     def step():
         b = state["k"] & 1
         state["k"] += 1
-        hist, hstats, d80 = hist2[b], hstats2[b], d80_2[b]
+        hist, hstats, d80, mom, cnt = hist2[b], hstats2[b], d80_2[b], mom2[b], cnt2[b]
+        state["last"] = b
         if side_done[b] is not None:
             main_stream.wait_event(side_done[b])  # the search that read this buffer pair two steps ago
         hist.zero_()
@@ -501,12 +503,14 @@ def main():
         side.wait_event(ev)
         R.check(R.rbg_containment_radius(nang, hist.data_ptr(), 200, -4., 10., 200, -7., 7., hstats.data_ptr(), 0.8, d80.data_ptr(), local, side.cuda_stream))
         if dist is not None:
+            # the cross-rank reductions ride on the side stream as well (every reducer output is double-buffered): the next
+            # step's traces do not wait for the other ranks
             with torch.cuda.stream(side):
                 dist.all_gather_into_tensor(d80_all, d80)
-            dist.all_reduce(mom)
-            dist.all_reduce(cnt)
-            hsum = hist.clone()
-            dist.all_reduce(hsum)
+                dist.all_reduce(mom)
+                dist.all_reduce(cnt)
+                hsum2[b].copy_(hist)
+                dist.all_reduce(hsum2[b])
         side_done[b] = torch.cuda.Event()
         side_done[b].record(side)
 
@@ -533,6 +537,9 @@ def main():
         step()
         marks.append(torch.cuda.Event(enable_timing=True))
         marks[-1].record()
+    for ev_side in side_done:  # the timed region ends when the side stream's reducers and collectives of the last steps are done too
+        if ev_side is not None:
+            main_stream.wait_event(ev_side)
     e1.record()
     # rbg_trace only queues work, so the steps above are all in the stream long before the GPU is through the first one: the
     # clocks are read now, while it works on them, and no NVML call sits between two steps' launches.
@@ -559,6 +566,7 @@ def main():
     ms = float(tms.item())
     rays_per_step = n * nang * world
     value = rays_per_step * args.steps / (ms * 1e-3)
+    cnt = cnt2[state["last"]]
     counts = cnt.sum(0).cpu().numpy().tolist()
     focused_frac = counts[R.RBG_FOCUSED] / float(sum(counts))
 
