@@ -1753,7 +1753,7 @@ class AOpticsManager : public TGeoManager {
     r.status = icol[0]; r.last_node = icol[1]; r.npoints = icol[2];
     rbg_trace_opts opts;
     memset(&opts, 0, sizeof(opts));
-    opts.limit = fLimit;
+    opts.limit = fLimitForCall > 0 ? fLimitForCall : fLimit;
     opts.disable_fresnel = fDisableFresnelReflection;
     opts.quirks = fQuirks;
     opts.seed = fSeed;
@@ -1839,7 +1839,7 @@ class AOpticsManager : public TGeoManager {
     ray.GetLastPoint(p);
     ray.GetDirection(d);
     tmp.AddRaw(p[0], p[1], p[2], p[3], d[0], d[1], d[2], ray.GetLambda());
-    TraceNonSequential(tmp);
+    TraceWithHeldPoints(tmp, ray.GetNpoints());
     const ARayArray::Table& T = tmp.GetTable();
     Double_t last[4] = {T.x[0], T.y[0], T.z[0], T.t[0]}, dir[3] = {T.dx[0], T.dy[0], T.dz[0]};
     const char* nn = (fNodeNames && T.last_node[0] >= 0) ? (*fNodeNames)[T.last_node[0]].c_str() : nullptr;
@@ -1848,30 +1848,50 @@ class AOpticsManager : public TGeoManager {
     if (fresh && T.HistCount(0) > 0) ray.SetHistory(&T.hpts[0], T.HistCount(0), &T.hnode[0], fNodeNames.get());
   }
   void TraceNonSequential(ARay* ray) { TraceNonSequential(*ray); }
-  // a TObjArray of ARay (src/AOpticsManager.cxx:335): the running rays go through the batch path in ONE call
+  // a TObjArray of ARay (src/AOpticsManager.cxx:335): the running rays go through the batch path in ONE call (one per number of
+  // points the rays already hold: the fLimit test counts those, see TraceWithHeldPoints)
   void TraceNonSequential(TObjArray* array) {
-    std::vector<ARay*> rays;
-    ARayArray tmp;
+    std::map<Int_t, std::vector<ARay*>> groups;
     for (Int_t i = 0; i <= array->GetLast(); i++) {
       auto* r = dynamic_cast<ARay*>(array->At(i));
-      if (!r || !r->IsRunning()) continue;
-      Double_t p[4], d[3];
-      r->GetLastPoint(p);
-      r->GetDirection(d);
-      tmp.AddRaw(p[0], p[1], p[2], p[3], d[0], d[1], d[2], r->GetLambda());
-      rays.push_back(r);
+      if (r && r->IsRunning()) groups[r->GetNpoints()].push_back(r);
     }
-    if (rays.empty()) return;
-    TraceNonSequential(tmp);
-    const ARayArray::Table& T = tmp.GetTable();
-    for (size_t j = 0; j < rays.size(); j++) {
-      ARay& ray = *rays[j];
-      Double_t last[4] = {T.x[j], T.y[j], T.z[j], T.t[j]}, dir[3] = {T.dx[j], T.dy[j], T.dz[j]};
-      const char* nn = (fNodeNames && T.last_node[j] >= 0) ? (*fNodeNames)[T.last_node[j]].c_str() : nullptr;
-      const bool was_fresh = ray.GetNpoints() == 1;
-      ray.SetTraced(last, dir, T.status[j], ray.GetNpoints() + T.npoints[j] - 1, nn);
-      if (was_fresh && T.HistCount(j) > 0) ray.SetHistory(&T.hpts[4 * T.hoff[j]], T.HistCount(j), &T.hnode[T.hoff[j]], fNodeNames.get());
+    for (auto& grp : groups) {
+      std::vector<ARay*>& rays = grp.second;
+      ARayArray tmp;
+      for (ARay* r : rays) {
+        Double_t p[4], d[3];
+        r->GetLastPoint(p);
+        r->GetDirection(d);
+        tmp.AddRaw(p[0], p[1], p[2], p[3], d[0], d[1], d[2], r->GetLambda());
+      }
+      TraceWithHeldPoints(tmp, grp.first);
+      const ARayArray::Table& T = tmp.GetTable();
+      for (size_t j = 0; j < rays.size(); j++) {
+        ARay& ray = *rays[j];
+        Double_t last[4] = {T.x[j], T.y[j], T.z[j], T.t[j]}, dir[3] = {T.dx[j], T.dy[j], T.dz[j]};
+        const char* nn = (fNodeNames && T.last_node[j] >= 0) ? (*fNodeNames)[T.last_node[j]].c_str() : nullptr;
+        const bool was_fresh = ray.GetNpoints() == 1;
+        ray.SetTraced(last, dir, T.status[j], ray.GetNpoints() + T.npoints[j] - 1, nn);
+        if (was_fresh && T.HistCount(j) > 0) ray.SetHistory(&T.hpts[4 * T.hoff[j]], T.HistCount(j), &T.hnode[T.hoff[j]], fNodeNames.get());
+      }
     }
+  }
+
+ private:
+  // The reference suspends a ray when ray->GetNpoints() >= fLimit (src/AOpticsManager.cxx:515-517), counting the points the ARay
+  // held before this call.  The device counts from 1, so rays that already hold `held` points are traced with the limit lowered by
+  // held - 1 (at least 2: a step is always taken before the test).
+  Int_t fLimitForCall = 0;
+  void TraceWithHeldPoints(ARayArray& tmp, Int_t held) {
+    fLimitForCall = held > 1 ? std::max<Int_t>(2, fLimit - (held - 1)) : 0;
+    try {
+      TraceNonSequential(tmp);
+    } catch (...) {
+      fLimitForCall = 0;
+      throw;
+    }
+    fLimitForCall = 0;
   }
 };
 

@@ -265,6 +265,7 @@ PYBIND11_MODULE(_robast, m) {
       .def("GetLastPoint", [](const ARay& r) { std::array<double, 4> p; r.GetLastPoint(p.data()); return p; })
       .def("GetFirstPoint", [](const ARay& r) { return std::vector<double>(r.GetFirstPoint(), r.GetFirstPoint() + 4); })
       .def("GetNpoints", &ARay::GetNpoints).def("GetLambda", &ARay::GetLambda).def("GetStatus", &ARay::GetStatus)
+      .def("AddPoint", &ARay::AddPoint)
       .def("GetLastNodeName", &ARay::GetLastNodeName)
       .def("GetPoint", [](const ARay& r, int i) { const double* p = r.GetPoint(i); return std::vector<double>(p, p + 4); })
       .def("GetNrecorded", &ARay::GetNrecorded)

@@ -189,6 +189,22 @@ def test_reference_style_unit_tests_on_gpu(R):
     ray = R.ARay(0, 400 * nm, 0, 0, 0, 0, 0, 0, -1)
     mgr.TraceNonSequential(ray)
     assert ray.GetNpoints() == 1000 and ray.IsSuspended()
+    # the limit counts the points an ARay already holds (ray->GetNpoints() >= fLimit, src/AOpticsManager.cxx:515-517)
+    mgr.SetLimit(5)
+    ray = R.ARay(0, 400 * nm, 0, 0, 0, 0, 0, 0, -1)
+    ray.AddPoint(0, 0, 0, 0)
+    ray.AddPoint(0, 0, 0, 0)
+    mgr.TraceNonSequential(ray)
+    assert ray.GetNpoints() == 5 and ray.IsSuspended()
+    held = [R.ARay(0, 400 * nm, 0, 0, 0, 0, 0, 0, -1) for _ in range(4)]
+    for k, r_ in enumerate(held):
+        for _ in range(k):
+            r_.AddPoint(0, 0, 0, 0)
+    arr = R.TObjArray()
+    for r_ in held:
+        arr.Add(r_)
+    mgr.TraceNonSequential(arr)
+    assert [r_.GetNpoints() for r_ in held] == [5, 5, 5, 5] and all(r_.IsSuspended() for r_ in held)
     # testFresnelReflection :122-160 (normal incidence on n = 3 with absorption)
     wl, idx = 400 * nm, 3.
     refidx = R.ARefractiveIndex(idx, R.ARefractiveIndex.AbsorptionLengthToExtinctionCoefficient(1 * um, wl))
