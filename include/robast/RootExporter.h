@@ -447,53 +447,70 @@ class GpuTracer {
 
   void TraceNonSequential(ARayArray& array) {
     TObjArray* running = array.GetRunning();
-    const Int_t n = running->GetLast() + 1;
-    if (n <= 0) return;
-    std::vector<double> col(8 * (size_t)n);
-    std::vector<int32_t> icol(3 * (size_t)n);
-    std::vector<ARay*> rays((size_t)n);
-    for (Int_t i = 0; i < n; i++) {
-      ARay* ray = static_cast<ARay*>(running->At(i));
-      rays[i] = ray;
-      Double_t x[4], d[3];
-      ray->GetLastPoint(x);
-      ray->GetDirection(d);
-      for (int k = 0; k < 4; k++) col[(size_t)k * n + i] = x[k];
-      for (int k = 0; k < 3; k++) col[(size_t)(4 + k) * n + i] = d[k];
-      col[(size_t)7 * n + i] = ray->GetLambda();
+    const Int_t ntot = running->GetLast() + 1;
+    if (ntot <= 0) return;
+    // The reference suspends a ray when ray->GetNpoints() >= fLimit (src/AOpticsManager.cxx:515-517), counting the points it held
+    // before the call; the device counts from 1.  Rays are therefore traced in groups of equal point count (one group — fresh
+    // rays — in every tutorial), each with the limit lowered by what its rays already hold.
+    std::vector<ARay*> all((size_t)ntot);
+    std::map<Int_t, std::vector<size_t>> groups;
+    for (Int_t i = 0; i < ntot; i++) {
+      all[i] = static_cast<ARay*>(running->At(i));
+      groups[all[i]->GetNpoints()].push_back((size_t)i);
     }
-    rbg_rays r;
-    std::memset(&r, 0, sizeof(r));
-    r.n = n;
-    r.on_device = 0;
-    double* c = col.data();
-    r.x = c; r.y = c + n; r.z = c + 2 * (size_t)n; r.t = c + 3 * (size_t)n;
-    r.dx = c + 4 * (size_t)n; r.dy = c + 5 * (size_t)n; r.dz = c + 6 * (size_t)n; r.lambda = c + 7 * (size_t)n;
-    r.ox = c; r.oy = c + n; r.oz = c + 2 * (size_t)n; r.ot = c + 3 * (size_t)n;  // in place
-    r.odx = c + 4 * (size_t)n; r.ody = c + 5 * (size_t)n; r.odz = c + 6 * (size_t)n;
-    r.status = icol.data(); r.last_node = icol.data() + n; r.npoints = icol.data() + 2 * (size_t)n;
-    rbg_trace_opts o;
-    std::memset(&o, 0, sizeof(o));
-    o.limit = Member<Int_t>(fManager, "AOpticsManager", "fLimit");
-    o.disable_fresnel = Member<Bool_t>(fManager, "AOpticsManager", "fDisableFresnelReflection") ? 1 : 0;
-    o.quirks = RBG_QUIRKS_DEFAULT;
-    o.seed = fSeed;
-    o.ray_id_offset = fRayCounter;
-    fRayCounter += (ULong64_t)n;
-    const int rc = fMulti ? rbg_multi_trace(fMulti, &o, &r) : rbg_trace(fScene, &o, &r, nullptr);
-    if (rc != RBG_OK) throw std::runtime_error(std::string("GpuTracer: ") + rbg_last_error());
-    // every ray leaves the running bucket; ARayArray::Add routes it by status and keeps the relative order (:571-582)
-    for (Int_t i = 0; i < n; i++) running->RemoveAt(i);
-    running->Expand(0);
-    for (Int_t i = 0; i < n; i++) {
-      ARay* ray = rays[i];
-      if (icol[(size_t)2 * n + i] > 1) {  // the last point (the polyline in between is kept only by rbg_trace_history)
-        ray->AddPoint(col[i], col[(size_t)n + i], col[2 * (size_t)n + i], col[3 * (size_t)n + i]);
-        const int32_t node = icol[(size_t)n + i];
-        if (node >= 0 && node < (int32_t)fExport.node_of_id.size()) ray->AddNode(fExport.node_of_id[node]);
+    std::vector<int32_t> status((size_t)ntot, RBG_RUN);
+    const Int_t limit = Member<Int_t>(fManager, "AOpticsManager", "fLimit");
+    for (auto& grp : groups) {
+      const std::vector<size_t>& ids = grp.second;
+      const size_t n = ids.size();
+      std::vector<double> col(8 * n);
+      std::vector<int32_t> icol(3 * n);
+      for (size_t j = 0; j < n; j++) {
+        ARay* ray = all[ids[j]];
+        Double_t x[4], d[3];
+        ray->GetLastPoint(x);
+        ray->GetDirection(d);
+        for (int k = 0; k < 4; k++) col[(size_t)k * n + j] = x[k];
+        for (int k = 0; k < 3; k++) col[(size_t)(4 + k) * n + j] = d[k];
+        col[(size_t)7 * n + j] = ray->GetLambda();
       }
-      ray->SetDirection(col[4 * (size_t)n + i], col[5 * (size_t)n + i], col[6 * (size_t)n + i]);
-      switch (icol[i]) {
+      rbg_rays r;
+      std::memset(&r, 0, sizeof(r));
+      r.n = (int64_t)n;
+      r.on_device = 0;
+      double* c = col.data();
+      r.x = c; r.y = c + n; r.z = c + 2 * n; r.t = c + 3 * n;
+      r.dx = c + 4 * n; r.dy = c + 5 * n; r.dz = c + 6 * n; r.lambda = c + 7 * n;
+      r.ox = c; r.oy = c + n; r.oz = c + 2 * n; r.ot = c + 3 * n;  // in place
+      r.odx = c + 4 * n; r.ody = c + 5 * n; r.odz = c + 6 * n;
+      r.status = icol.data(); r.last_node = icol.data() + n; r.npoints = icol.data() + 2 * n;
+      rbg_trace_opts o;
+      std::memset(&o, 0, sizeof(o));
+      o.limit = grp.first > 1 ? std::max<Int_t>(2, limit - (grp.first - 1)) : limit;
+      o.disable_fresnel = Member<Bool_t>(fManager, "AOpticsManager", "fDisableFresnelReflection") ? 1 : 0;
+      o.quirks = RBG_QUIRKS_DEFAULT;
+      o.seed = fSeed;
+      o.ray_id_offset = fRayCounter;
+      fRayCounter += (ULong64_t)n;
+      const int rc = fMulti ? rbg_multi_trace(fMulti, &o, &r) : rbg_trace(fScene, &o, &r, nullptr);
+      if (rc != RBG_OK) throw std::runtime_error(std::string("GpuTracer: ") + rbg_last_error());
+      for (size_t j = 0; j < n; j++) {
+        ARay* ray = all[ids[j]];
+        if (icol[2 * n + j] > 1) {  // the last point (the polyline in between is kept only by rbg_trace_history)
+          ray->AddPoint(col[j], col[n + j], col[2 * n + j], col[3 * n + j]);
+          const int32_t node = icol[n + j];
+          if (node >= 0 && node < (int32_t)fExport.node_of_id.size()) ray->AddNode(fExport.node_of_id[node]);
+        }
+        ray->SetDirection(col[4 * n + j], col[5 * n + j], col[6 * n + j]);
+        status[ids[j]] = icol[j];
+      }
+    }
+    // every ray leaves the running bucket; ARayArray::Add routes it by status and keeps the relative order (:571-582)
+    for (Int_t i = 0; i < ntot; i++) running->RemoveAt(i);
+    running->Expand(0);
+    for (Int_t i = 0; i < ntot; i++) {
+      ARay* ray = all[i];
+      switch (status[i]) {
         case RBG_STOP: ray->Stop(); break;
         case RBG_EXIT: ray->Exit(); break;
         case RBG_FOCUSED: ray->Focus(); break;

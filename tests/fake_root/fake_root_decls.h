@@ -221,7 +221,8 @@ class ARay : public TObject {
   void GetLastPoint(Double_t* x) const;
   void GetDirection(Double_t* d) const;
   Double_t GetLambda() const;
-  void AddPoint(Double_t x, Double_t y, Double_t z, Double_t t);
+  void AddPoint(Double_t x, Double_t y, Double_t z, Double_t t);  // TGeoTrack (ARay's base, include/ARay.h:24)
+  Int_t GetNpoints() const;                                       // TGeoTrack::GetNpoints, used at src/AOpticsManager.cxx:515
   void AddNode(TGeoNode* node);
   void SetDirection(Double_t dx, Double_t dy, Double_t dz);
   void Stop();
