@@ -324,6 +324,22 @@ def bench_one_config(R, torch, H, configs, dev, local, stream, cfg, reps, hbm_pe
     for _ in range(200):
         R.check(R.rbg_trace(scene, C.byref(opts), C.byref(rs), None))
     res["latency_us_1k_rays"] = (time.perf_counter() - t0) / 200 * 1e6
+    if cfg == 5:
+        # the same array with the coating's reflectance read from the table of AMultilayer::PreCalculateCoherentTMM
+        # (include/AMultilayer.h:243-262: 801 wavelengths x 90 angles), the macro author's other option
+        mgr2, _keep2 = configs.BUILDERS[5](precalc=True, **c["kw"])
+        ex2 = mgr2.ExportScene()
+        scene2 = C.c_void_p()
+        R.check(R.rbg_scene_create(ex2.desc_ptr(), local, C.byref(scene2)))
+        for _ in range(2):
+            R.check(R.rbg_trace(scene2, C.byref(opts), C.byref(b.struct), stream))
+        e0.record()
+        for _ in range(reps):
+            R.check(R.rbg_trace(scene2, C.byref(opts), C.byref(b.struct), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        res["value_with_precalculated_tmm_table"] = n / (e0.elapsed_time(e1) / reps * 1e-3)
+        R.rbg_scene_destroy(scene2)
     del b
     torch.cuda.empty_cache()
     if oracle is not None:

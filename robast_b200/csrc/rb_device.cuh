@@ -122,6 +122,7 @@ RB_HD inline double rng_gaus(Philox& g, double mean, double sigma) {
 }
 
 // ================================================================== tables: TGraph::Eval, TH2::Interpolate
+RB_HD inline int rb_min_i(int a, int b) { return a < b ? a : b; }
 RB_HD inline double graph_eval(const DScene& sc, int g, double x) {
   const rbg_graph gr = sc.graphs[g];
   const double *X = sc.gx + gr.first, *Y = sc.gy + gr.first;
@@ -133,9 +134,18 @@ RB_HD inline double graph_eval(const DScene& sc, int g, double x) {
   if (x <= X[0]) { if (x == X[0]) return Y[0]; lo = 0; hi = 1; }
   else if (x >= X[n - 1]) { if (x == X[n - 1]) return Y[n - 1]; lo = n - 2; hi = n - 1; }
   else {
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (X[mid] <= x) lo = mid; else hi = mid;
+    // tabulated optical constants sit on a (nearly) uniform grid: try the bracket a uniform grid would give before bisecting —
+    // the bracket is unique (largest lo with X[lo] <= x), so the value is the same either way, after 2 loads instead of log2(n)
+    // dependent ones
+    const double gf = (x - X[0]) / (X[n - 1] - X[0]) * (double)(n - 1);
+    const int g0 = gf >= 0. ? rb_min_i(n - 2, (int)gf) : 0;  // (a NaN abscissa takes the first bracket, as the bisection would)
+    if (X[g0] <= x && x < X[g0 + 1]) { lo = g0; hi = g0 + 1; }
+    else {
+      if (X[g0] <= x) lo = g0; else if (g0 > 0) hi = g0;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (X[mid] <= x) lo = mid; else hi = mid;
+      }
     }
     if (X[lo] == x) return Y[lo];
   }

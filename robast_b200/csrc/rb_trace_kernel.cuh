@@ -325,8 +325,11 @@ __global__ void __launch_bounds__(K::threads, K::min_blocks) k_nav(const __grid_
   }
 }
 
+#ifndef RB_SHADE_MB
+#define RB_SHADE_MB 0  // tuning builds: another register cap for the interaction kernel (blocks per SM), 0 = the instantiation's
+#endif
 template <class K>
-__global__ void __launch_bounds__(K::threads, K::min_blocks) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
+__global__ void __launch_bounds__(K::threads, RB_SHADE_MB > 0 ? RB_SHADE_MB : K::min_blocks) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DTraceParams tp,
                                                                      const __grid_constant__ DRays R, const __grid_constant__ DNavOut N,
                                                                      const int32_t* __restrict__ live, const int32_t* __restrict__ count, long long n_max,
                                                                      int init) {
