@@ -28,7 +28,7 @@ def func_table(path):
 
 def main():
     rep, obj = sys.argv[1], sys.argv[2]
-    kernel = sys.argv[3] if len(sys.argv) > 3 else 'k_bounce'
+    kernel = sys.argv[3] if len(sys.argv) > 3 else 'k_nav'
     launch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     lm = SL.line_map(obj, kernel)
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass', '--launch-skip', str(launch), '--launch-count', '1'],

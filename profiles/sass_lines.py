@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attribute ncu per-SASS-instruction counters to CUDA source lines (needs the .o/.cubin the profiled build came from).
 
-usage: sass_lines.py prof.ncu-rep build/rb_trace_v_X.o [launch_index] [top_n] [kernel name, default k_step]
+usage: sass_lines.py prof.ncu-rep build/rb_trace_v_X.o [launch_index] [top_n] [kernel name, default k_nav]
 Joins `ncu --page source --print-source sass` (instructions executed, stall samples, by address) with
 `nvdisasm -g` (address -> file:line) and prints the hottest source lines and functions."""
 import collections
@@ -16,7 +16,7 @@ import tempfile
 FUNCS = {}
 
 
-def line_map(obj, kernel='k_step'):
+def line_map(obj, kernel='k_nav'):
     """address -> (file, line) of the .text section of `kernel` only (each kernel's section starts at address 0)"""
     tmp = tempfile.mkdtemp()
     if obj.endswith('.cubin'):
@@ -55,7 +55,7 @@ def main():
     rep, obj = sys.argv[1], sys.argv[2]
     launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    lm = line_map(obj, sys.argv[5] if len(sys.argv) > 5 else 'k_step')
+    lm = line_map(obj, sys.argv[5] if len(sys.argv) > 5 else 'k_nav')
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass', '--launch-skip', str(launch), '--launch-count', '1'],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))

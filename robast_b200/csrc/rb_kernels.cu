@@ -679,10 +679,13 @@ static void launch_trace(const rb_variant* v, const DScene& sc, const DTracePara
   if (rc != 0) throw std::runtime_error(std::string("cuda: k_trace launch: ") + cudaGetErrorString((cudaError_t)rc));
 }
 
-static size_t wavefront_scratch_bytes(long long n) {
+static size_t wavefront_scratch_bytes(long long n, bool with_record) {
   size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
-  // cur, ndraw, liveA, liveB, cells (uint16), the nav record (6 x 16 B) + bounce counters + tile state + tile counter + cell histogram
-  return 4 * ((size_t)n * 4 + 256) + ((size_t)n * 2 + 256) + 6 * ((size_t)n * 16 + 256) + ((size_t)n * 8 + 256) + 256 + ntile * 8 + 256 + 256 + SB_BINS * 4 + 512;
+  // cur, ndraw, liveA, liveB, cells (uint16) + bounce counters + tile state + tile counter + cell histogram; and for the split bounce
+  // the record between k_nav and k_shade (6 x 16 B + 8 B per ray)
+  size_t b = 4 * ((size_t)n * 4 + 256) + ((size_t)n * 2 + 256) + 256 + ntile * 8 + 256 + 256 + SB_BINS * 4 + 512;
+  if (with_record) b += 6 * ((size_t)n * 16 + 256) + ((size_t)n * 8 + 256);
+  return b;
 }
 
 // Device-resident trace of n rays (n < 2^31) enqueued on stream st; never waits for the device.
@@ -713,7 +716,10 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   keep_pool(s->device);
   const int call = s->calls.fetch_add(1);
   char* base = nullptr;
-  CK(cudaMallocAsync((void**)&base, wavefront_scratch_bytes(n), st));
+  // RB_FUSED_BOUNCE=1 / 0 overrides the instantiation's choice between one k_trace launch per bounce and k_nav + k_shade
+  static const int fused_env = getenv("RB_FUSED_BOUNCE") ? atoi(getenv("RB_FUSED_BOUNCE")) : -1;
+  const bool fused = fused_env >= 0 ? fused_env != 0 : s->variant->fused_bounce != 0;
+  CK(cudaMallocAsync((void**)&base, wavefront_scratch_bytes(n, !fused), st));
   try {
     size_t ntile = (size_t)((n + CP_TILE - 1) / CP_TILE);
     size_t off = 0;
@@ -724,9 +730,12 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     int32_t* liveB = (int32_t*)take(n * 4);
     uint16_t* cells = (uint16_t*)take(n * 2);
     DNavOut N;
-    N.pxy = (double2*)take(n * 16); N.pzs = (double2*)take(n * 16);
-    N.loc = (int4*)take(n * 16); N.hit = (int4*)take(n * 16); N.vis = (int4*)take(2 * n * 16);
-    N.ent = (double*)take(n * 8);
+    memset(&N, 0, sizeof(N));
+    if (!fused) {
+      N.pxy = (double2*)take(n * 16); N.pzs = (double2*)take(n * 16);
+      N.loc = (int4*)take(n * 16); N.hit = (int4*)take(n * 16); N.vis = (int4*)take(2 * n * 16);
+      N.ent = (double*)take(n * 8);
+    }
     N.n = n;
     int32_t* d_counts = (int32_t*)take((RB_MAX_ROUNDS + 2) * 4);
     unsigned long long* tile_state = (unsigned long long*)take(ntile * 8);
@@ -797,9 +806,6 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
     const float inv_batch = 1.f / (float)n;
     const int vec_ok = (reinterpret_cast<uintptr_t>(R.status) & 15) == 0;
     const int tiles = (int)ntile;
-    // RB_FUSED_BOUNCE=1 / 0 overrides the instantiation's choice between one k_trace launch per bounce and k_nav + k_shade
-    static const int fused_env = getenv("RB_FUSED_BOUNCE") ? atoi(getenv("RB_FUSED_BOUNCE")) : -1;
-    const bool fused = fused_env >= 0 ? fused_env != 0 : s->variant->fused_bounce != 0;
     for (int b = 0; b < rounds; b++) {
       if (fused) launch_trace(s->variant, s->d, tp, R, live, count, estimate(b), n, b == 0, 1, st);
       else {
