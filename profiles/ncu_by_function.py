@@ -36,7 +36,7 @@ def main():
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
-    tables = {f: func_table(os.path.join(HERE, '..', 'robast_b200', 'csrc', f)) for f in ('rb_device.cuh', 'rb_trace_kernel.cuh')}
+    tables = {f: func_table(os.path.join(os.environ.get('RB_PROFILE_SRC') or os.path.join(HERE, '..', 'robast_b200', 'csrc'), f)) for f in ('rb_device.cuh', 'rb_trace_kernel.cuh')}
     inst, smp = collections.Counter(), collections.Counter()
     base = None
     for r in rows[2:]:

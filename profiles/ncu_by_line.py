@@ -38,7 +38,7 @@ for r in rows[2:]:
     thr[key] += te
     first[key] = max(first.get(key, 0), ie)
 tot = sum(inst.values())
-src = {f: open(os.path.join(HERE, '..', 'robast_b200', 'csrc', f)).read().splitlines() for f in ('rb_device.cuh', 'rb_trace_kernel.cuh')}
+src = {f: open(os.path.join(os.environ.get('RB_PROFILE_SRC') or os.path.join(HERE, '..', 'robast_b200', 'csrc'), f)).read().splitlines() for f in ('rb_device.cuh', 'rb_trace_kernel.cuh')}
 print('total warp instructions', tot)
 for (f, l), v in inst.most_common(top):
     text = src[f][l - 1].strip()[:110] if f in src and 0 < l <= len(src[f]) else ''

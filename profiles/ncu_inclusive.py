@@ -12,7 +12,7 @@ import sys
 import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(HERE, '..', 'robast_b200', 'csrc')
+CSRC = os.environ.get('RB_PROFILE_SRC') or os.path.join(HERE, '..', 'robast_b200', 'csrc')  # RB_PROFILE_SRC: the sources the profiled build came from
 
 
 def func_table(path):

@@ -41,7 +41,7 @@ for i, (a, s, ie) in enumerate(ins):
             kind = 'div' if '8.98846567431157953865e+307' in body else 'sqrt' if 'RSQ64H' in body else 'rcp'
             for k in range(j, i + 1):
                 helpers[ins[k][0]] = (kind, ins[j][0])
-src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'robast_b200', 'csrc', 'rb_device.cuh')).read().splitlines()
+src = open(os.path.join(os.environ.get('RB_PROFILE_SRC') or os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'robast_b200', 'csrc'), 'rb_device.cuh')).read().splitlines()
 by = collections.Counter()
 for a, s, ie in ins:
     m = re.search(r'CALL\.REL\.NOINC\s+0x([0-9a-f]+)', s)
