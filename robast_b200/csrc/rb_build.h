@@ -84,7 +84,14 @@ struct SceneBuilder {
       const rbg_shape& s = D->shapes[i];
       const double* P = D->dpar + s.ipar;
       DShape& o = shapes[i];
-      o.type = s.type; o.left = s.left; o.right = s.right; o.lmat = s.lmat; o.rmat = s.rmat;
+      o.type = s.type; o.left = s.left; o.right = s.right;
+      auto tag = [&](int m) {  // RB_MAT_TRANS: the device skips the rotation of a pure translation
+        if (m < 0) return m;
+        const double* r = D->matrices[m].rot;
+        const bool unit = r[0] == 1 && r[4] == 1 && r[8] == 1 && r[1] == 0 && r[2] == 0 && r[3] == 0 && r[5] == 0 && r[6] == 0 && r[7] == 0;
+        return unit ? (m | RB_MAT_TRANS) : m;
+      };
+      o.lmat = tag(s.lmat); o.rmat = tag(s.rmat);
       o.ipar = (int)dpar.size();
       Box b = box_empty();
       auto setbox = [&](double x, double y, double zlo, double zhi) { b = Box{{-x, -y, zlo}, {x, y, zhi}}; };

@@ -1694,8 +1694,15 @@ template <unsigned SM> struct Csg<0, SM> {
   static RB_HD RB_PRIM_CALL V3 normal(const DScene& sc, int sh, V3 p, V3 d, int) { return prim_normal<SM>(sc, sc.shapes[sh], p, d); }
 };
 
-RB_HD inline V3 op_point(const DScene& sc, int m, V3 p) { return m < 0 ? p : to_local(sc.mats[m], p); }
-RB_HD inline V3 op_vec(const DScene& sc, int m, V3 d) { return m < 0 ? d : to_local_vec(sc.mats[m], d); }
+RB_HD inline V3 op_point(const DScene& sc, int m, V3 p) {
+  if (m < 0) return p;
+  if (m & RB_MAT_TRANS) {
+    const double* t = sc.mats[m & ~RB_MAT_TRANS].t;
+    return v3(p.x - t[0], p.y - t[1], p.z - t[2]);
+  }
+  return to_local(sc.mats[m], p);
+}
+RB_HD inline V3 op_vec(const DScene& sc, int m, V3 d) { return (m < 0 || (m & RB_MAT_TRANS)) ? d : to_local_vec(sc.mats[m], d); }
 
 template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE bool Csg<DEPTH, SM>::contains(const DScene& sc, int sh, V3 p) {
   const DShape s = sc.shapes[sh];
@@ -1879,7 +1886,7 @@ template <int DEPTH, unsigned SM> RB_HD RB_NOINLINE V3 Csg<DEPTH, SM>::normal(co
   }
   int m = side == 1 ? s.lmat : s.rmat;
   V3 ln = Sub::normal(sc, side == 1 ? s.left : s.right, op_point(sc, m, p), op_vec(sc, m, d), sel >> 2);
-  return m < 0 ? ln : to_master_vec(sc.mats[m], ln);
+  return (m < 0 || (m & RB_MAT_TRANS)) ? ln : to_master_vec(sc.mats[m], ln);
 }
 
 // ================================================================== flat leaf evaluators
@@ -2035,7 +2042,7 @@ template <class C> struct Bool2 {
     const double* P = sc.dpar + sc.shapes[side == 1 ? s.left : s.right].ipar;
     V3 lp = op_point(sc, m, p), ld = op_vec(sc, m, d);
     V3 ln = side == 1 ? PL::normal(P, lp, ld) : PR::normal(P, lp, ld);
-    return m < 0 ? ln : to_master_vec(sc.mats[m], ln);
+    return (m < 0 || (m & RB_MAT_TRANS)) ? ln : to_master_vec(sc.mats[m], ln);
   }
 };
 

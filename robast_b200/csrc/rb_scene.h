@@ -64,6 +64,9 @@ struct DBox {   // 32 B: padded fp32 AABB of one daughter (the leaves of the mot
   int32_t pad_;
 };
 
+// operand matrix index of a boolean: -1 = identity; RB_MAT_TRANS set = pure translation (the rotation block is the unit matrix and
+// is not read: "mirSphere:transZ", "boxCamera:transZ1" — most operand matrices of real telescopes)
+#define RB_MAT_TRANS 0x40000000
 struct DShape {
   int32_t type;
   int32_t ipar;
