@@ -854,8 +854,9 @@ template <bool CONE> RB_HD inline bool poly_slab(const double* P, int k, V3 p, V
       if (fd > 0) tout = rb_min(tout, -f0 / fd);
       else if (fd < 0) tin = rb_max(tin, -f0 / fd);
       else if (f0 > 0) return false;
+      if (!(tin < tout)) return false;  // already empty: the remaining edges can only shrink it further
     }
-    return tin < tout;
+    return true;
   }
 }
 template <bool CONE> RB_HD inline double poly_dist_out(const double* P, V3 p, V3 d) {
