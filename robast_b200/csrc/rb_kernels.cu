@@ -703,7 +703,17 @@ static void trace_device(rbg_scene* s, const rbg_trace_opts* o, DRays R, long lo
   tp.quirks = o->quirks;
   // steps_per_launch: > 0 as given; 0 = auto (wavefront with one boundary step per bounce kernel for large
   // batches, where compaction pays for itself; a single launch for small ones); < 0 = single launch
-  tp.max_steps = o->steps_per_launch > 0 ? o->steps_per_launch : (o->steps_per_launch == 0 && n >= 262144 ? 1 : 0);
+  bool auto_wavefront = o->steps_per_launch == 0 && n >= 262144;
+  // An instantiation of a few plain shapes (fused_bounce == 2) leaves the wavefront once the scene has shown that its rays end
+  // within two boundary steps (the survivor shares of an earlier call, pinned memory): compaction buys nothing then —
+  // SimpleParabolicTelescope runs 8 % faster at 9e6 rays and 32 % faster at 1e6 in one launch.  A scene of the same shapes that
+  // keeps its rays bouncing stays with the wavefront.
+  if (auto_wavefront && s->variant->fused_bounce == 2 && !R.hist.x && s->calls.load() > 0) {
+    const long long tail = std::max<long long>(4096, n / 512);
+    const float f1 = s->h_frac[1];
+    if (f1 >= 0.f && (double)f1 * (double)n <= (double)tail) auto_wavefront = false;
+  }
+  tp.max_steps = o->steps_per_launch > 0 ? o->steps_per_launch : (auto_wavefront ? 1 : 0);
   if (R.hist.x) tp.max_steps = 0;  // the polyline record is written by the single-launch mode only
   tp.seed = o->seed;
   tp.ray_id_offset = id_offset;

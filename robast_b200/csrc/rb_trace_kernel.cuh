@@ -394,6 +394,8 @@ struct rb_variant {
   // 1: the wavefront takes a bounce as one k_trace launch.  Scenes of a few plain shapes have a step small enough for the
   // instruction cache; skipping the record between k_nav and k_shade (176 B per ray and bounce) is then worth 7-35 %
   // (SimpleParabolicTelescope, SchwarzschildCouder).  The Davies-Cotton dish loses 3 % that way, the Schmidt-Cassegrain 25 %.
+  // 2: as 1, and once a call has shown that the rays end within two steps the automatic mode drops the wavefront: one k_trace
+  // launch runs every ray to its end.
   int fused_bounce;
 };
 #ifndef RB_VARIANT_FUSED
