@@ -89,6 +89,44 @@ def make_clock_reader():
     return read_smi
 
 
+_AFFINITY = {}
+
+
+def all_host_cpus():
+    """undo pin_to_gpu_numa_node for the CPU legs: the oracle rows use every core of the host"""
+    if "full" in _AFFINITY:
+        os.sched_setaffinity(0, _AFFINITY["full"])
+
+
+def gpu_side_cpus():
+    if "gpu" in _AFFINITY:
+        os.sched_setaffinity(0, _AFFINITY["gpu"])
+
+
+def pin_to_gpu_numa_node(dev):
+    """Bind this rank's threads to the CPUs next to its GPU (NVML's ideal affinity) before any pinned host buffer exists: the
+    buffers of the host-buffer path are then first touched, and the copy pipeline driven, on the GPU's own NUMA node.  Returns
+    the number of CPUs in the mask, or None when NVML (or the call) is unavailable."""
+    if os.environ.get("RB_BENCH_NO_AFFINITY"):
+        return None
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(dev)
+        words = N.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        full = os.sched_getaffinity(0)
+        cpus &= full
+        if not cpus:
+            return None
+        _AFFINITY.setdefault("full", full)
+        _AFFINITY["gpu"] = cpus
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def sample_clocks(stop, out, read):
     """background sampler, used only with the nvidia-smi fallback.  NVML queries from a second thread contend for the driver lock
     with the launching thread: measured on B200, steps of 78.5 ms became 110-770 ms now and then.  The NVML reader is therefore
@@ -146,28 +184,32 @@ def spread_sample(oracle, H, beam, n_total, n_sample, windows=64):
 def cpu_rows(oracle, H, export, beam, n_total, opts, threads, seconds, flags):
     """-> (cpu_baseline dict with voxels, dict of the full daughter walk): rays/s of the oracle on `threads` host threads on a
     spread-out sample sized for about `seconds` of work each"""
-    import numpy as np
-    rows = {}
-    for vox in (1, 0):
-        oracle.orc_set_voxels(vox)
-        try:
-            probe = H.Rays(spread_sample(oracle, H, beam, n_total, 4096 * 4).T)
-            t0 = time.perf_counter()
-            H.trace_with(oracle.orc_trace, export, probe, opts, nthreads=threads)
-            rate = probe.n / (time.perf_counter() - t0)
-            ns = int(min(8e6, max(20000, rate * (seconds if vox else seconds / 3))))
-            rays = H.Rays(spread_sample(oracle, H, beam, n_total, ns).T)
-            t0 = time.perf_counter()
-            H.trace_with(oracle.orc_trace, export, rays, opts, nthreads=threads)
-            dt = time.perf_counter() - t0
-            rows[vox] = {"value": rays.n / dt, "unit": "rays/s", "cores": threads, "per_thread": rays.n / dt / threads,
-                         "kind": "port+voxels" if vox else "port",
-                         "sample": "%d rays in 64 windows spread evenly over the beam, %.1f s; reference algorithm restated in C++ (oracle/, %s), ROOT unavailable%s"
-                                   % (rays.n, dt, flags, "; daughter-box trees in TGeoVoxelFinder's role, results bit-identical to the full walk" if vox else
-                                      "; every daughter of a volume examined at every step")}
-        finally:
-            oracle.orc_set_voxels(1)
-    return rows[1], rows[0]
+    all_host_cpus()
+    try:
+        import numpy as np
+        rows = {}
+        for vox in (1, 0):
+            oracle.orc_set_voxels(vox)
+            try:
+                probe = H.Rays(spread_sample(oracle, H, beam, n_total, 4096 * 4).T)
+                t0 = time.perf_counter()
+                H.trace_with(oracle.orc_trace, export, probe, opts, nthreads=threads)
+                rate = probe.n / (time.perf_counter() - t0)
+                ns = int(min(8e6, max(20000, rate * (seconds if vox else seconds / 3))))
+                rays = H.Rays(spread_sample(oracle, H, beam, n_total, ns).T)
+                t0 = time.perf_counter()
+                H.trace_with(oracle.orc_trace, export, rays, opts, nthreads=threads)
+                dt = time.perf_counter() - t0
+                rows[vox] = {"value": rays.n / dt, "unit": "rays/s", "cores": threads, "per_thread": rays.n / dt / threads,
+                             "kind": "port+voxels" if vox else "port",
+                             "sample": "%d rays in 64 windows spread evenly over the beam, %.1f s; reference algorithm restated in C++ (oracle/, %s), ROOT unavailable%s"
+                                       % (rays.n, dt, flags, "; daughter-box trees in TGeoVoxelFinder's role, results bit-identical to the full walk" if vox else
+                                          "; every daughter of a volume examined at every step")}
+            finally:
+                oracle.orc_set_voxels(1)
+        return rows[1], rows[0]
+    finally:
+        gpu_side_cpus()
 
 
 def run_reference(args):
@@ -444,6 +486,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the tracer has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -713,7 +756,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "DaviesCotton.C (BASELINE configs[1]): 88 hex facets + camera + masts, 9 field angles 0-4 deg, Square(400 nm, 14 m, n=3334) each",
                        "rays_per_step_per_gpu": n * nang, "rays_per_step": rays_per_step, "l2_policy": "inputs (711 MB per batch) larger than L2, no flush",
-                       "steps_per_launch": args.steps_per_launch, "parallelism": "rays sharded over %d GPU(s), geometry replicated" % world},
+                       "cpus_bound_to_gpu_numa_node": numa, "steps_per_launch": args.steps_per_launch, "parallelism": "rays sharded over %d GPU(s), geometry replicated" % world},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_full_walk": cpu_full, "clocks": clocks_summary(samples),
             "step_ms": step_ms,
             "check": {"focused_fraction": focused_frac, "status_counts": counts, "d80_cm_by_angle": [round(v, 4) for v in d80_2[(state["k"] - 1) & 1][:, 0].cpu().numpy().tolist()]},
