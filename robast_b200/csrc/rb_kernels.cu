@@ -449,16 +449,27 @@ __global__ void k_hist2d(long long n, const double* __restrict__ x, const double
     __syncthreads();
   }
   double sx = nx / (xmax - xmin), sy = ny / (ymax - ymin);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (status[i] != sel) continue;
-    double vx = x[i] - x0, vy = y[i] - y0;
-    if (vx < xmin || !(vx < xmax) || vy < ymin || !(vy < ymax)) continue;
-    int bx = (int)((vx - xmin) * sx), by = (int)((vy - ymin) * sy);
-    bx = bx >= nx ? nx - 1 : bx;
-    by = by >= ny ? ny - 1 : by;
-    if (use_smem) atomicAdd(&sh[bx + nx * by], 1u);
-    else atomicAdd(&hist[bx + nx * by], 1ull);
-    st[0] += 1; st[1] += vx; st[2] += vy; st[3] += vx * vx; st[4] += vy * vy;
+  // warp-uniform trip count: the lanes of a warp (neighbouring rays of a beam, which land in the same few bins of a PSF) merge
+  // their fills — one atomic per distinct bin and warp instead of one per ray
+  const int lane = threadIdx.x & 31;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + lane;
+    int bin = -1;
+    if (i < n && status[i] == sel) {
+      double vx = x[i] - x0, vy = y[i] - y0;
+      if (!(vx < xmin || !(vx < xmax) || vy < ymin || !(vy < ymax))) {
+        int bx = (int)((vx - xmin) * sx), by = (int)((vy - ymin) * sy);
+        bx = bx >= nx ? nx - 1 : bx;
+        by = by >= ny ? ny - 1 : by;
+        bin = bx + nx * by;
+        st[0] += 1; st[1] += vx; st[2] += vy; st[3] += vx * vx; st[4] += vy * vy;
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && lane == __ffs(peers) - 1) {
+      if (use_smem) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+      else atomicAdd(&hist[bin], (unsigned long long)__popc(peers));
+    }
   }
   if (stats) {
 #pragma unroll
